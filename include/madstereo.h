@@ -1,0 +1,129 @@
+/* libmadstereo — C ABI of the B200-native real-time self-adaptive stereo engine.
+ *
+ * Drop-in boundary for ONE hot path of CVLAB-Unibo/Real-time-self-adaptive-deep-stereo: the per-frame
+ * MADNet/DispNet forward + (MAD | FULL) backward + momentum update.  Every entry point names the reference
+ * interface it replaces (paths relative to the reference checkout).
+ *
+ * Conventions: all tensors are NHWC fp32 in DEVICE memory owned by the caller; `cs` arguments are channel
+ * strides in floats (>= channels) so tensors can live inside concat buffers; `stream` is a cudaStream_t
+ * passed as void*; every function returns 0 on success and a negative code on failure, with the message
+ * available from ms_last_error().  Nothing allocates on the step path.  One host thread per GPU.
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef MADSTEREO_H
+#define MADSTEREO_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int ms_version(void);
+const char* ms_last_error(void);
+
+/* ---- operator level ------------------------------------------------------------------------------ */
+
+/* Replaces ShiftCorrKernelLauncher (Nets/Native/shift_corr.cu.cc:193-233), the TF op "ShiftCorr"
+ * (Nets/Native/shift_corr.cc:5-9,25-56) and sharedLayers.correlation / correlation_tf
+ * (Nets/sharedLayers.py:23-51).  Unlike the native op the inputs are NOT pre-padded and the output is NHWC.
+ *   out[b,y,x,out_coff+i] = mean_c left[b,y,x,c] * RW[b,y,x+(-max_disp+i*stride),c]
+ * `u` (optional, may be NULL) fuses MadNet._linear_warping (Nets/MadNet.py:400-436) of `right` by the
+ * horizontal offsets u[b,y,x].  copy_left != 0 additionally writes left into out[...,0:C] (the tf.concat of
+ * MadNet._stereo_cost_volume_correlation, Nets/MadNet.py:370-375) and the corr channels start at C. */
+int ms_corr_fwd(const float* left, int left_cs, const float* right, int right_cs, const float* u, int u_cs,
+                float* out, int out_cs, int B, int h, int w, int C, int max_disp, int stride, int copy_left,
+                int u_chan, void* stream);
+
+/* Replaces ShiftCorrGradKernelLauncher (Nets/Native/shift_corr.cu.cc:235-289) / TF op "ShiftCorrGrad"
+ * (Nets/Native/shift_corr.cc:11-17,62-93) with the mathematical gradient of correlation_tf (the native
+ * backward is defective: wrong input wiring shift_corr.cc:76, CHW/NHWC mix-up and out-of-bounds writes
+ * shift_corr.cu.cc:80,129,143,187).  dcost holds corr grads at channel offset C (and, if add_left_slice,
+ * the concat-slice grads of `left` at [0,C)).  du (optional) receives the warp-coordinate gradient. */
+int ms_corr_bwd(const float* left, int left_cs, const float* right, int right_cs, const float* u, int u_cs,
+                const float* dcost, int dcost_cs, float* dleft, int dleft_cs, float* dright, int dright_cs,
+                float* du, int du_cs, int B, int h, int w, int C, int max_disp, int stride, int add_left_slice,
+                void* stream);
+
+/* Replaces sharedLayers.conv2d / dilated_conv2d (Nets/sharedLayers.py:54-77): act(conv2d_SAME(x,W)+b),
+ * W in HWIO, act = max(alpha*v, v) (alpha = 1 -> linear). */
+int ms_conv2d_fwd(const float* x, int n, int h, int w, int cin, int x_cs, const float* weights /*HWIO*/,
+                  const float* bias, float* y, int cout, int y_cs, int kh, int kw, int stride, int dilation,
+                  float alpha, void* stream);
+/* Gradients tf.gradients derives for the op above.  dy = grad wrt the PRE-activation output.
+ * scratch: >= kh*kw*cin*cout floats (dgrad) / ms_conv2d_wgrad_workspace() floats (wgrad). */
+int ms_conv2d_dgrad(const float* dy, int n, int oh, int ow, int cout, int dy_cs, const float* weights,
+                    float* dx, int h, int w, int cin, int dx_cs, int kh, int kw, int stride, int dilation,
+                    float* scratch, void* stream);
+size_t ms_conv2d_wgrad_workspace(int kh, int kw, int cin, int cout, size_t out_pixels);
+int ms_conv2d_wgrad(const float* x, int n, int h, int w, int cin, int x_cs, const float* dy, int oh, int ow,
+                    int cout, int dy_cs, float* dw /*HWIO*/, float* db, int kh, int kw, int stride,
+                    int dilation, float* workspace, size_t workspace_floats, void* stream);
+/* Replaces sharedLayers.conv2d_transpose (Nets/sharedLayers.py:80-92); weights [kh,kw,cout,cin]. */
+int ms_conv2d_transpose_fwd(const float* x, int n, int h, int w, int cin, int x_cs, const float* weights,
+                            const float* bias, float* y, int cout, int y_cs, int kh, int kw, int stride,
+                            float alpha, float* scratch, void* stream);
+
+/* Replaces tf.image.resize_images (legacy bilinear) + resize_image_with_crop_or_pad + the relu/scale
+ * of MadNet._make_disp (Nets/MadNet.py:68-71,274,362-364): dst = post(resize(pre(src)))[centre crop]. */
+int ms_resize_bilinear(const float* src, int src_cs, int B, int ih, int iw, float* dst, int dst_cs, int rh,
+                       int rw, int oh, int ow, float pre_scale, int pre_relu, float post_scale, int post_relu,
+                       void* stream);
+int ms_resize_bilinear_bwd(const float* dout, int dout_cs, const float* src, int src_cs, int B, int ih, int iw,
+                           float* dsrc, int dsrc_cs, int rh, int rw, int oh, int ow, float pre_scale,
+                           int pre_relu, float post_scale, int post_relu, int accumulate,
+                           float* tmp /* B*oh*iw floats */, void* stream);
+
+/* Replaces loss_factory.get_reprojection_loss('mean_SSIM_l1') (Losses/loss_factory.py:353-395) with
+ * preprocessing.warp_image (Data_utils/preprocessing.py:121-230); ddisp may be NULL (forward only). */
+size_t ms_reproj_loss_workspace(int B, int H, int W);
+int ms_reproj_loss(const float* left, const float* right, const float* disp, int B, int H, int W,
+                   float* loss_out /*device scalar*/, float* ddisp, float* workspace, float grad_scale,
+                   void* stream);
+
+/* Replaces tf.train.MomentumOptimizer(lr,0.9) apply ops (Stereo_Online_Adaptation.py:85,118,128). */
+int ms_momentum_update(float* w, const float* g, float* m, size_t n, float lr, float mu, float grad_scale,
+                       void* stream);
+
+/* Replaces preprocessing.pad_image REFLECT padding (Data_utils/preprocessing.py:7-29). */
+int ms_pad_reflect(const float* src, int B, int H, int W, int C, float* dst, int Hp, int Wp, int dst_cs,
+                   float scale, float bias, void* stream);
+
+/* ---- engine level: what one sess.run(fetches) does (Stereo_Online_Adaptation.py:194-208) ---------- */
+
+/* Replaces Nets.get_stereo_net(name,args) graph construction (Nets/__init__.py:9-13, Nets/MadNet.py:251-364).
+ * net_name: "MADNet" | "Dispnet".  Returns NULL on failure. */
+void* ms_engine_create(const char* net_name, int B, int H, int W, int radius_d, int corr_stride, int warping);
+int ms_engine_destroy(void* e);
+int ms_engine_num_layers(void* e);
+/* dims: kh,kw,cin,cout,stride,dilation,transposed ; alpha_out: leaky slope (1 = linear) */
+int ms_engine_layer_info(void* e, int i, char* name, int name_cap, char* scope, int scope_cap, char* bias_name,
+                         int bias_cap, int* dims7, float* alpha_out);
+/* Replaces the per-module var_list construction from block_config JSON (Stereo_Online_Adaptation.py:110-118,
+ * Nets/Stereo_net.py:213-222): group_of_layer[i] = MAD module index of layer i, or -1. Fixes the arena order. */
+int ms_engine_set_groups(void* e, const int* group_of_layer, int n_layers, int n_groups);
+int ms_engine_sizes(void* e, size_t* n_param_floats, size_t* workspace_floats);
+int ms_engine_param_offsets(void* e, int i, size_t* w_off, size_t* b_off);
+int ms_engine_group_range(void* e, int g, size_t* begin, size_t* end);
+int ms_engine_bind(void* e, float* weights, float* grads, float* momentum, float* workspace,
+                   size_t workspace_floats, void* stream);
+/* left/right: [B,H,W,3] fp32 0..255, host (pinned recommended) or device pointers. */
+int ms_engine_set_input(void* e, const float* left, const float* right, void* stream);
+int ms_engine_set_gt(void* e, const float* gt, void* stream);
+/* disp_mask bit i => materialise get_disparities()[i] (MADNet: D6,D5,D4,D3,D2ctx,full). */
+int ms_engine_forward(void* e, int disp_mask, void* stream);
+/* slot 0 = full-res loss fetched every frame (Stereo_Online_Adaptation.py:70,209), slot 1 = train loss */
+int ms_engine_loss(void* e, int which_disp, int with_grad, int slot, float grad_scale, void* stream);
+/* mode 1 = MAD (train op `group`, Stereo_Online_Adaptation.py:87-121), 2 = FULL (:126-128) */
+int ms_engine_backward(void* e, int mode, int group, void* stream);
+int ms_engine_update(void* e, int group /* -1 = all */, float lr, float mu, float grad_scale, void* stream);
+/* scalars: [0]=slot-0 loss, [1]=slot-1 loss, [2]=EPE, [3]=bad3. Synchronises `stream`. */
+int ms_engine_read_scalars(void* e, float* host4, void* stream);
+int ms_engine_metrics(void* e, void* stream);
+int ms_engine_num_tensors(void* e);
+int ms_engine_tensor_name(void* e, int i, char* name, int cap);
+/* dims: n,h,w,c,cs */
+int ms_engine_tensor(void* e, const char* name, float** ptr, int* dims5);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

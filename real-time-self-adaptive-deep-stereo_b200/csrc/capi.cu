@@ -1,0 +1,269 @@
+// extern "C" surface of libmadstereo (declared in include/madstereo.h).
+#include <cstring>
+
+#pragma GCC visibility push(default)
+#include "../../include/madstereo.h"
+#pragma GCC visibility pop
+#include "engine.h"
+
+namespace ms { const char* last_error_cstr(); }
+using namespace ms;
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static void same_pad_c(int in, int k, int s, int d, int& out, int& before) {
+    int keff = (k - 1) * d + 1;
+    out = (in + s - 1) / s;
+    int total = (out - 1) * s + keff - in;
+    if (total < 0) total = 0;
+    before = total / 2;
+}
+static void copy_str(char* dst, int cap, const std::string& s) {
+    if (!dst || cap <= 0) return;
+    size_t n = std::min((size_t)cap - 1, s.size());
+    memcpy(dst, s.data(), n);
+    dst[n] = 0;
+}
+
+extern "C" {
+
+int ms_version(void) { return 100; }
+const char* ms_last_error(void) { return ms::last_error_cstr(); }
+
+int ms_corr_fwd(const float* left, int left_cs, const float* right, int right_cs, const float* u, int u_cs,
+                float* out, int out_cs, int B, int h, int w, int C, int max_disp, int stride, int copy_left,
+                int u_chan, void* stream) {
+    CorrFwd p{};
+    p.left = left; p.lcs = left_cs; p.right = right; p.rcs = right_cs; p.u = u; p.ucs = u_cs;
+    p.out = out; p.ocs = out_cs; p.out2 = nullptr; p.o2cs = 0;
+    p.B = B; p.h = h; p.w = w; p.C = C; p.max_disp = max_disp; p.stride = stride; p.copy_left = copy_left;
+    p.u_chan = u_chan;
+    return corr_fwd(p, S(stream));
+}
+
+int ms_corr_bwd(const float* left, int left_cs, const float* right, int right_cs, const float* u, int u_cs,
+                const float* dcost, int dcost_cs, float* dleft, int dleft_cs, float* dright, int dright_cs,
+                float* du, int du_cs, int B, int h, int w, int C, int max_disp, int stride, int add_left_slice,
+                void* stream) {
+    CorrBwd p{};
+    p.left = left; p.lcs = left_cs; p.right = right; p.rcs = right_cs; p.u = u; p.ucs = u_cs;
+    p.dcost = dcost; p.dcs = dcost_cs; p.dleft = dleft; p.dlcs = dleft_cs; p.dright = dright; p.drcs = dright_cs;
+    p.du = du; p.ducs = du_cs;
+    p.B = B; p.h = h; p.w = w; p.C = C; p.max_disp = max_disp; p.stride = stride;
+    p.add_left_slice = add_left_slice; p.acc_left = 0; p.acc_right = 0;
+    return corr_bwd(p, S(stream));
+}
+
+int ms_conv2d_fwd(const float* x, int n, int h, int w, int cin, int x_cs, const float* weights, const float* bias,
+                  float* y, int cout, int y_cs, int kh, int kw, int stride, int dilation, float alpha, void* stream) {
+    int oh, ow, pt, pl;
+    same_pad_c(h, kh, stride, dilation, oh, pt);
+    same_pad_c(w, kw, stride, dilation, ow, pl);
+    ConvGemm p{};
+    p.x = view(const_cast<float*>(x), n, h, w, cin, x_cs);
+    p.y = view(y, n, oh, ow, cout, y_cs);
+    p.wmat = weights; p.bias = bias; p.kh = kh; p.kw = kw;
+    p.mul = stride; p.off_y = -pt; p.off_x = -pl; p.step = dilation; p.div = 1;
+    p.alpha = alpha; p.mask = nullptr; p.mask_alpha = 1.f; p.res = nullptr; p.accumulate = 0;
+    return conv_gemm(p, S(stream));
+}
+
+int ms_conv2d_dgrad(const float* dy, int n, int oh, int ow, int cout, int dy_cs, const float* weights, float* dx,
+                    int h, int w, int cin, int dx_cs, int kh, int kw, int stride, int dilation, float* scratch,
+                    void* stream) {
+    int oh2, ow2, pt, pl;
+    same_pad_c(h, kh, stride, dilation, oh2, pt);
+    same_pad_c(w, kw, stride, dilation, ow2, pl);
+    if (oh2 != oh || ow2 != ow) { set_error("ms_conv2d_dgrad: shape mismatch"); return -2; }
+    if (transpose_taps(weights, scratch, kh * kw, cin, cout, S(stream))) return -1;
+    ConvGemm p{};
+    p.x = view(const_cast<float*>(dy), n, oh, ow, cout, dy_cs);
+    p.y = view(dx, n, h, w, cin, dx_cs);
+    p.wmat = scratch; p.bias = nullptr; p.kh = kh; p.kw = kw;
+    p.mul = 1; p.off_y = pt; p.off_x = pl; p.step = -dilation; p.div = stride;
+    p.alpha = 1.f; p.mask = nullptr; p.mask_alpha = 1.f; p.res = nullptr; p.accumulate = 0;
+    return conv_gemm(p, S(stream));
+}
+
+size_t ms_conv2d_wgrad_workspace(int kh, int kw, int cin, int cout, size_t out_pixels) {
+    return conv_wgrad_workspace_floats(kh * kw, cin, cout, out_pixels);
+}
+
+int ms_conv2d_wgrad(const float* x, int n, int h, int w, int cin, int x_cs, const float* dy, int oh, int ow, int cout,
+                    int dy_cs, float* dw, float* db, int kh, int kw, int stride, int dilation, float* workspace,
+                    size_t workspace_floats, void* stream) {
+    int oh2, ow2, pt, pl;
+    same_pad_c(h, kh, stride, dilation, oh2, pt);
+    same_pad_c(w, kw, stride, dilation, ow2, pl);
+    if (oh2 != oh || ow2 != ow) { set_error("ms_conv2d_wgrad: shape mismatch"); return -2; }
+    ConvWgrad q{};
+    q.x = view(const_cast<float*>(x), n, h, w, cin, x_cs);
+    q.dy = view(const_cast<float*>(dy), n, oh, ow, cout, dy_cs);
+    q.dw = dw; q.db = db; q.kh = kh; q.kw = kw; q.stride = stride; q.dil = dilation; q.pad_t = pt; q.pad_l = pl;
+    q.workspace = workspace; q.workspace_floats = workspace_floats; q.accumulate = 0;
+    return conv_wgrad(q, S(stream));
+}
+
+int ms_conv2d_transpose_fwd(const float* x, int n, int h, int w, int cin, int x_cs, const float* weights,
+                            const float* bias, float* y, int cout, int y_cs, int kh, int kw, int stride, float alpha,
+                            float* scratch, void* stream) {
+    const int oh = h * stride, ow = w * stride;
+    int t0, t1, pt, pl;
+    same_pad_c(oh, kh, stride, 1, t0, pt);
+    same_pad_c(ow, kw, stride, 1, t1, pl);
+    if (transpose_taps(weights, scratch, kh * kw, cout, cin, S(stream))) return -1;   // [tap][cout][cin] -> [tap][cin][cout]
+    ConvGemm p{};
+    p.x = view(const_cast<float*>(x), n, h, w, cin, x_cs);
+    p.y = view(y, n, oh, ow, cout, y_cs);
+    p.wmat = scratch; p.bias = bias; p.kh = kh; p.kw = kw;
+    p.mul = 1; p.off_y = pt; p.off_x = pl; p.step = -1; p.div = stride;
+    p.alpha = alpha; p.mask = nullptr; p.mask_alpha = 1.f; p.res = nullptr; p.accumulate = 0;
+    return conv_gemm(p, S(stream));
+}
+
+int ms_resize_bilinear(const float* src, int src_cs, int B, int ih, int iw, float* dst, int dst_cs, int rh, int rw,
+                       int oh, int ow, float pre_scale, int pre_relu, float post_scale, int post_relu, void* stream) {
+    return resize_bilinear(src, src_cs, B, ih, iw, dst, dst_cs, rh, rw, oh, ow, pre_scale, pre_relu, post_scale,
+                           post_relu, S(stream));
+}
+int ms_resize_bilinear_bwd(const float* dout, int dout_cs, const float* src, int src_cs, int B, int ih, int iw,
+                           float* dsrc, int dsrc_cs, int rh, int rw, int oh, int ow, float pre_scale, int pre_relu,
+                           float post_scale, int post_relu, int accumulate, float* tmp, void* stream) {
+    return resize_bilinear_bwd(dout, dout_cs, src, src_cs, B, ih, iw, dsrc, dsrc_cs, rh, rw, oh, ow, pre_scale,
+                               pre_relu, post_scale, post_relu, accumulate, tmp, S(stream));
+}
+
+size_t ms_reproj_loss_workspace(int B, int H, int W) { return loss_workspace_floats(B, H, W); }
+int ms_reproj_loss(const float* left, const float* right, const float* disp, int B, int H, int W, float* loss_out,
+                   float* ddisp, float* workspace, float grad_scale, void* stream) {
+    ReprojLoss p{};
+    p.left = left; p.right = right; p.disp = disp; p.loss = loss_out; p.ddisp = ddisp; p.workspace = workspace;
+    p.B = B; p.H = H; p.W = W; p.grad_scale = grad_scale;
+    return reproj_loss(p, S(stream));
+}
+
+int ms_momentum_update(float* w, const float* g, float* m, size_t n, float lr, float mu, float grad_scale,
+                       void* stream) {
+    return momentum_update(w, g, m, n, lr, mu, grad_scale, S(stream));
+}
+
+int ms_pad_reflect(const float* src, int B, int H, int W, int C, float* dst, int Hp, int Wp, int dst_cs, float scale,
+                   float bias, void* stream) {
+    return pad_reflect(src, B, H, W, C, dst, Hp, Wp, dst_cs, scale, bias, S(stream));
+}
+
+// ---- engine --------------------------------------------------------------------------------------
+void* ms_engine_create(const char* net_name, int B, int H, int W, int radius_d, int corr_stride, int warping) {
+    if (!net_name || B < 1 || H < 8 || W < 8 || radius_d < 0 || corr_stride < 1) {
+        set_error("ms_engine_create: bad arguments");
+        return nullptr;
+    }
+    Engine* e = new Engine();
+    e->B = B; e->H = H; e->W = W;
+    e->Hp = (H + 63) / 64 * 64; e->Wp = (W + 63) / 64 * 64;
+    e->radius_d = radius_d; e->corr_stride = corr_stride; e->warping = warping;
+    if (!strcmp(net_name, "MADNet")) { e->net = 0; e->build_madnet(); }
+    else { set_error(std::string("Unrecognized network name: ") + net_name); delete e; return nullptr; }
+    e->finalize_groups(nullptr, 0);
+    return e;
+}
+int ms_engine_destroy(void* h) { delete static_cast<Engine*>(h); return 0; }
+int ms_engine_num_layers(void* h) { return (int)static_cast<Engine*>(h)->layers.size(); }
+int ms_engine_layer_info(void* h, int i, char* name, int name_cap, char* scope, int scope_cap, char* bias_name,
+                         int bias_cap, int* dims7, float* alpha_out) {
+    Engine* e = static_cast<Engine*>(h);
+    if (i < 0 || i >= (int)e->layers.size()) { set_error("layer index out of range"); return -2; }
+    const ConvLayer& L = e->layers[i];
+    copy_str(name, name_cap, L.name); copy_str(scope, scope_cap, L.scope); copy_str(bias_name, bias_cap, L.bname);
+    if (dims7) { dims7[0] = L.kh; dims7[1] = L.kw; dims7[2] = L.cin; dims7[3] = L.cout; dims7[4] = L.stride; dims7[5] = L.dil; dims7[6] = L.transposed; }
+    if (alpha_out) *alpha_out = L.alpha;
+    return 0;
+}
+int ms_engine_set_groups(void* h, const int* group_of_layer, int n_layers, int n_groups) {
+    Engine* e = static_cast<Engine*>(h);
+    if (e->bound) { set_error("ms_engine_set_groups: engine already bound"); return -2; }
+    if (n_layers != (int)e->layers.size()) { set_error("ms_engine_set_groups: layer count mismatch"); return -2; }
+    return e->finalize_groups(group_of_layer, n_groups);
+}
+int ms_engine_sizes(void* h, size_t* n_param_floats, size_t* workspace_floats) {
+    Engine* e = static_cast<Engine*>(h);
+    if (n_param_floats) *n_param_floats = e->n_params;
+    if (workspace_floats) *workspace_floats = e->layout(nullptr);
+    return 0;
+}
+int ms_engine_param_offsets(void* h, int i, size_t* w_off, size_t* b_off) {
+    Engine* e = static_cast<Engine*>(h);
+    if (i < 0 || i >= (int)e->layers.size()) { set_error("layer index out of range"); return -2; }
+    *w_off = e->layers[i].w_off; *b_off = e->layers[i].b_off;
+    return 0;
+}
+int ms_engine_group_range(void* h, int g, size_t* begin, size_t* end) {
+    Engine* e = static_cast<Engine*>(h);
+    if (g < 0 || g >= e->n_groups) { set_error("group index out of range"); return -2; }
+    *begin = e->group_begin[g]; *end = e->group_end[g];
+    return 0;
+}
+int ms_engine_bind(void* h, float* weights, float* grads, float* momentum, float* workspace, size_t workspace_floats,
+                   void* stream) {
+    Engine* e = static_cast<Engine*>(h);
+    size_t need = e->layout(nullptr);
+    if (workspace_floats < need) { set_error("ms_engine_bind: workspace too small"); return -2; }
+    if (((uintptr_t)weights | (uintptr_t)grads | (uintptr_t)momentum | (uintptr_t)workspace) & 255) {
+        set_error("ms_engine_bind: arenas must be 256-byte aligned"); return -2;
+    }
+    e->Wt = weights; e->Gr = grads; e->Mo = momentum; e->ws = workspace; e->ws_floats = workspace_floats;
+    e->layout(workspace);
+    MS_CHECK_CUDA(cudaMemsetAsync(workspace, 0, need * sizeof(float), S(stream)));
+    MS_CHECK_CUDA(cudaMemsetAsync(grads, 0, e->n_params * sizeof(float), S(stream)));
+    e->bound = true;
+    return 0;
+}
+int ms_engine_set_input(void* h, const float* left, const float* right, void* stream) {
+    return static_cast<Engine*>(h)->set_input(left, right, S(stream));
+}
+int ms_engine_set_gt(void* h, const float* gt, void* stream) {
+    Engine* e = static_cast<Engine*>(h);
+    if (!e->bound) { set_error("engine not bound"); return -2; }
+    MS_CHECK_CUDA(cudaMemcpyAsync(e->gt, gt, (size_t)e->B * e->H * e->W * sizeof(float), cudaMemcpyDefault, S(stream)));
+    return 0;
+}
+int ms_engine_forward(void* h, int disp_mask, void* stream) { return static_cast<Engine*>(h)->forward(disp_mask, S(stream)); }
+int ms_engine_loss(void* h, int which, int with_grad, int slot, float grad_scale, void* stream) {
+    return static_cast<Engine*>(h)->loss(which, with_grad, slot, grad_scale, S(stream));
+}
+int ms_engine_backward(void* h, int mode, int group, void* stream) {
+    return static_cast<Engine*>(h)->backward(mode, group, S(stream));
+}
+int ms_engine_update(void* h, int group, float lr, float mu, float grad_scale, void* stream) {
+    return static_cast<Engine*>(h)->update(group, lr, mu, grad_scale, S(stream));
+}
+int ms_engine_metrics(void* h, void* stream) {
+    Engine* e = static_cast<Engine*>(h);
+    if (!e->bound) { set_error("engine not bound"); return -2; }
+    return epe_bad3(e->disp[5].p, e->gt, e->B * e->H * e->W, e->scalars + 2, e->loss_ws, S(stream));
+}
+int ms_engine_read_scalars(void* h, float* host4, void* stream) {
+    Engine* e = static_cast<Engine*>(h);
+    if (!e->bound) { set_error("engine not bound"); return -2; }
+    MS_CHECK_CUDA(cudaMemcpyAsync(host4, e->scalars, 4 * sizeof(float), cudaMemcpyDeviceToHost, S(stream)));
+    MS_CHECK_CUDA(cudaStreamSynchronize(S(stream)));
+    return 0;
+}
+int ms_engine_num_tensors(void* h) { return (int)static_cast<Engine*>(h)->tensors.size(); }
+int ms_engine_tensor_name(void* h, int i, char* name, int cap) {
+    Engine* e = static_cast<Engine*>(h);
+    if (i < 0 || i >= (int)e->tensors.size()) { set_error("tensor index out of range"); return -2; }
+    auto it = e->tensors.begin();
+    std::advance(it, i);
+    copy_str(name, cap, it->first);
+    return 0;
+}
+int ms_engine_tensor(void* h, const char* name, float** ptr, int* dims5) {
+    Engine* e = static_cast<Engine*>(h);
+    auto it = e->tensors.find(name);
+    if (it == e->tensors.end()) { set_error(std::string("unknown tensor: ") + name); return -2; }
+    if (ptr) *ptr = it->second.p;
+    if (dims5) { dims5[0] = it->second.n; dims5[1] = it->second.h; dims5[2] = it->second.w; dims5[3] = it->second.c; dims5[4] = it->second.cs; }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,140 @@
+// Shared declarations for libmadstereo (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace ms {
+
+// NHWC fp32 view: `cs` = floats between consecutive pixels (>= c), so that a tensor can live as a
+// channel slice of a wider concat buffer (zero-copy tf.concat).
+struct TView {
+    float* p;
+    int n, h, w, c, cs;
+    __host__ __device__ size_t pixels() const { return (size_t)n * h * w; }
+};
+
+inline TView view(float* p, int n, int h, int w, int c, int cs = 0) {
+    TView v; v.p = p; v.n = n; v.h = h; v.w = w; v.c = c; v.cs = cs ? cs : c; return v;
+}
+inline TView slice(const TView& t, int c0, int c) { TView v = t; v.p = t.p + c0; v.c = c; return v; }
+inline TView batch(const TView& t, int n0, int n) {
+    TView v = t; v.p = t.p + (size_t)n0 * t.h * t.w * t.cs; v.n = n; return v;
+}
+
+void set_error(const std::string& s);
+int check_launch(const char* what);
+
+#define MS_CHECK_CUDA(expr)                                                                   \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            ms::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                \
+            return -1;                                                                        \
+        }                                                                                     \
+    } while (0)
+
+#define MS_REQUIRE(cond, msg)                                                                 \
+    do {                                                                                      \
+        if (!(cond)) { ms::set_error(std::string("requirement failed: ") + msg); return -2; } \
+    } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline size_t cdivz(size_t a, size_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------
+// conv geometry: generic "gather GEMM".  For output pixel (oy,ox) and tap (r,s) the gathered
+// input coordinate is   t = o*mul + off + tap*step ;  if (div>1) { require t % div == 0; t /= div }.
+//   forward conv      : mul=stride, off=-pad_before, step=+dilation, div=1
+//   dgrad / conv_transpose : mul=1, off=+pad_before, step=-dilation, div=stride
+// ---------------------------------------------------------------------------------------------
+struct ConvGemm {
+    TView x;              // gathered operand  [n, xh, xw, K-channels]
+    const float* wmat;    // [taps][x.c][y.c] row-major
+    const float* bias;    // [y.c] or nullptr
+    TView y;              // output [n, yh, yw, N-channels]
+    int kh, kw;
+    int mul, off_y, off_x, step, div;
+    float alpha;          // epilogue leaky slope (1 = linear)
+    const float* mask; int mask_cs; float mask_alpha;   // optional: y *= (mask>0 ? 1 : mask_alpha)
+    const float* res;  int res_cs;                      // optional: y += res (same channel index)
+    int accumulate;       // y += existing y (applied before mask)
+};
+int conv_gemm(const ConvGemm& p, cudaStream_t st);
+
+struct ConvWgrad {
+    TView x;              // forward-conv input   [n, xh, xw, ci]
+    TView dy;             // grad wrt conv pre-activation output [n, yh, yw, co]
+    float* dw;            // [taps][ci][co]
+    float* db;            // [co] or nullptr
+    int kh, kw, stride, dil, pad_t, pad_l;
+    float* workspace; size_t workspace_floats;   // split-K partials
+    int accumulate;       // dw += (shared weights called twice); normally 0
+};
+int conv_wgrad(const ConvWgrad& p, cudaStream_t st);
+size_t conv_wgrad_workspace_floats(int taps, int ci, int co, size_t pixels);
+
+int transpose_taps(const float* w, float* wt, int taps, int ci, int co, cudaStream_t st);
+
+// correlation / warp (corr.cu)
+struct CorrFwd {
+    const float* left;  int lcs;     // [B,h,w,C] view
+    const float* right; int rcs;     // [B,h,w,C] view (un-warped)
+    const float* u;     int ucs;     // optional [B,h,w,1] horizontal offsets (nullptr = no warp)
+    float* out; int ocs;             // cost buffer: channels [0,C)=left (if copy_left), [C,C+nd)=corr
+    float* out2; int o2cs;           // optional 2nd destination for the left copy (context input)
+    int B, h, w, C, max_disp, stride, copy_left;
+    int u_chan;                      // 1 if the concat buffer keeps a `u` channel right after the corr channels
+};
+int corr_fwd(const CorrFwd& p, cudaStream_t st);
+
+struct CorrBwd {
+    const float* left;  int lcs;
+    const float* right; int rcs;
+    const float* u;     int ucs;     // nullptr = no warp
+    const float* dcost; int dcs;     // grad of cost buffer; corr grads at channel offset C
+    float* dleft;  int dlcs;         // out: d(left feature)  = dcost[:, :C]*add_left_slice + corr term
+    float* dright; int drcs;         // out: d(right feature) (scatter through the warp)
+    float* du;     int ducs;         // optional out: d(u) from the warp coordinates (FULL mode)
+    int B, h, w, C, max_disp, stride, add_left_slice, acc_left, acc_right;
+};
+int corr_bwd(const CorrBwd& p, cudaStream_t st);
+
+// elementwise / resampling (elementwise.cu)
+int pad_reflect(const float* src, int B, int H, int W, int C, float* dst, int Hp, int Wp, int dcs,
+                float scale, float bias, cudaStream_t st);
+// dst = post( resize_bilinear_legacy( pre(src) ) ) cropped (centre) to [oh,ow] from [rh,rw]
+//   pre(v)  = pre_relu ? max(v*pre_scale,0) : v*pre_scale ;  post(v) = post_relu ? max(v*post_scale,0) : v*post_scale
+int resize_bilinear(const float* src, int scs, int B, int ih, int iw, float* dst, int dcs, int rh, int rw,
+                    int oh, int ow, float pre_scale, int pre_relu, float post_scale, int post_relu,
+                    cudaStream_t st);
+// gradient of the above wrt src (gather form, deterministic). needs src for the relu masks.
+int resize_bilinear_bwd(const float* dout, int docs, const float* src, int scs, int B, int ih, int iw,
+                        float* dsrc, int dscs, int rh, int rw, int oh, int ow, float pre_scale, int pre_relu,
+                        float post_scale, int post_relu, int accumulate, float* tmp /* B*oh*iw floats */,
+                        cudaStream_t st);
+int leaky_bwd(float* g, int gcs, const float* act, int acs, size_t pixels, int c, float alpha, cudaStream_t st);
+int add_channels(float* dst, int dcs, const float* src, int scs, size_t pixels, int c, float scale,
+                 int accumulate, cudaStream_t st);
+int fill(float* p, size_t n, float v, cudaStream_t st);
+
+// loss (loss.cu)
+struct ReprojLoss {
+    const float* left; const float* right;   // [B,H,W,3], 0..255
+    const float* disp;                        // [B,H,W,1]
+    float* loss;                              // device scalar out
+    float* ddisp;                             // optional [B,H,W,1] gradient out (nullptr = forward only)
+    float* workspace;                         // >= loss_workspace_floats(B,H,W)
+    int B, H, W;
+    float grad_scale;                         // multiplies the gradient (1 for a single rank)
+};
+size_t loss_workspace_floats(int B, int H, int W);
+int reproj_loss(const ReprojLoss& p, cudaStream_t st);
+int epe_bad3(const float* disp, const float* gt, int n, float* out2, float* workspace, cudaStream_t st);
+
+// optimizer (optim.cu)
+int momentum_update(float* w, const float* g, float* m, size_t n, float lr, float mu, float gscale,
+                    cudaStream_t st);
+
+}  // namespace ms

@@ -1,0 +1,377 @@
+// Horizontal correlation cost volume, fused with the MADNet linear warp and the cost-volume concat.
+//
+// Replaces sharedLayers.correlation / correlation_tf (reference Nets/sharedLayers.py:23-51), the native
+// ShiftCorr op it can optionally call (Nets/Native/shift_corr.cu.cc:17-70,193-233 forward;
+// :73-191,235-289 backward -- whose backward is defective, see DESIGN.md, so the *mathematical* gradient
+// of correlation_tf is implemented), MadNet._linear_warping (Nets/MadNet.py:400-436) and
+// MadNet._stereo_cost_volume_correlation's tf.concat (Nets/MadNet.py:370-375).
+//
+//   corr[b,y,x,i] = (1/C) * sum_c L[b,y,x,c] * RW[b,y,x+d_i,c],   d_i = -max_disp + i*stride, 0 outside
+//   RW[x'] = wt0*R[x0s] + wt1*R[x1s]  with cx = x'+u[x'], x0=floor(cx), taps outside [0,w-1] weight 0
+//
+// One CTA owns one image row segment; the left/right feature rows are staged into shared memory with
+// 1-D TMA bulk copies (cp.async.bulk + mbarrier); 8 lanes share a pixel (float4 channel chunks) and
+// reduce the displacement sums with warp shuffles; results go out as 128-bit stores straight into the
+// concat buffer the first estimator conv reads.  No tensor cores: it is a shifted inner product.
+#include "common.cuh"
+#include <cstdlib>
+
+namespace ms {
+
+// ---- PTX helpers (mbarrier + bulk async copy) ------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const uint32_t a = smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+struct WarpTap { int i0, i1; float w0, w1; };
+
+// warp coordinates for target column xp (already known to be inside [0,w)); uu = u[xp] or 0
+__device__ __forceinline__ WarpTap warp_tap(int xp, float uu, int w, bool warped) {
+    WarpTap t;
+    if (!warped) { t.i0 = xp; t.i1 = xp; t.w0 = 1.f; t.w1 = 0.f; return t; }
+    float cx = (float)xp + uu;
+    float x0 = floorf(cx), x1 = x0 + 1.f;
+    float x0s = fminf(fmaxf(x0, 0.f), (float)(w - 1));
+    float x1s = fminf(fmaxf(x1, 0.f), (float)(w - 1));
+    t.w0 = (x1 - cx) * (x0 == x0s ? 1.f : 0.f);
+    t.w1 = (cx - x0) * (x1 == x1s ? 1.f : 0.f);
+    t.i0 = (int)x0s; t.i1 = (int)x1s;
+    return t;
+}
+
+// stage the contiguous feature row segment [wlo,whi) x C of one image row into smem
+__device__ __forceinline__ void stage_row(float* dst, const float* src_row, int cs, int C, int wlo, int whi,
+                                          bool use_tma, uint64_t* bar) {
+    const int npx = whi - wlo;
+    if (use_tma) {
+        if (threadIdx.x == 0) {
+            uint32_t bytes = (uint32_t)npx * C * 4u;
+            uint32_t off = 0;
+            while (off < bytes) {   // <=32 KB pieces keep each bulk request modest
+                uint32_t n = min(bytes - off, 32768u);
+                bulk_g2s(reinterpret_cast<char*>(dst) + off,
+                         reinterpret_cast<const char*>(src_row + (size_t)wlo * cs) + off, n, bar);
+                off += n;
+            }
+        }
+    } else {
+        const int nvec = C / 4;
+        for (int e = threadIdx.x; e < npx * nvec; e += blockDim.x) {
+            int px = e / nvec, q = e - px * nvec;
+            reinterpret_cast<float4*>(dst)[e] =
+                *reinterpret_cast<const float4*>(src_row + (size_t)(wlo + px) * cs + q * 4);
+        }
+    }
+}
+
+constexpr int CORR_NT = 256;
+constexpr int LPP = 8;  // lanes per pixel
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CORR_NT) corr_fwd_kernel(CorrFwd p, int TW, int nd, int use_tma) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    const int C = p.C, w = p.w, d = p.max_disp;
+    const bool warped = p.u != nullptr;
+    const int row = blockIdx.y;                 // b*h + y
+    const int x0 = blockIdx.x * TW, x1 = min(w, x0 + TW);
+    const int rlo = warped ? 0 : max(0, x0 - d), rhi = warped ? w : min(w, x1 + d);
+    float* Ls = reinterpret_cast<float*>(smem_raw);                 // [TW][C]
+    float* Rs = Ls + (size_t)TW * C;                                  // [rhi-rlo][C]
+    float* Us = Rs + (size_t)(warped ? w : (TW + 2 * d)) * C;        // [w] (warped only)
+
+    const float* lrow = p.left + (size_t)row * w * p.lcs;
+    const float* rrow = p.right + (size_t)row * w * p.rcs;
+
+    if (use_tma && threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    if (use_tma && threadIdx.x == 0) mbar_expect_tx(&bar, (uint32_t)((x1 - x0) + (rhi - rlo)) * C * 4u);
+    stage_row(Ls, lrow, p.lcs, C, x0, x1, use_tma, &bar);
+    stage_row(Rs, rrow, p.rcs, C, rlo, rhi, use_tma, &bar);
+    if (warped)
+        for (int e = threadIdx.x; e < w; e += blockDim.x) Us[e] = p.u[((size_t)row * w + e) * p.ucs];
+    __syncthreads();
+    if (use_tma) mbar_wait(&bar, 0);
+
+    const int lane = threadIdx.x & 31, sub = lane & (LPP - 1);
+    const int grp = threadIdx.x / LPP, ngrp = CORR_NT / LPP;
+    const int nchunk = C / 4;
+    const float invC = 1.f / (float)C;
+    float* orow = p.out + (size_t)row * w * p.ocs;
+    float* o2row = p.out2 ? p.out2 + (size_t)row * w * p.o2cs : nullptr;
+    const int coff = p.copy_left ? C : 0;
+    const int tail0 = coff + nd + p.u_chan;            // first pad channel (the u channel is left untouched)
+
+    for (int xb = x0; xb < x1; xb += ngrp) {   // uniform trip count: every lane reaches the shuffles
+        const bool act = xb + grp < x1;
+        const int x = act ? xb + grp : x0;       // x is uniform across the 8 lanes of a group
+        const float4* L4 = reinterpret_cast<const float4*>(Ls + (size_t)(x - x0) * C);
+        // copy of the left features into the concat buffer(s)
+        if (p.copy_left && act) {
+            for (int q = sub; q < nchunk; q += LPP) {
+                float4 v = L4[q];
+                *reinterpret_cast<float4*>(orow + (size_t)x * p.ocs + q * 4) = v;
+                if (o2row) *reinterpret_cast<float4*>(o2row + (size_t)x * p.o2cs + q * 4) = v;
+            }
+        }
+        for (int i = 0; i < nd; ++i) {
+            const int xp = x + (-d + i * p.stride);
+            float s = 0.f;
+            if (act && xp >= 0 && xp < w) {
+                WarpTap t = warp_tap(xp, warped ? Us[xp] : 0.f, w, warped);
+                const float4* R0 = reinterpret_cast<const float4*>(Rs + (size_t)(t.i0 - rlo) * C);
+                const float4* R1 = reinterpret_cast<const float4*>(Rs + (size_t)(t.i1 - rlo) * C);
+                for (int q = sub; q < nchunk; q += LPP) {
+                    float4 l = L4[q], a = R0[q];
+                    if (warped) {
+                        float4 b = R1[q];
+                        a.x = t.w0 * a.x + t.w1 * b.x; a.y = t.w0 * a.y + t.w1 * b.y;
+                        a.z = t.w0 * a.z + t.w1 * b.z; a.w = t.w0 * a.w + t.w1 * b.w;
+                    }
+                    s = fmaf(l.x, a.x, s); s = fmaf(l.y, a.y, s); s = fmaf(l.z, a.z, s); s = fmaf(l.w, a.w, s);
+                }
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            if (act && sub == (i & (LPP - 1))) orow[(size_t)x * p.ocs + coff + i] = s * invC;
+        }
+        if (act && sub == 0 && p.copy_left)
+            for (int c = tail0; c < p.ocs; ++c) orow[(size_t)x * p.ocs + c] = 0.f;
+    }
+}
+
+static bool corr_use_tma() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MS_CORR_NO_TMA"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
+}
+static bool a16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static int pick_tw(int w, int C, int d, bool warped, size_t row_bufs_full, size_t budget, size_t extra) {
+    // warped: windows are the full row regardless of TW
+    const int cands[] = {w, 256, 128, 64, 32, 16, 8};
+    for (int tw : cands) {
+        if (tw > w) continue;
+        size_t win = warped ? (size_t)w : (size_t)(tw + 2 * d);
+        size_t bytes = (row_bufs_full * win + (size_t)tw) * C * 4 + extra;
+        if (bytes <= budget) return tw;
+        if (warped) break;
+    }
+    return -1;
+}
+
+int corr_fwd(const CorrFwd& p, cudaStream_t st) {
+    MS_REQUIRE(p.C % 4 == 0 && p.lcs % 4 == 0 && p.rcs % 4 == 0, "corr_fwd: C and strides must be multiples of 4");
+    MS_REQUIRE(a16(p.left) && a16(p.right) && a16(p.out), "corr_fwd: pointers must be 16B aligned");
+    MS_REQUIRE(!p.copy_left || (p.ocs % 4 == 0), "corr_fwd: concat stride must be a multiple of 4");
+    MS_REQUIRE(p.stride >= 1, "corr_fwd: stride");
+    const bool warped = p.u != nullptr;
+    const int nd = (2 * p.max_disp) / p.stride + 1;
+    const size_t budget = 200 * 1024;
+    int TW = pick_tw(p.w, p.C, p.max_disp, warped, 1, budget, (size_t)p.w * 4 + 64);
+    MS_REQUIRE(TW > 0, "corr_fwd: row does not fit in shared memory");
+    size_t smem = ((size_t)TW + (warped ? p.w : TW + 2 * p.max_disp)) * p.C * 4 + (warped ? (size_t)p.w * 4 : 0) + 64;
+    int tma = corr_use_tma() && p.lcs == p.C && p.rcs == p.C;
+    MS_CHECK_CUDA(cudaFuncSetAttribute(corr_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(cdiv(p.w, TW), p.B * p.h);
+    corr_fwd_kernel<<<grid, CORR_NT, smem, st>>>(p, TW, nd, tma);
+    return check_launch("corr_fwd");
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CORR_NT) corr_bwd_kernel(CorrBwd p, int TW, int nd, int use_tma) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    const int C = p.C, w = p.w, d = p.max_disp;
+    const bool warped = p.u != nullptr;
+    const int row = blockIdx.y;
+    const int x0 = blockIdx.x * TW, x1 = min(w, x0 + TW);
+    const int wlo = warped ? 0 : max(0, x0 - d), whi = warped ? w : min(w, x1 + d);
+    const int WIN = warped ? w : (TW + 2 * d);
+    float* Ls = reinterpret_cast<float*>(smem_raw);   // [WIN][C]   (later: scatter accumulator)
+    float* Rs = Ls + (size_t)WIN * C;                   // [WIN][C]
+    float* Ds = Rs + (size_t)WIN * C;                   // [TW][C]    d_rw (only when warped)
+    float* Gs = Ds + (size_t)(warped ? TW : 0) * C;     // [WIN][nd]  corr grads
+    float* Us = Gs + (size_t)WIN * nd;                  // [w]
+
+    const float* lrow = p.left + (size_t)row * w * p.lcs;
+    const float* rrow = p.right + (size_t)row * w * p.rcs;
+    const float* grow = p.dcost + (size_t)row * w * p.dcs;
+
+    if (use_tma && threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    if (use_tma && threadIdx.x == 0) mbar_expect_tx(&bar, (uint32_t)(2 * (whi - wlo)) * C * 4u);
+    stage_row(Ls, lrow, p.lcs, C, wlo, whi, use_tma, &bar);
+    stage_row(Rs, rrow, p.rcs, C, wlo, whi, use_tma, &bar);
+    for (int e = threadIdx.x; e < (whi - wlo) * nd; e += blockDim.x) {
+        int px = e / nd, i = e - px * nd;
+        Gs[e] = grow[(size_t)(wlo + px) * p.dcs + C + i];
+    }
+    if (warped)
+        for (int e = threadIdx.x; e < w; e += blockDim.x) Us[e] = p.u[((size_t)row * w + e) * p.ucs];
+    __syncthreads();
+    if (use_tma) mbar_wait(&bar, 0);
+
+    const int lane = threadIdx.x & 31, sub = lane & (LPP - 1);
+    const int grp = threadIdx.x / LPP, ngrp = CORR_NT / LPP;
+    const int nchunk = C / 4;
+    const float invC = 1.f / (float)C;
+    float* dlrow = p.dleft + (size_t)row * w * p.dlcs;
+    float* drrow = p.dright + (size_t)row * w * p.drcs;
+
+    for (int xb = x0; xb < x1; xb += ngrp) {   // uniform trip count (shuffles below)
+        const bool act = xb + grp < x1;
+        const int x = act ? xb + grp : x0;
+        // ---- dL[x,:] = slice + (1/C) sum_i g[x,i] * RW[x+d_i,:]
+        for (int q = sub; q < nchunk && act; q += LPP) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < nd; ++i) {
+                const int xp = x + (-d + i * p.stride);
+                if (xp < 0 || xp >= w) continue;
+                const float g = Gs[(size_t)(x - wlo) * nd + i];
+                WarpTap t = warp_tap(xp, warped ? Us[xp] : 0.f, w, warped);
+                float4 a = reinterpret_cast<const float4*>(Rs + (size_t)(t.i0 - wlo) * C)[q];
+                if (warped) {
+                    float4 b = reinterpret_cast<const float4*>(Rs + (size_t)(t.i1 - wlo) * C)[q];
+                    a.x = t.w0 * a.x + t.w1 * b.x; a.y = t.w0 * a.y + t.w1 * b.y;
+                    a.z = t.w0 * a.z + t.w1 * b.z; a.w = t.w0 * a.w + t.w1 * b.w;
+                }
+                acc.x = fmaf(g, a.x, acc.x); acc.y = fmaf(g, a.y, acc.y);
+                acc.z = fmaf(g, a.z, acc.z); acc.w = fmaf(g, a.w, acc.w);
+            }
+            acc.x *= invC; acc.y *= invC; acc.z *= invC; acc.w *= invC;
+            if (p.add_left_slice) {
+                float4 sl = *reinterpret_cast<const float4*>(grow + (size_t)x * p.dcs + q * 4);
+                acc.x += sl.x; acc.y += sl.y; acc.z += sl.z; acc.w += sl.w;
+            }
+            float4* dst = reinterpret_cast<float4*>(dlrow + (size_t)x * p.dlcs + q * 4);
+            if (p.acc_left) { float4 o = *dst; acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w; }
+            *dst = acc;
+        }
+        // ---- d_rw[x,:] = (1/C) sum_i g[x-d_i, i] * L[x-d_i,:]     (x plays the role of x')
+        float du_part = 0.f;
+        WarpTap tx_ = warp_tap(x, warped ? Us[x] : 0.f, w, warped);
+        for (int q = sub; q < nchunk && act; q += LPP) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < nd; ++i) {
+                const int xs = x - (-d + i * p.stride);
+                if (xs < 0 || xs >= w) continue;
+                const float g = Gs[(size_t)(xs - wlo) * nd + i];
+                float4 l = reinterpret_cast<const float4*>(Ls + (size_t)(xs - wlo) * C)[q];
+                acc.x = fmaf(g, l.x, acc.x); acc.y = fmaf(g, l.y, acc.y);
+                acc.z = fmaf(g, l.z, acc.z); acc.w = fmaf(g, l.w, acc.w);
+            }
+            acc.x *= invC; acc.y *= invC; acc.z *= invC; acc.w *= invC;
+            if (!warped) {
+                float4* dst = reinterpret_cast<float4*>(drrow + (size_t)x * p.drcs + q * 4);
+                if (p.acc_right) { float4 o = *dst; acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w; }
+                *dst = acc;
+            } else {
+                reinterpret_cast<float4*>(Ds + (size_t)(x - x0) * C)[q] = acc;
+                if (p.du) {
+                    float4 a = reinterpret_cast<const float4*>(Rs + (size_t)(tx_.i0 - wlo) * C)[q];
+                    float4 b = reinterpret_cast<const float4*>(Rs + (size_t)(tx_.i1 - wlo) * C)[q];
+                    // d(wt0)/d(cx) = -mask0 ; d(wt1)/d(cx) = +mask1
+                    float cx = (float)x + Us[x];
+                    float f0 = floorf(cx);
+                    float k0 = (f0 >= 0.f && f0 <= (float)(w - 1)) ? -1.f : 0.f;
+                    float k1 = (f0 + 1.f >= 0.f && f0 + 1.f <= (float)(w - 1)) ? 1.f : 0.f;
+                    du_part += acc.x * (k0 * a.x + k1 * b.x) + acc.y * (k0 * a.y + k1 * b.y) +
+                               acc.z * (k0 * a.z + k1 * b.z) + acc.w * (k0 * a.w + k1 * b.w);
+                }
+            }
+        }
+        if (warped && p.du) {
+            du_part += __shfl_xor_sync(0xffffffffu, du_part, 4);
+            du_part += __shfl_xor_sync(0xffffffffu, du_part, 2);
+            du_part += __shfl_xor_sync(0xffffffffu, du_part, 1);
+            if (act && sub == 0) p.du[((size_t)row * w + x) * p.ducs] = du_part;
+        }
+    }
+    if (!warped) return;
+
+    // ---- deterministic scatter of d_rw through the warp taps: one thread per channel, x' in order
+    __syncthreads();
+    float* Acc = Ls;   // L no longer needed (warped => TW == w, single tile per row)
+    for (int e = threadIdx.x; e < w * C; e += blockDim.x) Acc[e] = 0.f;
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        for (int xp = 0; xp < w; ++xp) {
+            WarpTap t = warp_tap(xp, Us[xp], w, true);
+            float v = Ds[(size_t)xp * C + c];
+            Acc[(size_t)t.i0 * C + c] += t.w0 * v;
+            Acc[(size_t)t.i1 * C + c] += t.w1 * v;
+        }
+    }
+    __syncthreads();
+    const int nvec = C / 4;
+    for (int e = threadIdx.x; e < w * nvec; e += blockDim.x) {
+        int px = e / nvec, q = e - px * nvec;
+        float4 v = reinterpret_cast<const float4*>(Acc)[e];
+        float4* dst = reinterpret_cast<float4*>(drrow + (size_t)px * p.drcs + q * 4);
+        if (p.acc_right) { float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+        *dst = v;
+    }
+}
+
+int corr_bwd(const CorrBwd& p, cudaStream_t st) {
+    MS_REQUIRE(p.C % 4 == 0 && p.lcs % 4 == 0 && p.rcs % 4 == 0 && p.dlcs % 4 == 0 && p.drcs % 4 == 0,
+               "corr_bwd: C and strides must be multiples of 4");
+    MS_REQUIRE(a16(p.left) && a16(p.right) && a16(p.dleft) && a16(p.dright), "corr_bwd: pointers must be 16B aligned");
+    MS_REQUIRE(!p.add_left_slice || (p.dcs % 4 == 0 && a16(p.dcost)), "corr_bwd: dcost slice alignment");
+    const bool warped = p.u != nullptr;
+    const int nd = (2 * p.max_disp) / p.stride + 1;
+    const size_t budget = 220 * 1024;
+    int TW;
+    if (warped) {
+        TW = p.w;
+        size_t bytes = (size_t)3 * p.w * p.C * 4 + (size_t)p.w * nd * 4 + (size_t)p.w * 4 + 64;
+        MS_REQUIRE(bytes <= budget, "corr_bwd: warped row does not fit in shared memory");
+    } else {
+        TW = -1;
+        const int cands[] = {p.w, 128, 64, 32, 16, 8};
+        for (int tw : cands) {
+            if (tw > p.w) continue;
+            size_t win = (size_t)tw + 2 * p.max_disp;
+            size_t bytes = 2 * win * p.C * 4 + win * nd * 4 + 64;
+            if (bytes <= (size_t)112 * 1024) { TW = tw; break; }
+        }
+        MS_REQUIRE(TW > 0, "corr_bwd: tile does not fit in shared memory");
+    }
+    const size_t WIN = warped ? p.w : TW + 2 * p.max_disp;
+    size_t smem = 2 * WIN * p.C * 4 + (warped ? (size_t)TW * p.C * 4 : 0) + WIN * nd * 4 + (warped ? (size_t)p.w * 4 : 0) + 64;
+    int tma = corr_use_tma() && p.lcs == p.C && p.rcs == p.C;
+    MS_CHECK_CUDA(cudaFuncSetAttribute(corr_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(cdiv(p.w, TW), p.B * p.h);
+    corr_bwd_kernel<<<grid, CORR_NT, smem, st>>>(p, TW, nd, tma);
+    return check_launch("corr_bwd");
+}
+
+}  // namespace ms

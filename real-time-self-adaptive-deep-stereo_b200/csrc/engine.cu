@@ -1,0 +1,475 @@
+// MADNet engine: forward, MAD / FULL backward and momentum update (see engine.h).
+//
+// Graph restated from the reference (never copied): pyramid encoder Nets/MadNet.py:173-249, per-level
+// warp -> correlation -> 6-conv estimator loop :251-351, context network :122-171, outputs :68-71,:362-364;
+// train-op structure Stereo_Online_Adaptation.py:87-128 (MAD: one module per step with gradients cut between
+// levels by `bulkhead`; FULL: everything, gradients also flow through the up-sampled disparities).
+#include "engine.h"
+
+#include <algorithm>
+#include <cmath>
+
+namespace ms {
+
+static const int PYR_CH[13] = {3, 16, 16, 32, 32, 64, 64, 96, 96, 128, 128, 192, 192};
+static const int EST_CH[6] = {128, 128, 96, 64, 32, 1};
+static const int CTX_CH[7] = {128, 128, 128, 96, 64, 32, 1};
+static const int CTX_RATE[7] = {1, 2, 4, 8, 16, 1, 1};
+static const float MAD_ALPHA = 0.2f;
+
+static inline int pad4(int c) { return (c + 3) / 4 * 4; }
+static inline int feat_of(int k) { return 2 * k; }
+static inline int est_layer(int k, int j) { return 12 + (6 - k) * 6 + (j - 1); }
+static inline int ctx_layer(int j) { return 42 + (j - 1); }
+
+static void same_pad(int in, int k, int s, int d, int& out, int& before) {
+    int keff = (k - 1) * d + 1;
+    out = (in + s - 1) / s;
+    int total = std::max((out - 1) * s + keff - in, 0);
+    before = total / 2;
+}
+
+Engine::Engine()
+    : net(0), B(1), H(0), W(0), Hp(0), Wp(0), radius_d(2), corr_stride(1), warping(1), n_groups(0), n_params(0),
+      Wt(nullptr), Gr(nullptr), Mo(nullptr), ws(nullptr), ws_floats(0), bound(false), wT(nullptr), wT_floats(0),
+      wg_ws(nullptr), wg_ws_floats(0), rs_tmp(nullptr), rs_tmp_floats(0), loss_ws(nullptr), loss_ws_floats(0),
+      scalars(nullptr), gt(nullptr) {}
+
+int Engine::build_madnet() {
+    layers.clear();
+    char buf[128];
+    for (int i = 1; i <= 12; ++i) {
+        ConvLayer L;
+        snprintf(buf, sizeof buf, "left/conv%d", i); L.name = buf;
+        snprintf(buf, sizeof buf, "model/gc-read-pyramid/conv%d", i); L.scope = buf;
+        L.bname = "biases";
+        L.kh = L.kw = 3; L.cin = PYR_CH[i - 1]; L.cout = PYR_CH[i]; L.stride = (i % 2) ? 2 : 1; L.dil = 1;
+        L.alpha = MAD_ALPHA; L.transposed = 0; L.group = -1; L.w_off = L.b_off = 0;
+        layers.push_back(L);
+    }
+    const int nd = (2 * radius_d) / corr_stride + 1;
+    for (int k = 6; k >= 2; --k) {
+        int cin = PYR_CH[feat_of(k)] + nd + (k < 6 ? 1 : 0);
+        for (int j = 1; j <= 6; ++j) {
+            ConvLayer L;
+            snprintf(buf, sizeof buf, "fgc-volume-filtering-%d/disp%d", k, j); L.name = buf;
+            snprintf(buf, sizeof buf, "model/G%d/fgc-volume-filtering-%d/disp-%d", k, k, j); L.scope = buf;
+            L.bname = "biases";
+            L.kh = L.kw = 3; L.cin = cin; L.cout = EST_CH[j - 1]; L.stride = 1; L.dil = 1;
+            L.alpha = j < 6 ? MAD_ALPHA : 1.f; L.transposed = 0; L.group = -1; L.w_off = L.b_off = 0;
+            layers.push_back(L);
+            cin = L.cout;
+        }
+    }
+    int cin = PYR_CH[4] + 1;
+    for (int j = 1; j <= 7; ++j) {
+        ConvLayer L;
+        snprintf(buf, sizeof buf, "context%d", j); L.name = buf;
+        snprintf(buf, sizeof buf, "model/context-%d", j); L.scope = buf;
+        L.bname = "biases";
+        L.kh = L.kw = 3; L.cin = cin; L.cout = CTX_CH[j - 1]; L.stride = 1; L.dil = CTX_RATE[j - 1];
+        L.alpha = j < 7 ? MAD_ALPHA : 1.f; L.transposed = 0; L.group = -1; L.w_off = L.b_off = 0;
+        layers.push_back(L);
+        cin = L.cout;
+    }
+    return 0;
+}
+
+int Engine::finalize_groups(const int* group_of_layer, int ng) {
+    n_groups = ng;
+    for (size_t i = 0; i < layers.size(); ++i) {
+        int g = group_of_layer ? group_of_layer[i] : -1;
+        MS_REQUIRE(g >= -1 && g < ng, "finalize_groups: group index out of range");
+        layers[i].group = g;
+    }
+    group_begin.assign(ng, 0);
+    group_end.assign(ng, 0);
+    size_t off = 0;
+    auto place = [&](ConvLayer& L) {
+        L.w_off = off; off += (size_t)L.kh * L.kw * L.cin * L.cout; off = (off + 3) / 4 * 4;
+        L.b_off = off; off += (size_t)L.cout; off = (off + 3) / 4 * 4;
+    };
+    for (int g = 0; g < ng; ++g) {
+        group_begin[g] = off;
+        for (auto& L : layers) if (L.group == g) place(L);
+        group_end[g] = off;
+    }
+    for (auto& L : layers) if (L.group < 0) place(L);
+    n_params = off;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace layout
+// ---------------------------------------------------------------------------------------------
+size_t Engine::layout(float* base) {
+    size_t off = 0;
+    auto alloc = [&](size_t n) -> float* {
+        float* p = base ? base + off : nullptr;
+        off += (n + 63) / 64 * 64;
+        return p;
+    };
+    auto tens = [&](int n, int h, int w, int c, int cs = 0) {
+        cs = cs ? cs : c;
+        return view(alloc((size_t)n * h * w * cs), n, h, w, c, cs);
+    };
+    tensors.clear();
+    char nm[128];
+    const int nd = (2 * radius_d) / corr_stride + 1;
+    TView raw_l = tens(B, H, W, 3), raw_r = tens(B, H, W, 3);
+    tensors["raw_left"] = raw_l; tensors["raw_right"] = raw_r;
+    img = tens(2 * B, Hp, Wp, 3, 4);
+    tensors["img"] = img;
+    size_t max_wg = 0, max_wt = 0;
+    auto track = [&](const ConvLayer& L, size_t pixels) {
+        max_wg = std::max(max_wg, conv_wgrad_workspace_floats(L.kh * L.kw, L.cin, L.cout, pixels));
+        max_wt = std::max(max_wt, (size_t)L.kh * L.kw * L.cin * L.cout);
+    };
+    int h = Hp, w = Wp;
+    for (int i = 1; i <= 12; ++i) {
+        if (i % 2) { h = (h + 1) / 2; w = (w + 1) / 2; }
+        pyr[i] = tens(2 * B, h, w, PYR_CH[i]);
+        g_pyr[i] = tens(2 * B, h, w, PYR_CH[i]);
+        track(layers[i - 1], (size_t)2 * B * h * w);
+        snprintf(nm, sizeof nm, "left/conv%d", i); tensors[nm] = batch(pyr[i], 0, B);
+        snprintf(nm, sizeof nm, "right/conv%d", i); tensors[nm] = batch(pyr[i], B, B);
+        snprintf(nm, sizeof nm, "grad/left/conv%d", i); tensors[nm] = batch(g_pyr[i], 0, B);
+        snprintf(nm, sizeof nm, "grad/right/conv%d", i); tensors[nm] = batch(g_pyr[i], B, B);
+    }
+    ctxin = tens(B, pyr[4].h, pyr[4].w, PYR_CH[4] + 1, pad4(PYR_CH[4] + 1));
+    g_ctxin = tens(B, pyr[4].h, pyr[4].w, PYR_CH[4] + 1, pad4(PYR_CH[4] + 1));
+    tensors["ctxin"] = ctxin; tensors["grad/ctxin"] = g_ctxin;
+    for (int k = 6; k >= 2; --k) {
+        const int f = feat_of(k), C = PYR_CH[f];
+        const int hh = pyr[f].h, ww = pyr[f].w;
+        const int ct = C + nd + (k < 6 ? 1 : 0);
+        cost[k] = tens(B, hh, ww, ct, pad4(ct));
+        g_cost[k] = tens(B, hh, ww, ct, pad4(ct));
+        snprintf(nm, sizeof nm, "cost%d", k); tensors[nm] = cost[k];
+        snprintf(nm, sizeof nm, "grad/cost%d", k); tensors[nm] = g_cost[k];
+        for (int j = 1; j <= 5; ++j) {
+            est[k][j] = tens(B, hh, ww, EST_CH[j - 1]);
+            g_est[k][j] = tens(B, hh, ww, EST_CH[j - 1]);
+            snprintf(nm, sizeof nm, "fgc-volume-filtering-%d/disp%d", k, j); tensors[nm] = est[k][j];
+            snprintf(nm, sizeof nm, "grad/fgc-volume-filtering-%d/disp%d", k, j); tensors[nm] = g_est[k][j];
+        }
+        if (k == 2) V[k] = slice(ctxin, PYR_CH[4], 1);
+        else V[k] = tens(B, hh, ww, 1);
+        g_V[k] = tens(B, hh, ww, 1);
+        g_u[k] = tens(B, hh, ww, 1);
+        snprintf(nm, sizeof nm, "fgc-volume-filtering-%d/disp6", k); tensors[nm] = V[k];
+        snprintf(nm, sizeof nm, "grad/fgc-volume-filtering-%d/disp6", k); tensors[nm] = g_V[k];
+        snprintf(nm, sizeof nm, "grad/u%d", k); tensors[nm] = g_u[k];
+        for (int j = 1; j <= 6; ++j) track(layers[est_layer(k, j)], (size_t)B * hh * ww);
+    }
+    for (int j = 1; j <= 6; ++j) {
+        ctx[j] = tens(B, pyr[4].h, pyr[4].w, CTX_CH[j - 1]);
+        g_ctx[j] = tens(B, pyr[4].h, pyr[4].w, CTX_CH[j - 1]);
+        snprintf(nm, sizeof nm, "context%d", j); tensors[nm] = ctx[j];
+        snprintf(nm, sizeof nm, "grad/context%d", j); tensors[nm] = g_ctx[j];
+    }
+    for (int j = 1; j <= 7; ++j) track(layers[ctx_layer(j)], (size_t)B * pyr[4].h * pyr[4].w);
+    final_ = tens(B, pyr[4].h, pyr[4].w, 1);
+    g_final = tens(B, pyr[4].h, pyr[4].w, 1);
+    tensors["final_disp"] = final_; tensors["grad/final_disp"] = g_final;
+    for (int i = 0; i < 6; ++i) {
+        disp[i] = tens(B, H, W, 1);
+        snprintf(nm, sizeof nm, "disp%d", i); tensors[nm] = disp[i];
+    }
+    tensors["rescaled_prediction"] = disp[5];
+    g_disp = tens(B, H, W, 1);
+    tensors["grad/disp"] = g_disp;
+    wT_floats = max_wt; wT = alloc(max_wt);
+    wg_ws_floats = max_wg; wg_ws = alloc(max_wg);
+    rs_tmp_floats = (size_t)B * H * Wp; rs_tmp = alloc(rs_tmp_floats);
+    loss_ws_floats = loss_workspace_floats(B, H, W); loss_ws = alloc(loss_ws_floats);
+    scalars = alloc(64);
+    gt = alloc((size_t)B * H * W);
+    return off;
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv helpers
+// ---------------------------------------------------------------------------------------------
+int Engine::conv_fwd(const ConvLayer& L, const TView& x, const TView& y, const float* res, int res_cs,
+                     cudaStream_t st) {
+    ConvGemm p{};
+    p.x = x; p.y = y; p.kh = L.kh; p.kw = L.kw;
+    p.bias = Wt + L.b_off;
+    p.alpha = L.alpha;
+    p.res = res; p.res_cs = res_cs;
+    p.mask = nullptr; p.mask_cs = 0; p.mask_alpha = 1.f; p.accumulate = 0;
+    int oh, ow, pt, pl;
+    if (!L.transposed) {
+        same_pad(x.h, L.kh, L.stride, L.dil, oh, pt);
+        same_pad(x.w, L.kw, L.stride, L.dil, ow, pl);
+        MS_REQUIRE(oh == y.h && ow == y.w && x.c == L.cin && y.c == L.cout, "conv_fwd: shape mismatch");
+        p.wmat = Wt + L.w_off;
+        p.mul = L.stride; p.off_y = -pt; p.off_x = -pl; p.step = L.dil; p.div = 1;
+    } else {
+        same_pad(y.h, L.kh, L.stride, 1, oh, pt);
+        same_pad(y.w, L.kw, L.stride, 1, ow, pl);
+        MS_REQUIRE(oh == x.h && ow == x.w && x.c == L.cin && y.c == L.cout, "conv_fwd(T): shape mismatch");
+        // canonical W is [tap][cout][cin]; the gather GEMM wants [tap][K=cin][N=cout]
+        if (transpose_taps(Wt + L.w_off, wT, L.kh * L.kw, L.cout, L.cin, st)) return -1;
+        p.wmat = wT;
+        p.mul = 1; p.off_y = pt; p.off_x = pl; p.step = -1; p.div = L.stride;
+    }
+    return conv_gemm(p, st);
+}
+
+// x: forward input of the layer; dpre: grad wrt pre-activation output; dx: where to write grad wrt x
+int Engine::conv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, const TView* dx, const TView* dx_mask,
+                     float mask_alpha, int dx_acc, int want_wgrad, cudaStream_t st) {
+    int oh, ow, pt, pl;
+    MS_REQUIRE(!L.transposed, "conv_bwd: transposed layers use deconv_bwd");
+    same_pad(x.h, L.kh, L.stride, L.dil, oh, pt);
+    same_pad(x.w, L.kw, L.stride, L.dil, ow, pl);
+    MS_REQUIRE(oh == dpre.h && ow == dpre.w && x.c == L.cin && dpre.c == L.cout, "conv_bwd: shape mismatch");
+    if (want_wgrad) {
+        ConvWgrad q{};
+        q.x = x; q.dy = dpre; q.dw = Gr + L.w_off; q.db = Gr + L.b_off;
+        q.kh = L.kh; q.kw = L.kw; q.stride = L.stride; q.dil = L.dil; q.pad_t = pt; q.pad_l = pl;
+        q.workspace = wg_ws; q.workspace_floats = wg_ws_floats; q.accumulate = 0;
+        if (conv_wgrad(q, st)) return -1;
+    }
+    if (dx) {
+        if (transpose_taps(Wt + L.w_off, wT, L.kh * L.kw, L.cin, L.cout, st)) return -1;   // -> [tap][cout][cin]
+        ConvGemm p{};
+        p.x = dpre; p.wmat = wT; p.bias = nullptr; p.y = *dx; p.kh = L.kh; p.kw = L.kw;
+        p.mul = 1; p.off_y = pt; p.off_x = pl; p.step = -L.dil; p.div = L.stride;
+        p.alpha = 1.f;
+        p.mask = dx_mask ? dx_mask->p : nullptr; p.mask_cs = dx_mask ? dx_mask->cs : 0; p.mask_alpha = mask_alpha;
+        p.res = nullptr; p.res_cs = 0; p.accumulate = dx_acc;
+        if (conv_gemm(p, st)) return -1;
+    }
+    return 0;
+}
+
+bool Engine::trainable(int layer, int mode, int group) const {
+    if (mode == 2) return true;
+    if (mode == 1) return layers[layer].group == group;
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// input / forward
+// ---------------------------------------------------------------------------------------------
+int Engine::set_input(const float* left, const float* right, cudaStream_t st) {
+    MS_REQUIRE(bound, "engine not bound");
+    TView rl = tensors["raw_left"], rr = tensors["raw_right"];
+    size_t bytes = (size_t)B * H * W * 3 * sizeof(float);
+    MS_CHECK_CUDA(cudaMemcpyAsync(rl.p, left, bytes, cudaMemcpyDefault, st));
+    MS_CHECK_CUDA(cudaMemcpyAsync(rr.p, right, bytes, cudaMemcpyDefault, st));
+    TView il = batch(img, 0, B), ir = batch(img, B, B);
+    const float sc = net == 1 ? 1.f / 255.f : 1.f, bi = net == 1 ? -100.f / 255.f : 0.f;
+    if (pad_reflect(rl.p, B, H, W, 3, il.p, Hp, Wp, img.cs, sc, bi, st)) return -1;
+    if (pad_reflect(rr.p, B, H, W, 3, ir.p, Hp, Wp, img.cs, sc, bi, st)) return -1;
+    return 0;
+}
+
+int Engine::forward(int disp_mask, cudaStream_t st) {
+    MS_REQUIRE(bound, "engine not bound");
+    MS_REQUIRE(net == 0, "forward: only MADNet is implemented in this engine build");
+    const int nd = (2 * radius_d) / corr_stride + 1;
+    TView x = img;
+    for (int i = 1; i <= 12; ++i) {
+        if (conv_fwd(layers[i - 1], x, pyr[i], nullptr, 0, st)) return -1;
+        x = pyr[i];
+    }
+    for (int k = 6; k >= 2; --k) {
+        const int f = feat_of(k), C = PYR_CH[f];
+        TView Lf = batch(pyr[f], 0, B), Rf = batch(pyr[f], B, B);
+        const float* u = nullptr;
+        if (k < 6) {
+            TView us = slice(cost[k], C + nd, 1);
+            if (resize_bilinear(V[k + 1].p, V[k + 1].cs, B, V[k + 1].h, V[k + 1].w, us.p, us.cs, cost[k].h, cost[k].w,
+                                cost[k].h, cost[k].w, 1.f, 0, 20.f / (float)(1 << k), 0, st)) return -1;
+            if (warping) u = us.p;
+        }
+        CorrFwd cf{};
+        cf.left = Lf.p; cf.lcs = Lf.cs; cf.right = Rf.p; cf.rcs = Rf.cs;
+        cf.u = u; cf.ucs = cost[k].cs;
+        cf.out = cost[k].p; cf.ocs = cost[k].cs;
+        cf.out2 = (k == 2) ? ctxin.p : nullptr; cf.o2cs = ctxin.cs;
+        cf.B = B; cf.h = cost[k].h; cf.w = cost[k].w; cf.C = C; cf.max_disp = radius_d; cf.stride = corr_stride;
+        cf.copy_left = 1; cf.u_chan = (k < 6) ? 1 : 0;
+        if (corr_fwd(cf, st)) return -1;
+        TView xin = cost[k];
+        for (int j = 1; j <= 6; ++j) {
+            TView y = (j < 6) ? est[k][j] : V[k];
+            if (conv_fwd(layers[est_layer(k, j)], xin, y, nullptr, 0, st)) return -1;
+            xin = y;
+        }
+    }
+    {
+        TView xin = ctxin;
+        for (int j = 1; j <= 7; ++j) {
+            TView y = (j < 7) ? ctx[j] : final_;
+            if (conv_fwd(layers[ctx_layer(j)], xin, y, j == 7 ? V[2].p : nullptr, V[2].cs, st)) return -1;
+            xin = y;
+        }
+    }
+    for (int i = 0; i < 6; ++i) {
+        if (!(disp_mask & (1 << i))) continue;
+        const TView& src = (i < 4) ? V[6 - i] : final_;
+        if (i < 5) {
+            if (resize_bilinear(src.p, src.cs, B, src.h, src.w, disp[i].p, 1, Hp, Wp, H, W, -20.f, 1, 1.f, 0, st)) return -1;
+        } else {
+            if (resize_bilinear(src.p, src.cs, B, src.h, src.w, disp[i].p, 1, Hp, Wp, H, W, 1.f, 0, -20.f, 1, st)) return -1;
+        }
+    }
+    return 0;
+}
+
+int Engine::loss(int which, int with_grad, int slot, float grad_scale, cudaStream_t st) {
+    MS_REQUIRE(bound && which >= 0 && which < 6 && slot >= 0 && slot < 2, "loss: bad arguments");
+    ReprojLoss p{};
+    p.left = tensors["raw_left"].p; p.right = tensors["raw_right"].p;
+    p.disp = disp[which].p; p.loss = scalars + slot;
+    p.ddisp = with_grad ? g_disp.p : nullptr;
+    p.workspace = loss_ws; p.B = B; p.H = H; p.W = W; p.grad_scale = grad_scale;
+    return reproj_loss(p, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+int Engine::backward(int mode, int group, cudaStream_t st) {
+    MS_REQUIRE(bound && net == 0, "backward: MADNet engine not bound");
+    MS_REQUIRE(mode == 2 || (mode == 1 && group >= 0 && group < n_groups), "backward: bad mode/group");
+    const int nd = (2 * radius_d) / corr_stride + 1;
+
+    // lowest-index trainable pyramid conv (13 = none)
+    int lo_pyr = 13;
+    for (int i = 1; i <= 12; ++i) if (trainable(i - 1, mode, group)) { lo_pyr = i; break; }
+    auto any_trainable = [&](int first, int last) {
+        for (int i = first; i <= last; ++i) if (trainable(i, mode, group)) return true;
+        return false;
+    };
+
+    // ---- estimator chain of level k: dpre(V_k) in g_V[k] -> (optionally) g_cost[k]
+    auto est_bwd = [&](int k, bool need_cost_grad) -> int {
+        TView dpre = g_V[k];
+        for (int j = 6; j >= 1; --j) {
+            const int li = est_layer(k, j);
+            TView xin = (j == 1) ? cost[k] : est[k][j - 1];
+            bool need_dx = (j > 1) ? (need_cost_grad || any_trainable(est_layer(k, 1), li - 1)) : need_cost_grad;
+            TView dx = (j > 1) ? g_est[k][j - 1] : g_cost[k];
+            TView mask = (j > 1) ? est[k][j - 1] : cost[k];
+            if (conv_bwd(layers[li], xin, dpre, need_dx ? &dx : nullptr, (j > 1) ? &mask : nullptr, MAD_ALPHA, 0,
+                         trainable(li, mode, group), st)) return -1;
+            if (!need_dx) break;
+            dpre = dx;
+        }
+        return 0;
+    };
+    // ---- context chain: g_final -> g_ctxin
+    auto ctx_bwd = [&](bool need_in_grad) -> int {
+        TView dpre = g_final;
+        for (int j = 7; j >= 1; --j) {
+            const int li = ctx_layer(j);
+            TView xin = (j == 1) ? ctxin : ctx[j - 1];
+            bool need_dx = (j > 1) ? (need_in_grad || any_trainable(ctx_layer(1), li - 1)) : need_in_grad;
+            TView dx = (j > 1) ? g_ctx[j - 1] : g_ctxin;
+            TView mask = (j > 1) ? ctx[j - 1] : ctxin;
+            if (conv_bwd(layers[li], xin, dpre, need_dx ? &dx : nullptr, (j > 1) ? &mask : nullptr, MAD_ALPHA, 0,
+                         trainable(li, mode, group), st)) return -1;
+            if (!need_dx) break;
+            dpre = dx;
+        }
+        return 0;
+    };
+    // ---- correlation + warp backward of level k -> g_pyr[f] (left|right halves), optional g_u[k]
+    auto corr_level_bwd = [&](int k, bool want_du) -> int {
+        const int f = feat_of(k), C = PYR_CH[f];
+        TView Lf = batch(pyr[f], 0, B), Rf = batch(pyr[f], B, B);
+        TView dL = batch(g_pyr[f], 0, B), dR = batch(g_pyr[f], B, B);
+        CorrBwd cb{};
+        cb.left = Lf.p; cb.lcs = Lf.cs; cb.right = Rf.p; cb.rcs = Rf.cs;
+        cb.u = (k < 6 && warping) ? slice(cost[k], C + nd, 1).p : nullptr; cb.ucs = cost[k].cs;
+        cb.dcost = g_cost[k].p; cb.dcs = g_cost[k].cs;
+        cb.dleft = dL.p; cb.dlcs = dL.cs; cb.dright = dR.p; cb.drcs = dR.cs;
+        cb.du = (want_du && cb.u) ? g_u[k].p : nullptr; cb.ducs = 1;
+        cb.B = B; cb.h = cost[k].h; cb.w = cost[k].w; cb.C = C; cb.max_disp = radius_d; cb.stride = corr_stride;
+        cb.add_left_slice = 1; cb.acc_left = 0; cb.acc_right = 0;
+        return corr_bwd(cb, st);
+    };
+    // ---- pyramid: g_pyr[top] holds d(post-activation output of conv `top`), complete
+    auto pyr_bwd = [&](int top, int lo, bool accumulate_feats) -> int {
+        if (lo > top) return 0;
+        if (leaky_bwd(g_pyr[top].p, g_pyr[top].cs, pyr[top].p, pyr[top].cs, g_pyr[top].pixels(), g_pyr[top].c,
+                      MAD_ALPHA, st)) return -1;
+        for (int i = top; i >= lo; --i) {
+            TView xin = (i > 1) ? pyr[i - 1] : img;
+            bool need_dx = i > lo;
+            int acc = 0;
+            if (need_dx && accumulate_feats && (i - 1) >= 4 && ((i - 1) % 2 == 0)) acc = 1;
+            TView dx = g_pyr[i > 1 ? i - 1 : 1];
+            TView mask = pyr[i > 1 ? i - 1 : 1];
+            if (conv_bwd(layers[i - 1], xin, g_pyr[i], need_dx ? &dx : nullptr, need_dx ? &mask : nullptr, MAD_ALPHA,
+                         acc, trainable(i - 1, mode, group), st)) return -1;
+        }
+        return 0;
+    };
+    auto ctx_tail = [&]() -> int {   // g_V[2] = g_final + g_ctxin[...,32]
+        if (add_channels(g_V[2].p, 1, g_final.p, 1, g_final.pixels(), 1, 1.f, 0, st)) return -1;
+        return add_channels(g_V[2].p, 1, g_ctxin.p + PYR_CH[4], g_ctxin.cs, g_final.pixels(), 1, 1.f, 1, st);
+    };
+    auto ctx_feat = [&]() -> int {   // g_pyr[4].left += g_ctxin[..., :32]
+        TView dL = batch(g_pyr[4], 0, B);
+        return add_channels(dL.p, dL.cs, g_ctxin.p, g_ctxin.cs, dL.pixels(), PYR_CH[4], 1.f, 1, st);
+    };
+
+    if (mode == 1) {
+        const int k = 6 - group;   // seed: disparity `group` of get_disparities() (D6,D5,D4,D3,D2ctx)
+        MS_REQUIRE(k >= 2 && k <= 6, "backward(MAD): group has no disparity head");
+        const int f = feat_of(k);
+        const bool need_feat = lo_pyr <= f;
+        const TView& head = (k == 2) ? final_ : V[k];
+        TView& ghead = (k == 2) ? g_final : g_V[k];
+        if (resize_bilinear_bwd(g_disp.p, 1, head.p, head.cs, B, head.h, head.w, ghead.p, 1, Hp, Wp, H, W, -20.f, 1,
+                                1.f, 0, 0, rs_tmp, st)) return -1;
+        if (k == 2) {
+            bool est_train = any_trainable(est_layer(2, 1), est_layer(2, 6));
+            if (ctx_bwd(need_feat || est_train)) return -1;
+            if (need_feat || est_train) { if (ctx_tail()) return -1; }
+            else return 0;
+        }
+        if (est_bwd(k, need_feat)) return -1;
+        if (!need_feat) return 0;
+        if (corr_level_bwd(k, false)) return -1;
+        if (k == 2 && ctx_feat()) return -1;
+        return pyr_bwd(f, lo_pyr, false);
+    }
+
+    // ---- FULL: loss on disp[5] = relu(resize(final)*-20)
+    if (resize_bilinear_bwd(g_disp.p, 1, final_.p, final_.cs, B, final_.h, final_.w, g_final.p, 1, Hp, Wp, H, W, 1.f, 0,
+                            -20.f, 1, 0, rs_tmp, st)) return -1;
+    if (ctx_bwd(true)) return -1;
+    if (ctx_tail()) return -1;
+    for (int k = 2; k <= 6; ++k) {
+        const int f = feat_of(k), C = PYR_CH[f];
+        if (est_bwd(k, true)) return -1;
+        if (corr_level_bwd(k, true)) return -1;
+        if (k == 2 && ctx_feat()) return -1;
+        if (k < 6) {
+            // d u_k = warp-coordinate grad (if warping) + estimator-input slice
+            const int acc = warping ? 1 : 0;
+            if (add_channels(g_u[k].p, 1, g_cost[k].p + C + nd, g_cost[k].cs, g_u[k].pixels(), 1, 1.f, acc, st)) return -1;
+            if (resize_bilinear_bwd(g_u[k].p, 1, V[k + 1].p, V[k + 1].cs, B, V[k + 1].h, V[k + 1].w, g_V[k + 1].p, 1,
+                                    cost[k].h, cost[k].w, cost[k].h, cost[k].w, 1.f, 0, 20.f / (float)(1 << k), 0, 0,
+                                    rs_tmp, st)) return -1;
+        }
+    }
+    return pyr_bwd(12, 1, true);
+}
+
+int Engine::update(int group, float lr, float mu, float gscale, cudaStream_t st) {
+    MS_REQUIRE(bound, "engine not bound");
+    size_t b = 0, e = n_params;
+    if (group >= 0) { MS_REQUIRE(group < n_groups, "update: bad group"); b = group_begin[group]; e = group_end[group]; }
+    return momentum_update(Wt + b, Gr + b, Mo + b, e - b, lr, mu, gscale, st);
+}
+
+}  // namespace ms

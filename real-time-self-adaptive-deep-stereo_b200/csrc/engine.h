@@ -1,0 +1,78 @@
+// Engine: per-frame MADNet / DispNet forward + (MAD | FULL) backward + momentum update, orchestrated in C++
+// over caller-owned device memory.  Replaces what one `sess.run(fetches)` executes in the reference's inner
+// loop (Stereo_Online_Adaptation.py:208) for the graphs built by Nets/MadNet.py and Nets/DispNet.py.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace ms {
+
+struct ConvLayer {
+    std::string name;     // reference layer name as used in block_config JSON ("left/conv1", "context3", ...)
+    std::string scope;    // TF variable scope ("model/gc-read-pyramid/conv1")
+    std::string bname;    // "biases" (MADNet) or "bias" (DispNet)
+    int kh, kw, cin, cout, stride, dil;
+    float alpha;          // leaky slope, 1 = linear
+    int transposed;       // conv2d_transpose (weights [kh,kw,cout,cin])
+    size_t w_off, b_off;  // float offsets in the parameter arena
+    int group;            // MAD module index or -1
+};
+
+struct Engine {
+    // configuration
+    int net;              // 0 = MADNet, 1 = DispNet
+    int B, H, W, Hp, Wp;
+    int radius_d, corr_stride, warping;
+    std::vector<ConvLayer> layers;
+    int n_groups;
+    std::vector<size_t> group_begin, group_end;   // float ranges in the arena
+    size_t n_params;      // arena floats (incl. alignment pads)
+
+    // bound memory
+    float *Wt, *Gr, *Mo;  // weights / grads / momentum arenas
+    float* ws; size_t ws_floats;
+    bool bound;
+
+    // tensors (valid after bind)
+    std::map<std::string, TView> tensors;
+    std::string last_plan_error;
+
+    // ---- MADNet buffers
+    TView img;                       // [2B,Hp,Wp,3] cs=4
+    TView pyr[13], g_pyr[13];        // 1..12
+    TView cost[7], g_cost[7];        // levels 2..6
+    TView est[7][7], g_est[7][7];    // [level][1..5]
+    TView V[7], g_V[7];              // [level] (V[2] is a slice of ctxin)
+    TView g_u[7];
+    TView ctxin, g_ctxin, ctx[8], g_ctx[8], final_, g_final;
+    TView disp[6];                   // D6,D5,D4,D3,D2ctx,full   [B,H,W,1]
+    TView g_disp;
+    float* wT; size_t wT_floats;     // transposed-weight scratch
+    float* wg_ws; size_t wg_ws_floats;
+    float* rs_tmp; size_t rs_tmp_floats;
+    float* loss_ws; size_t loss_ws_floats;
+    float* scalars;                  // [0]=full loss, [1]=train loss, [2]=epe, [3]=bad3
+    float* gt;                       // optional ground truth [B,H,W,1]
+
+    Engine();
+    size_t layout(float* base);      // returns floats needed; assigns views when base != nullptr
+    int build_madnet();
+    int finalize_groups(const int* group_of_layer, int n_groups);
+
+    int set_input(const float* left, const float* right, cudaStream_t st);
+    int forward(int disp_mask, cudaStream_t st);
+    int loss(int which, int with_grad, int slot, float grad_scale, cudaStream_t st);
+    int backward(int mode, int group, cudaStream_t st);     // mode 1 = MAD(group), 2 = FULL
+    int update(int group, float lr, float mu, float gscale, cudaStream_t st);
+
+    // helpers
+    int conv_fwd(const ConvLayer& L, const TView& x, const TView& y, const float* res, int res_cs, cudaStream_t st);
+    int conv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, const TView* dx, const TView* dx_mask,
+                 float mask_alpha, int dx_acc, int want_wgrad, cudaStream_t st);
+    bool trainable(int layer, int mode, int group) const;
+};
+
+}  // namespace ms

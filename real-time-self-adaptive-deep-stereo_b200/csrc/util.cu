@@ -1,0 +1,13 @@
+#include "common.cuh"
+#include <mutex>
+namespace ms {
+static std::mutex g_mu;
+static std::string g_err;
+void set_error(const std::string& s) { std::lock_guard<std::mutex> l(g_mu); g_err = s; }
+const char* last_error_cstr() { std::lock_guard<std::mutex> l(g_mu); return g_err.c_str(); }
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error(std::string(what) + ": " + cudaGetErrorString(e)); return -1; }
+    return 0;
+}
+}  // namespace ms

@@ -1,0 +1,151 @@
+"""Online adaptation loop — the reference inner loop (Stereo_Online_Adaptation.py:85-128,166-253) on the engine.
+
+Train-op construction follows the reference: for MAD, one train op per side disparity, whose var_list is the
+union of `net.get_variables(name)` over the layer names of that block_config group (:110-118); FULL trains
+every variable on the full-resolution loss (:126-128); one momentum slot per variable shared by all ops (:85).
+Per frame: sample blocks (:181-189) -> one engine step (forward, full-res loss, selected train ops) ->
+reward recurrence (:211-224) -> divergence reset (:242-244).
+
+Data parallel (new functionality): one process per GPU; the adapted module's gradient range and
+the scalar loss are summed with one NCCL all-reduce each and the 1/N is folded into the momentum kernel, so
+N ranks with one frame each equal the reference graph at batch N (every loss is a mean over the batch).
+"""
+import numpy as np
+import torch
+
+from Sampler import sampler_factory
+from .engine import MODE_FULL, MODE_MAD, MODE_NONE
+from ._lib import MadStereoError
+
+
+def softmax(x):
+    """Stereo_Online_Adaptation.py:25-27."""
+    return np.exp(x) / np.sum(np.exp(x), axis=0)
+
+
+class OnlineAdaptation(object):
+    def __init__(self, net, mode='MAD', train_config=None, lr=0.0001, momentum=0.9, sample_mode='SEQUENTIAL',
+                 num_blocks=1, fixed_id=0, sample_frequency=1, ssim_th=0.5, process_group=None):
+        assert mode in ('NONE', 'FULL', 'MAD')
+        self.net, self.engine, self.mode = net, net.engine, mode
+        self.lr, self.mu = float(lr), float(momentum)
+        self.sample_frequency, self.ssim_th = sample_frequency, ssim_th
+        self.pg = process_group
+        self.world = 1
+        self.rank = 0
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(self.pg)
+            self.rank = torch.distributed.get_rank(self.pg)
+        predictions = net.get_disparities()
+        self.groups = []
+        if mode == 'MAD':
+            if getattr(net, 'bulkhead', True) is not True:
+                print('WARNING: MAD adaptation on a net built without bulkhead; the engine always cuts gradients '
+                      'between modules in MAD mode (Stereo_Online_Adaptation.py:61)')
+            assert train_config is not None
+            assert (len(predictions[:-1]) == len(train_config))     # Stereo_Online_Adaptation.py:97
+            for layer_to_train in train_config:
+                var_accumulator = []
+                for name in layer_to_train:
+                    var_accumulator += net.get_variables(name)
+                idxs = sorted({net.layer_index_of_variable(v) for v in var_accumulator})
+                self.groups.append(idxs)
+            self.sampler = sampler_factory.get_sampler(sample_mode, num_blocks, fixed_id)
+        self.engine.set_groups(self.groups)
+        self.engine.bind()
+        self.num_actions = len(self.groups) if mode == 'MAD' else (1 if mode == 'FULL' else 0)
+        self.fetch_counter = [0] * self.num_actions
+        self.sample_distribution = np.zeros(shape=[self.num_actions])
+        self.loss_t_1 = self.loss_t_2 = 0.0
+        self.last_trained_blocks = []
+        self.blocks_to_train = []
+        self.reset_counter = 0
+        self.step_count = 0
+        self._snapshot = None
+
+    # ---- weights -----------------------------------------------------------------------------------
+    def load_weights(self, params):
+        """params: dict TF-variable-name -> array (HWIO).  Also becomes the snapshot used by the reset."""
+        self.engine.load_params(params)
+        self._snapshot = self.engine.weights.clone()
+
+    def restore(self):
+        """restorer.restore(sess, weights) (:242-244): weights only; momentum slots are left untouched."""
+        if self._snapshot is None:
+            raise MadStereoError('no weight snapshot to restore')
+        self.engine.weights.copy_(self._snapshot)
+
+    # ---- one frame ---------------------------------------------------------------------------------
+    def _allreduce(self, t):
+        if self.world > 1:
+            torch.distributed.all_reduce(t, group=self.pg)
+
+    def step(self, left, right, gt=None, want_disp_mask=0):
+        eng = self.engine
+        step = self.step_count
+        if self.mode == 'MAD' and step % self.sample_frequency == 0:
+            distribution = softmax(self.sample_distribution)
+            if self.world > 1:
+                blocks = [int(b) for b in self.sampler.sample(distribution)] if self.rank == 0 else [0] * len(
+                    self.blocks_to_train or [0] * self.sampler._blocks_to_fetch)
+                t = torch.tensor(blocks, dtype=torch.int32, device=eng.device)
+                torch.distributed.broadcast(t, 0, group=self.pg)
+                blocks = [int(b) for b in t.tolist()]
+            else:
+                blocks = [int(b) for b in self.sampler.sample(distribution)]
+            self.blocks_to_train = blocks
+            for l in blocks:
+                self.fetch_counter[l] += 1
+
+        eng.set_input(left, right)
+        if gt is not None:
+            eng.set_gt(gt)
+        mask = 0b100000 | want_disp_mask
+        if self.mode == 'MAD':
+            for b in self.blocks_to_train:
+                mask |= 1 << b
+        eng.forward(mask)
+        eng.loss(5, self.mode == 'FULL', 0)
+        if gt is not None:
+            eng.metrics()
+        gscale = 1.0 / self.world
+        if self.mode == 'FULL':
+            eng.backward(MODE_FULL)
+            self._allreduce(eng.grads)
+            eng.update(-1, self.lr, self.mu, gscale)
+        elif self.mode == 'MAD':
+            for b in self.blocks_to_train:
+                eng.loss(b, True, 1)
+                eng.backward(MODE_MAD, b)
+                if self.world > 1:
+                    lo, hi = eng.group_ranges[b]
+                    self._allreduce(eng.grads[lo:hi])
+                eng.update(b, self.lr, self.mu, gscale)
+        sc = eng.read_scalars()
+        new_loss = sc[0]
+        if self.world > 1:
+            t = torch.tensor([new_loss], dtype=torch.float64, device=eng.device)
+            self._allreduce(t)
+            new_loss = float(t.item()) / self.world
+
+        if self.mode == 'MAD':
+            if step == 0:
+                self.loss_t_2 = new_loss
+                self.loss_t_1 = new_loss
+            expected_loss = 2 * self.loss_t_1 - self.loss_t_2
+            gain_loss = expected_loss - new_loss
+            self.sample_distribution = 0.99 * self.sample_distribution
+            for i in self.last_trained_blocks:
+                self.sample_distribution[i] += 0.01 * gain_loss
+            self.last_trained_blocks = self.blocks_to_train
+            self.loss_t_2 = self.loss_t_1
+            self.loss_t_1 = new_loss
+
+        did_reset = False
+        if new_loss > self.ssim_th and self._snapshot is not None and self.mode != 'NONE':
+            self.restore()
+            self.reset_counter += 1
+            did_reset = True
+        self.step_count += 1
+        return {'loss': new_loss, 'train_loss': sc[1], 'epe': sc[2], 'bad3': sc[3],
+                'blocks': list(self.blocks_to_train), 'reset': did_reset}

@@ -1,0 +1,129 @@
+"""CPU tests of the host side: C-ABI exports, layer/group tables through the engine (no kernels run),
+samplers and the reward recurrence against the oracle transcription."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import PKG, ROOT
+from madstereo import _lib
+from oracle import adaptation as OA
+from oracle.madnet import param_shapes, mad_groups_full
+from Sampler import sampler_factory
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, 'include', 'madstereo.h')).read()
+    declared = set(re.findall(r'\b(ms_\w+)\s*\(', hdr))
+    assert len(declared) >= 30
+    h = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(h, name), 'missing export %s' % name
+    assert declared == set(_lib.EXPORTS)
+    assert _lib.lib().ms_version() >= 100
+
+
+def _engine_tables(groups_cfg):
+    L = _lib.lib()
+    e = L.ms_engine_create(b'MADNet', 1, 384, 1280, 2, 1, 1)
+    assert e
+    n = L.ms_engine_num_layers(e)
+    layers = []
+    for i in range(n):
+        nm, sc, bn = (ctypes.create_string_buffer(128) for _ in range(3))
+        dims = (ctypes.c_int * 7)(); alpha = ctypes.c_float()
+        assert L.ms_engine_layer_info(e, i, nm, 128, sc, 128, bn, 128, dims, ctypes.byref(alpha)) == 0
+        layers.append((nm.value.decode(), sc.value.decode(), bn.value.decode(), list(dims), alpha.value))
+    name_to_idx = {l[0]: i for i, l in enumerate(layers)}
+    arr = (ctypes.c_int * n)(*([-1] * n))
+    for g, names in enumerate(groups_cfg):
+        for nm in names:
+            if nm in name_to_idx:
+                arr[name_to_idx[nm]] = g
+    assert L.ms_engine_set_groups(e, arr, n, len(groups_cfg)) == 0
+    npar, nws = ctypes.c_size_t(), ctypes.c_size_t()
+    assert L.ms_engine_sizes(e, ctypes.byref(npar), ctypes.byref(nws)) == 0
+    ranges = []
+    for g in range(len(groups_cfg)):
+        b, en = ctypes.c_size_t(), ctypes.c_size_t()
+        assert L.ms_engine_group_range(e, g, ctypes.byref(b), ctypes.byref(en)) == 0
+        ranges.append((b.value, en.value))
+    offs = []
+    for i in range(n):
+        wo, bo = ctypes.c_size_t(), ctypes.c_size_t()
+        L.ms_engine_param_offsets(e, i, ctypes.byref(wo), ctypes.byref(bo))
+        offs.append((wo.value, bo.value))
+    L.ms_engine_destroy(e)
+    return layers, npar.value, nws.value, ranges, offs
+
+
+def test_engine_layer_table_matches_reference_variable_names():
+    cfg = json.load(open(os.path.join(PKG, 'block_config', 'MadNet_full.json')))
+    layers, npar, nws, ranges, offs = _engine_tables(cfg)
+    shapes = param_shapes()
+    names = []
+    for nm, sc, bn, d, alpha in layers:
+        assert shapes[sc + '/weights'] == (d[0], d[1], d[2], d[3])
+        assert shapes[sc + '/' + bn] == (d[3],)
+        names += [sc + '/weights', sc + '/' + bn]
+    assert set(names) == set(shapes)
+    # module sizes of SURVEY §8(a) a15 (arena ranges include <=3 floats of alignment padding per tensor)
+    expect = [1112801, 745185, 588449, 468577, 911058]
+    for (b, e), ex, grp in zip(ranges, expect, mad_groups_full()):
+        assert ex <= e - b <= ex + 4 * len(grp)
+    assert 3826070 <= npar <= 3826070 + 4 * 98
+    assert nws > 0
+    # groups are contiguous, ordered and disjoint
+    for (b0, e0), (b1, e1) in zip(ranges, ranges[1:]):
+        assert e0 == b1
+    # 16-byte alignment of every tensor (float4 loads)
+    assert all(w % 4 == 0 and b % 4 == 0 for w, b in offs)
+
+
+def test_unknown_network_name():
+    L = _lib.lib()
+    assert not L.ms_engine_create(b'NoSuchNet', 1, 64, 64, 2, 1, 1)
+    assert b'Unrecognized network name' in L.ms_last_error()
+
+
+def test_samplers_match_reference_semantics():
+    d = np.ones(5) / 5
+    s = sampler_factory.get_sampler('SEQUENTIAL', 2)
+    assert [s.sample(d) for _ in range(3)] == [[0, 1], [1, 2], [2, 3]]
+    o = OA.SequentialSampler(2)
+    assert [o.sample(d) for _ in range(3)] == [[0, 1], [1, 2], [2, 3]]
+    assert sampler_factory.get_sampler('FIXED', 1, [3]).sample(d) == [3]
+    assert sampler_factory.get_sampler('FIXED', 1, 2).sample(d) == [2]
+    a = sampler_factory.get_sampler('ARGMAX', 2).sample(np.array([0.1, 0.5, 0.05, 0.3, 0.05]))
+    assert set(int(x) for x in a) == {1, 3}
+    for name in ('RANDOM', 'PROBABILITY'):
+        np.random.seed(7)
+        mine = sampler_factory.get_sampler(name, 2).sample(d)
+        np.random.seed(7)
+        ref = OA.sample(name, 2, d)
+        assert list(mine) == list(ref)
+    with pytest.raises(AssertionError):
+        sampler_factory.get_sampler('SAMPLE', 1)          # the reference's invalid default (:303)
+    assert set(sampler_factory.AVAILABLE_SAMPLER) == {'FIXED', 'RANDOM', 'ARGMAX', 'SEQUENTIAL', 'PROBABILITY'}
+
+
+def test_reward_recurrence_matches_transcription():
+    from madstereo.adaptation import softmax
+    tr = OA.RewardTracker(5)
+    losses = [0.3, 0.28, 0.31, 0.25, 0.2]
+    blocks = [[0], [1], [2], [3], [4]]
+    h = np.zeros(5); l1 = l2 = 0.0; last = []
+    for t, (L, b) in enumerate(zip(losses, blocks)):
+        tr.update(L, b)
+        if t == 0:
+            l2 = l1 = L
+        gain = (2 * l1 - l2) - L
+        h = 0.99 * h
+        for i in last:
+            h[i] += 0.01 * gain
+        last = b; l2, l1 = l1, L
+        assert np.allclose(tr.h, h)
+    assert np.allclose(softmax(h).sum(), 1.0)

@@ -1,0 +1,222 @@
+"""GPU parity of the whole path: MADNet forward, every MAD module step and the FULL step vs the CPU oracle,
+through the reference-shaped Python API (Nets.get_stereo_net / OnlineAdaptation) and the C-ABI engine."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import PKG
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden', 'madnet_64x128.npz')
+
+# tolerances (north_star: disparities within 1e-3 relative L-inf of the fp32 reference forward)
+TOL_DISP = 1e-3
+TOL_LAYER = 2e-4
+TOL_GRAD = 2e-3          # relative L-inf per tensor, fp32 accumulation-order noise only
+TOL_WEIGHT = 1e-6        # absolute, after one lr=1e-4 momentum step
+
+
+def rel_linf(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def build(left, right, mode, cfg='MadNet_full.json', **kw):
+    import Nets
+    from madstereo.adaptation import OnlineAdaptation
+    from oracle.madnet import init_params
+    lt = torch.as_tensor(left).cuda(); rt = torch.as_tensor(right).cuda()
+    args = dict(left_img=lt, right_img=rt, split_layers=[None], sequence=True, train_portion='BEGIN',
+                bulkhead=(mode == 'MAD'), warping=True, context_net=True, radius_d=2, stride=1, is_training=False)
+    net = Nets.get_stereo_net('MADNet', args)
+    train_config = json.load(open(os.path.join(PKG, 'block_config', cfg)))
+    ad = OnlineAdaptation(net, mode=mode, train_config=train_config, lr=1e-4, sample_mode='FIXED', fixed_id=0, **kw)
+    params = init_params(seed=42)
+    ad.load_weights(params)
+    return net, ad, params, lt, rt
+
+
+def test_api_surface():
+    from madstereo.synthetic import make_pair
+    left, right, _ = make_pair(64, 128, seed=3)
+    net, ad, params, lt, rt = build(left, right, 'MAD')
+    assert len(net.get_disparities()) == 6
+    names = list(net.get_layers_names())
+    assert names[0] == 'left/conv1' and 'right/conv12' in names and names[-1] == 'rescaled_prediction'
+    vs = net.get_variables('left/conv1')
+    assert [v.name for v in vs] == ['model/gc-read-pyramid/conv1/weights:0', 'model/gc-read-pyramid/conv1/biases:0']
+    assert vs[0].shape == (3, 3, 3, 16)
+    assert net.get_variables('right/conv1') == [] and net.get_variables('rescaled_prediction') == []
+    assert len(net.get_variables('final_disp')) == 98
+    assert len(net.get_trainable_variables()) == 98
+    assert 'Prediction Layer rescaled_prediction: (1, 64, 128, 1)' in str(net)
+    with pytest.raises(Exception):
+        import Nets
+        Nets.get_stereo_net('nope', {})
+
+
+@pytest.mark.parametrize('hw', [(64, 128), (128, 256), (100, 200)])
+def test_forward_parity(hw):
+    from madstereo.synthetic import make_pair
+    from oracle.madnet import MadNetOracle
+    h, w = hw
+    left, right, _ = make_pair(h, w, seed=3)
+    net, ad, params, lt, rt = build(left, right, 'NONE')
+    eng = net.engine
+    eng.set_input(lt, rt)
+    eng.forward(0b111111)
+    torch.cuda.synchronize()
+    disps, layers = MadNetOracle(params).forward(left, right)
+    for name in ('left/conv1', 'left/conv4', 'right/conv4', 'left/conv12', 'right/conv12',
+                 'fgc-volume-filtering-6/disp1', 'fgc-volume-filtering-6/disp6', 'fgc-volume-filtering-4/disp3',
+                 'fgc-volume-filtering-2/disp6', 'context1', 'context5', 'final_disp'):
+        got = net[name].numpy()
+        assert rel_linf(got, layers[name].numpy()) < TOL_LAYER, name
+    for k in (6, 5, 4, 3, 2):
+        c = eng.tensor('cost%d' % k).cpu().numpy()
+        C = layers['left/conv%d' % (2 * k)].shape[-1]
+        assert rel_linf(c[..., C:C + 5], layers['corr%d' % k].numpy()) < TOL_LAYER, 'corr%d' % k
+    for i, (d, ref) in enumerate(zip(net.get_disparities(), disps)):
+        assert d.shape == tuple(ref.shape)
+        assert rel_linf(d.numpy(), ref.numpy()) < TOL_DISP, 'disparity %d' % i
+
+
+def test_forward_matches_golden_fixture():
+    g = np.load(GOLDEN)
+    left = g['left'].astype(np.float32); right = g['right'].astype(np.float32)
+    net, ad, params, lt, rt = build(left, right, 'NONE')
+    out = ad.step(lt, rt, want_disp_mask=0b111111)
+    for i, d in enumerate(net.get_disparities()):
+        assert rel_linf(d.numpy(), g['disp%d' % i]) < TOL_DISP
+    for key in g.files:
+        if key.startswith('layer:') and not key.startswith('layer:corr'):
+            assert rel_linf(net[key[6:]].numpy(), g[key]) < TOL_LAYER, key
+    assert abs(out['loss'] - float(g['full_loss'])) < 2e-5
+
+
+@pytest.mark.parametrize('module', [0, 1, 2, 3, 4])
+@pytest.mark.parametrize('hw', [(64, 128), (100, 200)])
+def test_mad_step_parity(module, hw):
+    from madstereo.synthetic import make_pair
+    from oracle.adaptation import OracleAdapter
+    h, w = hw
+    left, right, _ = make_pair(h, w, seed=3)
+    net, ad, params, lt, rt = build(left, right, 'MAD')
+    ad.sampler._fixed_id = module
+    orc = OracleAdapter(params, mode='MAD', lr=1e-4)
+    for it in range(2):                                   # second step exercises the momentum slots
+        out = ad.step(lt, rt)
+        ref = orc.step(left, right, module)
+        assert out['blocks'] == [module]
+        assert abs(out['loss'] - ref['full_loss']) < 2e-5
+        assert abs(out['train_loss'] - ref['train_loss']) < 2e-5
+        gviews = net.engine.param_views(net.engine.grads)
+        for n, gr in ref['grads'].items():
+            assert rel_linf(gviews[n].cpu().numpy(), gr) < TOL_GRAD, (it, n)
+        wviews = net.engine.export_params()
+        for n in ref['grads']:
+            assert np.abs(wviews[n] - orc.net.p[n].detach().numpy()).max() < TOL_WEIGHT, (it, n)
+    # parameters outside the module are untouched
+    trained = set(ref['grads'])
+    for n, v in net.engine.export_params().items():
+        if n not in trained:
+            assert np.array_equal(v, params[n]), n
+
+
+def test_mad_golden_gradients():
+    g = np.load(GOLDEN)
+    left = g['left'].astype(np.float32); right = g['right'].astype(np.float32)
+    for module in range(5):
+        net, ad, params, lt, rt = build(left, right, 'MAD')
+        ad.sampler._fixed_id = module
+        out = ad.step(lt, rt)
+        assert abs(out['train_loss'] - float(g['MAD%d:train_loss' % module])) < 2e-5
+        gviews = net.engine.param_views(net.engine.grads)
+        for key in g.files:
+            if key.startswith('MAD%d:grad:' % module):
+                assert rel_linf(gviews[key.split(':', 2)[2]].cpu().numpy(), g[key]) < TOL_GRAD, key
+            if key.startswith('MAD%d:gslice:' % module):
+                got = gviews[key.split(':', 2)[2]].reshape(-1)[:64].cpu().numpy()
+                ref_norm = float(g[key.replace('gslice', 'gnorm')])
+                assert np.abs(got - g[key]).max() < TOL_GRAD * max(np.abs(g[key]).max(), 1e-3 * ref_norm), key
+
+
+@pytest.mark.parametrize('hw', [(64, 128), (100, 200)])
+def test_full_step_parity(hw):
+    from madstereo.synthetic import make_pair
+    from oracle.adaptation import OracleAdapter
+    h, w = hw
+    left, right, _ = make_pair(h, w, seed=3)
+    net, ad, params, lt, rt = build(left, right, 'FULL')
+    orc = OracleAdapter(params, mode='FULL', lr=1e-4)
+    for it in range(2):
+        out = ad.step(lt, rt)
+        ref = orc.step(left, right)
+        assert abs(out['loss'] - ref['full_loss']) < 2e-5
+        gviews = net.engine.param_views(net.engine.grads)
+        worst = 0.0
+        for n, gr in ref['grads'].items():
+            r = rel_linf(gviews[n].cpu().numpy(), gr)
+            worst = max(worst, r)
+            assert r < 5e-3, (it, n, r)
+        wviews = net.engine.export_params()
+        for n in ref['grads']:
+            assert np.abs(wviews[n] - orc.net.p[n].detach().numpy()).max() < 2e-6, (it, n)
+
+
+def test_piramid_only_config_trains_estimators_only():
+    from madstereo.synthetic import make_pair
+    from oracle.adaptation import OracleAdapter
+    left, right, _ = make_pair(64, 128, seed=3)
+    net, ad, params, lt, rt = build(left, right, 'MAD', cfg='MadNet_piramid_only.json')
+    ad.sampler._fixed_id = 4
+    cfg = json.load(open(os.path.join(PKG, 'block_config', 'MadNet_piramid_only.json')))
+    groups = []
+    for names in cfg:
+        g = []
+        for nm in names:
+            for v in net.get_variables(nm):
+                g.append(v.op_name)
+        groups.append(g)
+    orc = OracleAdapter(params, mode='MAD', lr=1e-4, groups=groups)
+    out = ad.step(lt, rt)
+    ref = orc.step(left, right, 4)
+    gviews = net.engine.param_views(net.engine.grads)
+    for n, gr in ref['grads'].items():
+        assert rel_linf(gviews[n].cpu().numpy(), gr) < TOL_GRAD, n
+    exported = net.engine.export_params()
+    for n in params:
+        if n not in ref['grads']:
+            assert np.array_equal(exported[n], params[n]), n
+
+
+def test_divergence_reset_restores_weights_not_momentum():
+    from madstereo.synthetic import make_pair
+    left, right, _ = make_pair(64, 128, seed=3)
+    net, ad, params, lt, rt = build(left, right, 'MAD', ssim_th=0.0)      # every frame "diverges"
+    out = ad.step(lt, rt)
+    assert out['reset'] and ad.reset_counter == 1
+    for n, v in net.engine.export_params().items():
+        assert np.array_equal(v, params[n]), n
+    assert float(net.engine.momentum.abs().max()) > 0.0                    # slots survive (weights_utils.py:4-38)
+
+
+def test_sequential_sampler_and_reward_bookkeeping():
+    from madstereo.synthetic import make_pair
+    left, right, _ = make_pair(64, 128, seed=3)
+    import Nets
+    from madstereo.adaptation import OnlineAdaptation
+    from oracle.madnet import init_params
+    lt = torch.as_tensor(left).cuda(); rt = torch.as_tensor(right).cuda()
+    net = Nets.get_stereo_net('MADNet', dict(left_img=lt, right_img=rt, split_layers=[None], sequence=True,
+                                             train_portion='BEGIN', bulkhead=True))
+    cfg = json.load(open(os.path.join(PKG, 'block_config', 'MadNet_full.json')))
+    ad = OnlineAdaptation(net, mode='MAD', train_config=cfg, sample_mode='SEQUENTIAL')
+    ad.load_weights(init_params(seed=42))
+    seen = [ad.step(lt, rt)['blocks'][0] for _ in range(7)]
+    assert seen == [0, 1, 2, 3, 4, 0, 1]
+    assert ad.fetch_counter == [2, 2, 1, 1, 1]
+    assert ad.sample_distribution.shape == (5,) and np.isfinite(ad.sample_distribution).all()

@@ -1,0 +1,212 @@
+"""GPU parity: every CUDA op (through the C ABI) vs the CPU oracle on seeded random tensors."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_linf(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def cu(x):
+    return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32)).cuda()
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from madstereo import ops as o
+    return o
+
+
+def _oracle():
+    from oracle import tf1_ops as T
+    return T
+
+
+# shapes: MADNet levels at 1280x384 for the small ones, reduced width for the big ones
+CORR_SHAPES = [(1, 6, 20, 192, 2, 1), (1, 12, 40, 128, 2, 1), (2, 24, 80, 96, 2, 1), (1, 48, 160, 64, 2, 1),
+               (1, 96, 320, 32, 2, 1), (1, 8, 24, 32, 4, 2), (1, 5, 7, 8, 2, 1)]
+
+
+@pytest.mark.parametrize('shape', CORR_SHAPES)
+@pytest.mark.parametrize('warp', [False, True])
+def test_correlation_fwd_bwd(ops, shape, warp):
+    T = _oracle()
+    b, h, w, c, d, s = shape
+    rng = np.random.default_rng(hash(shape) % 1000)
+    x = rng.standard_normal((b, h, w, c)).astype(np.float32)
+    y = rng.standard_normal((b, h, w, c)).astype(np.float32)
+    u = (rng.uniform(-3.0, 3.0, (b, h, w, 1))).astype(np.float32) if warp else None
+    if warp:
+        u[0, 0, 0, 0] = -7.25; u[0, -1, -1, 0] = 9.5          # far outside on both borders
+    xt = torch.tensor(x, requires_grad=True); yt = torch.tensor(y, requires_grad=True)
+    ut = torch.tensor(u, requires_grad=True) if warp else None
+    yw = T.linear_warp(yt, ut) if warp else yt
+    ref = T.correlation(xt, yw, d, s)
+    out = ops.correlation(cu(x), cu(y), d, s, u=cu(u) if warp else None)
+    assert rel_linf(out.cpu().numpy(), ref.detach().numpy()) < 2e-5
+    g = rng.standard_normal(ref.shape).astype(np.float32)
+    grads = torch.autograd.grad(ref, [xt, yt] + ([ut] if warp else []), grad_outputs=torch.tensor(g))
+    dx, dy, du = ops.correlation_bwd(cu(x), cu(y), cu(g), d, s, u=cu(u) if warp else None, want_du=warp)
+    assert rel_linf(dx.cpu().numpy(), grads[0].numpy()) < 2e-5
+    assert rel_linf(dy.cpu().numpy(), grads[1].numpy()) < 2e-5
+    if warp:
+        assert rel_linf(du.cpu().numpy(), grads[2].numpy()) < 1e-4
+
+
+def test_cost_volume_concat(ops):
+    T = _oracle()
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((1, 12, 40, 32)).astype(np.float32)
+    y = rng.standard_normal((1, 12, 40, 32)).astype(np.float32)
+    u = rng.uniform(-2, 2, (1, 12, 40, 1)).astype(np.float32)
+    ref = torch.cat([torch.tensor(x), T.correlation(torch.tensor(x), T.linear_warp(torch.tensor(y), torch.tensor(u)), 2),
+                     torch.tensor(u)], -1)
+    out = ops.cost_volume(cu(x), cu(y), 2, 1, u=cu(u))
+    assert out.shape == ref.shape
+    assert rel_linf(out.cpu().numpy(), ref.numpy()) < 2e-5
+
+
+def test_correlation_matches_reference_native_kernel(ops):
+    """The reference's own CorrelateData kernel (compiled unmodified into oracle/_ref) on padded inputs."""
+    path = os.path.join(ROOT, 'oracle', '_ref', 'libref_shift_corr.so')
+    if not os.path.exists(path):
+        pytest.skip('oracle/_ref not built (reference sources absent at build time)')
+    ref = ctypes.CDLL(path)
+    ref.ref_shift_corr.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 5 + [ctypes.c_void_p]
+    rng = np.random.default_rng(5)
+    b, h, w, c, d = 2, 9, 33, 64, 2
+    x = cu(rng.standard_normal((b, h, w, c))); y = cu(rng.standard_normal((b, h, w, c)))
+    xp = torch.nn.functional.pad(x, (0, 0, d, d)).contiguous()
+    yp = torch.nn.functional.pad(y, (0, 0, d, d)).contiguous()
+    out_nchw = torch.zeros(b, 2 * d + 1, h, w, device='cuda')
+    torch.cuda.synchronize()
+    rc = ref.ref_shift_corr(xp.data_ptr(), yp.data_ptr(), d, b, h, w + 2 * d, c, out_nchw.data_ptr())
+    torch.cuda.synchronize()
+    assert rc == 0
+    mine = ops.correlation(x, y, d)
+    assert rel_linf(mine.cpu().numpy(), out_nchw.permute(0, 2, 3, 1).cpu().numpy()) < 2e-5
+
+
+CONV_CASES = [
+    # n, h, w, cin, cout, k, stride, dil, alpha
+    (2, 32, 64, 3, 16, 3, 2, 1, 0.2), (2, 16, 32, 16, 16, 3, 1, 1, 0.2), (1, 16, 32, 16, 32, 3, 2, 1, 0.2),
+    (1, 12, 40, 134, 128, 3, 1, 1, 0.2), (1, 24, 40, 128, 96, 3, 1, 1, 0.2), (1, 24, 40, 32, 1, 3, 1, 1, 1.0),
+    (1, 24, 40, 33, 128, 3, 1, 1, 0.2), (1, 24, 48, 128, 128, 3, 1, 4, 0.2), (1, 24, 48, 96, 64, 3, 1, 16, 0.2),
+    (1, 17, 23, 20, 24, 3, 2, 1, 0.1), (1, 32, 32, 3, 64, 7, 2, 1, 0.1), (1, 16, 16, 64, 128, 5, 2, 1, 0.1),
+    (1, 16, 16, 128, 64, 1, 1, 1, 0.1), (1, 6, 20, 197, 128, 3, 1, 1, 0.2),
+]
+
+
+@pytest.mark.parametrize('case', CONV_CASES)
+def test_conv2d_fwd_dgrad_wgrad(ops, case):
+    T = _oracle()
+    n, h, w, cin, cout, k, s, dil, alpha = case
+    rng = np.random.default_rng(sum(case[:8]))
+    x = rng.standard_normal((n, h, w, cin)).astype(np.float32)
+    wt = (rng.standard_normal((k, k, cin, cout)) / np.sqrt(k * k * cin)).astype(np.float32)
+    b = rng.uniform(-0.1, 0.1, cout).astype(np.float32)
+    xt = torch.tensor(x, requires_grad=True); wtt = torch.tensor(wt, requires_grad=True)
+    bt = torch.tensor(b, requires_grad=True)
+    ref = T.conv2d(xt, wtt, bt, stride=s, dilation=dil, alpha=None if alpha == 1.0 else alpha)
+    out = ops.conv2d(cu(x), cu(wt), cu(b), s, dil, alpha)
+    assert out.shape == ref.shape
+    assert rel_linf(out.cpu().numpy(), ref.detach().numpy()) < 2e-5
+    # backward of the linear part (dy = grad wrt pre-activation)
+    pre = T.conv2d(xt, wtt, bt, stride=s, dilation=dil, alpha=None)
+    g = rng.standard_normal(pre.shape).astype(np.float32)
+    gx, gw, gb = torch.autograd.grad(pre, [xt, wtt, bt], grad_outputs=torch.tensor(g))
+    dx = ops.conv2d_dgrad(cu(g), cu(wt), (h, w), s, dil)
+    assert rel_linf(dx.cpu().numpy(), gx.numpy()) < 3e-5
+    dw, db = ops.conv2d_wgrad(cu(x), cu(g), k, k, s, dil)
+    assert rel_linf(dw.cpu().numpy(), gw.numpy()) < 5e-5
+    assert rel_linf(db.cpu().numpy(), gb.numpy()) < 5e-5
+
+
+@pytest.mark.parametrize('case', [(1, 6, 8, 32, 16, 0.1), (2, 5, 7, 1, 1, 1.0), (1, 4, 4, 64, 32, 0.1)])
+def test_conv2d_transpose_fwd(ops, case):
+    T = _oracle()
+    n, h, w, cin, cout, alpha = case
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((n, h, w, cin)).astype(np.float32)
+    wt = (rng.standard_normal((4, 4, cout, cin)) / 4).astype(np.float32)
+    b = rng.uniform(-0.1, 0.1, cout).astype(np.float32)
+    ref = T.conv2d_transpose(torch.tensor(x), torch.tensor(wt), torch.tensor(b), 2, None if alpha == 1.0 else alpha)
+    out = ops.conv2d_transpose(cu(x), cu(wt), cu(b), 2, alpha)
+    assert rel_linf(out.cpu().numpy(), ref.numpy()) < 2e-5
+
+
+RESIZE_CASES = [
+    # ih, iw, rh, rw, oh, ow, pre_scale, pre_relu, post_scale, post_relu
+    (6, 20, 384, 1280, 384, 1280, -20.0, True, 1.0, False), (6, 20, 12, 40, 12, 40, 1.0, False, 0.625, False),
+    (24, 32, 128, 192, 100, 180, -20.0, True, 1.0, False), (24, 32, 128, 192, 100, 180, 1.0, False, -20.0, True),
+    (7, 9, 7, 9, 7, 9, 1.0, False, 2.0, False), (5, 11, 13, 17, 13, 17, 1.0, False, 1.0, False),
+]
+
+
+@pytest.mark.parametrize('case', RESIZE_CASES)
+def test_resize_fwd_bwd(ops, case):
+    T = _oracle()
+    ih, iw, rh, rw, oh, ow, prs, prr, pos, por = case
+    rng = np.random.default_rng(ih * iw)
+    x = rng.standard_normal((2, ih, iw, 1)).astype(np.float32)
+    xt = torch.tensor(x, requires_grad=True)
+    v = xt * prs
+    if prr: v = torch.relu(v)
+    v = T.resize_bilinear(v, rh, rw) * pos
+    if por: v = torch.relu(v)
+    ref = T.crop_or_pad(v, oh, ow)
+    out = ops.resize_bilinear(cu(x), rh, rw, oh, ow, prs, prr, pos, por)
+    assert rel_linf(out.cpu().numpy(), ref.detach().numpy()) < 1e-5
+    g = rng.standard_normal(ref.shape).astype(np.float32)
+    (gx,) = torch.autograd.grad(ref, xt, grad_outputs=torch.tensor(g))
+    dx = ops.resize_bilinear_bwd(cu(g), cu(x), rh, rw, prs, prr, pos, por)
+    assert rel_linf(dx.cpu().numpy(), gx.numpy()) < 2e-5
+
+
+@pytest.mark.parametrize('hw', [(40, 64), (96, 160), (37, 53)])
+def test_reprojection_loss_and_gradient(ops, hw):
+    T = _oracle()
+    from madstereo.synthetic import make_pair
+    h, w = hw
+    left, right, gt = make_pair(h, w, seed=2, batch=2)
+    rng = np.random.default_rng(3)
+    disp = (gt + rng.normal(0, 1.5, gt.shape)).astype(np.float32)
+    disp[0, 0, :4, 0] = -3.0; disp[0, 1, -3:, 0] = 500.0       # out-of-range samples hit the clamps
+    dt = torch.tensor(disp, requires_grad=True)
+    ref = T.reprojection_loss(dt, torch.tensor(left), torch.tensor(right))
+    (gref,) = torch.autograd.grad(ref, dt)
+    loss, dd = ops.reprojection_loss(cu(left), cu(right), cu(disp), with_grad=True)
+    assert abs(float(loss.cpu()) - float(ref)) < 2e-6 + 1e-5 * abs(float(ref))
+    assert rel_linf(dd.cpu().numpy(), gref.numpy()) < 5e-4
+    loss2, none = ops.reprojection_loss(cu(left), cu(right), cu(disp), with_grad=False)
+    assert none is None and float(loss2.cpu()) == float(loss.cpu())
+
+
+def test_momentum_update(ops):
+    T = _oracle()
+    rng = np.random.default_rng(0)
+    n = 100003
+    w = rng.standard_normal(n).astype(np.float32); g = rng.standard_normal(n).astype(np.float32)
+    m = rng.standard_normal(n).astype(np.float32)
+    wr, mr = T.momentum_update(torch.tensor(w), torch.tensor(g) * 0.5, torch.tensor(m), 1e-2, 0.9)
+    wc, gc, mc = cu(w)[:n], cu(g), cu(m)
+    ops.momentum_update(wc, gc, mc, 1e-2, 0.9, 0.5)
+    assert rel_linf(wc.cpu().numpy(), wr.numpy()) < 1e-6 and rel_linf(mc.cpu().numpy(), mr.numpy()) < 1e-6
+
+
+def test_pad_reflect(ops):
+    T = _oracle()
+    rng = np.random.default_rng(0)
+    x = rng.uniform(0, 255, (2, 100, 150, 3)).astype(np.float32)
+    ref = T.pad_reflect_to_multiple(torch.tensor(x), 64)
+    out = ops.pad_reflect(cu(x), 64)
+    assert out.shape == ref.shape and torch.equal(out.cpu(), ref)
