@@ -118,6 +118,13 @@ int ms_engine_update(void* e, int group /* -1 = all */, float lr, float mu, floa
 /* scalars: [0]=slot-0 loss, [1]=slot-1 loss, [2]=EPE, [3]=bad3. Synchronises `stream`. */
 int ms_engine_read_scalars(void* e, float* host4, void* stream);
 int ms_engine_metrics(void* e, void* stream);
+/* Profiling aid for bench.py (no reference counterpart): CUDA events around kernel groups on the launching
+ * stream.  Categories: 0 conv fwd, 1 conv dgrad, 2 conv wgrad, 3 corr fwd, 4 corr bwd, 5 loss, 6 other.
+ * Arrays have 7 entries: summed device ms, algorithmic MACs, algorithmic bytes, number of timed calls. */
+int ms_engine_profile(void* e, int enable);
+int ms_engine_profile_read(void* e, double* ms7, double* macs7, double* bytes7, long long* calls7);
+/* Kernels launched by this library in this process so far. */
+long long ms_launch_count(void);
 int ms_engine_num_tensors(void* e);
 int ms_engine_tensor_name(void* e, int i, char* name, int cap);
 /* dims: n,h,w,c,cs */

@@ -248,6 +248,24 @@ int ms_engine_read_scalars(void* h, float* host4, void* stream) {
     MS_CHECK_CUDA(cudaStreamSynchronize(S(stream)));
     return 0;
 }
+int ms_engine_profile(void* h, int enable) {
+    Engine* e = static_cast<Engine*>(h);
+    e->profiling = enable != 0;
+    if (enable) e->prof_reset();
+    return 0;
+}
+int ms_engine_profile_read(void* h, double* ms7, double* macs7, double* bytes7, long long* calls7) {
+    Engine* e = static_cast<Engine*>(h);
+    if (e->prof_collect()) return -1;
+    for (int i = 0; i < Engine::N_CAT; ++i) {
+        if (ms7) ms7[i] = e->cat_ms[i];
+        if (macs7) macs7[i] = e->cat_macs[i];
+        if (bytes7) bytes7[i] = e->cat_bytes[i];
+        if (calls7) calls7[i] = e->cat_calls[i];
+    }
+    return 0;
+}
+long long ms_launch_count(void) { return ms::launch_count(); }
 int ms_engine_num_tensors(void* h) { return (int)static_cast<Engine*>(h)->tensors.size(); }
 int ms_engine_tensor_name(void* h, int i, char* name, int cap) {
     Engine* e = static_cast<Engine*>(h);

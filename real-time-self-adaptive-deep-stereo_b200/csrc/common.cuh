@@ -24,7 +24,8 @@ inline TView batch(const TView& t, int n0, int n) {
 }
 
 void set_error(const std::string& s);
-int check_launch(const char* what);
+int check_launch(const char* what, int n_kernels = 1);
+long long launch_count();
 
 #define MS_CHECK_CUDA(expr)                                                                   \
     do {                                                                                      \

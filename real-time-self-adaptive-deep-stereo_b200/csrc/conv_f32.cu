@@ -452,7 +452,7 @@ int conv_wgrad(const ConvWgrad& p, cudaStream_t st) {
 #undef DB
 #undef DA
 #undef DN
-    if (check_launch("conv_wgrad")) return -1;
+    if (check_launch("conv_wgrad", 1)) return -1;
     wgrad_reduce_kernel<<<(unsigned)cdivz(wn, 256), 256, 0, st>>>(p.workspace, p.dw, wn, split, p.accumulate);
     if (p.db) {
         float* bp = p.workspace + (size_t)split * wn;
@@ -460,7 +460,7 @@ int conv_wgrad(const ConvWgrad& p, cudaStream_t st) {
         bias_partial_kernel<<<dim3(cdiv(co, 32), nb), dim3(32, 8), 0, st>>>(p.dy.p, p.dy.cs, co, P, bchunk, bp);
         wgrad_reduce_kernel<<<cdiv(co, 256), 256, 0, st>>>(bp, p.db, (size_t)co, nb, p.accumulate);
     }
-    return check_launch("conv_wgrad_reduce");
+    return check_launch("conv_wgrad_reduce", p.db ? 3 : 1);
 }
 
 // wt[tap][co][ci] = w[tap][ci][co]

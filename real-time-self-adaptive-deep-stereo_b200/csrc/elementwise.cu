@@ -180,7 +180,7 @@ int resize_bilinear_bwd(const float* dout, int docs, const float* src, int scs, 
     size_t t2 = (size_t)B * ih * iw;
     resize_bwd_y_kernel<<<(unsigned)cdivz(t2, 256), 256, 0, st>>>(tmp, src, scs, B, ih, iw, dsrc, dscs, rh, oh, ys,
                                                                  pre_scale, pre_relu, accumulate);
-    return check_launch("resize_bilinear_bwd");
+    return check_launch("resize_bilinear_bwd", 2);
 }
 
 __global__ void leaky_bwd_kernel(float* __restrict__ g, int gcs, const float* __restrict__ act, int acs,

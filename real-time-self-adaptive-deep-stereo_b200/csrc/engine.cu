@@ -33,7 +33,36 @@ Engine::Engine()
     : net(0), B(1), H(0), W(0), Hp(0), Wp(0), radius_d(2), corr_stride(1), warping(1), n_groups(0), n_params(0),
       Wt(nullptr), Gr(nullptr), Mo(nullptr), ws(nullptr), ws_floats(0), bound(false), wT(nullptr), wT_floats(0),
       wg_ws(nullptr), wg_ws_floats(0), rs_tmp(nullptr), rs_tmp_floats(0), loss_ws(nullptr), loss_ws_floats(0),
-      scalars(nullptr), gt(nullptr) {}
+      scalars(nullptr), gt(nullptr), profiling(false) { prof_reset(); }
+
+void Engine::prof_reset() {
+    for (int i = 0; i < N_CAT; ++i) { cat_ms[i] = 0; cat_macs[i] = 0; cat_bytes[i] = 0; cat_calls[i] = 0; }
+}
+void Engine::prof_begin(int cat, cudaStream_t st) {
+    if (!profiling) return;
+    Span s; s.cat = cat;
+    for (cudaEvent_t* e : {&s.a, &s.b}) {
+        if (!event_pool.empty()) { *e = event_pool.back(); event_pool.pop_back(); }
+        else cudaEventCreate(e);
+    }
+    cudaEventRecord(s.a, st);
+    spans.push_back(s);
+}
+void Engine::prof_end(cudaStream_t st) {
+    if (!profiling || spans.empty()) return;
+    cudaEventRecord(spans.back().b, st);
+}
+int Engine::prof_collect() {
+    for (auto& s : spans) {
+        MS_CHECK_CUDA(cudaEventSynchronize(s.b));
+        float ms = 0.f;
+        MS_CHECK_CUDA(cudaEventElapsedTime(&ms, s.a, s.b));
+        cat_ms[s.cat] += ms; cat_calls[s.cat] += 1;
+        event_pool.push_back(s.a); event_pool.push_back(s.b);
+    }
+    spans.clear();
+    return 0;
+}
 
 int Engine::build_madnet() {
     layers.clear();
@@ -215,7 +244,11 @@ int Engine::conv_fwd(const ConvLayer& L, const TView& x, const TView& y, const f
         p.wmat = wT;
         p.mul = 1; p.off_y = pt; p.off_x = pl; p.step = -1; p.div = L.stride;
     }
-    return conv_gemm(p, st);
+    prof_begin(CAT_CONV_FWD, st);
+    int rc = conv_gemm(p, st);
+    prof_end(st);
+    if (profiling) cat_macs[CAT_CONV_FWD] += (double)y.pixels() * L.kh * L.kw * L.cin * L.cout / (L.transposed ? L.stride * L.stride : 1);
+    return rc;
 }
 
 // x: forward input of the layer; dpre: grad wrt pre-activation output; dx: where to write grad wrt x
@@ -231,7 +264,11 @@ int Engine::conv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, cons
         q.x = x; q.dy = dpre; q.dw = Gr + L.w_off; q.db = Gr + L.b_off;
         q.kh = L.kh; q.kw = L.kw; q.stride = L.stride; q.dil = L.dil; q.pad_t = pt; q.pad_l = pl;
         q.workspace = wg_ws; q.workspace_floats = wg_ws_floats; q.accumulate = 0;
-        if (conv_wgrad(q, st)) return -1;
+        prof_begin(CAT_CONV_WGRAD, st);
+        int rc = conv_wgrad(q, st);
+        prof_end(st);
+        if (profiling) cat_macs[CAT_CONV_WGRAD] += (double)dpre.pixels() * L.kh * L.kw * L.cin * L.cout;
+        if (rc) return -1;
     }
     if (dx) {
         if (transpose_taps(Wt + L.w_off, wT, L.kh * L.kw, L.cin, L.cout, st)) return -1;   // -> [tap][cout][cin]
@@ -241,7 +278,11 @@ int Engine::conv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, cons
         p.alpha = 1.f;
         p.mask = dx_mask ? dx_mask->p : nullptr; p.mask_cs = dx_mask ? dx_mask->cs : 0; p.mask_alpha = mask_alpha;
         p.res = nullptr; p.res_cs = 0; p.accumulate = dx_acc;
-        if (conv_gemm(p, st)) return -1;
+        prof_begin(CAT_CONV_DGRAD, st);
+        int rc = conv_gemm(p, st);
+        prof_end(st);
+        if (profiling) cat_macs[CAT_CONV_DGRAD] += (double)dpre.pixels() * L.kh * L.kw * L.cin * L.cout;
+        if (rc) return -1;
     }
     return 0;
 }
@@ -294,7 +335,11 @@ int Engine::forward(int disp_mask, cudaStream_t st) {
         cf.out2 = (k == 2) ? ctxin.p : nullptr; cf.o2cs = ctxin.cs;
         cf.B = B; cf.h = cost[k].h; cf.w = cost[k].w; cf.C = C; cf.max_disp = radius_d; cf.stride = corr_stride;
         cf.copy_left = 1; cf.u_chan = (k < 6) ? 1 : 0;
-        if (corr_fwd(cf, st)) return -1;
+        prof_begin(CAT_CORR_FWD, st);
+        int crc = corr_fwd(cf, st);
+        prof_end(st);
+        if (profiling) cat_bytes[CAT_CORR_FWD] += (double)B * cf.h * cf.w * (2.0 * C + nd) * 4.0;
+        if (crc) return -1;
         TView xin = cost[k];
         for (int j = 1; j <= 6; ++j) {
             TView y = (j < 6) ? est[k][j] : V[k];
@@ -329,7 +374,10 @@ int Engine::loss(int which, int with_grad, int slot, float grad_scale, cudaStrea
     p.disp = disp[which].p; p.loss = scalars + slot;
     p.ddisp = with_grad ? g_disp.p : nullptr;
     p.workspace = loss_ws; p.B = B; p.H = H; p.W = W; p.grad_scale = grad_scale;
-    return reproj_loss(p, st);
+    prof_begin(CAT_LOSS, st);
+    int rc = reproj_loss(p, st);
+    prof_end(st);
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -393,7 +441,11 @@ int Engine::backward(int mode, int group, cudaStream_t st) {
         cb.du = (want_du && cb.u) ? g_u[k].p : nullptr; cb.ducs = 1;
         cb.B = B; cb.h = cost[k].h; cb.w = cost[k].w; cb.C = C; cb.max_disp = radius_d; cb.stride = corr_stride;
         cb.add_left_slice = 1; cb.acc_left = 0; cb.acc_right = 0;
-        return corr_bwd(cb, st);
+        prof_begin(CAT_CORR_BWD, st);
+        int crc = corr_bwd(cb, st);
+        prof_end(st);
+        if (profiling) cat_bytes[CAT_CORR_BWD] += (double)B * cb.h * cb.w * (4.0 * C + nd) * 4.0;
+        return crc;
     };
     // ---- pyramid: g_pyr[top] holds d(post-activation output of conv `top`), complete
     auto pyr_bwd = [&](int top, int lo, bool accumulate_feats) -> int {

@@ -57,6 +57,18 @@ struct Engine {
     float* scalars;                  // [0]=full loss, [1]=train loss, [2]=epe, [3]=bad3
     float* gt;                       // optional ground truth [B,H,W,1]
 
+    // ---- profiling (off by default): CUDA events around kernel groups on the launching stream
+    enum Cat { CAT_CONV_FWD = 0, CAT_CONV_DGRAD, CAT_CONV_WGRAD, CAT_CORR_FWD, CAT_CORR_BWD, CAT_LOSS, CAT_OTHER, N_CAT };
+    struct Span { int cat; cudaEvent_t a, b; };
+    bool profiling;
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> event_pool;
+    double cat_ms[N_CAT]; double cat_macs[N_CAT]; double cat_bytes[N_CAT]; long long cat_calls[N_CAT];
+    void prof_begin(int cat, cudaStream_t st);
+    void prof_end(cudaStream_t st);
+    int prof_collect();      // synchronises; folds spans into cat_ms
+    void prof_reset();
+
     Engine();
     size_t layout(float* base);      // returns floats needed; assigns views when base != nullptr
     int build_madnet();

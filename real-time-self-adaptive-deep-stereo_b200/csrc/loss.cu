@@ -180,7 +180,7 @@ int reproj_loss(const ReprojLoss& p, cudaStream_t st) {
     loss_ssim_kernel<<<nb2, LB, 0, st>>>(p, xw, p.ddisp ? coef : nullptr, ssp, (float)(0.85 * inv_nw));
     if (p.ddisp) loss_grad_kernel<<<nb1, LB, 0, st>>>(p, xw, dxw, coef, (float)(0.15 * inv_np));
     loss_final_kernel<<<1, 256, 0, st>>>(l1p, nb1, ssp, nb2, inv_np, inv_nw, p.loss);
-    return check_launch("reproj_loss");
+    return check_launch("reproj_loss", p.ddisp ? 4 : 3);
 }
 
 // EPE / bad3 against ground truth (reference Stereo_Online_Adaptation.py:74-82); out2 = {epe, bad3}
@@ -214,7 +214,7 @@ int epe_bad3(const float* disp, const float* gt, int n, float* out2, float* work
     int nb = cdiv(n, LB);
     epe_partial_kernel<<<nb, LB, 0, st>>>(disp, gt, n, workspace);
     epe_final_kernel<<<1, 256, 0, st>>>(workspace, nb, out2);
-    return check_launch("epe_bad3");
+    return check_launch("epe_bad3", 2);
 }
 
 }  // namespace ms

@@ -5,7 +5,10 @@ static std::mutex g_mu;
 static std::string g_err;
 void set_error(const std::string& s) { std::lock_guard<std::mutex> l(g_mu); g_err = s; }
 const char* last_error_cstr() { std::lock_guard<std::mutex> l(g_mu); return g_err.c_str(); }
-int check_launch(const char* what) {
+static long long g_launches = 0;
+long long launch_count() { return g_launches; }
+int check_launch(const char* what, int n_kernels) {
+    g_launches += n_kernels;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error(std::string(what) + ": " + cudaGetErrorString(e)); return -1; }
     return 0;

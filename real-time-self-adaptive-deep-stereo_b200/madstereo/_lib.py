@@ -53,6 +53,9 @@ _SIGS = {
     'ms_engine_update': (I, [P, I, F, F, F, P]),
     'ms_engine_read_scalars': (I, [P, POINTER(F), P]),
     'ms_engine_metrics': (I, [P, P]),
+    'ms_engine_profile': (I, [P, I]),
+    'ms_engine_profile_read': (I, [P, POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(ctypes.c_longlong)]),
+    'ms_launch_count': (ctypes.c_longlong, []),
     'ms_engine_num_tensors': (I, [P]),
     'ms_engine_tensor_name': (I, [P, I, c_char_p, I]),
     'ms_engine_tensor': (I, [P, c_char_p, POINTER(P), POINTER(I)]),

@@ -169,6 +169,23 @@ class StereoEngine:
             check(self._lib.ms_engine_read_scalars(self._h, out, _stream()), 'read_scalars')
         return list(out)
 
+    # ---- profiling -----------------------------------------------------------------------------
+    CATEGORIES = ('conv_fwd', 'conv_dgrad', 'conv_wgrad', 'corr_fwd', 'corr_bwd', 'loss', 'other')
+
+    def profile(self, enable):
+        check(self._lib.ms_engine_profile(self._h, 1 if enable else 0), 'profile')
+
+    def profile_read(self):
+        ms, macs, byts = ((ctypes.c_double * 7)() for _ in range(3))
+        calls = (ctypes.c_longlong * 7)()
+        with torch.cuda.device(self.device):
+            check(self._lib.ms_engine_profile_read(self._h, ms, macs, byts, calls), 'profile_read')
+        return {c: {'ms': ms[i], 'macs': macs[i], 'bytes': byts[i], 'calls': calls[i]}
+                for i, c in enumerate(self.CATEGORIES)}
+
+    def launch_count(self):
+        return int(self._lib.ms_launch_count())
+
     # ---- introspection -------------------------------------------------------------------------
     def tensor_names(self):
         n = self._lib.ms_engine_num_tensors(self._h)

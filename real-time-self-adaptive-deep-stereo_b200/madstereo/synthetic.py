@@ -50,3 +50,30 @@ def make_noise_pair(h, w, seed=0, batch=1):
     rng = np.random.default_rng(seed)
     return (rng.uniform(0, 255, (batch, h, w, 3)).astype(np.float32),
             rng.uniform(0, 255, (batch, h, w, 3)).astype(np.float32))
+
+
+def init_params(layers, seed=42, bias_range=0.1):
+    """Seeded stand-in for a pretrained checkpoint (none is reachable offline): xavier-uniform weights
+    (tf.contrib.layers.xavier_initializer, Nets/sharedLayers.py:4) rescaled so that activations stay O(1) on
+    0..255 inputs and every disparity head is alive, small non-zero biases.
+    `layers`: iterable of engine LayerInfo (scope, bias_name, kh, kw, cin, cout, transposed).
+    """
+    rng = np.random.default_rng(seed)
+    out = {}
+    for l in layers:
+        shape = (l.kh, l.kw, l.cout, l.cin) if l.transposed else (l.kh, l.kw, l.cin, l.cout)
+        limit = np.sqrt(6.0 / (l.kh * l.kw * (l.cin + l.cout)))
+        w = rng.uniform(-limit, limit, size=shape).astype(np.float32)
+        head = l.scope.endswith('disp-6') or l.scope.endswith('context-7')
+        if l.scope.endswith('gc-read-pyramid/conv1'):
+            w *= np.float32(1.0 / 48.0)
+        elif head:
+            w *= np.float32(0.5)
+        else:
+            w *= np.float32(1.3)
+        b = rng.uniform(-bias_range, bias_range, size=(l.cout,)).astype(np.float32)
+        if head:
+            b -= np.float32(0.05 if l.scope.endswith('context-7') else 0.35)
+        out[l.scope + '/weights'] = w
+        out[l.scope + '/' + l.bias_name] = b
+    return out
