@@ -53,6 +53,16 @@ int ms_conv2d_fwd(const float* x, int n, int h, int w, int cin, int x_cs, const 
 int ms_conv2d_dgrad(const float* dy, int n, int oh, int ow, int cout, int dy_cs, const float* weights,
                     float* dx, int h, int w, int cin, int dx_cs, int kh, int kw, int stride, int dilation,
                     float* scratch, void* stream);
+/* tcgen05 (5th-gen tensor core, 3xTF32 split => fp32-grade accuracy) variants of the two ops above for
+ * stride-1 convolutions; the engine uses them automatically for eligible layers (MS_CONV_TC=0 disables).
+ * scratch: ms_conv2d_tc_scratch() floats.  Returns -3 if the shape is not eligible. */
+int ms_conv2d_fwd_tc(const float* x, int n, int h, int w, int cin, int x_cs, const float* weights /*HWIO*/,
+                     const float* bias, float* y, int cout, int y_cs, int kh, int kw, int dilation, float alpha,
+                     float* scratch, size_t scratch_floats, void* stream);
+int ms_conv2d_dgrad_tc(const float* dy, int n, int h, int w, int cout, int dy_cs, const float* weights /*HWIO*/,
+                       float* dx, int cin, int dx_cs, int kh, int kw, int dilation, float* scratch,
+                       size_t scratch_floats, void* stream);
+size_t ms_conv2d_tc_scratch(int kh, int kw, int cin, int cout);
 size_t ms_conv2d_wgrad_workspace(int kh, int kw, int cin, int cout, size_t out_pixels);
 int ms_conv2d_wgrad(const float* x, int n, int h, int w, int cin, int x_cs, const float* dy, int oh, int ow,
                     int cout, int dy_cs, float* dw /*HWIO*/, float* db, int kh, int kw, int stride,

@@ -139,3 +139,10 @@ int momentum_update(float* w, const float* g, float* m, size_t n, float lr, floa
                     cudaStream_t st);
 
 }  // namespace ms
+
+namespace ms {
+// tcgen05 path (conv_tc.cu)
+bool conv_tc_supported(const ConvGemm& g);
+size_t conv_tc_scratch_floats(int taps, int N, int K);
+int conv_tc(const ConvGemm& g, int wmat_is_nk, float* scratch, size_t scratch_floats, cudaStream_t st);
+}  // namespace ms

@@ -1,0 +1,381 @@
+// tcgen05 implicit-GEMM convolution (stride 1, any dilation): the tensor-core path for the conv stacks.
+//
+// Replaces the cuDNN calls behind tf.nn.conv2d / tf.nn.atrous_conv2d (reference Nets/sharedLayers.py:58,72) and
+// their input-gradients for every stride-1 layer of MADNet/DispNet (estimators Nets/MadNet.py:73-120, context net
+// :122-171, the stride-1 pyramid convs :173-249).
+//
+// GEMM view: M = 128 output pixels (a TH x TW patch of one image), N = output channels (<=256, padded to x16),
+// K = taps x input channels in blocks of 32.  Per K-block one 4-D TMA box {32ch, TW, TH, 1} of the input at the
+// tap-shifted coordinate lands in shared memory as a K-major SWIZZLE_128B tile (out-of-image taps and channels
+// beyond C are zero-filled by TMA = the SAME padding), the weights arrive as a {32, N} K-major tile.
+// fp32 fidelity on tf32 tensor cores uses the 3xTF32 split  a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi
+// (hi = round-to-tf32, lo = exact remainder): the weight halves are prepared in global memory, the activation
+// halves by 4 "splitter" warps in shared memory.  Accumulators live in TMEM (128 lanes x N fp32 columns);
+// the same 4 warps run the epilogue (bias, leaky-ReLU, residual, dgrad mask/accumulate) from tcgen05.ld.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = splitter +
+// epilogue.  mbarrier pipeline: full[s] (TMA -> splitter), ready[s] (splitter -> MMA), empty[s] (tcgen05.commit ->
+// TMA), accum (tcgen05.commit -> epilogue).
+#include <cuda.h>
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace ms {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mb_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mb_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = s_addr(bar);
+    uint32_t ok = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(s_addr(dst)), "l"(map), "r"(s_addr(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(s_addr(dst)), "l"(map), "r"(s_addr(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO=1 | SBO=1024B |
+// version=1 (sm100) | layout_type=2 (SWIZZLE_128B).  Tile base must be 1024-byte aligned.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_byte_addr) {
+    return (uint64_t)((smem_byte_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// ------------------------------------------------------------------------------------------------
+struct ConvTCParams {
+    int kh, kw, off_y, off_x, step;   // gathered coordinate = out + off + tap*step
+    int kblocks;                      // ceil(K channels / 32)
+    int H, W, NB, TH, TW, tiles_x, tiles_y;
+    int N, BN, tmem_cols, stages;
+    float* y; int ycs;
+    const float* bias; float alpha;
+    const float* mask; int mask_cs; float mask_alpha;
+    const float* res; int res_cs;
+    int accumulate;
+};
+
+constexpr int TC_THREADS = 192;
+constexpr int A_TILE_BYTES = 128 * 128;   // 128 pixels x 32 fp32
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
+               const __grid_constant__ CUtensorMap mapBl, const ConvTCParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t full_bar[4], ready_bar[4], empty_bar[4], accum_bar;
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // 1024-byte aligned carve-up
+    const uint32_t base = (s_addr(smem_dyn) + 1023u) & ~1023u;
+    unsigned char* gbase = smem_dyn + (base - s_addr(smem_dyn));
+    const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+    const uint32_t stage_bytes = 2u * A_TILE_BYTES + 2u * b_bytes;
+
+    int bid = blockIdx.x;
+    const int tx = bid % p.tiles_x; bid /= p.tiles_x;
+    const int ty = bid % p.tiles_y;
+    const int img = bid / p.tiles_y;
+    const int x0 = tx * p.TW, y0 = ty * p.TH;
+    const int taps = p.kh * p.kw;
+    const int total = taps * p.kblocks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mb_init(&full_bar[s], 1); mb_init(&ready_bar[s], 4); mb_init(&empty_bar[s], 1); }
+        mb_init(&accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_addr(&tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int tap = 0, kb = 0;
+            for (int it = 0; it < total; ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                mb_wait(&empty_bar[s], ph ^ 1u);
+                unsigned char* st = gbase + (size_t)s * stage_bytes;
+                mb_expect_tx(&full_bar[s], (uint32_t)A_TILE_BYTES + 2u * b_bytes);
+                const int r = tap / p.kw, q = tap - r * p.kw;
+                tma_load_4d(st, &mapA, &full_bar[s], kb * 32, x0 + p.off_x + q * p.step, y0 + p.off_y + r * p.step, img);
+                tma_load_3d(st + 2 * A_TILE_BYTES, &mapBh, &full_bar[s], kb * 32, 0, tap);
+                tma_load_3d(st + 2 * A_TILE_BYTES + b_bytes, &mapBl, &full_bar[s], kb * 32, 0, tap);
+                if (++kb == p.kblocks) { kb = 0; ++tap; }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            // instruction descriptor: D=f32 (bit4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 @17, M>>4 @24
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+            for (int it = 0; it < total; ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                mb_wait(&full_bar[s], ph);
+                mb_wait(&ready_bar[s], ph);
+                tc_fence_after();
+                const uint32_t sa = base + (uint32_t)s * stage_bytes;
+                const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + A_TILE_BYTES);
+                const uint64_t b_hi = umma_desc_sw128(sa + 2 * A_TILE_BYTES), b_lo = umma_desc_sw128(sa + 2 * A_TILE_BYTES + b_bytes);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {          // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle row
+                    const uint64_t o = (uint64_t)(j * 2);
+                    tc_mma_tf32(tmem, a_lo + o, b_hi + o, idesc, (it > 0 || j > 0) ? 1u : 0u);
+                    tc_mma_tf32(tmem, a_hi + o, b_lo + o, idesc, 1u);
+                    tc_mma_tf32(tmem, a_hi + o, b_hi + o, idesc, 1u);
+                }
+                tc_commit(&empty_bar[s]);              // frees the stage once these MMAs have read it
+            }
+            tc_commit(&accum_bar);
+        }
+    } else {
+        // ================= splitter (warps 2..5) =================
+        const int st_tid = threadIdx.x - 64;           // 0..127
+        for (int it = 0; it < total; ++it) {
+            const int s = it % p.stages;
+            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+            mb_wait(&full_bar[s], ph);
+            float4* hi = reinterpret_cast<float4*>(gbase + (size_t)s * stage_bytes);
+            float4* lo = reinterpret_cast<float4*>(gbase + (size_t)s * stage_bytes + A_TILE_BYTES);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int idx = st_tid + e * 128;      // 1024 float4 per tile
+                float4 v = hi[idx];
+                float4 h, l;
+                h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+                l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+                hi[idx] = h;
+                lo[idx] = l;
+            }
+            fence_async_smem();                         // generic-proxy writes -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) mb_arrive(&ready_bar[s]);
+        }
+        // ================= epilogue =================
+        mb_wait(&accum_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;                        // TMEM lane quarter this warp may access
+        const int m = q * 32 + lane;                   // accumulator row = pixel inside the patch
+        const int py = y0 + m / p.TW, px = x0 + m % p.TW;
+        const bool valid = (py < p.H) && (px < p.W);
+        const size_t pix = ((size_t)img * p.H + py) * p.W + px;
+        float* yrow = p.y + pix * p.ycs;
+        const bool vec = ((p.ycs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+        for (int c0 = 0; c0 < p.BN; c0 += 16) {
+            float v[16];
+            tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            if (!valid) continue;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int n = c0 + j;
+                if (n < p.N) {
+                    float t = v[j];
+                    if (p.bias) t += p.bias[n];
+                    t = fmaxf(p.alpha * t, t);
+                    if (p.res) t += p.res[pix * p.res_cs + n];
+                    if (p.accumulate) t += yrow[n];
+                    if (p.mask) t *= (p.mask[pix * p.mask_cs + n] > 0.f) ? 1.f : p.mask_alpha;
+                    v[j] = t;
+                }
+            }
+            if (vec && c0 + 16 <= p.N) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(yrow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (c0 + j < p.N) yrow[c0 + j] = v[j];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight preparation: Bh/Bl[tap][n (BN rows)][k (Kpad)] from canonical HWIO
+//   transposed_src = 1 : src is [tap][K][N]  (forward conv: K = cin, N = cout)
+//   transposed_src = 0 : src is [tap][N][K]  (dgrad: N = cin, K = cout)
+// ------------------------------------------------------------------------------------------------
+__global__ void tc_prep_weights_kernel(const float* __restrict__ src, float* __restrict__ bh, float* __restrict__ bl,
+                                       int taps, int N, int K, int BN, int Kpad, int transposed_src) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)taps * BN * Kpad;
+    if (i >= total) return;
+    int k = (int)(i % Kpad);
+    size_t q = i / Kpad;
+    int n = (int)(q % BN);
+    int t = (int)(q / BN);
+    float v = 0.f;
+    if (n < N && k < K) v = transposed_src ? src[((size_t)t * K + k) * N + n] : src[((size_t)t * N + n) * K + k];
+    float h = tf32_rna(v);
+    bh[i] = h;
+    bl[i] = v - h;
+}
+
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static int make_map(CUtensorMap* m, void* addr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                    const cuuint32_t* box) {
+    EncodeTiledFn enc = get_encode();
+    MS_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, addr, dims, strides_bytes, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r)); return -1; }
+    return 0;
+}
+
+bool conv_tc_supported(const ConvGemm& g) {
+    if (g.mul != 1 || g.div != 1) return false;                       // stride-1 gathers only
+    if (g.x.h != g.y.h || g.x.w != g.y.w) return false;
+    if (g.x.c < 8 || g.y.c < 8 || g.y.c > 256) return false;
+    if ((g.x.cs & 3) || (reinterpret_cast<uintptr_t>(g.x.p) & 15)) return false;
+    if (g.y.h * g.y.w < 64) return false;
+    return true;
+}
+
+size_t conv_tc_scratch_floats(int taps, int N, int K) {
+    int BN = (N + 15) / 16 * 16, Kpad = (K + 31) / 32 * 32;
+    return 2 * (size_t)taps * BN * Kpad + 64;
+}
+
+// g.wmat must be the CANONICAL weights: [tap][x.c][y.c] if !wmat_is_nk else [tap][y.c][x.c].
+int conv_tc(const ConvGemm& g, int wmat_is_nk, float* scratch, size_t scratch_floats, cudaStream_t st) {
+    MS_REQUIRE(conv_tc_supported(g), "conv_tc: unsupported geometry");
+    const int taps = g.kh * g.kw, K = g.x.c, N = g.y.c;
+    const int BN = (N + 15) / 16 * 16, kblocks = (K + 31) / 32, Kpad = kblocks * 32;
+    const size_t per = (size_t)taps * BN * Kpad;
+    MS_REQUIRE(scratch_floats >= 2 * per, "conv_tc: scratch too small");
+    MS_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 15) == 0, "conv_tc: scratch must be 16B aligned");
+    float* bh = scratch;
+    float* bl = scratch + per;
+    tc_prep_weights_kernel<<<(unsigned)cdivz(per, 256), 256, 0, st>>>(g.wmat, bh, bl, taps, N, K, BN, Kpad, wmat_is_nk ? 0 : 1);
+    if (check_launch("tc_prep_weights")) return -1;
+
+    ConvTCParams p{};
+    p.kh = g.kh; p.kw = g.kw; p.off_y = g.off_y; p.off_x = g.off_x; p.step = g.step;
+    p.kblocks = kblocks; p.H = g.y.h; p.W = g.y.w; p.NB = g.y.n;
+    // patch shape: widest tile that the map can fill
+    if (g.y.w >= 16 || g.y.h < 16) { p.TW = 16; p.TH = 8; } else { p.TW = 8; p.TH = 16; }
+    p.tiles_x = cdiv(p.W, p.TW); p.tiles_y = cdiv(p.H, p.TH);
+    p.N = N; p.BN = BN;
+    p.tmem_cols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+    const size_t stage_bytes = 2 * (size_t)A_TILE_BYTES + 2 * (size_t)BN * 128;
+    int stages = (int)std::min<size_t>(4, (200 * 1024) / stage_bytes);
+    MS_REQUIRE(stages >= 2, "conv_tc: tile does not fit shared memory");
+    p.stages = stages;
+    p.y = g.y.p; p.ycs = g.y.cs; p.bias = g.bias; p.alpha = g.alpha;
+    p.mask = g.mask; p.mask_cs = g.mask_cs; p.mask_alpha = g.mask_alpha;
+    p.res = g.res; p.res_cs = g.res_cs; p.accumulate = g.accumulate;
+
+    CUtensorMap mapA, mapBh, mapBl;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)g.x.c, (cuuint64_t)g.x.w, (cuuint64_t)g.x.h, (cuuint64_t)g.x.n};
+        cuuint64_t strides[3] = {(cuuint64_t)g.x.cs * 4, (cuuint64_t)g.x.w * g.x.cs * 4, (cuuint64_t)g.x.h * g.x.w * g.x.cs * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+        if (make_map(&mapA, g.x.p, 4, dims, strides, box)) return -1;
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)Kpad, (cuuint64_t)BN, (cuuint64_t)taps};
+        cuuint64_t strides[2] = {(cuuint64_t)Kpad * 4, (cuuint64_t)BN * Kpad * 4};
+        cuuint32_t box[3] = {32, (cuuint32_t)BN, 1};
+        if (make_map(&mapBh, bh, 3, dims, strides, box)) return -1;
+        if (make_map(&mapBl, bl, 3, dims, strides, box)) return -1;
+    }
+    const size_t smem = (size_t)stages * stage_bytes + 1024;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        MS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    const int grid = p.NB * p.tiles_x * p.tiles_y;
+    conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(mapA, mapBh, mapBl, p);
+    return check_launch("conv_tc");
+}
+
+}  // namespace ms

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace ms {
 
@@ -33,7 +34,12 @@ Engine::Engine()
     : net(0), B(1), H(0), W(0), Hp(0), Wp(0), radius_d(2), corr_stride(1), warping(1), n_groups(0), n_params(0),
       Wt(nullptr), Gr(nullptr), Mo(nullptr), ws(nullptr), ws_floats(0), bound(false), wT(nullptr), wT_floats(0),
       wg_ws(nullptr), wg_ws_floats(0), rs_tmp(nullptr), rs_tmp_floats(0), loss_ws(nullptr), loss_ws_floats(0),
-      scalars(nullptr), gt(nullptr), profiling(false) { prof_reset(); }
+      scalars(nullptr), gt(nullptr), profiling(false) {
+    prof_reset();
+    tc_ws = nullptr; tc_ws_floats = 0;
+    const char* e = getenv("MS_CONV_TC");
+    use_tc = (e && e[0] == '0') ? 0 : 1;
+}
 
 void Engine::prof_reset() {
     for (int i = 0; i < N_CAT; ++i) { cat_ms[i] = 0; cat_macs[i] = 0; cat_bytes[i] = 0; cat_calls[i] = 0; }
@@ -149,10 +155,12 @@ size_t Engine::layout(float* base) {
     tensors["raw_left"] = raw_l; tensors["raw_right"] = raw_r;
     img = tens(2 * B, Hp, Wp, 3, 4);
     tensors["img"] = img;
-    size_t max_wg = 0, max_wt = 0;
+    size_t max_wg = 0, max_wt = 0, max_tc = 0;
     auto track = [&](const ConvLayer& L, size_t pixels) {
         max_wg = std::max(max_wg, conv_wgrad_workspace_floats(L.kh * L.kw, L.cin, L.cout, pixels));
         max_wt = std::max(max_wt, (size_t)L.kh * L.kw * L.cin * L.cout);
+        max_tc = std::max(max_tc, conv_tc_scratch_floats(L.kh * L.kw, L.cout, L.cin));
+        max_tc = std::max(max_tc, conv_tc_scratch_floats(L.kh * L.kw, L.cin, L.cout));
     };
     int h = Hp, w = Wp;
     for (int i = 1; i <= 12; ++i) {
@@ -210,6 +218,7 @@ size_t Engine::layout(float* base) {
     tensors["grad/disp"] = g_disp;
     wT_floats = max_wt; wT = alloc(max_wt);
     wg_ws_floats = max_wg; wg_ws = alloc(max_wg);
+    tc_ws_floats = max_tc; tc_ws = alloc(max_tc);
     rs_tmp_floats = (size_t)B * H * Wp; rs_tmp = alloc(rs_tmp_floats);
     loss_ws_floats = loss_workspace_floats(B, H, W); loss_ws = alloc(loss_ws_floats);
     scalars = alloc(64);
@@ -245,7 +254,9 @@ int Engine::conv_fwd(const ConvLayer& L, const TView& x, const TView& y, const f
         p.mul = 1; p.off_y = pt; p.off_x = pl; p.step = -1; p.div = L.stride;
     }
     prof_begin(CAT_CONV_FWD, st);
-    int rc = conv_gemm(p, st);
+    int rc;
+    if (use_tc && !L.transposed && conv_tc_supported(p)) rc = conv_tc(p, 0, tc_ws, tc_ws_floats, st);
+    else rc = conv_gemm(p, st);
     prof_end(st);
     if (profiling) cat_macs[CAT_CONV_FWD] += (double)y.pixels() * L.kh * L.kw * L.cin * L.cout / (L.transposed ? L.stride * L.stride : 1);
     return rc;
@@ -271,7 +282,6 @@ int Engine::conv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, cons
         if (rc) return -1;
     }
     if (dx) {
-        if (transpose_taps(Wt + L.w_off, wT, L.kh * L.kw, L.cin, L.cout, st)) return -1;   // -> [tap][cout][cin]
         ConvGemm p{};
         p.x = dpre; p.wmat = wT; p.bias = nullptr; p.y = *dx; p.kh = L.kh; p.kw = L.kw;
         p.mul = 1; p.off_y = pt; p.off_x = pl; p.step = -L.dil; p.div = L.stride;
@@ -279,7 +289,14 @@ int Engine::conv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, cons
         p.mask = dx_mask ? dx_mask->p : nullptr; p.mask_cs = dx_mask ? dx_mask->cs : 0; p.mask_alpha = mask_alpha;
         p.res = nullptr; p.res_cs = 0; p.accumulate = dx_acc;
         prof_begin(CAT_CONV_DGRAD, st);
-        int rc = conv_gemm(p, st);
+        int rc;
+        if (use_tc && conv_tc_supported(p)) {
+            p.wmat = Wt + L.w_off;                 // canonical [tap][cin][cout] == [tap][N][K] for the dgrad GEMM
+            rc = conv_tc(p, 1, tc_ws, tc_ws_floats, st);
+        } else {
+            rc = transpose_taps(Wt + L.w_off, wT, L.kh * L.kw, L.cin, L.cout, st);   // -> [tap][cout][cin]
+            if (!rc) rc = conv_gemm(p, st);
+        }
         prof_end(st);
         if (profiling) cat_macs[CAT_CONV_DGRAD] += (double)dpre.pixels() * L.kh * L.kw * L.cin * L.cout;
         if (rc) return -1;

@@ -51,6 +51,8 @@ struct Engine {
     TView disp[6];                   // D6,D5,D4,D3,D2ctx,full   [B,H,W,1]
     TView g_disp;
     float* wT; size_t wT_floats;     // transposed-weight scratch
+    float* tc_ws; size_t tc_ws_floats;   // tcgen05 weight halves (hi/lo) scratch
+    int use_tc;                      // route eligible convs through conv_tc (env MS_CONV_TC, default 1)
     float* wg_ws; size_t wg_ws_floats;
     float* rs_tmp; size_t rs_tmp_floats;
     float* loss_ws; size_t loss_ws_floats;

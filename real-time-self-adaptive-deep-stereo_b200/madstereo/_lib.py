@@ -27,6 +27,9 @@ _SIGS = {
     'ms_corr_bwd': (I, [P, I, P, I, P, I, P, I, P, I, P, I, P, I, I, I, I, I, I, I, I, P]),
     'ms_conv2d_fwd': (I, [P, I, I, I, I, I, P, P, P, I, I, I, I, I, I, F, P]),
     'ms_conv2d_dgrad': (I, [P, I, I, I, I, I, P, P, I, I, I, I, I, I, I, I, P, P]),
+    'ms_conv2d_fwd_tc': (I, [P, I, I, I, I, I, P, P, P, I, I, I, I, I, F, P, Z, P]),
+    'ms_conv2d_dgrad_tc': (I, [P, I, I, I, I, I, P, P, I, I, I, I, I, P, Z, P]),
+    'ms_conv2d_tc_scratch': (Z, [I, I, I, I]),
     'ms_conv2d_wgrad_workspace': (Z, [I, I, I, I, Z]),
     'ms_conv2d_wgrad': (I, [P, I, I, I, I, I, P, I, I, I, I, P, P, I, I, I, I, P, Z, P]),
     'ms_conv2d_transpose_fwd': (I, [P, I, I, I, I, I, P, P, P, I, I, I, I, I, F, P, P]),
