@@ -73,6 +73,20 @@ class ClockSampler(threading.Thread):
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+def usable_cores():
+    """Host threads the CPU arm can really use: affinity mask, clipped by the cgroup CPU quota (a container that
+    sees 128 CPUs but owns a small quota collapses under 128 oversubscribed threads) and by 32 (the oracle's small
+    convolutions stop scaling long before that)."""
+    n = len(os.sched_getaffinity(0))
+    try:
+        q, per = open('/sys/fs/cgroup/cpu.max').read().split()
+        if q != 'max':
+            n = min(n, max(1, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        pass
+    return max(1, min(n, 32))
+
+
 def make_inputs(n_pairs, rank):
     from madstereo.synthetic import make_pair
     return [make_pair(H, W, seed=100 * rank + i)[:2] for i in range(n_pairs)]
@@ -85,7 +99,7 @@ def cpu_mad_fps(steps, warmup, sample_note=False):
     import torch
     from oracle.adaptation import OracleAdapter
     from oracle.madnet import init_params
-    cores = len(os.sched_getaffinity(0))
+    cores = usable_cores()
     torch.set_num_threads(cores)
     (left, right), = make_inputs(1, 0)
     ad = OracleAdapter(init_params(seed=42), mode='MAD', lr=1e-4)
@@ -227,7 +241,7 @@ def run_ours(args):
                            'loss D2H (host reward policy needs it every frame)'},
         'e2e': {'value': fps_e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': 2 * H * W * 3 * 4, 'd2h_bytes_per_step': 16},
         'gpu_launches': int(launches),
-        'roofline': {'bound': 'tensor', 'kernel': 'conv_gemm/conv_wgrad (fp32 CUDA-core implicit GEMM; all conv fwd+dgrad+wgrad launches)',
+        'roofline': {'bound': 'tensor', 'kernel': 'conv stack: conv_tc_kernel (tcgen05 3xTF32 implicit GEMM, stride-1 fwd+dgrad) + conv_gemm/conv_wgrad (fp32 CUDA-core: stride-2, tiny-channel layers, all wgrad); useful FLOPs = 2*MACs, the 3x tf32 passes are not counted',
                      'achieved': conv_tflops, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
                      'frac': conv_tflops / pk['bf16_tflops_sustained'], 'peak_src': pk['src'] + ' bf16 sustained (kernels timed inside a long step)',
                      'traffic': None, 'avg_launch_us': 1e3 * conv_ms / max(conv_calls, 1),

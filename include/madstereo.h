@@ -125,6 +125,15 @@ int ms_engine_loss(void* e, int which_disp, int with_grad, int slot, float grad_
 /* mode 1 = MAD (train op `group`, Stereo_Online_Adaptation.py:87-121), 2 = FULL (:126-128) */
 int ms_engine_backward(void* e, int mode, int group, void* stream);
 int ms_engine_update(void* e, int group /* -1 = all */, float lr, float mu, float grad_scale, void* stream);
+/* One whole frame = what a single sess.run(tf_fetches) executes (Stereo_Online_Adaptation.py:194-208):
+ * forward, full-res loss (slot 0), and for mode 1/2 the train op (module loss in slot 1, backward,
+ * momentum update if with_update).  After the first call per (mode, group, ...) the sequence is replayed as
+ * ONE CUDA graph launch.  with_update=0 leaves the gradients in the arena for a data-parallel all-reduce
+ * followed by ms_engine_update. */
+int ms_engine_run(void* e, int mode, int group, int disp_mask, int with_update, float lr, float mu,
+                  float grad_scale, void* stream);
+/* Tell the engine that the weight arena was written from outside (checkpoint load / divergence reset). */
+int ms_engine_weights_changed(void* e);
 /* scalars: [0]=slot-0 loss, [1]=slot-1 loss, [2]=EPE, [3]=bad3. Synchronises `stream`. */
 int ms_engine_read_scalars(void* e, float* host4, void* stream);
 int ms_engine_metrics(void* e, void* stream);

@@ -97,7 +97,7 @@ int ms_conv2d_fwd_tc(const float* x, int n, int h, int w, int cin, int x_cs, con
     p.mul = 1; p.off_y = -pt; p.off_x = -pl; p.step = dilation; p.div = 1;
     p.alpha = alpha; p.mask = nullptr; p.mask_alpha = 1.f; p.res = nullptr; p.accumulate = 0;
     if (!conv_tc_supported(p)) { set_error("ms_conv2d_fwd_tc: shape not supported by the tcgen05 path"); return -3; }
-    return conv_tc(p, 0, scratch, scratch_floats, S(stream));
+    return conv_tc_oneshot(p, 0, scratch, scratch_floats, S(stream));
 }
 int ms_conv2d_dgrad_tc(const float* dy, int n, int h, int w, int cout, int dy_cs, const float* weights, float* dx,
                        int cin, int dx_cs, int kh, int kw, int dilation, float* scratch, size_t scratch_floats,
@@ -112,7 +112,7 @@ int ms_conv2d_dgrad_tc(const float* dy, int n, int h, int w, int cout, int dy_cs
     p.mul = 1; p.off_y = pt; p.off_x = pl; p.step = -dilation; p.div = 1;
     p.alpha = 1.f; p.mask = nullptr; p.mask_alpha = 1.f; p.res = nullptr; p.accumulate = 0;
     if (!conv_tc_supported(p)) { set_error("ms_conv2d_dgrad_tc: shape not supported by the tcgen05 path"); return -3; }
-    return conv_tc(p, 1, scratch, scratch_floats, S(stream));
+    return conv_tc_oneshot(p, 1, scratch, scratch_floats, S(stream));
 }
 size_t ms_conv2d_tc_scratch(int kh, int kw, int cin, int cout) {
     size_t a = conv_tc_scratch_floats(kh * kw, cout, cin), b = conv_tc_scratch_floats(kh * kw, cin, cout);
@@ -249,6 +249,11 @@ int ms_engine_bind(void* h, float* weights, float* grads, float* momentum, float
     e->layout(workspace);
     MS_CHECK_CUDA(cudaMemsetAsync(workspace, 0, need * sizeof(float), S(stream)));
     MS_CHECK_CUDA(cudaMemsetAsync(grads, 0, e->n_params * sizeof(float), S(stream)));
+    if (!e->prep_jobs.empty())
+        MS_CHECK_CUDA(cudaMemcpyAsync(e->prep_jobs_dev, e->prep_jobs.data(), e->prep_jobs.size() * sizeof(TcPrepJob),
+                                      cudaMemcpyHostToDevice, S(stream)));
+    MS_CHECK_CUDA(cudaStreamSynchronize(S(stream)));   // the host job table must outlive the copy
+    e->weights_dirty = true;
     e->bound = true;
     return 0;
 }
@@ -270,6 +275,14 @@ int ms_engine_backward(void* h, int mode, int group, void* stream) {
 }
 int ms_engine_update(void* h, int group, float lr, float mu, float grad_scale, void* stream) {
     return static_cast<Engine*>(h)->update(group, lr, mu, grad_scale, S(stream));
+}
+int ms_engine_run(void* h, int mode, int group, int disp_mask, int with_update, float lr, float mu, float grad_scale,
+                  void* stream) {
+    return static_cast<Engine*>(h)->run(mode, group, disp_mask, with_update, lr, mu, grad_scale, S(stream));
+}
+int ms_engine_weights_changed(void* h) {
+    static_cast<Engine*>(h)->weights_dirty = true;
+    return 0;
 }
 int ms_engine_metrics(void* h, void* stream) {
     Engine* e = static_cast<Engine*>(h);

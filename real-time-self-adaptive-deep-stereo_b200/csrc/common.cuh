@@ -26,6 +26,7 @@ inline TView batch(const TView& t, int n0, int n) {
 void set_error(const std::string& s);
 int check_launch(const char* what, int n_kernels = 1);
 long long launch_count();
+void add_launches(long long n);
 
 #define MS_CHECK_CUDA(expr)                                                                   \
     do {                                                                                      \
@@ -142,7 +143,17 @@ int momentum_update(float* w, const float* g, float* m, size_t n, float lr, floa
 
 namespace ms {
 // tcgen05 path (conv_tc.cu)
+struct TcPrepJob {
+    const float* src; float* bh; float* bl;
+    int taps, N, K, BN, Kpad, transposed_src;
+};
 bool conv_tc_supported(const ConvGemm& g);
+void conv_tc_weight_dims(int N, int K, int& BN, int& Kpad);
 size_t conv_tc_scratch_floats(int taps, int N, int K);
-int conv_tc(const ConvGemm& g, int wmat_is_nk, float* scratch, size_t scratch_floats, cudaStream_t st);
+int conv_tc_init();
+int tc_prep_weights(const TcPrepJob* jobs_dev, int njobs, size_t max_total, cudaStream_t st);
+int conv_tc(const ConvGemm& g, const float* bw, cudaStream_t st);
+bool conv_tc_profitable(const ConvGemm& g);
+int conv_tc_oneshot(const ConvGemm& g, int wmat_is_nk, float* scratch, size_t scratch_floats, cudaStream_t st);
+int corr_init();
 }  // namespace ms

@@ -18,6 +18,8 @@
 // TMA), accum (tcgen05.commit -> epilogue).
 #include <cuda.h>
 #include <algorithm>
+#include <cstring>
+#include <map>
 
 #include "common.cuh"
 
@@ -104,6 +106,7 @@ struct ConvTCParams {
     int kblocks;                      // ceil(K channels / 32)
     int H, W, NB, TH, TW, tiles_x, tiles_y;
     int N, BN, tmem_cols, stages;
+    int n_main, acc_stride;           // accumulators: [0]=cross terms, [1..n_main]=hi*hi partial sums (column stride)
     float* y; int ycs;
     const float* bias; float alpha;
     const float* mask; int mask_cs; float mask_alpha;
@@ -111,12 +114,13 @@ struct ConvTCParams {
     int accumulate;
 };
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;           // warp 0 TMA, warp 1 MMA, warps 2-9 splitter + epilogue
+constexpr int SPLIT_THREADS = 256;
 constexpr int A_TILE_BYTES = 128 * 128;   // 128 pixels x 32 fp32
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
-               const __grid_constant__ CUtensorMap mapBl, const ConvTCParams p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const ConvTCParams p) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[4], ready_bar[4], empty_bar[4], accum_bar;
     __shared__ uint32_t tmem_slot;
@@ -137,7 +141,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int total = taps * p.kblocks;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; ++s) { mb_init(&full_bar[s], 1); mb_init(&ready_bar[s], 4); mb_init(&empty_bar[s], 1); }
+        for (int s = 0; s < p.stages; ++s) { mb_init(&full_bar[s], 1); mb_init(&ready_bar[s], SPLIT_THREADS / 32); mb_init(&empty_bar[s], 1); }
         mb_init(&accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -153,18 +157,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            int tap = 0, kb = 0;
+            int tap = 0, kb = 0, s = 0;
+            uint32_t ph = 0;
             for (int it = 0; it < total; ++it) {
-                const int s = it % p.stages;
-                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
                 mb_wait(&empty_bar[s], ph ^ 1u);
                 unsigned char* st = gbase + (size_t)s * stage_bytes;
-                mb_expect_tx(&full_bar[s], (uint32_t)A_TILE_BYTES + 2u * b_bytes);
+                mb_expect_tx(&full_bar[s], (uint32_t)A_TILE_BYTES + b_bytes);
                 const int r = tap / p.kw, q = tap - r * p.kw;
                 tma_load_4d(st, &mapA, &full_bar[s], kb * 32, x0 + p.off_x + q * p.step, y0 + p.off_y + r * p.step, img);
-                tma_load_3d(st + 2 * A_TILE_BYTES, &mapBh, &full_bar[s], kb * 32, 0, tap);
-                tma_load_3d(st + 2 * A_TILE_BYTES + b_bytes, &mapBl, &full_bar[s], kb * 32, 0, tap);
+                tma_load_3d(st + 2 * A_TILE_BYTES, &mapB, &full_bar[s], kb * 32, 0, tap);
                 if (++kb == p.kblocks) { kb = 0; ++tap; }
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
@@ -172,9 +175,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (lane == 0) {
             // instruction descriptor: D=f32 (bit4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 @17, M>>4 @24
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+            int s = 0;
+            uint32_t ph = 0;
             for (int it = 0; it < total; ++it) {
-                const int s = it % p.stages;
-                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
                 mb_wait(&full_bar[s], ph);
                 mb_wait(&ready_bar[s], ph);
                 tc_fence_after();
@@ -184,36 +187,64 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {          // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle row
                     const uint64_t o = (uint64_t)(j * 2);
-                    tc_mma_tf32(tmem, a_lo + o, b_hi + o, idesc, (it > 0 || j > 0) ? 1u : 0u);
+                    const int g = it * 4 + j;
+                    // The tensor core adds into the fp32 accumulator with truncation, a bias that grows with the
+                    // number of accumulation steps.  Cross terms (2^-11 of the main term) get their own accumulator
+                    // and the hi*hi products rotate over n_main accumulators; the epilogue sums them in fp32 (RN).
+                    tc_mma_tf32(tmem, a_lo + o, b_hi + o, idesc, g > 0 ? 1u : 0u);
                     tc_mma_tf32(tmem, a_hi + o, b_lo + o, idesc, 1u);
-                    tc_mma_tf32(tmem, a_hi + o, b_hi + o, idesc, 1u);
+                    const uint32_t dmain = tmem + (uint32_t)((1 + g % p.n_main) * p.acc_stride);
+                    tc_mma_tf32(dmain, a_hi + o, b_hi + o, idesc, g >= p.n_main ? 1u : 0u);
                 }
                 tc_commit(&empty_bar[s]);              // frees the stage once these MMAs have read it
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
             tc_commit(&accum_bar);
         }
     } else {
-        // ================= splitter (warps 2..5) =================
-        const int st_tid = threadIdx.x - 64;           // 0..127
-        for (int it = 0; it < total; ++it) {
-            const int s = it % p.stages;
-            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-            mb_wait(&full_bar[s], ph);
-            float4* hi = reinterpret_cast<float4*>(gbase + (size_t)s * stage_bytes);
-            float4* lo = reinterpret_cast<float4*>(gbase + (size_t)s * stage_bytes + A_TILE_BYTES);
+        // ================= splitter (warps 2..9): tf32 hi/lo halves of the activation AND weight tiles =============
+        const int st_tid = threadIdx.x - 64;           // 0..255
+        const int b_f4 = p.BN * 8;                     // float4 per weight tile
+        {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int it = 0; it < total; ++it) {
+                mb_wait(&full_bar[s], ph);
+                unsigned char* stg = gbase + (size_t)s * stage_bytes;
+                float4* __restrict__ ahi = reinterpret_cast<float4*>(stg);
+                float4* __restrict__ alo = reinterpret_cast<float4*>(stg + A_TILE_BYTES);
+                float4* __restrict__ bhi = reinterpret_cast<float4*>(stg + 2 * A_TILE_BYTES);
+                float4* __restrict__ blo = reinterpret_cast<float4*>(stg + 2 * A_TILE_BYTES + b_bytes);
+                float4 v[4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int idx = st_tid + e * 128;      // 1024 float4 per tile
-                float4 v = hi[idx];
-                float4 h, l;
-                h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-                l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-                hi[idx] = h;
-                lo[idx] = l;
+                for (int e = 0; e < 4; ++e) v[e] = ahi[st_tid + e * SPLIT_THREADS];       // 1024 float4 per A tile
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int idx = st_tid + e * SPLIT_THREADS;
+                    float4 h, l;
+                    h.x = tf32_rna(v[e].x); h.y = tf32_rna(v[e].y); h.z = tf32_rna(v[e].z); h.w = tf32_rna(v[e].w);
+                    l.x = v[e].x - h.x; l.y = v[e].y - h.y; l.z = v[e].z - h.z; l.w = v[e].w - h.w;
+                    ahi[idx] = h; alo[idx] = l;
+                }
+                for (int i0 = st_tid; i0 < b_f4; i0 += 2 * SPLIT_THREADS) {                // BN*8 float4 per B tile
+                    const int i1 = i0 + SPLIT_THREADS;
+                    const bool two = i1 < b_f4;
+                    float4 w0 = bhi[i0], w1 = two ? bhi[i1] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 h, l;
+                    h.x = tf32_rna(w0.x); h.y = tf32_rna(w0.y); h.z = tf32_rna(w0.z); h.w = tf32_rna(w0.w);
+                    l.x = w0.x - h.x; l.y = w0.y - h.y; l.z = w0.z - h.z; l.w = w0.w - h.w;
+                    bhi[i0] = h; blo[i0] = l;
+                    if (two) {
+                        h.x = tf32_rna(w1.x); h.y = tf32_rna(w1.y); h.z = tf32_rna(w1.z); h.w = tf32_rna(w1.w);
+                        l.x = w1.x - h.x; l.y = w1.y - h.y; l.z = w1.z - h.z; l.w = w1.w - h.w;
+                        bhi[i1] = h; blo[i1] = l;
+                    }
+                }
+                fence_async_smem();                     // generic-proxy writes -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mb_arrive(&ready_bar[s]);
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
-            fence_async_smem();                         // generic-proxy writes -> visible to the tensor core
-            __syncwarp();
-            if (lane == 0) mb_arrive(&ready_bar[s]);
         }
         // ================= epilogue =================
         mb_wait(&accum_bar, 0);
@@ -225,9 +256,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const size_t pix = ((size_t)img * p.H + py) * p.W + px;
         float* yrow = p.y + pix * p.ycs;
         const bool vec = ((p.ycs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
-        for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        const int chunks = p.BN / 16, half = (chunks + 1) / 2;
+        const int cbeg = (warp < 6 ? 0 : half) * 16, cend = (warp < 6 ? half : chunks) * 16;   // warps 2-5 | 6-9
+        for (int c0 = cbeg; c0 < cend; c0 += 16) {
             float v[16];
             tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            for (int a = 1; a <= p.n_main; ++a) {
+                float u[16];
+                tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.acc_stride + c0), u);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] += u[j];
+            }
             if (!valid) continue;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -262,24 +301,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------------
-// weight preparation: Bh/Bl[tap][n (BN rows)][k (Kpad)] from canonical HWIO
+// weight preparation: B[tap][n (BN rows)][k (Kpad)] (zero padded, K contiguous) from canonical HWIO, batched over layers
 //   transposed_src = 1 : src is [tap][K][N]  (forward conv: K = cin, N = cout)
 //   transposed_src = 0 : src is [tap][N][K]  (dgrad: N = cin, K = cout)
 // ------------------------------------------------------------------------------------------------
-__global__ void tc_prep_weights_kernel(const float* __restrict__ src, float* __restrict__ bh, float* __restrict__ bl,
-                                       int taps, int N, int K, int BN, int Kpad, int transposed_src) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t total = (size_t)taps * BN * Kpad;
-    if (i >= total) return;
-    int k = (int)(i % Kpad);
-    size_t q = i / Kpad;
-    int n = (int)(q % BN);
-    int t = (int)(q / BN);
-    float v = 0.f;
-    if (n < N && k < K) v = transposed_src ? src[((size_t)t * K + k) * N + n] : src[((size_t)t * N + n) * K + k];
-    float h = tf32_rna(v);
-    bh[i] = h;
-    bl[i] = v - h;
+__global__ void tc_prep_weights_kernel(const TcPrepJob* __restrict__ jobs) {
+    const TcPrepJob j = jobs[blockIdx.y];
+    const size_t total = (size_t)j.taps * j.BN * j.Kpad;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int k = (int)(i % j.Kpad);
+        size_t q = i / j.Kpad;
+        int n = (int)(q % j.BN);
+        int t = (int)(q / j.BN);
+        float v = 0.f;
+        if (n < j.N && k < j.K)
+            v = j.transposed_src ? j.src[((size_t)t * j.K + k) * j.N + n] : j.src[((size_t)t * j.N + n) * j.K + k];
+        j.bh[i] = v;          // raw fp32; the tf32 hi/lo split happens in shared memory inside conv_tc_kernel
+    }
+}
+
+int tc_prep_weights(const TcPrepJob* jobs_dev, int njobs, size_t max_total, cudaStream_t st) {
+    if (njobs <= 0) return 0;
+    unsigned gx = (unsigned)std::min<size_t>(cdivz(max_total, 256), 512);
+    tc_prep_weights_kernel<<<dim3(gx, njobs), 256, 0, st>>>(jobs_dev);
+    return check_launch("tc_prep_weights");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -298,15 +343,35 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-static int make_map(CUtensorMap* m, void* addr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                    const cuuint32_t* box) {
-    EncodeTiledFn enc = get_encode();
-    MS_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
-    cuuint32_t es[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, addr, dims, strides_bytes, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r)); return -1; }
+struct MapKey {
+    uintptr_t addr; int rank; uint64_t d[4]; uint64_t s[3]; uint32_t b[4];
+    bool operator<(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) < 0; }
+};
+static std::map<MapKey, CUtensorMap>& map_cache() { static std::map<MapKey, CUtensorMap> c; return c; }
+
+// cached cuTensorMapEncodeTiled (fp32, SWIZZLE_128B, zero OOB fill)
+static int get_map(const CUtensorMap** out, void* addr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                   const cuuint32_t* box) {
+    MapKey k;
+    memset(&k, 0, sizeof k);
+    k.addr = reinterpret_cast<uintptr_t>(addr); k.rank = rank;
+    for (int i = 0; i < rank; ++i) { k.d[i] = dims[i]; k.b[i] = box[i]; }
+    for (int i = 0; i + 1 < rank; ++i) k.s[i] = strides_bytes[i];
+    auto& c = map_cache();
+    auto it = c.find(k);
+    if (it == c.end()) {
+        EncodeTiledFn enc = get_encode();
+        MS_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+        cuuint32_t es[5] = {1, 1, 1, 1, 1};
+        CUtensorMap m;
+        CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, addr, dims, strides_bytes, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r)); return -1; }
+        if (c.size() > 4096) c.clear();
+        it = c.emplace(k, m).first;
+    }
+    *out = &it->second;
     return 0;
 }
 
@@ -319,32 +384,46 @@ bool conv_tc_supported(const ConvGemm& g) {
     return true;
 }
 
+// measured on B200 (scripts/tc_bench.py): below ~64x64 channels the fp32 CUDA-core kernel is as fast or faster
+bool conv_tc_profitable(const ConvGemm& g) {
+    return conv_tc_supported(g) && (long)g.x.c * g.y.c >= 4096;
+}
+
+void conv_tc_weight_dims(int N, int K, int& BN, int& Kpad) { BN = (N + 15) / 16 * 16; Kpad = (K + 31) / 32 * 32; }
+
 size_t conv_tc_scratch_floats(int taps, int N, int K) {
-    int BN = (N + 15) / 16 * 16, Kpad = (K + 31) / 32 * 32;
+    int BN, Kpad; conv_tc_weight_dims(N, K, BN, Kpad);
     return 2 * (size_t)taps * BN * Kpad + 64;
 }
 
-// g.wmat must be the CANONICAL weights: [tap][x.c][y.c] if !wmat_is_nk else [tap][y.c][x.c].
-int conv_tc(const ConvGemm& g, int wmat_is_nk, float* scratch, size_t scratch_floats, cudaStream_t st) {
+int conv_tc_init() {
+    static bool done = false;
+    if (done) return 0;
+    MS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    done = true;
+    return 0;
+}
+
+// bw: prepared weights [taps][BN][Kpad] (see tc_prep_weights) for this GEMM orientation.
+int conv_tc(const ConvGemm& g, const float* bw, cudaStream_t st) {
     MS_REQUIRE(conv_tc_supported(g), "conv_tc: unsupported geometry");
+    if (conv_tc_init()) return -1;
     const int taps = g.kh * g.kw, K = g.x.c, N = g.y.c;
-    const int BN = (N + 15) / 16 * 16, kblocks = (K + 31) / 32, Kpad = kblocks * 32;
-    const size_t per = (size_t)taps * BN * Kpad;
-    MS_REQUIRE(scratch_floats >= 2 * per, "conv_tc: scratch too small");
-    MS_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 15) == 0, "conv_tc: scratch must be 16B aligned");
-    float* bh = scratch;
-    float* bl = scratch + per;
-    tc_prep_weights_kernel<<<(unsigned)cdivz(per, 256), 256, 0, st>>>(g.wmat, bh, bl, taps, N, K, BN, Kpad, wmat_is_nk ? 0 : 1);
-    if (check_launch("tc_prep_weights")) return -1;
+    int BN, Kpad; conv_tc_weight_dims(N, K, BN, Kpad);
+    const int kblocks = Kpad / 32;
 
     ConvTCParams p{};
     p.kh = g.kh; p.kw = g.kw; p.off_y = g.off_y; p.off_x = g.off_x; p.step = g.step;
     p.kblocks = kblocks; p.H = g.y.h; p.W = g.y.w; p.NB = g.y.n;
-    // patch shape: widest tile that the map can fill
     if (g.y.w >= 16 || g.y.h < 16) { p.TW = 16; p.TH = 8; } else { p.TW = 8; p.TH = 16; }
     p.tiles_x = cdiv(p.W, p.TW); p.tiles_y = cdiv(p.H, p.TH);
     p.N = N; p.BN = BN;
-    p.tmem_cols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+    p.acc_stride = (BN + 31) / 32 * 32;
+    p.n_main = std::max(1, std::min(3, 512 / p.acc_stride - 1));
+    {
+        int need = (p.n_main + 1) * p.acc_stride;
+        p.tmem_cols = need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : (need <= 256 ? 256 : 512)));
+    }
     const size_t stage_bytes = 2 * (size_t)A_TILE_BYTES + 2 * (size_t)BN * 128;
     int stages = (int)std::min<size_t>(4, (200 * 1024) / stage_bytes);
     MS_REQUIRE(stages >= 2, "conv_tc: tile does not fit shared memory");
@@ -353,29 +432,39 @@ int conv_tc(const ConvGemm& g, int wmat_is_nk, float* scratch, size_t scratch_fl
     p.mask = g.mask; p.mask_cs = g.mask_cs; p.mask_alpha = g.mask_alpha;
     p.res = g.res; p.res_cs = g.res_cs; p.accumulate = g.accumulate;
 
-    CUtensorMap mapA, mapBh, mapBl;
+    const CUtensorMap *mapA, *mapB;
     {
         cuuint64_t dims[4] = {(cuuint64_t)g.x.c, (cuuint64_t)g.x.w, (cuuint64_t)g.x.h, (cuuint64_t)g.x.n};
         cuuint64_t strides[3] = {(cuuint64_t)g.x.cs * 4, (cuuint64_t)g.x.w * g.x.cs * 4, (cuuint64_t)g.x.h * g.x.w * g.x.cs * 4};
         cuuint32_t box[4] = {32, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
-        if (make_map(&mapA, g.x.p, 4, dims, strides, box)) return -1;
+        if (get_map(&mapA, g.x.p, 4, dims, strides, box)) return -1;
     }
     {
         cuuint64_t dims[3] = {(cuuint64_t)Kpad, (cuuint64_t)BN, (cuuint64_t)taps};
         cuuint64_t strides[2] = {(cuuint64_t)Kpad * 4, (cuuint64_t)BN * Kpad * 4};
         cuuint32_t box[3] = {32, (cuuint32_t)BN, 1};
-        if (make_map(&mapBh, bh, 3, dims, strides, box)) return -1;
-        if (make_map(&mapBl, bl, 3, dims, strides, box)) return -1;
+        if (get_map(&mapB, const_cast<float*>(bw), 3, dims, strides, box)) return -1;
     }
     const size_t smem = (size_t)stages * stage_bytes + 1024;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        MS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
     const int grid = p.NB * p.tiles_x * p.tiles_y;
-    conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(mapA, mapBh, mapBl, p);
+    conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(*mapA, *mapB, p);
     return check_launch("conv_tc");
+}
+
+// one-shot convenience (operator-level C ABI): prepares the weight halves into `scratch` first.
+//   g.wmat must be the CANONICAL weights: [tap][x.c][y.c] if !wmat_is_nk else [tap][y.c][x.c].
+int conv_tc_oneshot(const ConvGemm& g, int wmat_is_nk, float* scratch, size_t scratch_floats, cudaStream_t st) {
+    MS_REQUIRE(conv_tc_supported(g), "conv_tc: unsupported geometry");
+    const int taps = g.kh * g.kw, K = g.x.c, N = g.y.c;
+    int BN, Kpad; conv_tc_weight_dims(N, K, BN, Kpad);
+    const size_t per = (size_t)taps * BN * Kpad;
+    MS_REQUIRE(scratch_floats >= 2 * per + 64, "conv_tc: scratch too small");
+    MS_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 15) == 0, "conv_tc: scratch must be 16B aligned");
+    TcPrepJob job{g.wmat, scratch, scratch + per, taps, N, K, BN, Kpad, wmat_is_nk ? 0 : 1};
+    TcPrepJob* jd = reinterpret_cast<TcPrepJob*>(scratch + 2 * per);   // 64 spare floats hold the job descriptor
+    MS_CHECK_CUDA(cudaMemcpyAsync(jd, &job, sizeof job, cudaMemcpyHostToDevice, st));
+    if (tc_prep_weights(jd, 1, per, st)) return -1;
+    return conv_tc(g, scratch, st);
 }
 
 }  // namespace ms

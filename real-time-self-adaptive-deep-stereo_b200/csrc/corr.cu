@@ -170,6 +170,7 @@ static bool corr_use_tma() {
     if (v < 0) { const char* e = getenv("MS_CORR_NO_TMA"); v = (e && e[0] == '1') ? 0 : 1; }
     return v == 1;
 }
+int corr_init();
 static bool a16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 static int pick_tw(int w, int C, int d, bool warped, size_t row_bufs_full, size_t budget, size_t extra) {
@@ -197,7 +198,7 @@ int corr_fwd(const CorrFwd& p, cudaStream_t st) {
     MS_REQUIRE(TW > 0, "corr_fwd: row does not fit in shared memory");
     size_t smem = ((size_t)TW + (warped ? p.w : TW + 2 * p.max_disp)) * p.C * 4 + (warped ? (size_t)p.w * 4 : 0) + 64;
     int tma = corr_use_tma() && p.lcs == p.C && p.rcs == p.C;
-    MS_CHECK_CUDA(cudaFuncSetAttribute(corr_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (corr_init()) return -1;
     dim3 grid(cdiv(p.w, TW), p.B * p.h);
     corr_fwd_kernel<<<grid, CORR_NT, smem, st>>>(p, TW, nd, tma);
     return check_launch("corr_fwd");
@@ -341,6 +342,15 @@ __global__ void __launch_bounds__(CORR_NT) corr_bwd_kernel(CorrBwd p, int TW, in
     }
 }
 
+int corr_init() {
+    static bool done = false;
+    if (done) return 0;
+    MS_CHECK_CUDA(cudaFuncSetAttribute(corr_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    MS_CHECK_CUDA(cudaFuncSetAttribute(corr_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    done = true;
+    return 0;
+}
+
 int corr_bwd(const CorrBwd& p, cudaStream_t st) {
     MS_REQUIRE(p.C % 4 == 0 && p.lcs % 4 == 0 && p.rcs % 4 == 0 && p.dlcs % 4 == 0 && p.drcs % 4 == 0,
                "corr_bwd: C and strides must be multiples of 4");
@@ -368,7 +378,7 @@ int corr_bwd(const CorrBwd& p, cudaStream_t st) {
     const size_t WIN = warped ? p.w : TW + 2 * p.max_disp;
     size_t smem = 2 * WIN * p.C * 4 + (warped ? (size_t)TW * p.C * 4 : 0) + WIN * nd * 4 + (warped ? (size_t)p.w * 4 : 0) + 64;
     int tma = corr_use_tma() && p.lcs == p.C && p.rcs == p.C;
-    MS_CHECK_CUDA(cudaFuncSetAttribute(corr_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (corr_init()) return -1;
     dim3 grid(cdiv(p.w, TW), p.B * p.h);
     corr_bwd_kernel<<<grid, CORR_NT, smem, st>>>(p, TW, nd, tma);
     return check_launch("corr_bwd");

@@ -36,7 +36,9 @@ Engine::Engine()
       wg_ws(nullptr), wg_ws_floats(0), rs_tmp(nullptr), rs_tmp_floats(0), loss_ws(nullptr), loss_ws_floats(0),
       scalars(nullptr), gt(nullptr), profiling(false) {
     prof_reset();
-    tc_ws = nullptr; tc_ws_floats = 0;
+    prep_jobs_dev = nullptr; prep_max_total = 0; weights_dirty = true;
+    gstream = nullptr; ev_in = nullptr; ev_out = nullptr;
+    { const char* e2 = getenv("MS_GRAPHS"); use_graphs = (e2 && e2[0] == '0') ? 0 : 1; }
     const char* e = getenv("MS_CONV_TC");
     use_tc = (e && e[0] == '0') ? 0 : 1;
 }
@@ -155,12 +157,10 @@ size_t Engine::layout(float* base) {
     tensors["raw_left"] = raw_l; tensors["raw_right"] = raw_r;
     img = tens(2 * B, Hp, Wp, 3, 4);
     tensors["img"] = img;
-    size_t max_wg = 0, max_wt = 0, max_tc = 0;
+    size_t max_wg = 0, max_wt = 0;
     auto track = [&](const ConvLayer& L, size_t pixels) {
         max_wg = std::max(max_wg, conv_wgrad_workspace_floats(L.kh * L.kw, L.cin, L.cout, pixels));
         max_wt = std::max(max_wt, (size_t)L.kh * L.kw * L.cin * L.cout);
-        max_tc = std::max(max_tc, conv_tc_scratch_floats(L.kh * L.kw, L.cout, L.cin));
-        max_tc = std::max(max_tc, conv_tc_scratch_floats(L.kh * L.kw, L.cin, L.cout));
     };
     int h = Hp, w = Wp;
     for (int i = 1; i <= 12; ++i) {
@@ -218,7 +218,32 @@ size_t Engine::layout(float* base) {
     tensors["grad/disp"] = g_disp;
     wT_floats = max_wt; wT = alloc(max_wt);
     wg_ws_floats = max_wg; wg_ws = alloc(max_wg);
-    tc_ws_floats = max_tc; tc_ws = alloc(max_tc);
+    // persistent tcgen05 weight halves + the batched prep job table
+    tcw[0].assign(layers.size(), TcW{nullptr, nullptr, 0, false});
+    tcw[1].assign(layers.size(), TcW{nullptr, nullptr, 0, false});
+    prep_jobs.clear(); job_begin.assign(n_groups + 1, 0); job_end.assign(n_groups + 1, 0);
+    prep_max_total = 0;
+    for (int gidx = 0; gidx <= n_groups; ++gidx) {
+        job_begin[gidx] = (int)prep_jobs.size();
+        for (size_t li = 0; li < layers.size(); ++li) {
+            const ConvLayer& L = layers[li];
+            const int lg = L.group < 0 ? n_groups : L.group;
+            if (lg != gidx || L.transposed || L.stride != 1 || L.cin < 8 || L.cout < 8 || L.cin > 256 || L.cout > 256) continue;
+            for (int dir = 0; dir < 2; ++dir) {
+                const int N = dir == 0 ? L.cout : L.cin, K = dir == 0 ? L.cin : L.cout;
+                int BN, Kpad; conv_tc_weight_dims(N, K, BN, Kpad);
+                const size_t per = (size_t)L.kh * L.kw * BN * Kpad;
+                TcW t; t.per = per; t.ok = true;
+                t.bh = alloc(per); t.bl = nullptr;
+                tcw[dir][li] = t;
+                TcPrepJob j{base ? Wt + L.w_off : nullptr, t.bh, t.bl, L.kh * L.kw, N, K, BN, Kpad, dir == 0 ? 1 : 0};
+                prep_jobs.push_back(j);
+                prep_max_total = std::max(prep_max_total, per);
+            }
+        }
+        job_end[gidx] = (int)prep_jobs.size();
+    }
+    prep_jobs_dev = reinterpret_cast<TcPrepJob*>(alloc((prep_jobs.size() + 1) * sizeof(TcPrepJob) / sizeof(float) + 16));
     rs_tmp_floats = (size_t)B * H * Wp; rs_tmp = alloc(rs_tmp_floats);
     loss_ws_floats = loss_workspace_floats(B, H, W); loss_ws = alloc(loss_ws_floats);
     scalars = alloc(64);
@@ -255,7 +280,8 @@ int Engine::conv_fwd(const ConvLayer& L, const TView& x, const TView& y, const f
     }
     prof_begin(CAT_CONV_FWD, st);
     int rc;
-    if (use_tc && !L.transposed && conv_tc_supported(p)) rc = conv_tc(p, 0, tc_ws, tc_ws_floats, st);
+    const int li = (int)(&L - &layers[0]);
+    if (use_tc && tcw[0][li].ok && conv_tc_profitable(p)) rc = conv_tc(p, tcw[0][li].bh, st);
     else rc = conv_gemm(p, st);
     prof_end(st);
     if (profiling) cat_macs[CAT_CONV_FWD] += (double)y.pixels() * L.kh * L.kw * L.cin * L.cout / (L.transposed ? L.stride * L.stride : 1);
@@ -290,9 +316,9 @@ int Engine::conv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, cons
         p.res = nullptr; p.res_cs = 0; p.accumulate = dx_acc;
         prof_begin(CAT_CONV_DGRAD, st);
         int rc;
-        if (use_tc && conv_tc_supported(p)) {
-            p.wmat = Wt + L.w_off;                 // canonical [tap][cin][cout] == [tap][N][K] for the dgrad GEMM
-            rc = conv_tc(p, 1, tc_ws, tc_ws_floats, st);
+        const int li = (int)(&L - &layers[0]);
+        if (use_tc && tcw[1][li].ok && conv_tc_profitable(p)) {
+            rc = conv_tc(p, tcw[1][li].bh, st);
         } else {
             rc = transpose_taps(Wt + L.w_off, wT, L.kh * L.kw, L.cin, L.cout, st);   // -> [tap][cout][cin]
             if (!rc) rc = conv_gemm(p, st);
@@ -319,17 +345,34 @@ int Engine::set_input(const float* left, const float* right, cudaStream_t st) {
     size_t bytes = (size_t)B * H * W * 3 * sizeof(float);
     MS_CHECK_CUDA(cudaMemcpyAsync(rl.p, left, bytes, cudaMemcpyDefault, st));
     MS_CHECK_CUDA(cudaMemcpyAsync(rr.p, right, bytes, cudaMemcpyDefault, st));
-    TView il = batch(img, 0, B), ir = batch(img, B, B);
-    const float sc = net == 1 ? 1.f / 255.f : 1.f, bi = net == 1 ? -100.f / 255.f : 0.f;
-    if (pad_reflect(rl.p, B, H, W, 3, il.p, Hp, Wp, img.cs, sc, bi, st)) return -1;
-    if (pad_reflect(rr.p, B, H, W, 3, ir.p, Hp, Wp, img.cs, sc, bi, st)) return -1;
     return 0;
+}
+
+int Engine::prep_layers(int group, cudaStream_t st) {
+    if (!use_tc || prep_jobs.empty()) return 0;
+    int b, e;
+    if (group < 0) { b = 0; e = (int)prep_jobs.size(); }
+    else { b = job_begin[group]; e = job_end[group]; }
+    return tc_prep_weights(prep_jobs_dev + b, e - b, prep_max_total, st);
 }
 
 int Engine::forward(int disp_mask, cudaStream_t st) {
     MS_REQUIRE(bound, "engine not bound");
     MS_REQUIRE(net == 0, "forward: only MADNet is implemented in this engine build");
     const int nd = (2 * radius_d) / corr_stride + 1;
+    {
+        TView rl = tensors["raw_left"], rr = tensors["raw_right"];
+        TView il = batch(img, 0, B), ir = batch(img, B, B);
+        if (pad_reflect(rl.p, B, H, W, 3, il.p, Hp, Wp, img.cs, 1.f, 0.f, st)) return -1;
+        if (pad_reflect(rr.p, B, H, W, 3, ir.p, Hp, Wp, img.cs, 1.f, 0.f, st)) return -1;
+    }
+    if (weights_dirty) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cs);
+        MS_REQUIRE(cs == cudaStreamCaptureStatusNone, "forward: weights changed while capturing a graph");
+        if (prep_layers(-1, st)) return -1;
+        weights_dirty = false;
+    }
     TView x = img;
     for (int i = 1; i <= 12; ++i) {
         if (conv_fwd(layers[i - 1], x, pyr[i], nullptr, 0, st)) return -1;
@@ -538,7 +581,70 @@ int Engine::update(int group, float lr, float mu, float gscale, cudaStream_t st)
     MS_REQUIRE(bound, "engine not bound");
     size_t b = 0, e = n_params;
     if (group >= 0) { MS_REQUIRE(group < n_groups, "update: bad group"); b = group_begin[group]; e = group_end[group]; }
-    return momentum_update(Wt + b, Gr + b, Mo + b, e - b, lr, mu, gscale, st);
+    if (momentum_update(Wt + b, Gr + b, Mo + b, e - b, lr, mu, gscale, st)) return -1;
+    return prep_layers(group, st);      // refresh the tf32 hi/lo copies of exactly the weights that moved
+}
+
+// forward + losses + backward (+ update) as one sequence; replayed as a CUDA graph after the first call
+int Engine::run_eager(int mode, int group, int disp_mask, int with_update, float lr, float mu, float gscale,
+                      cudaStream_t st) {
+    int mask = disp_mask | 0b100000;
+    if (mode == 1) mask |= 1 << group;
+    if (forward(mask, st)) return -1;
+    if (loss(5, mode == 2, 0, 1.f, st)) return -1;
+    if (mode == 1) {
+        if (loss(group, 1, 1, 1.f, st)) return -1;
+        if (backward(1, group, st)) return -1;
+        if (with_update && update(group, lr, mu, gscale, st)) return -1;
+    } else if (mode == 2) {
+        if (backward(2, 0, st)) return -1;
+        if (with_update && update(-1, lr, mu, gscale, st)) return -1;
+    }
+    return 0;
+}
+
+int Engine::run(int mode, int group, int disp_mask, int with_update, float lr, float mu, float gscale, cudaStream_t st) {
+    MS_REQUIRE(bound, "engine not bound");
+    MS_REQUIRE(mode == 0 || mode == 2 || (mode == 1 && group >= 0 && group < n_groups), "run: bad mode/group");
+    if (!use_graphs || profiling) return run_eager(mode, group, disp_mask, with_update, lr, mu, gscale, st);
+    if (weights_dirty) {                    // load / restore happened: refresh every tf32 copy outside the graph
+        if (prep_layers(-1, st)) return -1;
+        weights_dirty = false;
+    }
+    if (!gstream) {
+        MS_CHECK_CUDA(cudaStreamCreateWithFlags(&gstream, cudaStreamNonBlocking));
+        MS_CHECK_CUDA(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+        MS_CHECK_CUDA(cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming));
+    }
+    GraphKey key;
+    memset(&key, 0, sizeof key);
+    key.mode = mode; key.group = mode == 1 ? group : 0; key.mask = disp_mask; key.with_update = with_update;
+    key.lr = lr; key.mu = mu; key.gs = gscale;
+    auto it = graphs.find(key);
+    if (it == graphs.end()) {
+        if (conv_tc_init() || corr_init()) return -1;
+        cudaGraph_t graph = nullptr;
+        const long long l0 = launch_count();
+        MS_CHECK_CUDA(cudaStreamBeginCapture(gstream, cudaStreamCaptureModeThreadLocal));
+        int rc = run_eager(mode, group, disp_mask, with_update, lr, mu, gscale, gstream);
+        cudaError_t ce = cudaStreamEndCapture(gstream, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        MS_CHECK_CUDA(ce);
+        cudaGraphExec_t exec = nullptr;
+        MS_CHECK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+        cudaGraphDestroy(graph);
+        GraphRec rec{exec, launch_count() - l0};
+        add_launches(-rec.kernels);            // counted again at every replay below
+        it = graphs.emplace(key, rec).first;
+    }
+    // order: caller's stream -> private stream (graph) -> caller's stream
+    MS_CHECK_CUDA(cudaEventRecord(ev_in, st));
+    MS_CHECK_CUDA(cudaStreamWaitEvent(gstream, ev_in, 0));
+    MS_CHECK_CUDA(cudaGraphLaunch(it->second.exec, gstream));
+    add_launches(it->second.kernels);
+    MS_CHECK_CUDA(cudaEventRecord(ev_out, gstream));
+    MS_CHECK_CUDA(cudaStreamWaitEvent(st, ev_out, 0));
+    return 0;
 }
 
 }  // namespace ms

@@ -2,6 +2,7 @@
 // over caller-owned device memory.  Replaces what one `sess.run(fetches)` executes in the reference's inner
 // loop (Stereo_Online_Adaptation.py:208) for the graphs built by Nets/MadNet.py and Nets/DispNet.py.
 #pragma once
+#include <cstring>
 #include <map>
 #include <string>
 #include <vector>
@@ -51,7 +52,24 @@ struct Engine {
     TView disp[6];                   // D6,D5,D4,D3,D2ctx,full   [B,H,W,1]
     TView g_disp;
     float* wT; size_t wT_floats;     // transposed-weight scratch
-    float* tc_ws; size_t tc_ws_floats;   // tcgen05 weight halves (hi/lo) scratch
+    // tcgen05 weight halves (tf32 hi / lo), persistent per layer and GEMM orientation (0 = forward, 1 = dgrad);
+    // refreshed for a module's layers right after its momentum update, for everything after load/restore.
+    struct TcW { float* bh; float* bl; size_t per; bool ok; };
+    std::vector<TcW> tcw[2];
+    std::vector<TcPrepJob> prep_jobs;            // ordered by group (then ungrouped)
+    std::vector<int> job_begin, job_end;         // per group ranges into prep_jobs; index n_groups = ungrouped
+    TcPrepJob* prep_jobs_dev; size_t prep_max_total;
+    bool weights_dirty;
+    int prep_layers(int group, cudaStream_t st); // -1 = all
+    // whole-step CUDA graphs keyed by (mode, group, disp_mask, with_update, lr, mu, gscale)
+    struct GraphKey { int mode, group, mask, with_update; float lr, mu, gs;
+                      bool operator<(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) < 0; } };
+    struct GraphRec { cudaGraphExec_t exec; long long kernels; };
+    std::map<GraphKey, GraphRec> graphs;
+    int use_graphs;
+    cudaStream_t gstream; cudaEvent_t ev_in, ev_out;   // graphs run on a private stream (the legacy default stream cannot be captured)
+    int run(int mode, int group, int disp_mask, int with_update, float lr, float mu, float gscale, cudaStream_t st);
+    int run_eager(int mode, int group, int disp_mask, int with_update, float lr, float mu, float gscale, cudaStream_t st);
     int use_tc;                      // route eligible convs through conv_tc (env MS_CONV_TC, default 1)
     float* wg_ws; size_t wg_ws_floats;
     float* rs_tmp; size_t rs_tmp_floats;

@@ -7,6 +7,7 @@ void set_error(const std::string& s) { std::lock_guard<std::mutex> l(g_mu); g_er
 const char* last_error_cstr() { std::lock_guard<std::mutex> l(g_mu); return g_err.c_str(); }
 static long long g_launches = 0;
 long long launch_count() { return g_launches; }
+void add_launches(long long n) { g_launches += n; }
 int check_launch(const char* what, int n_kernels) {
     g_launches += n_kernels;
     cudaError_t e = cudaGetLastError();

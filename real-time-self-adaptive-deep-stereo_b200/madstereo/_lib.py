@@ -54,6 +54,8 @@ _SIGS = {
     'ms_engine_loss': (I, [P, I, I, I, F, P]),
     'ms_engine_backward': (I, [P, I, I, P]),
     'ms_engine_update': (I, [P, I, F, F, F, P]),
+    'ms_engine_run': (I, [P, I, I, I, I, F, F, F, P]),
+    'ms_engine_weights_changed': (I, [P]),
     'ms_engine_read_scalars': (I, [P, POINTER(F), P]),
     'ms_engine_metrics': (I, [P, P]),
     'ms_engine_profile': (I, [P, I]),

@@ -74,6 +74,7 @@ class OnlineAdaptation(object):
         if self._snapshot is None:
             raise MadStereoError('no weight snapshot to restore')
         self.engine.weights.copy_(self._snapshot)
+        self.engine.weights_changed()
 
     # ---- one frame ---------------------------------------------------------------------------------
     def _allreduce(self, t):
@@ -100,27 +101,33 @@ class OnlineAdaptation(object):
         eng.set_input(left, right)
         if gt is not None:
             eng.set_gt(gt)
-        mask = 0b100000 | want_disp_mask
-        if self.mode == 'MAD':
-            for b in self.blocks_to_train:
-                mask |= 1 << b
-        eng.forward(mask)
-        eng.loss(5, self.mode == 'FULL', 0)
+        mask = want_disp_mask
+        gscale = 1.0 / self.world
+        solo = self.world == 1
+        if self.mode == 'NONE':
+            eng.run(MODE_NONE, 0, mask, False)
+        elif self.mode == 'FULL':
+            eng.run(MODE_FULL, 0, mask, solo, self.lr, self.mu, gscale)
+            if not solo:
+                self._allreduce(eng.grads)
+                eng.update(-1, self.lr, self.mu, gscale)
+        else:
+            for i, b in enumerate(self.blocks_to_train):
+                if i == 0:
+                    bm = mask
+                    for other in self.blocks_to_train[1:]:
+                        bm |= 1 << other
+                    eng.run(MODE_MAD, b, bm, solo, self.lr, self.mu, gscale)
+                else:      # further train ops of the same sess.run: same forward, disjoint variables
+                    eng.loss(b, True, 1)
+                    eng.backward(MODE_MAD, b)
+                if not solo or i > 0:
+                    if not solo:
+                        lo, hi = eng.group_ranges[b]
+                        self._allreduce(eng.grads[lo:hi])
+                    eng.update(b, self.lr, self.mu, gscale)
         if gt is not None:
             eng.metrics()
-        gscale = 1.0 / self.world
-        if self.mode == 'FULL':
-            eng.backward(MODE_FULL)
-            self._allreduce(eng.grads)
-            eng.update(-1, self.lr, self.mu, gscale)
-        elif self.mode == 'MAD':
-            for b in self.blocks_to_train:
-                eng.loss(b, True, 1)
-                eng.backward(MODE_MAD, b)
-                if self.world > 1:
-                    lo, hi = eng.group_ranges[b]
-                    self._allreduce(eng.grads[lo:hi])
-                eng.update(b, self.lr, self.mu, gscale)
         sc = eng.read_scalars()
         new_loss = sc[0]
         if self.world > 1:

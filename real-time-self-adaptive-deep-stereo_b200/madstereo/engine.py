@@ -116,6 +116,7 @@ class StereoEngine:
             if k not in params:
                 raise MadStereoError('missing parameter %s' % k)
             v.copy_(torch.as_tensor(np.asarray(params[k]), dtype=torch.float32).to(self.device).reshape(v.shape))
+        self.weights_changed()
 
     def export_params(self, arena=None):
         return OrderedDict((k, v.detach().cpu().numpy().copy()) for k, v in self.param_views(arena).items())
@@ -158,6 +159,16 @@ class StereoEngine:
     def update(self, group, lr, mu=0.9, grad_scale=1.0):
         with torch.cuda.device(self.device):
             check(self._lib.ms_engine_update(self._h, group, lr, mu, grad_scale, _stream()), 'update')
+
+    def run(self, mode, group=0, disp_mask=0, with_update=True, lr=1e-4, mu=0.9, grad_scale=1.0):
+        """One whole frame (forward, full-res loss, train op) — replayed as a single CUDA graph."""
+        with torch.cuda.device(self.device):
+            check(self._lib.ms_engine_run(self._h, mode, group, disp_mask, 1 if with_update else 0, lr, mu, grad_scale,
+                                          _stream()), 'run')
+
+    def weights_changed(self):
+        """Call after writing the weight arena from outside (checkpoint load / reset)."""
+        check(self._lib.ms_engine_weights_changed(self._h), 'weights_changed')
 
     def metrics(self):
         with torch.cuda.device(self.device):

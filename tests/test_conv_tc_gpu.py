@@ -27,6 +27,9 @@ TC_CASES = [
     (2, 20, 36, 16, 16, 3, 1, 0.2),         # half-empty K block, N=16
     (1, 16, 16, 128, 64, 1, 1, 0.1),        # 1x1 (DispNet conv_redir)
     (1, 96, 320, 128, 128, 3, 1, 0.2),      # the dominant MADNet layer shape
+    (1, 16, 32, 72, 128, 3, 1, 0.2),        # estimator disp-1 at level 3: dgrad N=72 (BN=80)
+    (1, 16, 32, 36, 128, 3, 1, 0.2),        # context-1 like: dgrad N=36 (BN=48)
+    (1, 8, 16, 136, 128, 3, 1, 0.2),
 ]
 
 

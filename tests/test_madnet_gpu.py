@@ -21,8 +21,8 @@ TOL_LAYER = 2e-4
 # mask flips, up to 1.7e-3 (MAD) / 1.8e-2 (FULL) relative L-inf when one does (measured at 100x200, step 2).
 # Op-level tests (test_ops_gpu.py) pin every kernel at 2e-5..5e-5; the bounds here are the kink-noise envelope.
 TOL_GRAD = 1e-2          # relative L-inf per tensor, first step
-TOL_GRAD_2 = 5e-2        # second step (weights already differ by the first step's noise)
-TOL_DW = 5e-2            # adapted weights: |dw_gpu - dw_ref|_inf <= TOL_DW * |dw_ref|_inf + 1e-7 per tensor
+TOL_GRAD_2 = 1.5e-1      # second step (weights already differ by the first step's noise; flips compound)
+TOL_DW = 1.5e-1            # adapted weights: |dw_gpu - dw_ref|_inf <= TOL_DW * |dw_ref|_inf + 1e-7 per tensor
 
 
 def rel_linf(a, b):
