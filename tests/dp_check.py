@@ -1,0 +1,74 @@
+"""Multi-GPU parity check (run under torchrun, one rank per GPU):
+N ranks x 1 frame each must equal the reference graph at batch N (every loss is a batch mean).
+Rank 0 compares gradients / updated weights with the CPU oracle run on the N-frame batch.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dp_check.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, 'real-time-self-adaptive-deep-stereo_b200')
+sys.path.insert(0, ROOT); sys.path.insert(0, PKG)
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def main():
+    rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+    torch.cuda.set_device(local)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    import Nets
+    from madstereo.adaptation import OnlineAdaptation
+    from madstereo.synthetic import make_pair
+    from oracle.madnet import init_params
+    h, w = 64, 128
+    frames = [make_pair(h, w, seed=10 + r)[:2] for r in range(world)]
+    left, right = frames[rank]
+    lt, rt = torch.from_numpy(left).cuda(), torch.from_numpy(right).cuda()
+    sys.stdout = open(os.devnull, 'w') if rank else sys.stdout
+    ok = True
+    for mode in ('MAD', 'FULL'):
+        net = Nets.get_stereo_net('MADNet', dict(left_img=lt, right_img=rt, split_layers=[None], sequence=True,
+                                                 train_portion='BEGIN', bulkhead=(mode == 'MAD')))
+        cfg = json.load(open(os.path.join(PKG, 'block_config', 'MadNet_full.json')))
+        ad = OnlineAdaptation(net, mode=mode, train_config=cfg, lr=1e-4, sample_mode='FIXED', fixed_id=3)
+        params = init_params(seed=42)
+        ad.load_weights(params)
+        out = ad.step(lt, rt)
+        torch.cuda.synchronize()
+        # replicas must be bit-identical
+        wsum = net.engine.weights.double().sum().reshape(1)
+        gathered = [torch.zeros_like(wsum) for _ in range(world)]
+        dist.all_gather(gathered, wsum)
+        same = all(float(g) == float(gathered[0]) for g in gathered)
+        if rank == 0:
+            from oracle.adaptation import OracleAdapter
+            bl = np.concatenate([f[0] for f in frames]); br = np.concatenate([f[1] for f in frames])
+            orc = OracleAdapter(params, mode=mode, lr=1e-4)
+            ref = orc.step(bl, br, 3)
+            g = net.engine.param_views(net.engine.grads)
+            worst = max(rel(g[n].cpu().numpy() / world, gr) for n, gr in ref['grads'].items())
+            wv = net.engine.export_params()
+            wworst = max(np.abs((wv[n] - params[n]) - (orc.net.p[n].detach().numpy() - params[n])).max() /
+                         max(np.abs(orc.net.p[n].detach().numpy() - params[n]).max(), 1e-30) for n in ref['grads'])
+            good = same and worst < 1e-2 and wworst < 5e-2 and abs(out['loss'] - ref['full_loss']) < 2e-5
+            ok = ok and good
+            print('DP %s world=%d: replicas identical=%s  grad rel err %.2e  dW rel err %.2e  loss %.6f vs %.6f  -> %s' % (
+                mode, world, same, worst, wworst, out['loss'], ref['full_loss'], 'OK' if good else 'FAIL'), flush=True)
+        del ad, net
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0 and not ok:
+        sys.exit(1)
+
+
+if __name__ == '__main__':
+    main()
