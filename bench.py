@@ -146,6 +146,10 @@ def run_ours(args):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
+    # keep fd 1 clean for the single JSON line: NCCL / the banner of the reference-style constructors print to stdout
+    sys.stdout.flush()
+    saved_stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     if world != args.gpus and world > 1:
         raise SystemExit('--gpus %d but WORLD_SIZE=%d' % (args.gpus, world))
     if not torch.cuda.is_available():
@@ -205,13 +209,12 @@ def run_ours(args):
 
     # ---- kernel-level profile (separate instrumented steps: events around every kernel group)
     prof = None
-    if rank == 0:
-        eng.profile(True)
-        for i in range(10):
-            ad.step(*dev_pairs[i % n_pairs])
-        torch.cuda.synchronize()
-        prof = eng.profile_read()
-        eng.profile(False)
+    eng.profile(True)                         # every rank takes part: the DP step contains collectives
+    for i in range(10):
+        ad.step(*dev_pairs[i % n_pairs])
+    torch.cuda.synchronize()
+    prof = eng.profile_read()
+    eng.profile(False)
     barrier()
 
     if rank != 0:
@@ -258,7 +261,10 @@ def run_ours(args):
         line['cpu_baseline'] = {'value': fps_cpu, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
                                 'sample': '3 MAD steps (modules 1,2,3 of the SEQUENTIAL cycle) on one 1280x384 pair after '
                                           '1 warm-up; torch-CPU fp32 oracle restatement (TF1 cannot run here)'}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(saved_stdout_fd, 1)
+    print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
     return 0

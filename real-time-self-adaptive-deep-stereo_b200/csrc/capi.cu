@@ -49,7 +49,7 @@ int ms_corr_bwd(const float* left, int left_cs, const float* right, int right_cs
     p.dcost = dcost; p.dcs = dcost_cs; p.dleft = dleft; p.dlcs = dleft_cs; p.dright = dright; p.drcs = dright_cs;
     p.du = du; p.ducs = du_cs;
     p.B = B; p.h = h; p.w = w; p.C = C; p.max_disp = max_disp; p.stride = stride;
-    p.add_left_slice = add_left_slice; p.acc_left = 0; p.acc_right = 0;
+    p.add_left_slice = add_left_slice; p.acc_left = 0; p.acc_right = 0; p.gcoff = -1;
     return corr_bwd(p, S(stream));
 }
 
@@ -197,6 +197,7 @@ void* ms_engine_create(const char* net_name, int B, int H, int W, int radius_d, 
     e->Hp = (H + 63) / 64 * 64; e->Wp = (W + 63) / 64 * 64;
     e->radius_d = radius_d; e->corr_stride = corr_stride; e->warping = warping;
     if (!strcmp(net_name, "MADNet")) { e->net = 0; e->build_madnet(); }
+    else if (!strcmp(net_name, "Dispnet")) { e->net = 1; e->build_dispnet(); }
     else { set_error(std::string("Unrecognized network name: ") + net_name); delete e; return nullptr; }
     e->finalize_groups(nullptr, 0);
     return e;
@@ -287,7 +288,7 @@ int ms_engine_weights_changed(void* h) {
 int ms_engine_metrics(void* h, void* stream) {
     Engine* e = static_cast<Engine*>(h);
     if (!e->bound) { set_error("engine not bound"); return -2; }
-    return epe_bad3(e->disp[5].p, e->gt, e->B * e->H * e->W, e->scalars + 2, e->loss_ws, S(stream));
+    return epe_bad3(e->disp[e->n_disp - 1].p, e->gt, e->B * e->H * e->W, e->scalars + 2, e->loss_ws, S(stream));
 }
 int ms_engine_read_scalars(void* h, float* host4, void* stream) {
     Engine* e = static_cast<Engine*>(h);

@@ -77,6 +77,7 @@ struct ConvWgrad {
 int conv_wgrad(const ConvWgrad& p, cudaStream_t st);
 size_t conv_wgrad_workspace_floats(int taps, int ci, int co, size_t pixels);
 
+int bias_grad(const TView& dy, float* db, float* workspace, size_t workspace_floats, cudaStream_t st);
 int transpose_taps(const float* w, float* wt, int taps, int ci, int co, cudaStream_t st);
 
 // correlation / warp (corr.cu)
@@ -100,6 +101,7 @@ struct CorrBwd {
     float* dright; int drcs;         // out: d(right feature) (scatter through the warp)
     float* du;     int ducs;         // optional out: d(u) from the warp coordinates (FULL mode)
     int B, h, w, C, max_disp, stride, add_left_slice, acc_left, acc_right;
+    int gcoff;                       // channel offset of the corr grads inside dcost (-1 => C, the concat layout)
 };
 int corr_bwd(const CorrBwd& p, cudaStream_t st);
 

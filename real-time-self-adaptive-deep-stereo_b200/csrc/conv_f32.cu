@@ -463,6 +463,15 @@ int conv_wgrad(const ConvWgrad& p, cudaStream_t st) {
     return check_launch("conv_wgrad_reduce", p.db ? 3 : 1);
 }
 
+int bias_grad(const TView& dy, float* db, float* workspace, size_t workspace_floats, cudaStream_t st) {
+    const size_t Pz = dy.pixels();
+    const int P = (int)Pz, co = dy.c, nb = bias_blocks(Pz);
+    MS_REQUIRE(workspace_floats >= (size_t)nb * co, "bias_grad: workspace too small");
+    bias_partial_kernel<<<dim3(cdiv(co, 32), nb), dim3(32, 8), 0, st>>>(dy.p, dy.cs, co, P, cdiv(P, nb), workspace);
+    wgrad_reduce_kernel<<<cdiv(co, 256), 256, 0, st>>>(workspace, db, (size_t)co, nb, 0);
+    return check_launch("bias_grad", 2);
+}
+
 // wt[tap][co][ci] = w[tap][ci][co]
 __global__ void transpose_taps_kernel(const float* __restrict__ w, float* __restrict__ wt, int ci, int co) {
     __shared__ float tile[32][33];

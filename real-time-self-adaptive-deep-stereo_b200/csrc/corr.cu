@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(CORR_NT) corr_bwd_kernel(CorrBwd p, int TW, in
     const float* lrow = p.left + (size_t)row * w * p.lcs;
     const float* rrow = p.right + (size_t)row * w * p.rcs;
     const float* grow = p.dcost + (size_t)row * w * p.dcs;
+    const int gco = p.gcoff < 0 ? C : p.gcoff;
 
     if (use_tma && threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
     __syncthreads();
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(CORR_NT) corr_bwd_kernel(CorrBwd p, int TW, in
     stage_row(Rs, rrow, p.rcs, C, wlo, whi, use_tma, &bar);
     for (int e = threadIdx.x; e < (whi - wlo) * nd; e += blockDim.x) {
         int px = e / nd, i = e - px * nd;
-        Gs[e] = grow[(size_t)(wlo + px) * p.dcs + C + i];
+        Gs[e] = grow[(size_t)(wlo + px) * p.dcs + gco + i];
     }
     if (warped)
         for (int e = threadIdx.x; e < w; e += blockDim.x) Us[e] = p.u[((size_t)row * w + e) * p.ucs];

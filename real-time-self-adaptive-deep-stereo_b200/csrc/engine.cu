@@ -140,16 +140,9 @@ int Engine::finalize_groups(const int* group_of_layer, int ng) {
 // workspace layout
 // ---------------------------------------------------------------------------------------------
 size_t Engine::layout(float* base) {
-    size_t off = 0;
-    auto alloc = [&](size_t n) -> float* {
-        float* p = base ? base + off : nullptr;
-        off += (n + 63) / 64 * 64;
-        return p;
-    };
-    auto tens = [&](int n, int h, int w, int c, int cs = 0) {
-        cs = cs ? cs : c;
-        return view(alloc((size_t)n * h * w * cs), n, h, w, c, cs);
-    };
+    Bump A{base, 0};
+    auto alloc = [&](size_t n) -> float* { return A.alloc(n); };
+    auto tens = [&](int n, int h, int w, int c, int cs = 0) { return A.tens(n, h, w, c, cs); };
     tensors.clear();
     char nm[128];
     const int nd = (2 * radius_d) / corr_stride + 1;
@@ -162,6 +155,9 @@ size_t Engine::layout(float* base) {
         max_wg = std::max(max_wg, conv_wgrad_workspace_floats(L.kh * L.kw, L.cin, L.cout, pixels));
         max_wt = std::max(max_wt, (size_t)L.kh * L.kw * L.cin * L.cout);
     };
+    if (net == 1) {
+        layout_dispnet(A, max_wg, max_wt);
+    } else {
     int h = Hp, w = Wp;
     for (int i = 1; i <= 12; ++i) {
         if (i % 2) { h = (h + 1) / 2; w = (w + 1) / 2; }
@@ -209,11 +205,13 @@ size_t Engine::layout(float* base) {
     final_ = tens(B, pyr[4].h, pyr[4].w, 1);
     g_final = tens(B, pyr[4].h, pyr[4].w, 1);
     tensors["final_disp"] = final_; tensors["grad/final_disp"] = g_final;
-    for (int i = 0; i < 6; ++i) {
+    }   // net == 0
+    n_disp = net == 1 ? 7 : 6;
+    for (int i = 0; i < n_disp; ++i) {
         disp[i] = tens(B, H, W, 1);
         snprintf(nm, sizeof nm, "disp%d", i); tensors[nm] = disp[i];
     }
-    tensors["rescaled_prediction"] = disp[5];
+    tensors["rescaled_prediction"] = disp[n_disp - 1];
     g_disp = tens(B, H, W, 1);
     tensors["grad/disp"] = g_disp;
     wT_floats = max_wt; wT = alloc(max_wt);
@@ -228,9 +226,10 @@ size_t Engine::layout(float* base) {
         for (size_t li = 0; li < layers.size(); ++li) {
             const ConvLayer& L = layers[li];
             const int lg = L.group < 0 ? n_groups : L.group;
-            if (lg != gidx || L.transposed || L.stride != 1 || L.cin < 8 || L.cout < 8 || L.cin > 256 || L.cout > 256) continue;
+            if (lg != gidx || L.transposed || L.stride != 1 || L.cin < 8 || L.cout < 8) continue;
             for (int dir = 0; dir < 2; ++dir) {
                 const int N = dir == 0 ? L.cout : L.cin, K = dir == 0 ? L.cin : L.cout;
+                if (N > 256 || (long)N * K < 4096) continue;
                 int BN, Kpad; conv_tc_weight_dims(N, K, BN, Kpad);
                 const size_t per = (size_t)L.kh * L.kw * BN * Kpad;
                 TcW t; t.per = per; t.ok = true;
@@ -248,7 +247,7 @@ size_t Engine::layout(float* base) {
     loss_ws_floats = loss_workspace_floats(B, H, W); loss_ws = alloc(loss_ws_floats);
     scalars = alloc(64);
     gt = alloc((size_t)B * H * W);
-    return off;
+    return A.off;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -358,13 +357,14 @@ int Engine::prep_layers(int group, cudaStream_t st) {
 
 int Engine::forward(int disp_mask, cudaStream_t st) {
     MS_REQUIRE(bound, "engine not bound");
-    MS_REQUIRE(net == 0, "forward: only MADNet is implemented in this engine build");
     const int nd = (2 * radius_d) / corr_stride + 1;
     {
         TView rl = tensors["raw_left"], rr = tensors["raw_right"];
         TView il = batch(img, 0, B), ir = batch(img, B, B);
-        if (pad_reflect(rl.p, B, H, W, 3, il.p, Hp, Wp, img.cs, 1.f, 0.f, st)) return -1;
-        if (pad_reflect(rr.p, B, H, W, 3, ir.p, Hp, Wp, img.cs, 1.f, 0.f, st)) return -1;
+        // DispNet normalises (x/255 - 100/255, Nets/DispNet.py:59-73); MADNet feeds raw 0..255 (Nets/MadNet.py:56-66)
+        const float sc = net == 1 ? 1.f / 255.f : 1.f, bi = net == 1 ? -100.f / 255.f : 0.f;
+        if (pad_reflect(rl.p, B, H, W, 3, il.p, Hp, Wp, img.cs, sc, bi, st)) return -1;
+        if (pad_reflect(rr.p, B, H, W, 3, ir.p, Hp, Wp, img.cs, sc, bi, st)) return -1;
     }
     if (weights_dirty) {
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -373,6 +373,7 @@ int Engine::forward(int disp_mask, cudaStream_t st) {
         if (prep_layers(-1, st)) return -1;
         weights_dirty = false;
     }
+    if (net == 1) return forward_dispnet(disp_mask, st);
     TView x = img;
     for (int i = 1; i <= 12; ++i) {
         if (conv_fwd(layers[i - 1], x, pyr[i], nullptr, 0, st)) return -1;
@@ -428,7 +429,7 @@ int Engine::forward(int disp_mask, cudaStream_t st) {
 }
 
 int Engine::loss(int which, int with_grad, int slot, float grad_scale, cudaStream_t st) {
-    MS_REQUIRE(bound && which >= 0 && which < 6 && slot >= 0 && slot < 2, "loss: bad arguments");
+    MS_REQUIRE(bound && which >= 0 && which < n_disp && slot >= 0 && slot < 2, "loss: bad arguments");
     ReprojLoss p{};
     p.left = tensors["raw_left"].p; p.right = tensors["raw_right"].p;
     p.disp = disp[which].p; p.loss = scalars + slot;
@@ -444,7 +445,13 @@ int Engine::loss(int which, int with_grad, int slot, float grad_scale, cudaStrea
 // backward
 // ---------------------------------------------------------------------------------------------
 int Engine::backward(int mode, int group, cudaStream_t st) {
-    MS_REQUIRE(bound && net == 0, "backward: MADNet engine not bound");
+    MS_REQUIRE(bound, "backward: engine not bound");
+    if (net == 1) {
+        // the reference cannot run MAD on DispNet either: 6 side predictions vs 5 groups trips the assert at
+        // Stereo_Online_Adaptation.py:97
+        MS_REQUIRE(mode == 2, "backward: DispNet supports FULL adaptation only");
+        return backward_dispnet(st);
+    }
     MS_REQUIRE(mode == 2 || (mode == 1 && group >= 0 && group < n_groups), "backward: bad mode/group");
     const int nd = (2 * radius_d) / corr_stride + 1;
 
@@ -500,7 +507,7 @@ int Engine::backward(int mode, int group, cudaStream_t st) {
         cb.dleft = dL.p; cb.dlcs = dL.cs; cb.dright = dR.p; cb.drcs = dR.cs;
         cb.du = (want_du && cb.u) ? g_u[k].p : nullptr; cb.ducs = 1;
         cb.B = B; cb.h = cost[k].h; cb.w = cost[k].w; cb.C = C; cb.max_disp = radius_d; cb.stride = corr_stride;
-        cb.add_left_slice = 1; cb.acc_left = 0; cb.acc_right = 0;
+        cb.add_left_slice = 1; cb.acc_left = 0; cb.acc_right = 0; cb.gcoff = -1;
         prof_begin(CAT_CORR_BWD, st);
         int crc = corr_bwd(cb, st);
         prof_end(st);
@@ -588,10 +595,11 @@ int Engine::update(int group, float lr, float mu, float gscale, cudaStream_t st)
 // forward + losses + backward (+ update) as one sequence; replayed as a CUDA graph after the first call
 int Engine::run_eager(int mode, int group, int disp_mask, int with_update, float lr, float mu, float gscale,
                       cudaStream_t st) {
-    int mask = disp_mask | 0b100000;
+    const int full = n_disp - 1;
+    int mask = disp_mask | (1 << full);
     if (mode == 1) mask |= 1 << group;
     if (forward(mask, st)) return -1;
-    if (loss(5, mode == 2, 0, 1.f, st)) return -1;
+    if (loss(full, mode == 2, 0, 1.f, st)) return -1;
     if (mode == 1) {
         if (loss(group, 1, 1, 1.f, st)) return -1;
         if (backward(1, group, st)) return -1;

@@ -22,6 +22,12 @@ struct ConvLayer {
     int group;            // MAD module index or -1
 };
 
+struct Bump {            // workspace bump allocator (sizes only when base == nullptr)
+    float* base; size_t off;
+    float* alloc(size_t n) { float* p = base ? base + off : nullptr; off += (n + 63) / 64 * 64; return p; }
+    TView tens(int n, int h, int w, int c, int cs = 0) { cs = cs ? cs : c; return view(alloc((size_t)n * h * w * cs), n, h, w, c, cs); }
+};
+
 struct Engine {
     // configuration
     int net;              // 0 = MADNet, 1 = DispNet
@@ -49,7 +55,8 @@ struct Engine {
     TView V[7], g_V[7];              // [level] (V[2] is a slice of ctxin)
     TView g_u[7];
     TView ctxin, g_ctxin, ctx[8], g_ctx[8], final_, g_final;
-    TView disp[6];                   // D6,D5,D4,D3,D2ctx,full   [B,H,W,1]
+    TView disp[7];                   // MADNet: D6,D5,D4,D3,D2ctx,full ; DispNet: up5..up1 predict, prediction, full
+    int n_disp;
     TView g_disp;
     float* wT; size_t wT_floats;     // transposed-weight scratch
     // tcgen05 weight halves (tf32 hi / lo), persistent per layer and GEMM orientation (0 = forward, 1 = dgrad);
@@ -88,6 +95,15 @@ struct Engine {
     void prof_end(cudaStream_t st);
     int prof_collect();      // synchronises; folds spans into cat_ms
     void prof_reset();
+
+    // ---- DispNet buffers (engine_dispnet.cu)
+    TView d_c1, d_c2, d_cat3, d_enc[8], d_cat[5], d_pr[5], d_cc[5], d_pred;
+    TView gd_c1, gd_c2, gd_cat3, gd_enc[8], gd_cat[5], gd_pr[5], gd_cc[5], gd_pred;
+    int build_dispnet();
+    void layout_dispnet(Bump& A, size_t& max_wg, size_t& max_wt);
+    int forward_dispnet(int disp_mask, cudaStream_t st);
+    int backward_dispnet(cudaStream_t st);
+    int deconv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, const TView* dx, int dx_acc, cudaStream_t st);
 
     Engine();
     size_t layout(float* base);      // returns floats needed; assigns views when base != nullptr
