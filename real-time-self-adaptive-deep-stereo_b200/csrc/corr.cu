@@ -372,7 +372,7 @@ int corr_bwd(const CorrBwd& p, cudaStream_t st) {
             if (tw > p.w) continue;
             size_t win = (size_t)tw + 2 * p.max_disp;
             size_t bytes = 2 * win * p.C * 4 + win * nd * 4 + 64;
-            if (bytes <= (size_t)112 * 1024) { TW = tw; break; }
+            if (bytes <= (size_t)200 * 1024) { TW = tw; break; }
         }
         MS_REQUIRE(TW > 0, "corr_bwd: tile does not fit in shared memory");
     }
