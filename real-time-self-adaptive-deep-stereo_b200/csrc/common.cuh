@@ -158,4 +158,5 @@ int conv_tc(const ConvGemm& g, const float* bw, cudaStream_t st);
 bool conv_tc_profitable(const ConvGemm& g);
 int conv_tc_oneshot(const ConvGemm& g, int wmat_is_nk, float* scratch, size_t scratch_floats, cudaStream_t st);
 int corr_init();
+int conv_tc_read_prof(unsigned long long* out32, int reset);
 }  // namespace ms

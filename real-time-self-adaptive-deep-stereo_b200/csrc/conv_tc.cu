@@ -18,6 +18,7 @@
 // TMA), accum (tcgen05.commit -> epilogue).
 #include <cuda.h>
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -89,6 +90,33 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+          "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+          "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+          "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+          "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO=1 | SBO=1024B |
 // version=1 (sm100) | layout_type=2 (SWIZZLE_128B).  Tile base must be 1024-byte aligned.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_byte_addr) {
@@ -112,6 +140,7 @@ struct ConvTCParams {
     const float* mask; int mask_cs; float mask_alpha;
     const float* res; int res_cs;
     int accumulate;
+    int dbg;                          // timing experiments only (MS_TC_DEBUG): 1 no split, 2 no proxy fence, 4 no MMA
 };
 
 constexpr int TC_THREADS = 320;           // warp 0 TMA, warp 1 MMA, warps 2-9 splitter + epilogue
@@ -184,6 +213,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const uint32_t sa = base + (uint32_t)s * stage_bytes;
                 const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + A_TILE_BYTES);
                 const uint64_t b_hi = umma_desc_sw128(sa + 2 * A_TILE_BYTES), b_lo = umma_desc_sw128(sa + 2 * A_TILE_BYTES + b_bytes);
+                if (!(p.dbg & 4))
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {          // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle row
                     const uint64_t o = (uint64_t)(j * 2);
@@ -215,6 +245,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 float4* __restrict__ alo = reinterpret_cast<float4*>(stg + A_TILE_BYTES);
                 float4* __restrict__ bhi = reinterpret_cast<float4*>(stg + 2 * A_TILE_BYTES);
                 float4* __restrict__ blo = reinterpret_cast<float4*>(stg + 2 * A_TILE_BYTES + b_bytes);
+                if (!(p.dbg & 1)) {
                 float4 v[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) v[e] = ahi[st_tid + e * SPLIT_THREADS];       // 1024 float4 per A tile
@@ -240,7 +271,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         bhi[i1] = h; blo[i1] = l;
                     }
                 }
-                fence_async_smem();                     // generic-proxy writes -> visible to the tensor core
+                }
+                if (!(p.dbg & 2)) fence_async_smem();   // generic-proxy writes -> visible to the tensor core
                 __syncwarp();
                 if (lane == 0) mb_arrive(&ready_bar[s]);
                 if (++s == p.stages) { s = 0; ph ^= 1u; }
@@ -301,6 +333,483 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------------
+// v2 kernel for small tap extents (undilated 3x3, 1x1): the activation patch (tile + halo) is loaded ONCE per
+// 32-channel block and the 9 tap-shifted A tiles are gathered from it in shared memory by the splitter warps while
+// they compute the tf32 hi/lo halves (6x less activation traffic than one TMA box per tap); weights stream through a
+// deeper raw ring; two operand stages decouple the splitter from the MMA issuer.
+//   smem: op[2] x {A_hi, A_lo, B_hi, B_lo} | braw[NB] | patch[2]
+//   barriers: pfull/pempty[2] (patch), bfull/bempty[NB] (weights), ready/free[2] (operands), accum
+// ------------------------------------------------------------------------------------------------
+__device__ unsigned long long g_tc_prof[32];
+#define TCP_T0() const long long _t0 = clock64()
+#define TCP_ADD(slot, cond) do { if (cond) g_tc_prof[slot] += (unsigned long long)(clock64() - _t0); } while (0)
+
+struct ConvTCHaloParams {
+    ConvTCParams c;
+    int PW, PH;            // patch width / height in pixels
+    int minx, miny;        // patch origin relative to the tile origin
+    int nb_slots;          // weight ring depth
+    uint32_t patch_bytes;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapB,
+                    const ConvTCHaloParams hp) {
+    const ConvTCParams& p = hp.c;
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t pfull[2], pempty[2], bfull[8], bempty[8], ready_bar[2], free_bar[2], accum_bar;
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t base = (s_addr(smem_dyn) + 1023u) & ~1023u;
+    unsigned char* gbase = smem_dyn + (base - s_addr(smem_dyn));
+    const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+    const uint32_t op_bytes = 2u * A_TILE_BYTES + 2u * b_bytes;
+    const uint32_t braw_off = 2u * op_bytes;
+    const uint32_t patch_stride = (hp.patch_bytes + 1023u) & ~1023u;
+    const uint32_t patch_off = braw_off + (uint32_t)hp.nb_slots * b_bytes;
+    const int NB = hp.nb_slots;
+
+    int bid = blockIdx.x;
+    const int tx = bid % p.tiles_x; bid /= p.tiles_x;
+    const int ty = bid % p.tiles_y;
+    const int img = bid / p.tiles_y;
+    const int x0 = tx * p.TW, y0 = ty * p.TH;
+    const int taps = p.kh * p.kw;
+    const int total = taps * p.kblocks;
+    const bool prof = (p.dbg & 8) && blockIdx.x == 0;
+    const long long t_start = clock64();
+    long long t_epi = 0;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mb_init(&pfull[i], 1); mb_init(&pempty[i], SPLIT_THREADS / 32);
+            mb_init(&ready_bar[i], SPLIT_THREADS / 32); mb_init(&free_bar[i], 1);
+        }
+        for (int i = 0; i < NB; ++i) { mb_init(&bfull[i], 1); mb_init(&bempty[i], SPLIT_THREADS / 32); }
+        mb_init(&accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_addr(&tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer: patches (per channel block) + weight tiles (per channel block x tap) ======
+        if (lane == 0) {
+            auto load_patch = [&](int kb) {
+                const int pb = kb & 1;
+                mb_wait(&pempty[pb], (((uint32_t)kb >> 1) & 1u) ^ 1u);
+                mb_expect_tx(&pfull[pb], hp.patch_bytes);
+                tma_load_4d(gbase + patch_off + (size_t)pb * patch_stride, &mapP, &pfull[pb], kb * 32, x0 + hp.minx, y0 + hp.miny, img);
+            };
+            load_patch(0);
+            int slot = 0;
+            uint32_t bph = 0;
+            const int ahead = min(NB, taps) - 1;
+            for (int kb = 0; kb < p.kblocks; ++kb) {
+                for (int tap = 0; tap < taps; ++tap) {
+                    { TCP_T0(); mb_wait(&bempty[slot], bph ^ 1u); TCP_ADD(0, prof); }
+                    mb_expect_tx(&bfull[slot], b_bytes);
+                    tma_load_3d(gbase + braw_off + (size_t)slot * b_bytes, &mapB, &bfull[slot], kb * 32, 0, tap);
+                    if (++slot == NB) { slot = 0; bph ^= 1u; }
+                    if (tap == ahead && kb + 1 < p.kblocks) load_patch(kb + 1);   // the splitter has left patch kb-1 by now
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+            for (int it = 0; it < total; ++it) {
+                const int s = it & 1;
+                { TCP_T0(); mb_wait(&ready_bar[s], ((uint32_t)it >> 1) & 1u); TCP_ADD(1, prof); }
+                const long long t_issue = clock64();
+                tc_fence_after();
+                const uint32_t sa = base + (uint32_t)s * op_bytes;
+                const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + A_TILE_BYTES);
+                const uint64_t b_hi = umma_desc_sw128(sa + 2 * A_TILE_BYTES), b_lo = umma_desc_sw128(sa + 2 * A_TILE_BYTES + b_bytes);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint64_t o = (uint64_t)(j * 2);
+                    const int g = it * 4 + j;
+                    tc_mma_tf32(tmem, a_lo + o, b_hi + o, idesc, g > 0 ? 1u : 0u);
+                    tc_mma_tf32(tmem, a_hi + o, b_lo + o, idesc, 1u);
+                    const uint32_t dmain = tmem + (uint32_t)((1 + g % p.n_main) * p.acc_stride);
+                    tc_mma_tf32(dmain, a_hi + o, b_hi + o, idesc, g >= p.n_main ? 1u : 0u);
+                }
+                tc_commit(&free_bar[s]);
+                if (prof) g_tc_prof[2] += (unsigned long long)(clock64() - t_issue);
+            }
+            tc_commit(&accum_bar);
+        }
+    } else {
+        // ================= splitter / gatherer (warps 2..9) =================
+        const int st_tid = threadIdx.x - 64;           // 0..255
+        const int b_f4 = p.BN * 8;
+        {
+            int slot = 0;
+            uint32_t bph = 0;
+            int it = 0;
+            for (int kb = 0; kb < p.kblocks; ++kb) {
+                const int pb = kb & 1;
+                const bool sp = prof && threadIdx.x == 64;
+                { TCP_T0(); mb_wait(&pfull[pb], ((uint32_t)kb >> 1) & 1u); TCP_ADD(3, sp); }
+                const unsigned char* patch = gbase + patch_off + (size_t)pb * patch_stride;
+                for (int tap = 0; tap < taps; ++tap, ++it) {
+                    const int s = it & 1;
+                    { TCP_T0(); mb_wait(&free_bar[s], (((uint32_t)it >> 1) & 1u) ^ 1u); TCP_ADD(4, sp); }   // operand stage released by the MMAs of it-2
+                    { TCP_T0(); mb_wait(&bfull[slot], bph); TCP_ADD(5, sp); }
+                    const long long t_work = clock64();
+                    unsigned char* stg = gbase + (size_t)s * op_bytes;
+                    float4* __restrict__ ahi = reinterpret_cast<float4*>(stg);
+                    float4* __restrict__ alo = reinterpret_cast<float4*>(stg + A_TILE_BYTES);
+                    float4* __restrict__ bhi = reinterpret_cast<float4*>(stg + 2 * A_TILE_BYTES);
+                    float4* __restrict__ blo = reinterpret_cast<float4*>(stg + 2 * A_TILE_BYTES + b_bytes);
+                    const float4* __restrict__ braw = reinterpret_cast<const float4*>(gbase + braw_off + (size_t)slot * b_bytes);
+                    // ---- A: gather the tap-shifted tile out of the patch, split, write swizzled (SWIZZLE_128B)
+                    const int tr = tap / p.kw, ts = tap - tr * p.kw;
+                    const int dy = p.off_y + tr * p.step - hp.miny, dx = p.off_x + ts * p.step - hp.minx;
+                    float4 v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int idx = st_tid + e * SPLIT_THREADS;        // 0..1023 = row*8 + chunk
+                        const int row = idx >> 3, ch = idx & 7;
+                        const int py = row / p.TW + dy, px = row % p.TW + dx;
+                        v[e] = *reinterpret_cast<const float4*>(patch + ((size_t)(py * hp.PW + px) * 128 + ch * 16));
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int idx = st_tid + e * SPLIT_THREADS;
+                        const int row = idx >> 3, ch = idx & 7;
+                        const int d = row * 8 + (ch ^ (row & 7));
+                        float4 h, l;
+                        h.x = tf32_rna(v[e].x); h.y = tf32_rna(v[e].y); h.z = tf32_rna(v[e].z); h.w = tf32_rna(v[e].w);
+                        l.x = v[e].x - h.x; l.y = v[e].y - h.y; l.z = v[e].z - h.z; l.w = v[e].w - h.w;
+                        ahi[d] = h; alo[d] = l;
+                    }
+                    // ---- B: elementwise split (the TMA already wrote the swizzled layout)
+                    for (int i0 = st_tid; i0 < b_f4; i0 += 2 * SPLIT_THREADS) {
+                        const int i1 = i0 + SPLIT_THREADS;
+                        const bool two = i1 < b_f4;
+                        float4 w0 = braw[i0], w1 = two ? braw[i1] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        float4 h, l;
+                        h.x = tf32_rna(w0.x); h.y = tf32_rna(w0.y); h.z = tf32_rna(w0.z); h.w = tf32_rna(w0.w);
+                        l.x = w0.x - h.x; l.y = w0.y - h.y; l.z = w0.z - h.z; l.w = w0.w - h.w;
+                        bhi[i0] = h; blo[i0] = l;
+                        if (two) {
+                            h.x = tf32_rna(w1.x); h.y = tf32_rna(w1.y); h.z = tf32_rna(w1.z); h.w = tf32_rna(w1.w);
+                            l.x = w1.x - h.x; l.y = w1.y - h.y; l.z = w1.z - h.z; l.w = w1.w - h.w;
+                            bhi[i1] = h; blo[i1] = l;
+                        }
+                    }
+                    if (sp) g_tc_prof[6] += (unsigned long long)(clock64() - t_work);
+                    { TCP_T0(); fence_async_smem(); TCP_ADD(7, sp); }
+                    __syncwarp();
+                    if (lane == 0) { mb_arrive(&ready_bar[s]); mb_arrive(&bempty[slot]); }
+                    if (++slot == NB) { slot = 0; bph ^= 1u; }
+                }
+                __syncwarp();
+                if (lane == 0) mb_arrive(&pempty[pb]);
+            }
+        }
+        // ================= epilogue =================
+        t_epi = clock64();
+        mb_wait(&accum_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const int py = y0 + m / p.TW, px = x0 + m % p.TW;
+        const bool valid = (py < p.H) && (px < p.W);
+        const size_t pix = ((size_t)img * p.H + py) * p.W + px;
+        float* yrow = p.y + pix * p.ycs;
+        const bool vec = ((p.ycs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+        const int chunks = p.BN / 16, half = (chunks + 1) / 2;
+        const int cbeg = (warp < 6 ? 0 : half) * 16, cend = (warp < 6 ? half : chunks) * 16;
+        for (int c0 = cbeg; c0 < cend; c0 += 16) {
+            float v[16];
+            tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            for (int a = 1; a <= p.n_main; ++a) {
+                float u[16];
+                tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.acc_stride + c0), u);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] += u[j];
+            }
+            if (!valid) continue;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int n = c0 + j;
+                if (n < p.N) {
+                    float t = v[j];
+                    if (p.bias) t += p.bias[n];
+                    t = fmaxf(p.alpha * t, t);
+                    if (p.res) t += p.res[pix * p.res_cs + n];
+                    if (p.accumulate) t += yrow[n];
+                    if (p.mask) t *= (p.mask[pix * p.mask_cs + n] > 0.f) ? 1.f : p.mask_alpha;
+                    v[j] = t;
+                }
+            }
+            if (vec && c0 + 16 <= p.N) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(yrow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (c0 + j < p.N) yrow[c0 + j] = v[j];
+            }
+        }
+    }
+    if (prof && threadIdx.x == 64) { g_tc_prof[8] += (unsigned long long)(clock64() - t_epi); g_tc_prof[9] += (unsigned long long)(t_epi - t_start); g_tc_prof[10] += 1; }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// v3 kernel ("TS"): like the halo kernel, but the A operand lives in TENSOR MEMORY.  Profiling the v1/v2 kernels
+// (per-role clock64 counters) showed the 3xTF32 scheme to be shared-memory-bandwidth bound: per K-block
+// the splitter moved 96 KB and the three SS-mode MMAs re-read 96 KB of operands.  Here each splitter thread owns one
+// accumulator row (= one output pixel): it reads its pixel's 32 channels from the (swizzled) halo patch, computes the
+// tf32 hi/lo halves in registers and writes them straight to TMEM with tcgen05.st; the MMAs take A from TMEM
+// (tcgen05.mma ... [a_tmem]) and only B from shared memory.  smem traffic per K-block: 16 KB (patch reads) + 48 KB
+// (weight split) + 48 KB (B operand reads) instead of 192 KB, and the freed 64 KB deepen the weight ring.
+//   TMEM columns: [0, (n_main+1)*acc_stride) accumulators | then 2 stages x {32 hi, 32 lo} columns of A
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapB,
+                  const ConvTCHaloParams hp) {
+    const ConvTCParams& p = hp.c;
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t pfull[2], pempty[2], bfull[8], bempty[8], ready_bar[2], free_bar[2], accum_bar;
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t base = (s_addr(smem_dyn) + 1023u) & ~1023u;
+    unsigned char* gbase = smem_dyn + (base - s_addr(smem_dyn));
+    const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+    const uint32_t op_bytes = 2u * b_bytes;                       // B_hi, B_lo
+    const uint32_t braw_off = 2u * op_bytes;
+    const uint32_t patch_stride = (hp.patch_bytes + 1023u) & ~1023u;
+    const uint32_t patch_off = braw_off + (uint32_t)hp.nb_slots * b_bytes;
+    const int NB = hp.nb_slots;
+    const uint32_t a_col0 = (uint32_t)((p.n_main + 1) * p.acc_stride);
+
+    int bid = blockIdx.x;
+    const int tx = bid % p.tiles_x; bid /= p.tiles_x;
+    const int ty = bid % p.tiles_y;
+    const int img = bid / p.tiles_y;
+    const int x0 = tx * p.TW, y0 = ty * p.TH;
+    const int taps = p.kh * p.kw;
+    const int total = taps * p.kblocks;
+    const bool prof = (p.dbg & 8) && blockIdx.x == 0;
+    const long long t_start = clock64();
+    long long t_epi = 0;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mb_init(&pfull[i], 1); mb_init(&pempty[i], SPLIT_THREADS / 32);
+            mb_init(&ready_bar[i], SPLIT_THREADS / 32); mb_init(&free_bar[i], 1);
+        }
+        for (int i = 0; i < NB; ++i) { mb_init(&bfull[i], 1); mb_init(&bempty[i], SPLIT_THREADS / 32); }
+        mb_init(&accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_addr(&tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            auto load_patch = [&](int kb) {
+                const int pb = kb & 1;
+                mb_wait(&pempty[pb], (((uint32_t)kb >> 1) & 1u) ^ 1u);
+                mb_expect_tx(&pfull[pb], hp.patch_bytes);
+                tma_load_4d(gbase + patch_off + (size_t)pb * patch_stride, &mapP, &pfull[pb], kb * 32, x0 + hp.minx, y0 + hp.miny, img);
+            };
+            load_patch(0);
+            int slot = 0;
+            uint32_t bph = 0;
+            const int ahead = min(NB, taps) - 1;
+            for (int kb = 0; kb < p.kblocks; ++kb) {
+                for (int tap = 0; tap < taps; ++tap) {
+                    { TCP_T0(); mb_wait(&bempty[slot], bph ^ 1u); TCP_ADD(0, prof); }
+                    mb_expect_tx(&bfull[slot], b_bytes);
+                    tma_load_3d(gbase + braw_off + (size_t)slot * b_bytes, &mapB, &bfull[slot], kb * 32, 0, tap);
+                    if (++slot == NB) { slot = 0; bph ^= 1u; }
+                    if (tap == ahead && kb + 1 < p.kblocks) load_patch(kb + 1);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+            for (int it = 0; it < total; ++it) {
+                const int s = it & 1;
+                { TCP_T0(); mb_wait(&ready_bar[s], ((uint32_t)it >> 1) & 1u); TCP_ADD(1, prof); }
+                const long long t_issue = clock64();
+                tc_fence_after();
+                const uint32_t sb = base + (uint32_t)s * op_bytes;
+                const uint64_t b_hi = umma_desc_sw128(sb), b_lo = umma_desc_sw128(sb + b_bytes);
+                const uint32_t a_hi = tmem + a_col0 + (uint32_t)s * 64u, a_lo = a_hi + 32u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint64_t o = (uint64_t)(j * 2);
+                    const uint32_t ao = (uint32_t)(j * 8);
+                    const int g = it * 4 + j;
+                    tc_mma_tf32_ts(tmem, a_lo + ao, b_hi + o, idesc, g > 0 ? 1u : 0u);
+                    tc_mma_tf32_ts(tmem, a_hi + ao, b_lo + o, idesc, 1u);
+                    const uint32_t dmain = tmem + (uint32_t)((1 + g % p.n_main) * p.acc_stride);
+                    tc_mma_tf32_ts(dmain, a_hi + ao, b_hi + o, idesc, g >= p.n_main ? 1u : 0u);
+                }
+                tc_commit(&free_bar[s]);
+                if (prof) g_tc_prof[2] += (unsigned long long)(clock64() - t_issue);
+            }
+            tc_commit(&accum_bar);
+        }
+    } else {
+        // ================= splitter (warps 2..9): thread <-> accumulator row =================
+        const int st_tid = threadIdx.x - 64;
+        const int b_f4 = p.BN * 8;
+        const int q = warp & 3;                        // TMEM lane quarter of this warp
+        const int hsel = (warp - 2) >> 2;              // which 16-channel half of the 32-channel block
+        const int m = q * 32 + lane;
+        const int my = m / p.TW, mx = m % p.TW;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        {
+            int slot = 0;
+            uint32_t bph = 0;
+            int it = 0;
+            for (int kb = 0; kb < p.kblocks; ++kb) {
+                const int pb = kb & 1;
+                const bool sp = prof && threadIdx.x == 64;
+                { TCP_T0(); mb_wait(&pfull[pb], ((uint32_t)kb >> 1) & 1u); TCP_ADD(3, sp); }
+                const unsigned char* patch = gbase + patch_off + (size_t)pb * patch_stride;
+                for (int tap = 0; tap < taps; ++tap, ++it) {
+                    const int s = it & 1;
+                    { TCP_T0(); mb_wait(&free_bar[s], (((uint32_t)it >> 1) & 1u) ^ 1u); TCP_ADD(4, sp); }
+                    { TCP_T0(); mb_wait(&bfull[slot], bph); TCP_ADD(5, sp); }
+                    const long long t_work = clock64();
+                    // ---- A: this thread's pixel, 16 channels -> tf32 hi / lo -> TMEM
+                    const int tr = tap / p.kw, ts = tap - tr * p.kw;
+                    const int pp = (my + p.off_y + tr * p.step - hp.miny) * hp.PW + (mx + p.off_x + ts * p.step - hp.minx);
+                    const unsigned char* prow = patch + (size_t)pp * 128;
+                    float hi[16], lo[16];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int ch = hsel * 4 + e;
+                        const float4 v = *reinterpret_cast<const float4*>(prow + ((ch ^ (pp & 7)) * 16));
+                        hi[4 * e] = tf32_rna(v.x); hi[4 * e + 1] = tf32_rna(v.y); hi[4 * e + 2] = tf32_rna(v.z); hi[4 * e + 3] = tf32_rna(v.w);
+                        lo[4 * e] = v.x - hi[4 * e]; lo[4 * e + 1] = v.y - hi[4 * e + 1];
+                        lo[4 * e + 2] = v.z - hi[4 * e + 2]; lo[4 * e + 3] = v.w - hi[4 * e + 3];
+                    }
+                    const uint32_t acol = tmem + lane_base + a_col0 + (uint32_t)s * 64u + (uint32_t)hsel * 16u;
+                    tc_st16(acol, hi);
+                    tc_st16(acol + 32u, lo);
+                    // ---- B: elementwise split raw -> hi / lo (layout already swizzled by TMA)
+                    unsigned char* stg = gbase + (size_t)s * op_bytes;
+                    float4* __restrict__ bhi = reinterpret_cast<float4*>(stg);
+                    float4* __restrict__ blo = reinterpret_cast<float4*>(stg + b_bytes);
+                    const float4* __restrict__ braw = reinterpret_cast<const float4*>(gbase + braw_off + (size_t)slot * b_bytes);
+                    for (int i0 = st_tid; i0 < b_f4; i0 += 2 * SPLIT_THREADS) {
+                        const int i1 = i0 + SPLIT_THREADS;
+                        const bool two = i1 < b_f4;
+                        float4 w0 = braw[i0], w1 = two ? braw[i1] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        float4 h, l;
+                        h.x = tf32_rna(w0.x); h.y = tf32_rna(w0.y); h.z = tf32_rna(w0.z); h.w = tf32_rna(w0.w);
+                        l.x = w0.x - h.x; l.y = w0.y - h.y; l.z = w0.z - h.z; l.w = w0.w - h.w;
+                        bhi[i0] = h; blo[i0] = l;
+                        if (two) {
+                            h.x = tf32_rna(w1.x); h.y = tf32_rna(w1.y); h.z = tf32_rna(w1.z); h.w = tf32_rna(w1.w);
+                            l.x = w1.x - h.x; l.y = w1.y - h.y; l.z = w1.z - h.z; l.w = w1.w - h.w;
+                            bhi[i1] = h; blo[i1] = l;
+                        }
+                    }
+                    if (sp) g_tc_prof[6] += (unsigned long long)(clock64() - t_work);
+                    { TCP_T0(); tc_wait_st(); fence_async_smem(); tc_fence_before(); TCP_ADD(7, sp); }
+                    __syncwarp();
+                    if (lane == 0) { mb_arrive(&ready_bar[s]); mb_arrive(&bempty[slot]); }
+                    if (++slot == NB) { slot = 0; bph ^= 1u; }
+                }
+                __syncwarp();
+                if (lane == 0) mb_arrive(&pempty[pb]);
+            }
+        }
+        // ================= epilogue =================
+        t_epi = clock64();
+        mb_wait(&accum_bar, 0);
+        if (prof && threadIdx.x == 64) g_tc_prof[11] += (unsigned long long)(clock64() - t_epi);
+        tc_fence_after();
+        const int py = y0 + my, px = x0 + mx;
+        const bool valid = (py < p.H) && (px < p.W);
+        const size_t pix = ((size_t)img * p.H + py) * p.W + px;
+        float* yrow = p.y + pix * p.ycs;
+        const bool vec = ((p.ycs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+        const int chunks = p.BN / 16, half = (chunks + 1) / 2;
+        const int cbeg = (warp < 6 ? 0 : half) * 16, cend = (warp < 6 ? half : chunks) * 16;
+        for (int c0 = cbeg; c0 < cend; c0 += 16) {
+            uint32_t r0[16], r1[16], r2[16], r3[16];
+            tc_ld16_nowait(tmem + lane_base + (uint32_t)c0, r0);
+            tc_ld16_nowait(tmem + lane_base + (uint32_t)(p.acc_stride + c0), r1);
+            if (p.n_main > 1) tc_ld16_nowait(tmem + lane_base + (uint32_t)(2 * p.acc_stride + c0), r2);
+            if (p.n_main > 2) tc_ld16_nowait(tmem + lane_base + (uint32_t)(3 * p.acc_stride + c0), r3);
+            tc_wait_ld();
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float t = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+                if (p.n_main > 1) t += __uint_as_float(r2[j]);
+                if (p.n_main > 2) t += __uint_as_float(r3[j]);
+                v[j] = t;
+            }
+            if (!valid) continue;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int n = c0 + j;
+                if (n < p.N) {
+                    float t = v[j];
+                    if (p.bias) t += p.bias[n];
+                    t = fmaxf(p.alpha * t, t);
+                    if (p.res) t += p.res[pix * p.res_cs + n];
+                    if (p.accumulate) t += yrow[n];
+                    if (p.mask) t *= (p.mask[pix * p.mask_cs + n] > 0.f) ? 1.f : p.mask_alpha;
+                    v[j] = t;
+                }
+            }
+            if (vec && c0 + 16 <= p.N) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(yrow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (c0 + j < p.N) yrow[c0 + j] = v[j];
+            }
+        }
+    }
+    if (prof && threadIdx.x == 64) { g_tc_prof[8] += (unsigned long long)(clock64() - t_epi); g_tc_prof[9] += (unsigned long long)(t_epi - t_start); g_tc_prof[10] += 1; }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // weight preparation: B[tap][n (BN rows)][k (Kpad)] (zero padded, K contiguous) from canonical HWIO, batched over layers
 //   transposed_src = 1 : src is [tap][K][N]  (forward conv: K = cin, N = cout)
 //   transposed_src = 0 : src is [tap][N][K]  (dgrad: N = cin, K = cout)
@@ -344,17 +853,17 @@ static EncodeTiledFn get_encode() {
 }
 
 struct MapKey {
-    uintptr_t addr; int rank; uint64_t d[4]; uint64_t s[3]; uint32_t b[4];
+    uintptr_t addr; int rank; int swz; uint64_t d[4]; uint64_t s[3]; uint32_t b[4];
     bool operator<(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) < 0; }
 };
 static std::map<MapKey, CUtensorMap>& map_cache() { static std::map<MapKey, CUtensorMap> c; return c; }
 
 // cached cuTensorMapEncodeTiled (fp32, SWIZZLE_128B, zero OOB fill)
 static int get_map(const CUtensorMap** out, void* addr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                   const cuuint32_t* box) {
+                   const cuuint32_t* box, bool swizzle128 = true) {
     MapKey k;
     memset(&k, 0, sizeof k);
-    k.addr = reinterpret_cast<uintptr_t>(addr); k.rank = rank;
+    k.addr = reinterpret_cast<uintptr_t>(addr); k.rank = rank; k.swz = swizzle128 ? 1 : 0;
     for (int i = 0; i < rank; ++i) { k.d[i] = dims[i]; k.b[i] = box[i]; }
     for (int i = 0; i + 1 < rank; ++i) k.s[i] = strides_bytes[i];
     auto& c = map_cache();
@@ -365,7 +874,8 @@ static int get_map(const CUtensorMap** out, void* addr, int rank, const cuuint64
         cuuint32_t es[5] = {1, 1, 1, 1, 1};
         CUtensorMap m;
         CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, addr, dims, strides_bytes, box, es,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r)); return -1; }
         if (c.size() > 4096) c.clear();
@@ -389,6 +899,12 @@ bool conv_tc_profitable(const ConvGemm& g) {
     return conv_tc_supported(g) && (long)g.x.c * g.y.c >= 4096;
 }
 
+int conv_tc_read_prof(unsigned long long* out32, int reset) {
+    MS_CHECK_CUDA(cudaMemcpyFromSymbol(out32, g_tc_prof, sizeof(unsigned long long) * 32));
+    if (reset) { unsigned long long z[32] = {0}; MS_CHECK_CUDA(cudaMemcpyToSymbol(g_tc_prof, z, sizeof z)); }
+    return 0;
+}
+
 void conv_tc_weight_dims(int N, int K, int& BN, int& Kpad) { BN = (N + 15) / 16 * 16; Kpad = (K + 31) / 32 * 32; }
 
 size_t conv_tc_scratch_floats(int taps, int N, int K) {
@@ -400,6 +916,8 @@ int conv_tc_init() {
     static bool done = false;
     if (done) return 0;
     MS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    MS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    MS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
     done = true;
     return 0;
 }
@@ -431,22 +949,84 @@ int conv_tc(const ConvGemm& g, const float* bw, cudaStream_t st) {
     p.y = g.y.p; p.ycs = g.y.cs; p.bias = g.bias; p.alpha = g.alpha;
     p.mask = g.mask; p.mask_cs = g.mask_cs; p.mask_alpha = g.mask_alpha;
     p.res = g.res; p.res_cs = g.res_cs; p.accumulate = g.accumulate;
+    { const char* e = getenv("MS_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
 
     const CUtensorMap *mapA, *mapB;
-    {
-        cuuint64_t dims[4] = {(cuuint64_t)g.x.c, (cuuint64_t)g.x.w, (cuuint64_t)g.x.h, (cuuint64_t)g.x.n};
-        cuuint64_t strides[3] = {(cuuint64_t)g.x.cs * 4, (cuuint64_t)g.x.w * g.x.cs * 4, (cuuint64_t)g.x.h * g.x.w * g.x.cs * 4};
-        cuuint32_t box[4] = {32, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
-        if (get_map(&mapA, g.x.p, 4, dims, strides, box)) return -1;
-    }
     {
         cuuint64_t dims[3] = {(cuuint64_t)Kpad, (cuuint64_t)BN, (cuuint64_t)taps};
         cuuint64_t strides[2] = {(cuuint64_t)Kpad * 4, (cuuint64_t)BN * Kpad * 4};
         cuuint32_t box[3] = {32, (cuuint32_t)BN, 1};
         if (get_map(&mapB, const_cast<float*>(bw), 3, dims, strides, box)) return -1;
     }
-    const size_t smem = (size_t)stages * stage_bytes + 1024;
     const int grid = p.NB * p.tiles_x * p.tiles_y;
+    // ---- v2 (halo patch) when the tap extent is small: undilated 3x3 / 1x1
+    {
+        const int ext_x = (g.kw - 1) * std::abs(g.step), ext_y = (g.kh - 1) * std::abs(g.step);
+        static int halo_enabled = -1;
+        if (halo_enabled < 0) { const char* e = getenv("MS_TC_HALO"); halo_enabled = (e && e[0] == '0') ? 0 : 1; }
+        static int ts_enabled = -1;
+        if (ts_enabled < 0) { const char* e = getenv("MS_TC_TS"); ts_enabled = (e && e[0] == '0') ? 0 : 1; }
+        if (ts_enabled && halo_enabled && ext_x <= 2 && ext_y <= 2) {
+            // ---- v3: A operand in tensor memory
+            ConvTCHaloParams hp{};
+            ConvTCParams pt = p;
+            pt.n_main = std::max(1, std::min(3, (512 - 128) / pt.acc_stride - 1));
+            const int need = (pt.n_main + 1) * pt.acc_stride + 128;
+            if (need <= 512) {
+                pt.tmem_cols = need <= 256 ? 256 : 512;
+                hp.c = pt;
+                hp.PW = p.TW + ext_x; hp.PH = p.TH + ext_y;
+                hp.minx = g.off_x + (g.step < 0 ? (g.kw - 1) * g.step : 0);
+                hp.miny = g.off_y + (g.step < 0 ? (g.kh - 1) * g.step : 0);
+                hp.patch_bytes = (uint32_t)hp.PW * hp.PH * 128u;
+                const size_t b_bytes = (size_t)BN * 128, op_bytes = 2 * b_bytes;
+                const size_t patch_stride = (hp.patch_bytes + 1023) & ~(size_t)1023;
+                const size_t fixed = 2 * op_bytes + 2 * patch_stride + 1024;
+                int nb = fixed + 2 * b_bytes <= 224 * 1024 ? (int)std::min<size_t>(8, (224 * 1024 - fixed) / b_bytes) : 0;
+                if (nb >= 2) {
+                    hp.nb_slots = nb;
+                    const CUtensorMap* mapP;
+                    cuuint64_t dims[4] = {(cuuint64_t)g.x.c, (cuuint64_t)g.x.w, (cuuint64_t)g.x.h, (cuuint64_t)g.x.n};
+                    cuuint64_t strides[3] = {(cuuint64_t)g.x.cs * 4, (cuuint64_t)g.x.w * g.x.cs * 4, (cuuint64_t)g.x.h * g.x.w * g.x.cs * 4};
+                    cuuint32_t box[4] = {32, (cuuint32_t)hp.PW, (cuuint32_t)hp.PH, 1};
+                    if (get_map(&mapP, g.x.p, 4, dims, strides, box, true)) return -1;
+                    const size_t smem2 = fixed + (size_t)nb * b_bytes;
+                    conv_tc_ts_kernel<<<grid, TC_THREADS, smem2, st>>>(*mapP, *mapB, hp);
+                    return check_launch("conv_tc_ts");
+                }
+            }
+        }
+        if (halo_enabled && ext_x <= 2 && ext_y <= 2) {
+            ConvTCHaloParams hp{};
+            hp.c = p;
+            hp.PW = p.TW + ext_x; hp.PH = p.TH + ext_y;
+            hp.minx = g.off_x + (g.step < 0 ? (g.kw - 1) * g.step : 0);
+            hp.miny = g.off_y + (g.step < 0 ? (g.kh - 1) * g.step : 0);
+            hp.patch_bytes = (uint32_t)hp.PW * hp.PH * 128u;
+            const size_t b_bytes = (size_t)BN * 128, op_bytes = 2 * (size_t)A_TILE_BYTES + 2 * b_bytes;
+            const size_t patch_stride = (hp.patch_bytes + 1023) & ~(size_t)1023;
+            const size_t fixed = 2 * op_bytes + 2 * patch_stride + 1024;
+            int nb = fixed + 2 * b_bytes <= 224 * 1024 ? (int)std::min<size_t>(8, (224 * 1024 - fixed) / b_bytes) : 0;
+            if (nb >= 2) {
+                hp.nb_slots = nb;
+                const CUtensorMap* mapP;
+                cuuint64_t dims[4] = {(cuuint64_t)g.x.c, (cuuint64_t)g.x.w, (cuuint64_t)g.x.h, (cuuint64_t)g.x.n};
+                cuuint64_t strides[3] = {(cuuint64_t)g.x.cs * 4, (cuuint64_t)g.x.w * g.x.cs * 4, (cuuint64_t)g.x.h * g.x.w * g.x.cs * 4};
+                cuuint32_t box[4] = {32, (cuuint32_t)hp.PW, (cuuint32_t)hp.PH, 1};
+                if (get_map(&mapP, g.x.p, 4, dims, strides, box, false)) return -1;
+                const size_t smem2 = fixed + (size_t)nb * b_bytes;
+                conv_tc_halo_kernel<<<grid, TC_THREADS, smem2, st>>>(*mapP, *mapB, hp);
+                return check_launch("conv_tc_halo");
+            }
+        }
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)g.x.c, (cuuint64_t)g.x.w, (cuuint64_t)g.x.h, (cuuint64_t)g.x.n};
+        cuuint64_t strides[3] = {(cuuint64_t)g.x.cs * 4, (cuuint64_t)g.x.w * g.x.cs * 4, (cuuint64_t)g.x.h * g.x.w * g.x.cs * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+        if (get_map(&mapA, g.x.p, 4, dims, strides, box)) return -1;
+    }
+    const size_t smem = (size_t)stages * stage_bytes + 1024;
     conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(*mapA, *mapB, p);
     return check_launch("conv_tc");
 }
