@@ -154,7 +154,8 @@ void conv_tc_weight_dims(int N, int K, int& BN, int& Kpad);
 size_t conv_tc_scratch_floats(int taps, int N, int K);
 int conv_tc_init();
 int tc_prep_weights(const TcPrepJob* jobs_dev, int njobs, size_t max_total, cudaStream_t st);
-int conv_tc(const ConvGemm& g, const float* bw, cudaStream_t st);
+int conv_tc(const ConvGemm& g, const float* bw, cudaStream_t st, float* part);
+size_t conv_tc_part_floats();
 bool conv_tc_profitable(const ConvGemm& g);
 int conv_tc_oneshot(const ConvGemm& g, int wmat_is_nk, float* scratch, size_t scratch_floats, cudaStream_t st);
 int corr_init();

@@ -140,6 +140,8 @@ struct ConvTCParams {
     const float* mask; int mask_cs; float mask_alpha;
     const float* res; int res_cs;
     int accumulate;
+    int ksplit;                       // split-K over channel blocks (small maps): partial sums -> `part`, then tc_splitk_reduce
+    float* part;                      // [ksplit][pixels][BN]
     int dbg;                          // timing experiments only (MS_TC_DEBUG): 1 no split, 2 no proxy fence, 4 no MMA
 };
 
@@ -609,7 +611,9 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
     const int img = bid / p.tiles_y;
     const int x0 = tx * p.TW, y0 = ty * p.TH;
     const int taps = p.kh * p.kw;
-    const int total = taps * p.kblocks;
+    const int kb0 = (int)(((long)blockIdx.y * p.kblocks) / p.ksplit), kb1 = (int)(((long)(blockIdx.y + 1) * p.kblocks) / p.ksplit);
+    const int nkb = kb1 - kb0;
+    const int total = taps * nkb;
     const bool prof = (p.dbg & 8) && blockIdx.x == 0;
     const long long t_start = clock64();
     long long t_epi = 0;
@@ -634,23 +638,23 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
 
     if (warp == 0) {
         if (lane == 0) {
-            auto load_patch = [&](int kb) {
-                const int pb = kb & 1;
-                mb_wait(&pempty[pb], (((uint32_t)kb >> 1) & 1u) ^ 1u);
+            auto load_patch = [&](int kl) {           // kl = local channel-block index
+                const int pb = kl & 1;
+                mb_wait(&pempty[pb], (((uint32_t)kl >> 1) & 1u) ^ 1u);
                 mb_expect_tx(&pfull[pb], hp.patch_bytes);
-                tma_load_4d(gbase + patch_off + (size_t)pb * patch_stride, &mapP, &pfull[pb], kb * 32, x0 + hp.minx, y0 + hp.miny, img);
+                tma_load_4d(gbase + patch_off + (size_t)pb * patch_stride, &mapP, &pfull[pb], (kb0 + kl) * 32, x0 + hp.minx, y0 + hp.miny, img);
             };
             load_patch(0);
             int slot = 0;
             uint32_t bph = 0;
             const int ahead = min(NB, taps) - 1;
-            for (int kb = 0; kb < p.kblocks; ++kb) {
+            for (int kb = 0; kb < nkb; ++kb) {
                 for (int tap = 0; tap < taps; ++tap) {
                     { TCP_T0(); mb_wait(&bempty[slot], bph ^ 1u); TCP_ADD(0, prof); }
                     mb_expect_tx(&bfull[slot], b_bytes);
-                    tma_load_3d(gbase + braw_off + (size_t)slot * b_bytes, &mapB, &bfull[slot], kb * 32, 0, tap);
+                    tma_load_3d(gbase + braw_off + (size_t)slot * b_bytes, &mapB, &bfull[slot], (kb0 + kb) * 32, 0, tap);
                     if (++slot == NB) { slot = 0; bph ^= 1u; }
-                    if (tap == ahead && kb + 1 < p.kblocks) load_patch(kb + 1);
+                    if (tap == ahead && kb + 1 < nkb) load_patch(kb + 1);
                 }
             }
         }
@@ -693,7 +697,7 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
             int slot = 0;
             uint32_t bph = 0;
             int it = 0;
-            for (int kb = 0; kb < p.kblocks; ++kb) {
+            for (int kb = 0; kb < nkb; ++kb) {
                 const int pb = kb & 1;
                 const bool sp = prof && threadIdx.x == 64;
                 { TCP_T0(); mb_wait(&pfull[pb], ((uint32_t)kb >> 1) & 1u); TCP_ADD(3, sp); }
@@ -776,6 +780,13 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
                 v[j] = t;
             }
             if (!valid) continue;
+            if (p.ksplit > 1) {                     // raw partial sums; bias / activation happen in tc_splitk_reduce
+                float* prow = p.part + ((size_t)blockIdx.y * ((size_t)p.NB * p.H * p.W) + pix) * p.BN + c0;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(prow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                continue;
+            }
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int n = c0 + j;
@@ -807,6 +818,22 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmem_cols) : "memory");
     }
+}
+
+__global__ void tc_splitk_reduce_kernel(ConvTCParams p, size_t npix) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix * p.N) return;
+    const size_t pix = i / p.N;
+    const int n = (int)(i - pix * p.N);
+    float t = 0.f;
+    for (int ks = 0; ks < p.ksplit; ++ks) t += p.part[((size_t)ks * npix + pix) * p.BN + n];
+    if (p.bias) t += p.bias[n];
+    t = fmaxf(p.alpha * t, t);
+    if (p.res) t += p.res[pix * p.res_cs + n];
+    float* yrow = p.y + pix * p.ycs;
+    if (p.accumulate) t += yrow[n];
+    if (p.mask) t *= (p.mask[pix * p.mask_cs + n] > 0.f) ? 1.f : p.mask_alpha;
+    yrow[n] = t;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -896,7 +923,7 @@ bool conv_tc_supported(const ConvGemm& g) {
 
 // measured on B200 (scripts/tc_bench.py): below ~64x64 channels the fp32 CUDA-core kernel is as fast or faster
 bool conv_tc_profitable(const ConvGemm& g) {
-    return conv_tc_supported(g) && (long)g.x.c * g.y.c >= 4096;
+    return conv_tc_supported(g) && (long)g.x.c * g.y.c >= 1024;
 }
 
 int conv_tc_read_prof(unsigned long long* out32, int reset) {
@@ -923,7 +950,9 @@ int conv_tc_init() {
 }
 
 // bw: prepared weights [taps][BN][Kpad] (see tc_prep_weights) for this GEMM orientation.
-int conv_tc(const ConvGemm& g, const float* bw, cudaStream_t st) {
+size_t conv_tc_part_floats() { return (size_t)8 << 20; }      // 32 MB split-K partial-sum scratch
+
+int conv_tc(const ConvGemm& g, const float* bw, cudaStream_t st, float* part) {
     MS_REQUIRE(conv_tc_supported(g), "conv_tc: unsupported geometry");
     if (conv_tc_init()) return -1;
     const int taps = g.kh * g.kw, K = g.x.c, N = g.y.c;
@@ -950,6 +979,7 @@ int conv_tc(const ConvGemm& g, const float* bw, cudaStream_t st) {
     p.mask = g.mask; p.mask_cs = g.mask_cs; p.mask_alpha = g.mask_alpha;
     p.res = g.res; p.res_cs = g.res_cs; p.accumulate = g.accumulate;
     { const char* e = getenv("MS_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
+    p.ksplit = 1; p.part = nullptr;
 
     const CUtensorMap *mapA, *mapB;
     {
@@ -991,7 +1021,19 @@ int conv_tc(const ConvGemm& g, const float* bw, cudaStream_t st) {
                     cuuint32_t box[4] = {32, (cuuint32_t)hp.PW, (cuuint32_t)hp.PH, 1};
                     if (get_map(&mapP, g.x.p, 4, dims, strides, box, true)) return -1;
                     const size_t smem2 = fixed + (size_t)nb * b_bytes;
-                    conv_tc_ts_kernel<<<grid, TC_THREADS, smem2, st>>>(*mapP, *mapB, hp);
+                    // small maps leave most SMs idle while each CTA walks the whole K loop: split K over channel blocks
+                    const size_t npix = (size_t)p.NB * p.H * p.W;
+                    int ksplit = 1;
+                    if (part && grid <= 74 && kblocks > 1) {
+                        ksplit = std::min(kblocks, std::max(1, 148 / grid));
+                        if ((size_t)ksplit * npix * BN > conv_tc_part_floats()) ksplit = 1;
+                    }
+                    hp.c.ksplit = ksplit; hp.c.part = part;
+                    conv_tc_ts_kernel<<<dim3(grid, ksplit), TC_THREADS, smem2, st>>>(*mapP, *mapB, hp);
+                    if (ksplit > 1) {
+                        tc_splitk_reduce_kernel<<<(unsigned)cdivz(npix * p.N, 256), 256, 0, st>>>(hp.c, npix);
+                        return check_launch("conv_tc_ts+reduce", 2);
+                    }
                     return check_launch("conv_tc_ts");
                 }
             }
@@ -1044,7 +1086,7 @@ int conv_tc_oneshot(const ConvGemm& g, int wmat_is_nk, float* scratch, size_t sc
     TcPrepJob* jd = reinterpret_cast<TcPrepJob*>(scratch + 2 * per);   // 64 spare floats hold the job descriptor
     MS_CHECK_CUDA(cudaMemcpyAsync(jd, &job, sizeof job, cudaMemcpyHostToDevice, st));
     if (tc_prep_weights(jd, 1, per, st)) return -1;
-    return conv_tc(g, scratch, st);
+    return conv_tc(g, scratch, st, nullptr);
 }
 
 }  // namespace ms

@@ -229,7 +229,7 @@ size_t Engine::layout(float* base) {
             if (lg != gidx || L.transposed || L.stride != 1 || L.cin < 8 || L.cout < 8) continue;
             for (int dir = 0; dir < 2; ++dir) {
                 const int N = dir == 0 ? L.cout : L.cin, K = dir == 0 ? L.cin : L.cout;
-                if (N > 256 || (long)N * K < 4096) continue;
+                if (N > 256 || (long)N * K < 1024) continue;
                 int BN, Kpad; conv_tc_weight_dims(N, K, BN, Kpad);
                 const size_t per = (size_t)L.kh * L.kw * BN * Kpad;
                 TcW t; t.per = per; t.ok = true;
@@ -242,6 +242,7 @@ size_t Engine::layout(float* base) {
         }
         job_end[gidx] = (int)prep_jobs.size();
     }
+    tc_part = alloc(conv_tc_part_floats());
     prep_jobs_dev = reinterpret_cast<TcPrepJob*>(alloc((prep_jobs.size() + 1) * sizeof(TcPrepJob) / sizeof(float) + 16));
     rs_tmp_floats = (size_t)B * H * Wp; rs_tmp = alloc(rs_tmp_floats);
     loss_ws_floats = loss_workspace_floats(B, H, W); loss_ws = alloc(loss_ws_floats);
@@ -280,7 +281,7 @@ int Engine::conv_fwd(const ConvLayer& L, const TView& x, const TView& y, const f
     prof_begin(CAT_CONV_FWD, st);
     int rc;
     const int li = (int)(&L - &layers[0]);
-    if (use_tc && tcw[0][li].ok && conv_tc_profitable(p)) rc = conv_tc(p, tcw[0][li].bh, st);
+    if (use_tc && tcw[0][li].ok && conv_tc_profitable(p)) rc = conv_tc(p, tcw[0][li].bh, st, tc_part);
     else rc = conv_gemm(p, st);
     prof_end(st);
     if (profiling) cat_macs[CAT_CONV_FWD] += (double)y.pixels() * L.kh * L.kw * L.cin * L.cout / (L.transposed ? L.stride * L.stride : 1);
@@ -317,7 +318,7 @@ int Engine::conv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, cons
         int rc;
         const int li = (int)(&L - &layers[0]);
         if (use_tc && tcw[1][li].ok && conv_tc_profitable(p)) {
-            rc = conv_tc(p, tcw[1][li].bh, st);
+            rc = conv_tc(p, tcw[1][li].bh, st, tc_part);
         } else {
             rc = transpose_taps(Wt + L.w_off, wT, L.kh * L.kw, L.cin, L.cout, st);   // -> [tap][cout][cin]
             if (!rc) rc = conv_gemm(p, st);

@@ -66,6 +66,7 @@ struct Engine {
     std::vector<TcPrepJob> prep_jobs;            // ordered by group (then ungrouped)
     std::vector<int> job_begin, job_end;         // per group ranges into prep_jobs; index n_groups = ungrouped
     TcPrepJob* prep_jobs_dev; size_t prep_max_total;
+    float* tc_part;                              // split-K partial sums of the tcgen05 conv on small maps
     bool weights_dirty;
     int prep_layers(int group, cudaStream_t st); // -1 = all
     // whole-step CUDA graphs keyed by (mode, group, disp_mask, with_update, lr, mu, gscale)
