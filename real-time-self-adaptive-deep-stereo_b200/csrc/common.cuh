@@ -62,6 +62,8 @@ struct ConvGemm {
     const float* mask; int mask_cs; float mask_alpha;   // optional: y *= (mask>0 ? 1 : mask_alpha)
     const float* res;  int res_cs;                      // optional: y += res (same channel index)
     int accumulate;       // y += existing y (applied before mask)
+    float* part; size_t part_floats;   // optional split-K scratch (small grids): partial sums, then a reduce+epilogue pass
+    int ksplit;           // set by conv_gemm()
 };
 int conv_gemm(const ConvGemm& p, cudaStream_t st);
 

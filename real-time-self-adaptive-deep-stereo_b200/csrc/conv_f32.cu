@@ -68,7 +68,9 @@ __global__ void __launch_bounds__(NT) conv_gemm_kernel(ConvGemm p, int M) {
     const int xc = p.x.c, yc = p.y.c;
     const int kc_tiles = (xc + BK - 1) / BK;
     const int taps = p.kh * p.kw;
-    const int total = taps * kc_tiles;
+    const int total_all = taps * kc_tiles;
+    const int it0 = (int)(((long)blockIdx.z * total_all) / p.ksplit), it1 = (int)(((long)(blockIdx.z + 1) * total_all) / p.ksplit);
+    const int total = it1 - it0;
 
     // --- per-thread A row metadata
     int row_iy0[AR], row_ix0[AR], row_img[AR];
@@ -180,9 +182,11 @@ __global__ void __launch_bounds__(NT) conv_gemm_kernel(ConvGemm p, int M) {
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
     const int tm = t >> 4, tn = t & 15;
-    int tap = 0, kc = 0;
-    load_tiles(0, 0);
+    int tap = it0 / kc_tiles, kc = it0 - tap * kc_tiles;
+    if (total > 0) {
+    load_tiles(tap, kc * BK);
     store_tiles(0);
+    }
     __syncthreads();
     for (int it = 0; it < total; ++it) {
         const int buf = it & 1;
@@ -207,6 +211,7 @@ __global__ void __launch_bounds__(NT) conv_gemm_kernel(ConvGemm p, int M) {
             const int n = n0 + tn * TN + j;
             if (n >= yc) continue;
             float v = acc[i][j];
+            if (p.ksplit > 1) { p.part[((size_t)blockIdx.z * M + m) * yc + n] = v; continue; }
             if (p.bias) v += p.bias[n];
             v = leaky_f(v, p.alpha);
             if (p.res) v += p.res[(size_t)m * p.res_cs + n];
@@ -217,9 +222,27 @@ __global__ void __launch_bounds__(NT) conv_gemm_kernel(ConvGemm p, int M) {
     }
 }
 
+__global__ void gemm_splitk_reduce_kernel(ConvGemm p, int M) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int yc = p.y.c;
+    if (i >= (size_t)M * yc) return;
+    const size_t m = i / yc;
+    const int n = (int)(i - m * yc);
+    float v = 0.f;
+    for (int z = 0; z < p.ksplit; ++z) v += p.part[((size_t)z * M + m) * yc + n];
+    if (p.bias) v += p.bias[n];
+    v = leaky_f(v, p.alpha);
+    if (p.res) v += p.res[m * p.res_cs + n];
+    float* yrow = p.y.p + m * p.y.cs;
+    if (p.accumulate) v += yrow[n];
+    if (p.mask) v *= (p.mask[m * p.mask_cs + n] > 0.f) ? 1.f : p.mask_alpha;
+    yrow[n] = v;
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-int conv_gemm(const ConvGemm& p, cudaStream_t st) {
+int conv_gemm(const ConvGemm& p_in, cudaStream_t st) {
+    ConvGemm p = p_in;
     MS_REQUIRE(p.x.n == p.y.n, "conv_gemm: batch mismatch");
     const size_t Mz = (size_t)p.y.n * p.y.h * p.y.w;
     MS_REQUIRE(Mz < (1u << 30), "conv_gemm: too many output pixels");
@@ -228,6 +251,16 @@ int conv_gemm(const ConvGemm& p, cudaStream_t st) {
     const bool bvec = (p.y.c % 4 == 0) && aligned16(p.wmat);
     const int tn = p.y.c > 32 ? 4 : (p.y.c > 16 ? 2 : 1);
     dim3 grid(cdiv(M, 128), cdiv(p.y.c, 16 * tn));
+    // few CTAs walking a long K loop (coarse pyramid levels, heads): split K across CTAs, reduce afterwards
+    p.ksplit = 1;
+    {
+        const int ctas = grid.x * grid.y, total_k = p.kh * p.kw * cdiv(p.x.c, BK);
+        if (p.part && ctas <= 74 && total_k >= 8) {
+            int ks = std::min(total_k / 4, std::max(1, 296 / ctas));
+            if (ks > 32) ks = 32;
+            if (ks > 1 && (size_t)ks * M * p.y.c <= p.part_floats) { p.ksplit = ks; grid.z = ks; }
+        }
+    }
 #define LAUNCH(TN_, AV_, BV_) conv_gemm_kernel<TN_, AV_, BV_><<<grid, NT, 0, st>>>(p, M)
 #define DISPATCH_B(TN_, AV_) do { if (bvec) LAUNCH(TN_, AV_, true); else LAUNCH(TN_, AV_, false); } while (0)
 #define DISPATCH_A(TN_) do { if (avec) DISPATCH_B(TN_, true); else DISPATCH_B(TN_, false); } while (0)
@@ -235,6 +268,10 @@ int conv_gemm(const ConvGemm& p, cudaStream_t st) {
 #undef LAUNCH
 #undef DISPATCH_A
 #undef DISPATCH_B
+    if (p.ksplit > 1) {
+        gemm_splitk_reduce_kernel<<<(unsigned)cdivz((size_t)M * p.y.c, 256), 256, 0, st>>>(p, M);
+        return check_launch("conv_gemm+reduce", 2);
+    }
     return check_launch("conv_gemm");
 }
 

@@ -262,6 +262,7 @@ int Engine::conv_fwd(const ConvLayer& L, const TView& x, const TView& y, const f
     p.alpha = L.alpha;
     p.res = res; p.res_cs = res_cs;
     p.mask = nullptr; p.mask_cs = 0; p.mask_alpha = 1.f; p.accumulate = 0;
+    p.part = tc_part; p.part_floats = conv_tc_part_floats();
     int oh, ow, pt, pl;
     if (!L.transposed) {
         same_pad(x.h, L.kh, L.stride, L.dil, oh, pt);
@@ -314,6 +315,7 @@ int Engine::conv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, cons
         p.alpha = 1.f;
         p.mask = dx_mask ? dx_mask->p : nullptr; p.mask_cs = dx_mask ? dx_mask->cs : 0; p.mask_alpha = mask_alpha;
         p.res = nullptr; p.res_cs = 0; p.accumulate = dx_acc;
+        p.part = tc_part; p.part_floats = conv_tc_part_floats();
         prof_begin(CAT_CONV_DGRAD, st);
         int rc;
         const int li = (int)(&L - &layers[0]);

@@ -169,6 +169,7 @@ int Engine::deconv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, co
         p.x = dpre; p.wmat = Wt + L.w_off; p.bias = nullptr; p.y = *dx; p.kh = L.kh; p.kw = L.kw;
         p.mul = L.stride; p.off_y = -pt; p.off_x = -pl; p.step = 1; p.div = 1;
         p.alpha = 1.f; p.mask = nullptr; p.mask_alpha = 1.f; p.res = nullptr; p.accumulate = dx_acc;
+        p.part = tc_part; p.part_floats = conv_tc_part_floats();
         prof_begin(CAT_CONV_DGRAD, st);
         int rc = conv_gemm(p, st);
         prof_end(st);
