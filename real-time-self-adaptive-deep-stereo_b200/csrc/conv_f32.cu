@@ -37,7 +37,11 @@ __device__ __forceinline__ void mma_tile(const float* __restrict__ As, const flo
         } else {
             a[0] = As[k * LDA + tm];
         }
-        if constexpr (TN == 4) {
+        if constexpr (TN == 8) {
+            float4 v = *reinterpret_cast<const float4*>(&Bs[k * LDB + tn * 8]);
+            float4 u = *reinterpret_cast<const float4*>(&Bs[k * LDB + tn * 8 + 4]);
+            b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w; b[4] = u.x; b[5] = u.y; b[6] = u.z; b[7] = u.w;
+        } else if constexpr (TN == 4) {
             float4 v = *reinterpret_cast<const float4*>(&Bs[k * LDB + tn * 4]);
             b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
         } else if constexpr (TN == 2) {
@@ -297,10 +301,12 @@ __global__ void __launch_bounds__(NT) conv_wgrad_kernel(ConvWgrad p, int P, int 
     const int p_end = min(P, p_begin + chunk);
     const int iters = (p_end > p_begin) ? (p_end - p_begin + BK - 1) / BK : 0;
 
-    constexpr int ANV = AVEC ? 1 : TM;   // loads per thread
-    constexpr int BNV = BVEC ? 1 : TN;
-    float areg[AVEC ? 4 : TM];
-    float breg[BVEC ? 4 : TN];
+    constexpr int AF4 = (BK * BM / 4 + NT - 1) / NT;   // float4 loads per thread (vector path)
+    constexpr int BF4 = (BK * BN / 4 + NT - 1) / NT;
+    constexpr int ANV = AVEC ? AF4 : TM;   // loads per thread
+    constexpr int BNV = BVEC ? BF4 : TN;
+    float areg[AVEC ? 4 * AF4 : TM];
+    float breg[BVEC ? 4 * BF4 : TN];
 
     auto load_tiles = [&](int pbase) {
         // ---- A: rows = pixels, cols = ci
@@ -308,7 +314,7 @@ __global__ void __launch_bounds__(NT) conv_wgrad_kernel(ConvWgrad p, int P, int 
         for (int j = 0; j < ANV; ++j) {
             int k, m;
             bool act;
-            if (AVEC) { constexpr int F4 = BM / 4; act = t < BK * F4; k = t / F4; m = (t % F4) * 4; }
+            if (AVEC) { constexpr int F4 = BM / 4; int e = t + NT * j; act = e < BK * F4; k = e / F4; m = (e % F4) * 4; }
             else { int e = t + NT * j; act = true; k = e / BM; m = e % BM; }
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             int pp = pbase + k;
@@ -331,7 +337,7 @@ __global__ void __launch_bounds__(NT) conv_wgrad_kernel(ConvWgrad p, int P, int 
                     }
                 }
             }
-            if (AVEC) { areg[0] = v.x; areg[1] = v.y; areg[2] = v.z; areg[3] = v.w; }
+            if (AVEC) { areg[4 * j] = v.x; areg[4 * j + 1] = v.y; areg[4 * j + 2] = v.z; areg[4 * j + 3] = v.w; }
             else areg[j] = v.x;
         }
         // ---- B: rows = pixels, cols = co
@@ -339,7 +345,7 @@ __global__ void __launch_bounds__(NT) conv_wgrad_kernel(ConvWgrad p, int P, int 
         for (int j = 0; j < BNV; ++j) {
             int k, n;
             bool act;
-            if (BVEC) { constexpr int F4 = BN / 4; act = t < BK * F4; k = t / F4; n = (t % F4) * 4; }
+            if (BVEC) { constexpr int F4 = BN / 4; int e = t + NT * j; act = e < BK * F4; k = e / F4; n = (e % F4) * 4; }
             else { int e = t + NT * j; act = true; k = e / BN; n = e % BN; }
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             int pp = pbase + k;
@@ -354,7 +360,7 @@ __global__ void __launch_bounds__(NT) conv_wgrad_kernel(ConvWgrad p, int P, int 
                     v.x = *src;
                 }
             }
-            if (BVEC) { breg[0] = v.x; breg[1] = v.y; breg[2] = v.z; breg[3] = v.w; }
+            if (BVEC) { breg[4 * j] = v.x; breg[4 * j + 1] = v.y; breg[4 * j + 2] = v.z; breg[4 * j + 3] = v.w; }
             else breg[j] = v.x;
         }
     };
@@ -363,18 +369,26 @@ __global__ void __launch_bounds__(NT) conv_wgrad_kernel(ConvWgrad p, int P, int 
         float* bs = Bs[buf];
         if (AVEC) {
             constexpr int F4 = BM / 4;
-            if (t < BK * F4)
-                *reinterpret_cast<float4*>(&as[(t / F4) * LDA + (t % F4) * 4]) =
-                    make_float4(areg[0], areg[1], areg[2], areg[3]);
+#pragma unroll
+            for (int j = 0; j < AF4; ++j) {
+                int e = t + NT * j;
+                if (e < BK * F4)
+                    *reinterpret_cast<float4*>(&as[(e / F4) * LDA + (e % F4) * 4]) =
+                        make_float4(areg[4 * j], areg[4 * j + 1], areg[4 * j + 2], areg[4 * j + 3]);
+            }
         } else {
 #pragma unroll
             for (int j = 0; j < TM; ++j) { int e = t + NT * j; as[(e / BM) * LDA + e % BM] = areg[j]; }
         }
         if (BVEC) {
             constexpr int F4 = BN / 4;
-            if (t < BK * F4)
-                *reinterpret_cast<float4*>(&bs[(t / F4) * LDB + (t % F4) * 4]) =
-                    make_float4(breg[0], breg[1], breg[2], breg[3]);
+#pragma unroll
+            for (int j = 0; j < BF4; ++j) {
+                int e = t + NT * j;
+                if (e < BK * F4)
+                    *reinterpret_cast<float4*>(&bs[(e / F4) * LDB + (e % F4) * 4]) =
+                        make_float4(breg[4 * j], breg[4 * j + 1], breg[4 * j + 2], breg[4 * j + 3]);
+            }
         } else {
 #pragma unroll
             for (int j = 0; j < TN; ++j) { int e = t + NT * j; bs[(e / BN) * LDB + e % BN] = breg[j]; }
@@ -452,6 +466,7 @@ static int wgrad_split(int tiles, size_t P) {
     return split;
 }
 static void wgrad_tiles(int ci, int co, int& tm, int& tn) {
+    // 8x8 thread tiles (128x128 CTA tiles) were measured slower than 4x4 here (fewer resident CTAs per SM)
     tm = ci > 32 ? 4 : (ci > 16 ? 2 : 1);
     tn = co > 32 ? 4 : (co > 16 ? 2 : 1);
 }
@@ -483,8 +498,8 @@ int conv_wgrad(const ConvWgrad& p, cudaStream_t st) {
 #define L(TM_, TN_, AV_, BV_) conv_wgrad_kernel<TM_, TN_, AV_, BV_><<<grid, NT, 0, st>>>(p, P, chunk, mtiles, ntiles, p.workspace)
 #define DB(TM_, TN_, AV_) do { if (bvec) L(TM_, TN_, AV_, true); else L(TM_, TN_, AV_, false); } while (0)
 #define DA(TM_, TN_) do { if (avec) DB(TM_, TN_, true); else DB(TM_, TN_, false); } while (0)
-#define DN(TM_) do { if (tn == 4) DA(TM_, 4); else if (tn == 2) DA(TM_, 2); else DA(TM_, 1); } while (0)
-    if (tm == 4) DN(4); else if (tm == 2) DN(2); else DN(1);
+#define DN(TM_) do { if (tn == 8) DA(TM_, 8); else if (tn == 4) DA(TM_, 4); else if (tn == 2) DA(TM_, 2); else DA(TM_, 1); } while (0)
+    if (tm == 8) DN(8); else if (tm == 4) DN(4); else if (tm == 2) DN(2); else DN(1);
 #undef L
 #undef DB
 #undef DA
