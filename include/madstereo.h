@@ -63,6 +63,11 @@ int ms_conv2d_dgrad_tc(const float* dy, int n, int h, int w, int cout, int dy_cs
                        float* dx, int cin, int dx_cs, int kh, int kw, int dilation, float* scratch,
                        size_t scratch_floats, void* stream);
 size_t ms_conv2d_tc_scratch(int kh, int kw, int cin, int cout);
+/* tcgen05 weight gradient of a stride-1 conv (same outputs as ms_conv2d_wgrad); workspace from ..._workspace(). */
+int ms_conv2d_wgrad_tc(const float* x, int n, int h, int w, int cin, int x_cs, const float* dy, int cout, int dy_cs,
+                       float* dw /*HWIO*/, float* db, int kh, int kw, int dilation, float* workspace,
+                       size_t workspace_floats, void* stream);
+size_t ms_conv2d_wgrad_tc_workspace(int kh, int kw, int cin, int cout, int n, int h, int w);
 size_t ms_conv2d_wgrad_workspace(int kh, int kw, int cin, int cout, size_t out_pixels);
 int ms_conv2d_wgrad(const float* x, int n, int h, int w, int cin, int x_cs, const float* dy, int oh, int ow,
                     int cout, int dy_cs, float* dw /*HWIO*/, float* db, int kh, int kw, int stride,

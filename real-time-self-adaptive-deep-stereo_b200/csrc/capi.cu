@@ -138,6 +138,24 @@ int ms_conv2d_wgrad(const float* x, int n, int h, int w, int cin, int x_cs, cons
     return conv_wgrad(q, S(stream));
 }
 
+int ms_conv2d_wgrad_tc(const float* x, int n, int h, int w, int cin, int x_cs, const float* dy, int cout, int dy_cs,
+                       float* dw, float* db, int kh, int kw, int dilation, float* workspace, size_t workspace_floats,
+                       void* stream) {
+    int oh, ow, pt, pl;
+    same_pad_c(h, kh, 1, dilation, oh, pt);
+    same_pad_c(w, kw, 1, dilation, ow, pl);
+    ConvWgrad q{};
+    q.x = view(const_cast<float*>(x), n, h, w, cin, x_cs);
+    q.dy = view(const_cast<float*>(dy), n, h, w, cout, dy_cs);
+    q.dw = dw; q.db = db; q.kh = kh; q.kw = kw; q.stride = 1; q.dil = dilation; q.pad_t = pt; q.pad_l = pl;
+    q.workspace = workspace; q.workspace_floats = workspace_floats; q.accumulate = 0;
+    if (!wgrad_tc_supported(q)) { set_error("ms_conv2d_wgrad_tc: shape not supported by the tcgen05 path"); return -3; }
+    return wgrad_tc(q, S(stream));
+}
+size_t ms_conv2d_wgrad_tc_workspace(int kh, int kw, int cin, int cout, int n, int h, int w) {
+    return wgrad_tc_workspace_floats(kh * kw, cin, cout, n, h, w);
+}
+
 int ms_conv2d_transpose_fwd(const float* x, int n, int h, int w, int cin, int x_cs, const float* weights,
                             const float* bias, float* y, int cout, int y_cs, int kh, int kw, int stride, float alpha,
                             float* scratch, void* stream) {

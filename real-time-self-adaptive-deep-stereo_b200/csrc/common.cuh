@@ -161,5 +161,9 @@ size_t conv_tc_part_floats();
 bool conv_tc_profitable(const ConvGemm& g);
 int conv_tc_oneshot(const ConvGemm& g, int wmat_is_nk, float* scratch, size_t scratch_floats, cudaStream_t st);
 int corr_init();
+bool wgrad_tc_supported(const ConvWgrad& q);
+size_t wgrad_tc_workspace_floats(int taps, int ci, int co, int n, int h, int w);
+int wgrad_tc_init();
+int wgrad_tc(const ConvWgrad& q, cudaStream_t st);
 int conv_tc_read_prof(unsigned long long* out32, int reset);
 }  // namespace ms

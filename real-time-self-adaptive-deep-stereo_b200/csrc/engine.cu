@@ -39,6 +39,7 @@ Engine::Engine()
     prep_jobs_dev = nullptr; prep_max_total = 0; weights_dirty = true;
     gstream = nullptr; ev_in = nullptr; ev_out = nullptr;
     { const char* e2 = getenv("MS_GRAPHS"); use_graphs = (e2 && e2[0] == '0') ? 0 : 1; }
+    { const char* e3 = getenv("MS_TC_WGRAD"); use_tc_wgrad = (e3 && e3[0] == '0') ? 0 : 1; }
     const char* e = getenv("MS_CONV_TC");
     use_tc = (e && e[0] == '0') ? 0 : 1;
 }
@@ -153,6 +154,8 @@ size_t Engine::layout(float* base) {
     size_t max_wg = 0, max_wt = 0;
     auto track = [&](const ConvLayer& L, size_t pixels) {
         max_wg = std::max(max_wg, conv_wgrad_workspace_floats(L.kh * L.kw, L.cin, L.cout, pixels));
+        if (L.stride == 1 && L.cout <= 192)   // tcgen05 wgrad: NCHW copy of dY + <=64 split partials + bias partials
+            max_wg = std::max(max_wg, pixels * L.cout + 64 * (size_t)L.kh * L.kw * L.cin * L.cout + 128 * (size_t)L.cout + 8192);
         max_wt = std::max(max_wt, (size_t)L.kh * L.kw * L.cin * L.cout);
     };
     if (net == 1) {
@@ -303,7 +306,7 @@ int Engine::conv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, cons
         q.kh = L.kh; q.kw = L.kw; q.stride = L.stride; q.dil = L.dil; q.pad_t = pt; q.pad_l = pl;
         q.workspace = wg_ws; q.workspace_floats = wg_ws_floats; q.accumulate = 0;
         prof_begin(CAT_CONV_WGRAD, st);
-        int rc = conv_wgrad(q, st);
+        int rc = (use_tc && use_tc_wgrad && wgrad_tc_supported(q)) ? wgrad_tc(q, st) : conv_wgrad(q, st);
         prof_end(st);
         if (profiling) cat_macs[CAT_CONV_WGRAD] += (double)dpre.pixels() * L.kh * L.kw * L.cin * L.cout;
         if (rc) return -1;
@@ -633,7 +636,7 @@ int Engine::run(int mode, int group, int disp_mask, int with_update, float lr, f
     key.lr = lr; key.mu = mu; key.gs = gscale;
     auto it = graphs.find(key);
     if (it == graphs.end()) {
-        if (conv_tc_init() || corr_init()) return -1;
+        if (conv_tc_init() || corr_init() || wgrad_tc_init()) return -1;
         cudaGraph_t graph = nullptr;
         const long long l0 = launch_count();
         MS_CHECK_CUDA(cudaStreamBeginCapture(gstream, cudaStreamCaptureModeThreadLocal));

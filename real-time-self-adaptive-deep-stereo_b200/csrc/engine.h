@@ -75,6 +75,7 @@ struct Engine {
     struct GraphRec { cudaGraphExec_t exec; long long kernels; };
     std::map<GraphKey, GraphRec> graphs;
     int use_graphs;
+    int use_tc_wgrad;                            // MS_TC_WGRAD (default 1)
     cudaStream_t gstream; cudaEvent_t ev_in, ev_out;   // graphs run on a private stream (the legacy default stream cannot be captured)
     int run(int mode, int group, int disp_mask, int with_update, float lr, float mu, float gscale, cudaStream_t st);
     int run_eager(int mode, int group, int disp_mask, int with_update, float lr, float mu, float gscale, cudaStream_t st);

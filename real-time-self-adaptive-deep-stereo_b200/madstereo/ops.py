@@ -127,6 +127,19 @@ def conv2d_wgrad(x, dy, kh, kw, stride=1, dilation=1):
     return dw, db
 
 
+def conv2d_wgrad_tc(x, dy, kh, kw, dilation=1):
+    """tcgen05 / 3xTF32 weight + bias gradient of a stride-1 conv."""
+    n, h, wd, cin = x.shape
+    cout = dy.shape[3]
+    dw = torch.empty(kh, kw, cin, cout, device=x.device, dtype=torch.float32)
+    db = torch.empty(cout, device=x.device, dtype=torch.float32)
+    nws = lib().ms_conv2d_wgrad_tc_workspace(kh, kw, cin, cout, n, h, wd)
+    ws = torch.empty(nws, device=x.device, dtype=torch.float32)
+    check(lib().ms_conv2d_wgrad_tc(_p(x), n, h, wd, cin, cin, _p(dy), cout, cout, _p(dw), _p(db), kh, kw, dilation,
+                                   _p(ws), nws, _s()), 'ms_conv2d_wgrad_tc')
+    return dw, db
+
+
 def conv2d_transpose(x, w, b, stride=2, alpha=1.0):
     """sharedLayers.conv2d_transpose (Nets/sharedLayers.py:80-92). w [kh,kw,cout,cin]."""
     n, h, wd, cin = x.shape
