@@ -14,6 +14,7 @@
 // reduce the displacement sums with warp shuffles; results go out as 128-bit stores straight into the
 // concat buffer the first estimator conv reads.  No tensor cores: it is a shifted inner product.
 #include "common.cuh"
+#include <algorithm>
 #include <cstdlib>
 
 namespace ms {
@@ -165,6 +166,140 @@ __global__ void __launch_bounds__(CORR_NT) corr_fwd_kernel(CorrFwd p, int TW, in
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// forward v2: small x-tiles (many CTAs per SM so loads / math / stores of different tiles overlap), warp taps
+// computed once per column, the warped right row RW materialised once per tile in shared memory (each RW column feeds
+// nd output columns), and a BOUNDED right-feature window staged by TMA: the window is sized from the actual taps of
+// the tile; taps that fall outside the cap (pathological disparities) are read straight from global memory.
+// ---------------------------------------------------------------------------------------------
+struct Tap { int i0, i1; float w0, w1; };
+
+__global__ void __launch_bounds__(CORR_NT) corr_fwd2_kernel(CorrFwd p, int TW, int RCAP, int nd, int use_tma) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ int s_lo, s_hi;
+    const int C = p.C, w = p.w, d = p.max_disp;
+    const bool warped = p.u != nullptr;
+    const int row = blockIdx.y;
+    const int x0 = blockIdx.x * TW, x1 = min(w, x0 + TW);
+    const int wlo = max(0, x0 - d), whi = min(w, x1 + d);          // RW columns needed: [wlo, whi)
+    const int NW = whi - wlo;
+    float* Ls = reinterpret_cast<float*>(smem_raw);                  // [TW][C]
+    float* RWs = Ls + (size_t)TW * C;                                 // [TW+2d][C]  warped right features
+    float* Rs = RWs + (size_t)(TW + 2 * d) * C;                       // [RCAP][C]   raw right window (warped only)
+    Tap* taps = reinterpret_cast<Tap*>(Rs + (size_t)(warped ? RCAP : 0) * C);   // [TW+2d]
+
+    const float* lrow = p.left + (size_t)row * w * p.lcs;
+    const float* rrow = p.right + (size_t)row * w * p.rcs;
+    const float* urow = warped ? p.u + (size_t)row * w * p.ucs : nullptr;
+
+    if (threadIdx.x == 0) { s_lo = w; s_hi = -1; if (use_tma) { mbar_init(&bar, 1); fence_mbar_init(); } }
+    __syncthreads();
+    // ---- phase 1: taps + the right-feature window they touch
+    int rlo = wlo, rhi = whi;                                          // raw window [rlo, rhi)
+    if (warped) {
+        for (int t = threadIdx.x; t < NW; t += blockDim.x) {
+            WarpTap wt = warp_tap(wlo + t, urow[(size_t)(wlo + t) * p.ucs], w, true);
+            Tap tp; tp.i0 = wt.i0; tp.i1 = wt.i1; tp.w0 = wt.w0; tp.w1 = wt.w1;
+            taps[t] = tp;
+            if (wt.w0 != 0.f) { atomicMin(&s_lo, wt.i0); atomicMax(&s_hi, wt.i0); }
+            if (wt.w1 != 0.f) { atomicMin(&s_lo, wt.i1); atomicMax(&s_hi, wt.i1); }
+        }
+        __syncthreads();
+        rlo = s_lo; rhi = s_hi + 1;
+        if (rhi <= rlo) { rlo = 0; rhi = 0; }
+        if (rhi - rlo > RCAP) rhi = rlo + RCAP;                        // the rest goes through the global slow path
+    }
+    // ---- phase 2: stage L tile and the right window
+    const uint32_t lbytes = (uint32_t)(x1 - x0) * C * 4u, rbytes = (uint32_t)(rhi - rlo) * C * 4u;
+    float* rdst = warped ? Rs : RWs;
+    if (use_tma && threadIdx.x == 0) mbar_expect_tx(&bar, lbytes + rbytes);
+    stage_row(Ls, lrow, p.lcs, C, x0, x1, use_tma, &bar);
+    if (rhi > rlo) stage_row(rdst, rrow, p.rcs, C, rlo, rhi, use_tma, &bar);
+    __syncthreads();
+    if (use_tma) mbar_wait(&bar, 0);
+
+    const int lane = threadIdx.x & 31, sub = lane & (LPP - 1);
+    const int grp = threadIdx.x / LPP, ngrp = CORR_NT / LPP;
+    const int nchunk = C / 4;
+    // ---- phase 3: RW[t] = w0*R[i0] + w1*R[i1]
+    if (warped) {
+        for (int t = grp; t < NW; t += ngrp) {
+            const Tap tp = taps[t];
+            const bool in0 = tp.i0 >= rlo && tp.i0 < rhi, in1 = tp.i1 >= rlo && tp.i1 < rhi;
+            const float4* R0 = in0 ? reinterpret_cast<const float4*>(Rs + (size_t)(tp.i0 - rlo) * C)
+                                   : reinterpret_cast<const float4*>(rrow + (size_t)tp.i0 * p.rcs);
+            const float4* R1 = in1 ? reinterpret_cast<const float4*>(Rs + (size_t)(tp.i1 - rlo) * C)
+                                   : reinterpret_cast<const float4*>(rrow + (size_t)tp.i1 * p.rcs);
+            float4* dst = reinterpret_cast<float4*>(RWs + (size_t)t * C);
+            for (int q = sub; q < nchunk; q += LPP) {
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+                if (tp.w0 != 0.f) a = R0[q];
+                if (tp.w1 != 0.f) b = R1[q];
+                a.x = tp.w0 * a.x + tp.w1 * b.x; a.y = tp.w0 * a.y + tp.w1 * b.y;
+                a.z = tp.w0 * a.z + tp.w1 * b.z; a.w = tp.w0 * a.w + tp.w1 * b.w;
+                dst[q] = a;
+            }
+        }
+        __syncthreads();
+    }
+    const int rwbase = warped ? wlo : rlo;                              // column held by RWs[0]
+    const float invC = 1.f / (float)C;
+    float* orow = p.out + (size_t)row * w * p.ocs;
+    float* o2row = p.out2 ? p.out2 + (size_t)row * w * p.o2cs : nullptr;
+    const int coff = p.copy_left ? C : 0;
+    const int tail0 = coff + nd + p.u_chan;
+    // ---- phase 5 (first, coalesced): left copy into the concat buffer(s)
+    if (p.copy_left) {
+        const int nvec = C / 4;
+        for (int e = threadIdx.x; e < (x1 - x0) * nvec; e += blockDim.x) {
+            const int px = e / nvec, q = e - px * nvec;
+            const float4 v = reinterpret_cast<const float4*>(Ls)[e];
+            *reinterpret_cast<float4*>(orow + (size_t)(x0 + px) * p.ocs + q * 4) = v;
+            if (o2row) *reinterpret_cast<float4*>(o2row + (size_t)(x0 + px) * p.o2cs + q * 4) = v;
+        }
+    }
+    // ---- phase 4: correlation
+    const bool pack8 = p.copy_left && nd == 5 && (p.ocs & 3) == 0 && (coff & 3) == 0 && tail0 + (p.u_chan ? 0 : 0) <= coff + 8 &&
+                       p.ocs >= coff + 8;
+    for (int xb = x0; xb < x1; xb += ngrp) {
+        const bool act = xb + grp < x1;
+        const int x = act ? xb + grp : x0;
+        const float4* L4 = reinterpret_cast<const float4*>(Ls + (size_t)(x - x0) * C);
+        float keep0 = 0.f, keep1 = 0.f, keep2 = 0.f, keep3 = 0.f, keep4 = 0.f;
+        for (int i = 0; i < nd; ++i) {
+            const int xp = x + (-d + i * p.stride);
+            float s = 0.f;
+            if (act && xp >= 0 && xp < w) {
+                const float4* R4 = reinterpret_cast<const float4*>(RWs + (size_t)(xp - rwbase) * C);
+                for (int q = sub; q < nchunk; q += LPP) {
+                    const float4 l = L4[q], a = R4[q];
+                    s = fmaf(l.x, a.x, s); s = fmaf(l.y, a.y, s); s = fmaf(l.z, a.z, s); s = fmaf(l.w, a.w, s);
+                }
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s *= invC;
+            if (pack8) {
+                if (i == 0) keep0 = s; else if (i == 1) keep1 = s; else if (i == 2) keep2 = s; else if (i == 3) keep3 = s; else keep4 = s;
+            } else if (act && sub == (i & (LPP - 1))) {
+                orow[(size_t)x * p.ocs + coff + i] = s;
+            }
+        }
+        if (act && pack8) {           // [c0 c1 c2 c3][c4 u 0 0] as two 128-bit stores
+            float* o = orow + (size_t)x * p.ocs + coff;
+            if (sub == 0) *reinterpret_cast<float4*>(o) = make_float4(keep0, keep1, keep2, keep3);
+            if (sub == 1) {
+                const float uu = p.u_chan ? o[5] : 0.f;                 // the u channel was written by the resize kernel
+                *reinterpret_cast<float4*>(o + 4) = make_float4(keep4, uu, 0.f, 0.f);
+            }
+        } else if (act && sub == 0 && p.copy_left) {
+            for (int c = tail0; c < p.ocs; ++c) orow[(size_t)x * p.ocs + c] = 0.f;
+        }
+    }
+}
+
 static bool corr_use_tma() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("MS_CORR_NO_TMA"); v = (e && e[0] == '1') ? 0 : 1; }
@@ -193,12 +328,26 @@ int corr_fwd(const CorrFwd& p, cudaStream_t st) {
     MS_REQUIRE(p.stride >= 1, "corr_fwd: stride");
     const bool warped = p.u != nullptr;
     const int nd = (2 * p.max_disp) / p.stride + 1;
+    int tma = corr_use_tma() && p.lcs == p.C && p.rcs == p.C;
+    if (corr_init()) return -1;
+    static int v1 = -1;
+    if (v1 < 0) { const char* e = getenv("MS_CORR_V1"); v1 = (e && e[0] == '1') ? 1 : 0; }
+    if (!v1) {
+        // tile width: aim at >= 3 CTAs per SM
+        int TW = std::min(p.w, p.C >= 128 ? 32 : 64);
+        const int RCAP = warped ? TW + 2 * p.max_disp + 64 : 0;
+        const size_t smem = ((size_t)TW + (size_t)(TW + 2 * p.max_disp) + (size_t)RCAP) * p.C * 4 +
+                            (size_t)(TW + 2 * p.max_disp) * sizeof(Tap) + 64;
+        if (smem <= 200 * 1024) {
+            dim3 grid(cdiv(p.w, TW), p.B * p.h);
+            corr_fwd2_kernel<<<grid, CORR_NT, smem, st>>>(p, TW, RCAP, nd, tma);
+            return check_launch("corr_fwd2");
+        }
+    }
     const size_t budget = 200 * 1024;
     int TW = pick_tw(p.w, p.C, p.max_disp, warped, 1, budget, (size_t)p.w * 4 + 64);
     MS_REQUIRE(TW > 0, "corr_fwd: row does not fit in shared memory");
     size_t smem = ((size_t)TW + (warped ? p.w : TW + 2 * p.max_disp)) * p.C * 4 + (warped ? (size_t)p.w * 4 : 0) + 64;
-    int tma = corr_use_tma() && p.lcs == p.C && p.rcs == p.C;
-    if (corr_init()) return -1;
     dim3 grid(cdiv(p.w, TW), p.B * p.h);
     corr_fwd_kernel<<<grid, CORR_NT, smem, st>>>(p, TW, nd, tma);
     return check_launch("corr_fwd");
@@ -347,6 +496,7 @@ int corr_init() {
     static bool done = false;
     if (done) return 0;
     MS_CHECK_CUDA(cudaFuncSetAttribute(corr_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    MS_CHECK_CUDA(cudaFuncSetAttribute(corr_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
     MS_CHECK_CUDA(cudaFuncSetAttribute(corr_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
     done = true;
     return 0;
