@@ -174,7 +174,9 @@ __global__ void __launch_bounds__(CORR_NT) corr_fwd_kernel(CorrFwd p, int TW, in
 // ---------------------------------------------------------------------------------------------
 struct Tap { int i0, i1; float w0, w1; };
 
-__global__ void __launch_bounds__(CORR_NT) corr_fwd2_kernel(CorrFwd p, int TW, int RCAP, int nd, int use_tma) {
+template <int ND_CT>
+__global__ void __launch_bounds__(CORR_NT) corr_fwd2_kernel(CorrFwd p, int TW, int RCAP, int nd_rt, int use_tma) {
+    const int nd = ND_CT > 0 ? ND_CT : nd_rt;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ int s_lo, s_hi;
@@ -267,6 +269,7 @@ __global__ void __launch_bounds__(CORR_NT) corr_fwd2_kernel(CorrFwd p, int TW, i
         const int x = act ? xb + grp : x0;
         const float4* L4 = reinterpret_cast<const float4*>(Ls + (size_t)(x - x0) * C);
         float keep0 = 0.f, keep1 = 0.f, keep2 = 0.f, keep3 = 0.f, keep4 = 0.f;
+#pragma unroll
         for (int i = 0; i < nd; ++i) {
             const int xp = x + (-d + i * p.stride);
             float s = 0.f;
@@ -300,6 +303,149 @@ __global__ void __launch_bounds__(CORR_NT) corr_fwd2_kernel(CorrFwd p, int TW, i
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// forward v3: ncu on v2 (profiles/r1_ncu_corr_fwd2_L2_1920x1088_B8.txt) showed the kernel instruction-issue bound
+// (155 M warp instructions for 1.04 M pixels, 66 % issue-active, DRAM 16 %): with 8 lanes per pixel every lane owns a
+// single float4 chunk, so address arithmetic and the shuffle reductions dominate.  Here LP = 1..8 lanes share a pixel
+// and each lane owns CPL >= 3 consecutive chunks; the left chunk is held in registers across the nd displacements;
+// shared-memory tiles are stored with an XOR swizzle of the chunk index (low 3 bits ^ column&7) so that lane=column
+// accesses are bank-conflict free.  Tiles are staged with coalesced 128-bit loads (the swizzle rules out the 1-D bulk
+// copy used by v1/v2, which remain available: MS_CORR_V=1|2).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int swz_m(int q, int col, int m) { return (q & ~m) | ((q ^ col) & m); }
+
+template <int ND_CT>
+__global__ void __launch_bounds__(CORR_NT) corr_fwd3_kernel(CorrFwd p, int TW, int LP, int RCAP, int nd_rt, int smask) {
+    auto swz = [smask](int q, int col) { return swz_m(q, col, smask); };
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ int s_lo, s_hi;
+    const int nd = ND_CT > 0 ? ND_CT : nd_rt;
+    const int C = p.C, w = p.w, d = p.max_disp;
+    const bool warped = p.u != nullptr;
+    const int row = blockIdx.y;
+    const int x0 = blockIdx.x * TW, x1 = min(w, x0 + TW);
+    const int wlo = max(0, x0 - d), whi = min(w, x1 + d);
+    const int NW = whi - wlo;
+    const int nchunk = C / 4, CPL = nchunk / LP;
+    float4* Ls = reinterpret_cast<float4*>(smem_raw);                        // [TW][nchunk]       swizzled by local column
+    float4* RWs = Ls + (size_t)TW * nchunk;                                   // [TW+2d][nchunk]    swizzled by (column - wlo)
+    float4* Rs = RWs + (size_t)(TW + 2 * d) * nchunk;                         // [RCAP][nchunk]     swizzled by (column - rlo)
+    Tap* taps = reinterpret_cast<Tap*>(Rs + (size_t)(warped ? RCAP : 0) * nchunk);
+
+    const float* lrow = p.left + (size_t)row * w * p.lcs;
+    const float* rrow = p.right + (size_t)row * w * p.rcs;
+    const float* urow = warped ? p.u + (size_t)row * w * p.ucs : nullptr;
+    float* orow = p.out + (size_t)row * w * p.ocs;
+    float* o2row = p.out2 ? p.out2 + (size_t)row * w * p.o2cs : nullptr;
+
+    if (threadIdx.x == 0) { s_lo = w; s_hi = -1; }
+    __syncthreads();
+    int rlo = wlo, rhi = whi;
+    if (warped) {
+        for (int t = threadIdx.x; t < NW; t += blockDim.x) {
+            WarpTap wt = warp_tap(wlo + t, urow[(size_t)(wlo + t) * p.ucs], w, true);
+            Tap tp; tp.i0 = wt.i0; tp.i1 = wt.i1; tp.w0 = wt.w0; tp.w1 = wt.w1;
+            taps[t] = tp;
+            if (wt.w0 != 0.f) { atomicMin(&s_lo, wt.i0); atomicMax(&s_hi, wt.i0); }
+            if (wt.w1 != 0.f) { atomicMin(&s_lo, wt.i1); atomicMax(&s_hi, wt.i1); }
+        }
+    }
+    // ---- left tile: global -> (concat buffers) + swizzled smem
+    for (int e = threadIdx.x; e < (x1 - x0) * nchunk; e += blockDim.x) {
+        const int j = e / nchunk, q = e - j * nchunk;
+        const float4 v = *reinterpret_cast<const float4*>(lrow + (size_t)(x0 + j) * p.lcs + q * 4);
+        Ls[(size_t)j * nchunk + swz(q, j)] = v;
+        if (p.copy_left) {
+            *reinterpret_cast<float4*>(orow + (size_t)(x0 + j) * p.ocs + q * 4) = v;
+            if (o2row) *reinterpret_cast<float4*>(o2row + (size_t)(x0 + j) * p.o2cs + q * 4) = v;
+        }
+    }
+    __syncthreads();
+    if (warped) {
+        rlo = s_lo; rhi = s_hi + 1;
+        if (rhi <= rlo) { rlo = 0; rhi = 0; }
+        if (rhi - rlo > RCAP) rhi = rlo + RCAP;
+    }
+    // ---- right window: raw (warped) or final (unwarped) tile
+    {
+        float4* dst = warped ? Rs : RWs;
+        for (int e = threadIdx.x; e < (rhi - rlo) * nchunk; e += blockDim.x) {
+            const int j = e / nchunk, q = e - j * nchunk;
+            dst[(size_t)j * nchunk + swz(q, j)] = *reinterpret_cast<const float4*>(rrow + (size_t)(rlo + j) * p.rcs + q * 4);
+        }
+    }
+    __syncthreads();
+    const int sub = threadIdx.x % LP, pl = threadIdx.x / LP, npl = CORR_NT / LP;   // lane-in-pixel, pixel slot
+    if (warped) {
+        for (int t = pl; t < NW; t += npl) {
+            const Tap tp = taps[t];
+            const int r0 = tp.i0 - rlo, r1 = tp.i1 - rlo;
+            const bool in0 = r0 >= 0 && tp.i0 < rhi, in1 = r1 >= 0 && tp.i1 < rhi;
+#pragma unroll 2
+            for (int e = 0; e < CPL; ++e) {
+                const int q = sub * CPL + e;
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+                if (tp.w0 != 0.f) a = in0 ? Rs[(size_t)r0 * nchunk + swz(q, r0)] : *reinterpret_cast<const float4*>(rrow + (size_t)tp.i0 * p.rcs + q * 4);
+                if (tp.w1 != 0.f) b = in1 ? Rs[(size_t)r1 * nchunk + swz(q, r1)] : *reinterpret_cast<const float4*>(rrow + (size_t)tp.i1 * p.rcs + q * 4);
+                a.x = tp.w0 * a.x + tp.w1 * b.x; a.y = tp.w0 * a.y + tp.w1 * b.y;
+                a.z = tp.w0 * a.z + tp.w1 * b.z; a.w = tp.w0 * a.w + tp.w1 * b.w;
+                RWs[(size_t)t * nchunk + swz(q, t)] = a;
+            }
+        }
+        __syncthreads();
+    }
+    const int rwbase = warped ? wlo : rlo;
+    const float invC = 1.f / (float)C;
+    const int coff = p.copy_left ? C : 0;
+    const int tail0 = coff + nd + p.u_chan;
+    const bool pack8 = p.copy_left && nd == 5 && (p.ocs & 3) == 0 && (coff & 3) == 0 && p.ocs >= coff + 8;
+    constexpr int AB = ND_CT > 0 ? ND_CT : 8;                       // accumulators per pass
+    for (int xb = x0; xb < x1; xb += npl) {                        // uniform trip count (shuffles below)
+        const bool act = xb + pl < x1;
+        const int x = act ? xb + pl : x0;
+        const int j = x - x0;
+        for (int i0 = 0; i0 < nd; i0 += AB) {
+            float acc[AB];
+#pragma unroll
+            for (int k = 0; k < AB; ++k) acc[k] = 0.f;
+            for (int e = 0; e < CPL; ++e) {
+                const int q = sub * CPL + e;
+                const float4 l = Ls[(size_t)j * nchunk + swz(q, j)];
+#pragma unroll
+                for (int k = 0; k < AB; ++k) {
+                    const int i = i0 + k;
+                    const int xp = x + (-d + i * p.stride);
+                    if (i < nd && xp >= 0 && xp < w) {
+                        const int t = xp - rwbase;
+                        const float4 a = RWs[(size_t)t * nchunk + swz(q, t)];
+                        acc[k] = fmaf(l.x, a.x, acc[k]); acc[k] = fmaf(l.y, a.y, acc[k]);
+                        acc[k] = fmaf(l.z, a.z, acc[k]); acc[k] = fmaf(l.w, a.w, acc[k]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < AB; ++k) {
+                for (int o = LP >> 1; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+                acc[k] *= invC;
+            }
+            if (act && sub == 0) {
+                float* o = orow + (size_t)x * p.ocs + coff;
+                if (ND_CT == 5 && pack8) {
+                    const float uu = p.u_chan ? o[5] : 0.f;
+                    *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                    *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], uu, 0.f, 0.f);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < AB; ++k)
+                        if (i0 + k < nd) o[i0 + k] = acc[k];
+                }
+            }
+        }
+        if (act && sub == 0 && p.copy_left && !(ND_CT == 5 && pack8))
+            for (int c = tail0; c < p.ocs; ++c) orow[(size_t)x * p.ocs + c] = 0.f;
+    }
+}
+
 static bool corr_use_tma() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("MS_CORR_NO_TMA"); v = (e && e[0] == '1') ? 0 : 1; }
@@ -330,17 +476,38 @@ int corr_fwd(const CorrFwd& p, cudaStream_t st) {
     const int nd = (2 * p.max_disp) / p.stride + 1;
     int tma = corr_use_tma() && p.lcs == p.C && p.rcs == p.C;
     if (corr_init()) return -1;
-    static int v1 = -1;
-    if (v1 < 0) { const char* e = getenv("MS_CORR_V1"); v1 = (e && e[0] == '1') ? 1 : 0; }
-    if (!v1) {
+    static int ver = -1;
+    if (ver < 0) { const char* e = getenv("MS_CORR_V"); ver = e ? atoi(e) : 3; }
+    if (ver >= 3) {
+        const int nchunk = p.C / 4;
+        const int LP = nchunk >= 24 ? 8 : (nchunk >= 16 ? 4 : (nchunk >= 8 ? 2 : 1));
+        // measured (scripts/corr_bench.py): v3 wins for C<=32 (level 2, which moves most of the bytes), v2 for wider features / nd=81
+        if (nchunk % LP == 0 && p.C <= 32 && nd <= 8) {
+            const int TW = std::min(p.w, CORR_NT / LP);
+            const int RCAP = warped ? TW + 2 * p.max_disp + 32 : 0;
+            const size_t smem = ((size_t)TW + (size_t)(TW + 2 * p.max_disp) + (size_t)RCAP) * p.C * 4 +
+                                (size_t)(TW + 2 * p.max_disp) * sizeof(Tap) + 64;
+            if (smem <= 200 * 1024) {
+                dim3 grid(cdiv(p.w, TW), p.B * p.h);
+                const int smask = nchunk % 8 == 0 ? 7 : (nchunk % 4 == 0 ? 3 : (nchunk % 2 == 0 ? 1 : 0));
+                if (nd == 5) corr_fwd3_kernel<5><<<grid, CORR_NT, smem, st>>>(p, TW, LP, RCAP, nd, smask);
+                else corr_fwd3_kernel<0><<<grid, CORR_NT, smem, st>>>(p, TW, LP, RCAP, nd, smask);
+                return check_launch("corr_fwd3");
+            }
+        }
+    }
+    if (ver >= 2) {
         // tile width: aim at >= 3 CTAs per SM
-        int TW = std::min(p.w, p.C >= 128 ? 32 : 64);
-        const int RCAP = warped ? TW + 2 * p.max_disp + 64 : 0;
+        static int tw_env = -1, slack_env = -1;
+        if (tw_env < 0) { const char* e = getenv("MS_CORR_TW"); tw_env = e ? atoi(e) : 0; const char* f = getenv("MS_CORR_SLACK"); slack_env = f ? atoi(f) : 0; }
+        int TW = std::min(p.w, tw_env > 0 ? tw_env : (p.C >= 128 ? 32 : 64));
+        const int RCAP = warped ? TW + 2 * p.max_disp + (slack_env > 0 ? slack_env : 64) : 0;
         const size_t smem = ((size_t)TW + (size_t)(TW + 2 * p.max_disp) + (size_t)RCAP) * p.C * 4 +
                             (size_t)(TW + 2 * p.max_disp) * sizeof(Tap) + 64;
         if (smem <= 200 * 1024) {
             dim3 grid(cdiv(p.w, TW), p.B * p.h);
-            corr_fwd2_kernel<<<grid, CORR_NT, smem, st>>>(p, TW, RCAP, nd, tma);
+            if (nd == 5) corr_fwd2_kernel<5><<<grid, CORR_NT, smem, st>>>(p, TW, RCAP, nd, tma);
+            else corr_fwd2_kernel<0><<<grid, CORR_NT, smem, st>>>(p, TW, RCAP, nd, tma);
             return check_launch("corr_fwd2");
         }
     }
@@ -496,7 +663,10 @@ int corr_init() {
     static bool done = false;
     if (done) return 0;
     MS_CHECK_CUDA(cudaFuncSetAttribute(corr_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-    MS_CHECK_CUDA(cudaFuncSetAttribute(corr_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    MS_CHECK_CUDA(cudaFuncSetAttribute(corr_fwd2_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    MS_CHECK_CUDA(cudaFuncSetAttribute(corr_fwd2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    MS_CHECK_CUDA(cudaFuncSetAttribute(corr_fwd3_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    MS_CHECK_CUDA(cudaFuncSetAttribute(corr_fwd3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
     MS_CHECK_CUDA(cudaFuncSetAttribute(corr_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
     done = true;
     return 0;
