@@ -278,7 +278,7 @@ def run_ours(args):
                            'loss D2H (host reward policy needs it every frame)'},
         'e2e': {'value': fps_e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': 2 * H * W * 3 * 4, 'd2h_bytes_per_step': 16},
         'gpu_launches': int(launches),
-        'roofline': {'bound': 'tensor', 'kernel': 'conv stack: conv_tc_kernel (tcgen05 3xTF32 implicit GEMM, stride-1 fwd+dgrad) + conv_gemm/conv_wgrad (fp32 CUDA-core: stride-2, tiny-channel layers, all wgrad); useful FLOPs = 2*MACs, the 3x tf32 passes are not counted',
+        'roofline': {'bound': 'tensor', 'kernel': 'conv stack: conv_tc_ts/conv_tc kernels (tcgen05 3xTF32 implicit GEMM, stride-1 fwd+dgrad) + wgrad_tc_kernel (tcgen05 stride-1 wgrad) + conv_gemm/conv_wgrad (fp32 CUDA-core: stride-2, cin=3 and cout=1 layers); useful FLOPs = 2*MACs, the 3x tf32 passes are not counted',
                      'achieved': conv_tflops, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
                      'frac': conv_tflops / pk['bf16_tflops_sustained'], 'peak_src': pk['src'] + ' bf16 sustained (kernels timed inside a long step)',
                      'traffic': None, 'avg_launch_us': 1e3 * conv_ms / max(conv_calls, 1),
