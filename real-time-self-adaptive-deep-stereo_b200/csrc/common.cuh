@@ -79,6 +79,14 @@ struct ConvWgrad {
 int conv_wgrad(const ConvWgrad& p, cudaStream_t st);
 size_t conv_wgrad_workspace_floats(int taps, int ci, int co, size_t pixels);
 
+// conv_small.cu: direct kernels for the full-resolution 3->16 / 16->16 pyramid layers
+bool conv_small_fwd_supported(const ConvGemm& p);
+int conv_small_fwd(const ConvGemm& p, cudaStream_t st);
+bool conv_small_wgrad_shape(int taps, int ci, int co);
+bool conv_small_wgrad_supported(const ConvWgrad& p);
+size_t conv_small_wgrad_workspace_floats(int taps, int ci, int co, size_t pixels);
+int conv_small_wgrad(const ConvWgrad& p, int* split_out, cudaStream_t st);
+
 int bias_grad(const TView& dy, float* db, float* workspace, size_t workspace_floats, cudaStream_t st);
 int transpose_taps(const float* w, float* wt, int taps, int ci, int co, cudaStream_t st);
 
@@ -93,6 +101,7 @@ struct CorrFwd {
     int u_chan;                      // 1 if the concat buffer keeps a `u` channel right after the corr channels
 };
 int corr_fwd(const CorrFwd& p, cudaStream_t st);
+int corr_fwd4(const CorrFwd& p, cudaStream_t st);   // corr_tma.cu: 0 launched, 1 shape not handled, -1 error
 
 struct CorrBwd {
     const float* left;  int lcs;

@@ -8,6 +8,7 @@
 // tcgen05 path (conv_tc.cu) does not cover (stride 2, cin=3, cout=1, transposed) and as its checker.
 #include "common.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace ms {
 
@@ -248,6 +249,11 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 int conv_gemm(const ConvGemm& p_in, cudaStream_t st) {
     ConvGemm p = p_in;
     MS_REQUIRE(p.x.n == p.y.n, "conv_gemm: batch mismatch");
+    {
+        static int small_env = -1;
+        if (small_env < 0) { const char* e = getenv("MS_CONV_SMALL"); small_env = (e && e[0] == '0') ? 0 : 1; }
+        if (small_env && conv_small_fwd_supported(p)) return conv_small_fwd(p, st);     // cin = 3 (conv_small.cu)
+    }
     const size_t Mz = (size_t)p.y.n * p.y.h * p.y.w;
     MS_REQUIRE(Mz < (1u << 30), "conv_gemm: too many output pixels");
     const int M = (int)Mz;
@@ -475,7 +481,9 @@ static int bias_blocks(size_t P) { return (int)std::min<size_t>(128, std::max<si
 size_t conv_wgrad_workspace_floats(int taps, int ci, int co, size_t P) {
     int tm, tn; wgrad_tiles(ci, co, tm, tn);
     int tiles = taps * cdiv(ci, 16 * tm) * cdiv(co, 16 * tn);
-    return (size_t)wgrad_split(tiles, P) * taps * ci * co + (size_t)bias_blocks(P) * co + 64;
+    size_t main_part = (size_t)wgrad_split(tiles, P) * taps * ci * co;
+    if (conv_small_wgrad_shape(taps, ci, co)) main_part = std::max(main_part, conv_small_wgrad_workspace_floats(taps, ci, co, P));
+    return main_part + (size_t)bias_blocks(P) * co + 64;
 }
 
 int conv_wgrad(const ConvWgrad& p, cudaStream_t st) {
@@ -486,11 +494,18 @@ int conv_wgrad(const ConvWgrad& p, cudaStream_t st) {
     const int taps = p.kh * p.kw, ci = p.x.c, co = p.dy.c;
     int tm, tn; wgrad_tiles(ci, co, tm, tn);
     const int mtiles = cdiv(ci, 16 * tm), ntiles = cdiv(co, 16 * tn);
-    const int split = wgrad_split(taps * mtiles * ntiles, Pz);
-    int chunk = cdiv(P, split);
-    chunk = cdiv(chunk, BK) * BK;
     const size_t wn = (size_t)taps * ci * co;
     const int nb = bias_blocks(Pz);
+    static int small_env = -1;
+    if (small_env < 0) { const char* e = getenv("MS_CONV_SMALL"); small_env = (e && e[0] == '0') ? 0 : 1; }
+    const bool small = small_env && conv_small_wgrad_supported(p) &&
+                       p.workspace_floats >= conv_small_wgrad_workspace_floats(taps, ci, co, Pz) + (size_t)nb * co;
+    int split = wgrad_split(taps * mtiles * ntiles, Pz);
+    int chunk = cdiv(P, split);
+    chunk = cdiv(chunk, BK) * BK;
+    if (small) {                                          // tiny channel counts: register-resident direct kernel (conv_small.cu)
+        if (conv_small_wgrad(p, &split, st)) return -1;
+    } else {
     MS_REQUIRE(p.workspace_floats >= (size_t)split * wn + (size_t)nb * co, "conv_wgrad: workspace too small");
     const bool avec = (p.x.cs % 4 == 0) && aligned16(p.x.p) && ci >= 4;
     const bool bvec = (p.dy.cs % 4 == 0) && aligned16(p.dy.p) && co >= 4;
@@ -505,6 +520,7 @@ int conv_wgrad(const ConvWgrad& p, cudaStream_t st) {
 #undef DA
 #undef DN
     if (check_launch("conv_wgrad", 1)) return -1;
+    }
     wgrad_reduce_kernel<<<(unsigned)cdivz(wn, 256), 256, 0, st>>>(p.workspace, p.dw, wn, split, p.accumulate);
     if (p.db) {
         float* bp = p.workspace + (size_t)split * wn;

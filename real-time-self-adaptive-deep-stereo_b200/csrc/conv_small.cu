@@ -1,0 +1,254 @@
+// Direct fp32 kernels for the two full-resolution pyramid layers whose channel counts are too small for a GEMM tile:
+// MADNet conv1 (3 -> 16, 3x3 stride 2) and conv2 (16 -> 16, 3x3), reference Nets/MadNet.py:173-190 built from
+// sharedLayers.conv2d (Nets/sharedLayers.py:54-63), and the filter gradients tf.gradients derives for them in the
+// module-2 train op (Stereo_Online_Adaptation.py:118).
+//
+// The launch list (profiles/r1_launches_final_summary.txt) had the gather GEMM at 105 us for conv1 forward (0.2 GFLOP,
+// 27 MB: it should be a ~10 us HBM-bound kernel) and 319 + 271 us for the conv1 / conv2 weight gradients (432 / 2304
+// outputs reduced over 245 760 pixels: a 16 x 16 output tile leaves the GEMM kernel with 9 CTAs per K split).
+//   forward  : one thread computes two adjacent output pixels x 16 output channels; the 27 x 16 weights sit in shared
+//              memory and are read as broadcast float4.
+//   wgrad    : a thread owns one input channel ("role") and keeps all 9 taps x 16 output channels = 144 partial sums
+//              in registers while it walks its share of the pixels (9 input loads + 16 dY loads per 144 FMAs, next
+//              pixel prefetched); lanes of equal role are combined by shuffles, warps through shared memory, CTAs by
+//              the fixed-order wgrad_reduce pass (deterministic).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace ms {
+
+static __host__ __device__ bool al16s(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ---------------------------------------------------------------------------------------------
+// forward, cin = 3
+// ---------------------------------------------------------------------------------------------
+constexpr int C3_NT = 128;
+
+template <int CO>
+__global__ void __launch_bounds__(C3_NT) conv_c3_fwd_kernel(ConvGemm p, int pairs_per_row, int total_pairs) {
+    __shared__ __align__(16) float ws[27 * CO];
+    __shared__ float bs[CO];
+    for (int i = threadIdx.x; i < 27 * CO; i += C3_NT) ws[i] = p.wmat[i];          // [tap][ci][co]
+    for (int i = threadIdx.x; i < CO; i += C3_NT) bs[i] = p.bias ? p.bias[i] : 0.f;
+    __syncthreads();
+    const int e = blockIdx.x * C3_NT + threadIdx.x;
+    if (e >= total_pairs) return;
+    const int xp = e % pairs_per_row;
+    const int q = e / pairs_per_row;
+    const int oy = q % p.y.h, img = q / p.y.h;
+    const int ox0 = xp * 2;
+    float acc[2][CO];
+#pragma unroll
+    for (int j = 0; j < CO; ++j) { acc[0][j] = bs[j]; acc[1][j] = bs[j]; }
+    const float* ximg = p.x.p + (size_t)img * p.x.h * p.x.w * p.x.cs;
+#pragma unroll
+    for (int ty = 0; ty < 3; ++ty) {
+        const int iy = oy * p.mul + p.off_y + ty * p.step;
+        const bool rok = iy >= 0 && iy < p.x.h;
+        const float* xrow = ximg + (size_t)(rok ? iy : 0) * p.x.w * p.x.cs;
+        float xin[2][3][3];
+#pragma unroll
+        for (int pi = 0; pi < 2; ++pi)
+#pragma unroll
+            for (int tx = 0; tx < 3; ++tx) {
+                const int ix = (ox0 + pi) * p.mul + p.off_x + tx * p.step;
+                const bool ok = rok && ix >= 0 && ix < p.x.w;
+                const float* s = xrow + (size_t)(ok ? ix : 0) * p.x.cs;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) xin[pi][tx][c] = ok ? __ldg(s + c) : 0.f;
+            }
+#pragma unroll
+        for (int tx = 0; tx < 3; ++tx)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float4* wr = reinterpret_cast<const float4*>(ws + ((ty * 3 + tx) * 3 + c) * CO);
+                const float a0 = xin[0][tx][c], a1 = xin[1][tx][c];
+#pragma unroll
+                for (int j4 = 0; j4 < CO / 4; ++j4) {
+                    const float4 w = wr[j4];
+                    acc[0][4 * j4] = fmaf(a0, w.x, acc[0][4 * j4]); acc[0][4 * j4 + 1] = fmaf(a0, w.y, acc[0][4 * j4 + 1]);
+                    acc[0][4 * j4 + 2] = fmaf(a0, w.z, acc[0][4 * j4 + 2]); acc[0][4 * j4 + 3] = fmaf(a0, w.w, acc[0][4 * j4 + 3]);
+                    acc[1][4 * j4] = fmaf(a1, w.x, acc[1][4 * j4]); acc[1][4 * j4 + 1] = fmaf(a1, w.y, acc[1][4 * j4 + 1]);
+                    acc[1][4 * j4 + 2] = fmaf(a1, w.z, acc[1][4 * j4 + 2]); acc[1][4 * j4 + 3] = fmaf(a1, w.w, acc[1][4 * j4 + 3]);
+                }
+            }
+    }
+    const bool vec = (p.y.cs & 3) == 0 && al16s(p.y.p);
+#pragma unroll
+    for (int pi = 0; pi < 2; ++pi) {
+        const int ox = ox0 + pi;
+        if (ox >= p.y.w) break;
+        float* yrow = p.y.p + ((size_t)(img * p.y.h + oy) * p.y.w + ox) * p.y.cs;
+#pragma unroll
+        for (int j = 0; j < CO; ++j) acc[pi][j] = fmaxf(p.alpha * acc[pi][j], acc[pi][j]);
+        if (vec) {
+#pragma unroll
+            for (int j = 0; j < CO; j += 4)
+                *reinterpret_cast<float4*>(yrow + j) = make_float4(acc[pi][j], acc[pi][j + 1], acc[pi][j + 2], acc[pi][j + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < CO; ++j) yrow[j] = acc[pi][j];
+        }
+    }
+}
+
+bool conv_small_fwd_supported(const ConvGemm& p) {
+    return p.x.c == 3 && p.y.c == 16 && p.kh == 3 && p.kw == 3 && p.div == 1 && p.mul >= 1 && p.step >= 1 && !p.mask &&
+           !p.res && !p.accumulate && p.alpha <= 1.f && p.alpha >= 0.f && p.x.n == p.y.n;
+}
+
+int conv_small_fwd(const ConvGemm& p, cudaStream_t st) {
+    const int pairs_per_row = cdiv(p.y.w, 2);
+    const size_t total = (size_t)p.y.n * p.y.h * pairs_per_row;
+    MS_REQUIRE(total < (1u << 30), "conv_small_fwd: too many output pixels");
+    conv_c3_fwd_kernel<16><<<(unsigned)cdivz(total, C3_NT), C3_NT, 0, st>>>(p, pairs_per_row, (int)total);
+    return check_launch("conv_c3_fwd");
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight gradient, 3x3, co = 16, ci <= 16
+// ---------------------------------------------------------------------------------------------
+constexpr int SW_NT = 256;
+constexpr int SW_CO = 16;
+constexpr int SW_TAPS = 9;
+constexpr int SW_ACC = SW_TAPS * SW_CO;     // 144 partial sums per thread
+
+struct SwOperands { float x[SW_TAPS]; float4 d[SW_CO / 4]; };
+
+template <int RP>   // roles per pixel slot: ci padded to 4 / 8 / 16
+__global__ void __launch_bounds__(SW_NT, 1) conv_small_wgrad_kernel(ConvWgrad p, int P, int chunk, float* __restrict__ partial) {
+    extern __shared__ float sw_smem[];                       // [warps][RP][144]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int role = tid % RP, slot = tid / RP;
+    constexpr int NSLOT = SW_NT / RP;
+    const int ci = p.x.c;
+    const bool live = role < ci;
+    const int W = p.dy.w, H = p.dy.h;
+    const bool dvec = (p.dy.cs & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.dy.p) & 15) == 0);
+    const int p_begin = blockIdx.x * chunk, p_end = min(P, p_begin + chunk);
+
+    float acc[SW_TAPS][SW_CO];
+#pragma unroll
+    for (int t = 0; t < SW_TAPS; ++t)
+#pragma unroll
+        for (int j = 0; j < SW_CO; ++j) acc[t][j] = 0.f;
+
+    int pp = p_begin + slot;
+    int ox = 0, oy = 0, img = 0;
+    if (pp < p_end) { ox = pp % W; const int q = pp / W; oy = q % H; img = q / H; }
+
+    auto load = [&](int pix, int lx, int ly, int limg, SwOperands& o) {
+        const bool ok = pix < p_end;
+#pragma unroll
+        for (int j4 = 0; j4 < SW_CO / 4; ++j4) o.d[j4] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) {
+            const float* dsrc = p.dy.p + (size_t)pix * p.dy.cs;
+            if (dvec) {
+#pragma unroll
+                for (int j4 = 0; j4 < SW_CO / 4; ++j4) o.d[j4] = __ldg(reinterpret_cast<const float4*>(dsrc) + j4);
+            } else {
+#pragma unroll
+                for (int j4 = 0; j4 < SW_CO / 4; ++j4)
+                    o.d[j4] = make_float4(__ldg(dsrc + 4 * j4), __ldg(dsrc + 4 * j4 + 1), __ldg(dsrc + 4 * j4 + 2), __ldg(dsrc + 4 * j4 + 3));
+            }
+        }
+        const float* ximg = p.x.p + (size_t)limg * p.x.h * p.x.w * p.x.cs + role;
+#pragma unroll
+        for (int t = 0; t < SW_TAPS; ++t) {
+            const int iy = ly * p.stride - p.pad_t + (t / 3) * p.dil;
+            const int ix = lx * p.stride - p.pad_l + (t % 3) * p.dil;
+            const bool in = ok && live && iy >= 0 && iy < p.x.h && ix >= 0 && ix < p.x.w;
+            o.x[t] = in ? __ldg(ximg + ((size_t)iy * p.x.w + ix) * p.x.cs) : 0.f;
+        }
+    };
+    auto advance = [&](int& lx, int& ly, int& limg) {
+        lx += NSLOT;
+        while (lx >= W) { lx -= W; if (++ly >= H) { ly = 0; ++limg; } }
+    };
+
+    SwOperands cur, nxt;
+    load(pp, ox, oy, img, cur);
+    while (pp < p_end) {
+        const int pn = pp + NSLOT;
+        advance(ox, oy, img);
+        load(pn, ox, oy, img, nxt);
+#pragma unroll
+        for (int t = 0; t < SW_TAPS; ++t) {
+            const float a = cur.x[t];
+#pragma unroll
+            for (int j4 = 0; j4 < SW_CO / 4; ++j4) {
+                acc[t][4 * j4] = fmaf(a, cur.d[j4].x, acc[t][4 * j4]);
+                acc[t][4 * j4 + 1] = fmaf(a, cur.d[j4].y, acc[t][4 * j4 + 1]);
+                acc[t][4 * j4 + 2] = fmaf(a, cur.d[j4].z, acc[t][4 * j4 + 2]);
+                acc[t][4 * j4 + 3] = fmaf(a, cur.d[j4].w, acc[t][4 * j4 + 3]);
+            }
+        }
+        cur = nxt;
+        pp = pn;
+    }
+    // lanes of equal role (lane % RP) -> lane < RP
+#pragma unroll
+    for (int t = 0; t < SW_TAPS; ++t)
+#pragma unroll
+        for (int j = 0; j < SW_CO; ++j) {
+            float v = acc[t][j];
+#pragma unroll
+            for (int off = RP; off < 32; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            acc[t][j] = v;
+        }
+    if (lane < RP) {
+        float* dst = sw_smem + ((size_t)warp * RP + lane) * SW_ACC;
+#pragma unroll
+        for (int t = 0; t < SW_TAPS; ++t)
+#pragma unroll
+            for (int j = 0; j < SW_CO; ++j) dst[t * SW_CO + j] = acc[t][j];
+    }
+    __syncthreads();
+    float* out = partial + (size_t)blockIdx.x * SW_TAPS * ci * SW_CO;        // [tap][ci][co]
+    for (int e = tid; e < ci * SW_ACC; e += SW_NT) {
+        const int r = e / SW_ACC, rem = e - r * SW_ACC;
+        const int t = rem / SW_CO, j = rem - t * SW_CO;
+        float s = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < SW_NT / 32; ++wv) s += sw_smem[((size_t)wv * RP + r) * SW_ACC + rem];
+        out[((size_t)t * ci + r) * SW_CO + j] = s;
+    }
+}
+
+bool conv_small_wgrad_shape(int taps, int ci, int co) { return taps == 9 && co == SW_CO && ci >= 1 && ci <= 16; }
+
+static int small_wgrad_split(size_t P) { return (int)std::min<size_t>(148, std::max<size_t>(1, P / 512)); }
+
+size_t conv_small_wgrad_workspace_floats(int taps, int ci, int co, size_t P) {
+    return (size_t)small_wgrad_split(P) * taps * ci * co;
+}
+
+bool conv_small_wgrad_supported(const ConvWgrad& p) {
+    return p.kh == 3 && p.kw == 3 && conv_small_wgrad_shape(9, p.x.c, p.dy.c) && p.x.n == p.dy.n &&
+           (size_t)p.dy.n * p.dy.h * p.dy.w >= 4096;
+}
+
+// partial sums -> p.workspace[0 .. split*taps*ci*co); returns the split through *split_out
+int conv_small_wgrad(const ConvWgrad& p, int* split_out, cudaStream_t st) {
+    const size_t Pz = (size_t)p.dy.n * p.dy.h * p.dy.w;
+    MS_REQUIRE(Pz < (1u << 30), "conv_small_wgrad: too many pixels");
+    const int P = (int)Pz, ci = p.x.c;
+    const int split = small_wgrad_split(Pz);
+    const int chunk = cdiv(P, split);
+    MS_REQUIRE(p.workspace_floats >= (size_t)split * 9 * ci * SW_CO, "conv_small_wgrad: workspace too small");
+    static bool attr = false;
+    if (!attr) {
+        MS_CHECK_CUDA(cudaFuncSetAttribute(conv_small_wgrad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr = true;
+    }
+    const int rp = ci <= 4 ? 4 : (ci <= 8 ? 8 : 16);
+    const size_t smem = (size_t)(SW_NT / 32) * rp * SW_ACC * sizeof(float);
+    if (rp == 4) conv_small_wgrad_kernel<4><<<split, SW_NT, smem, st>>>(p, P, chunk, p.workspace);
+    else if (rp == 8) conv_small_wgrad_kernel<8><<<split, SW_NT, smem, st>>>(p, P, chunk, p.workspace);
+    else conv_small_wgrad_kernel<16><<<split, SW_NT, smem, st>>>(p, P, chunk, p.workspace);
+    *split_out = split;
+    return check_launch("conv_small_wgrad");
+}
+
+}  // namespace ms

@@ -14,6 +14,7 @@
 // reduce the displacement sums with warp shuffles; results go out as 128-bit stores straight into the
 // concat buffer the first estimator conv reads.  No tensor cores: it is a shifted inner product.
 #include "common.cuh"
+#include "corr_common.cuh"
 #include <algorithm>
 #include <cstdlib>
 
@@ -44,22 +45,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "r"(a), "r"(parity)
             : "memory");
     } while (!ok);
-}
-
-struct WarpTap { int i0, i1; float w0, w1; };
-
-// warp coordinates for target column xp (already known to be inside [0,w)); uu = u[xp] or 0
-__device__ __forceinline__ WarpTap warp_tap(int xp, float uu, int w, bool warped) {
-    WarpTap t;
-    if (!warped) { t.i0 = xp; t.i1 = xp; t.w0 = 1.f; t.w1 = 0.f; return t; }
-    float cx = (float)xp + uu;
-    float x0 = floorf(cx), x1 = x0 + 1.f;
-    float x0s = fminf(fmaxf(x0, 0.f), (float)(w - 1));
-    float x1s = fminf(fmaxf(x1, 0.f), (float)(w - 1));
-    t.w0 = (x1 - cx) * (x0 == x0s ? 1.f : 0.f);
-    t.w1 = (cx - x0) * (x1 == x1s ? 1.f : 0.f);
-    t.i0 = (int)x0s; t.i1 = (int)x1s;
-    return t;
 }
 
 // stage the contiguous feature row segment [wlo,whi) x C of one image row into smem
@@ -172,8 +157,6 @@ __global__ void __launch_bounds__(CORR_NT) corr_fwd_kernel(CorrFwd p, int TW, in
 // nd output columns), and a BOUNDED right-feature window staged by TMA: the window is sized from the actual taps of
 // the tile; taps that fall outside the cap (pathological disparities) are read straight from global memory.
 // ---------------------------------------------------------------------------------------------
-struct Tap { int i0, i1; float w0, w1; };
-
 template <int ND_CT>
 __global__ void __launch_bounds__(CORR_NT) corr_fwd2_kernel(CorrFwd p, int TW, int RCAP, int nd_rt, int use_tma) {
     const int nd = ND_CT > 0 ? ND_CT : nd_rt;
@@ -477,7 +460,11 @@ int corr_fwd(const CorrFwd& p, cudaStream_t st) {
     int tma = corr_use_tma() && p.lcs == p.C && p.rcs == p.C;
     if (corr_init()) return -1;
     static int ver = -1;
-    if (ver < 0) { const char* e = getenv("MS_CORR_V"); ver = e ? atoi(e) : 3; }
+    if (ver < 0) { const char* e = getenv("MS_CORR_V"); ver = e ? atoi(e) : 4; }
+    if (ver >= 4) {                                     // MADNet cost volume (d=2, C%32==0): tensor-map TMA kernel, corr_tma.cu
+        const int r = corr_fwd4(p, st);
+        if (r <= 0) return r;
+    }
     if (ver >= 3) {
         const int nchunk = p.C / 4;
         const int LP = nchunk >= 24 ? 8 : (nchunk >= 16 ? 4 : (nchunk >= 8 ? 2 : 1));

@@ -62,17 +62,23 @@ def test_correlation_fwd_bwd(ops, shape, warp):
         assert rel_linf(du.cpu().numpy(), grads[2].numpy()) < 1e-4
 
 
-def test_cost_volume_concat(ops):
+@pytest.mark.parametrize('shape', [(1, 12, 40, 32, 2.0), (2, 5, 136, 64, 3.0), (1, 3, 300, 32, 70.0), (1, 4, 72, 96, 40.0)])
+def test_cost_volume_concat(ops, shape):
+    """Fused warp + correlation + concat (MadNet.py:370-375): multi-tile rows, a ragged last tile, and warp offsets wide
+    enough that taps leave the staged right-feature window (the kernel's direct-from-global path)."""
     T = _oracle()
+    b, h, w, c, umax = shape
     rng = np.random.default_rng(1)
-    x = rng.standard_normal((1, 12, 40, 32)).astype(np.float32)
-    y = rng.standard_normal((1, 12, 40, 32)).astype(np.float32)
-    u = rng.uniform(-2, 2, (1, 12, 40, 1)).astype(np.float32)
+    x = rng.standard_normal((b, h, w, c)).astype(np.float32)
+    y = rng.standard_normal((b, h, w, c)).astype(np.float32)
+    u = rng.uniform(-umax, umax, (b, h, w, 1)).astype(np.float32)
     ref = torch.cat([torch.tensor(x), T.correlation(torch.tensor(x), T.linear_warp(torch.tensor(y), torch.tensor(u)), 2),
                      torch.tensor(u)], -1)
     out = ops.cost_volume(cu(x), cu(y), 2, 1, u=cu(u))
     assert out.shape == ref.shape
     assert rel_linf(out.cpu().numpy(), ref.numpy()) < 2e-5
+    plain = ops.correlation(cu(x), cu(y), 2, 1, u=cu(u))
+    assert rel_linf(plain.cpu().numpy(), ref.numpy()[..., c:c + 5]) < 2e-5
 
 
 def test_correlation_matches_reference_native_kernel(ops):
@@ -103,6 +109,9 @@ CONV_CASES = [
     (1, 24, 40, 33, 128, 3, 1, 1, 0.2), (1, 24, 48, 128, 128, 3, 1, 4, 0.2), (1, 24, 48, 96, 64, 3, 1, 16, 0.2),
     (1, 17, 23, 20, 24, 3, 2, 1, 0.1), (1, 32, 32, 3, 64, 7, 2, 1, 0.1), (1, 16, 16, 64, 128, 5, 2, 1, 0.1),
     (1, 16, 16, 128, 64, 1, 1, 1, 0.1), (1, 6, 20, 197, 128, 3, 1, 1, 0.2),
+    # full-resolution pyramid layers (direct small-channel kernels, csrc/conv_small.cu): >= 4096 output pixels, odd widths
+    (2, 96, 130, 3, 16, 3, 2, 1, 0.2), (1, 70, 72, 16, 16, 3, 1, 1, 0.2), (1, 65, 67, 3, 16, 3, 1, 1, 1.0),
+    (1, 68, 64, 8, 16, 3, 1, 2, 0.2),
 ]
 
 
