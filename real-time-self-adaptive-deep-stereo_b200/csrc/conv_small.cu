@@ -6,8 +6,8 @@
 // The launch list (profiles/r1_launches_final_summary.txt) had the gather GEMM at 105 us for conv1 forward (0.2 GFLOP,
 // 27 MB: it should be a ~10 us HBM-bound kernel) and 319 + 271 us for the conv1 / conv2 weight gradients (432 / 2304
 // outputs reduced over 245 760 pixels: a 16 x 16 output tile leaves the GEMM kernel with 9 CTAs per K split).
-//   forward  : one thread computes two adjacent output pixels x 16 output channels; the 27 x 16 weights sit in shared
-//              memory and are read as broadcast float4.
+//   forward  : one thread computes two adjacent output pixels x all output channels; the weights sit in shared memory
+//              and are read as broadcast float4 (also used for conv2 forward / dgrad and conv3 forward: 16 -> 16 | 32).
 //   wgrad    : a thread owns one input channel ("role") and keeps all 9 taps x 16 output channels = 144 partial sums
 //              in registers while it walks its share of the pixels (9 input loads + 16 dY loads per 144 FMAs, next
 //              pixel prefetched); lanes of equal role are combined by shuffles, warps through shared memory, CTAs by
@@ -21,18 +21,18 @@ namespace ms {
 static __host__ __device__ bool al16s(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // ---------------------------------------------------------------------------------------------
-// forward, cin = 3
+// forward / stride-1 dgrad gather, 3x3, (cin, cout) in {(3,16), (16,16), (16,32)}
 // ---------------------------------------------------------------------------------------------
-constexpr int C3_NT = 128;
+constexpr int CS_NT = 128;
 
-template <int CO>
-__global__ void __launch_bounds__(C3_NT) conv_c3_fwd_kernel(ConvGemm p, int pairs_per_row, int total_pairs) {
-    __shared__ __align__(16) float ws[27 * CO];
+template <int CIN, int CO>
+__global__ void __launch_bounds__(CS_NT) conv_small_fwd_kernel(ConvGemm p, int pairs_per_row, int total_pairs) {
+    __shared__ __align__(16) float ws[9 * CIN * CO];                               // [tap][ci][co]
     __shared__ float bs[CO];
-    for (int i = threadIdx.x; i < 27 * CO; i += C3_NT) ws[i] = p.wmat[i];          // [tap][ci][co]
-    for (int i = threadIdx.x; i < CO; i += C3_NT) bs[i] = p.bias ? p.bias[i] : 0.f;
+    for (int i = threadIdx.x; i < 9 * CIN * CO; i += CS_NT) ws[i] = p.wmat[i];
+    for (int i = threadIdx.x; i < CO; i += CS_NT) bs[i] = p.bias ? p.bias[i] : 0.f;
     __syncthreads();
-    const int e = blockIdx.x * C3_NT + threadIdx.x;
+    const int e = blockIdx.x * CS_NT + threadIdx.x;
     if (e >= total_pairs) return;
     const int xp = e % pairs_per_row;
     const int q = e / pairs_per_row;
@@ -42,46 +42,57 @@ __global__ void __launch_bounds__(C3_NT) conv_c3_fwd_kernel(ConvGemm p, int pair
 #pragma unroll
     for (int j = 0; j < CO; ++j) { acc[0][j] = bs[j]; acc[1][j] = bs[j]; }
     const float* ximg = p.x.p + (size_t)img * p.x.h * p.x.w * p.x.cs;
-#pragma unroll
-    for (int ty = 0; ty < 3; ++ty) {
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+        const int ty = tap / 3, tx = tap - ty * 3;
         const int iy = oy * p.mul + p.off_y + ty * p.step;
         const bool rok = iy >= 0 && iy < p.x.h;
-        const float* xrow = ximg + (size_t)(rok ? iy : 0) * p.x.w * p.x.cs;
-        float xin[2][3][3];
+        float xin[2][CIN];
 #pragma unroll
-        for (int pi = 0; pi < 2; ++pi)
+        for (int pi = 0; pi < 2; ++pi) {
+            const int ix = (ox0 + pi) * p.mul + p.off_x + tx * p.step;
+            const bool ok = rok && ix >= 0 && ix < p.x.w;
+            const float* s = ximg + ((size_t)(ok ? iy : 0) * p.x.w + (ok ? ix : 0)) * p.x.cs;
+            if constexpr (CIN % 4 == 0) {
 #pragma unroll
-            for (int tx = 0; tx < 3; ++tx) {
-                const int ix = (ox0 + pi) * p.mul + p.off_x + tx * p.step;
-                const bool ok = rok && ix >= 0 && ix < p.x.w;
-                const float* s = xrow + (size_t)(ok ? ix : 0) * p.x.cs;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) xin[pi][tx][c] = ok ? __ldg(s + c) : 0.f;
-            }
-#pragma unroll
-        for (int tx = 0; tx < 3; ++tx)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float4* wr = reinterpret_cast<const float4*>(ws + ((ty * 3 + tx) * 3 + c) * CO);
-                const float a0 = xin[0][tx][c], a1 = xin[1][tx][c];
-#pragma unroll
-                for (int j4 = 0; j4 < CO / 4; ++j4) {
-                    const float4 w = wr[j4];
-                    acc[0][4 * j4] = fmaf(a0, w.x, acc[0][4 * j4]); acc[0][4 * j4 + 1] = fmaf(a0, w.y, acc[0][4 * j4 + 1]);
-                    acc[0][4 * j4 + 2] = fmaf(a0, w.z, acc[0][4 * j4 + 2]); acc[0][4 * j4 + 3] = fmaf(a0, w.w, acc[0][4 * j4 + 3]);
-                    acc[1][4 * j4] = fmaf(a1, w.x, acc[1][4 * j4]); acc[1][4 * j4 + 1] = fmaf(a1, w.y, acc[1][4 * j4 + 1]);
-                    acc[1][4 * j4 + 2] = fmaf(a1, w.z, acc[1][4 * j4 + 2]); acc[1][4 * j4 + 3] = fmaf(a1, w.w, acc[1][4 * j4 + 3]);
+                for (int c4 = 0; c4 < CIN / 4; ++c4) {
+                    const float4 v = ok ? __ldg(reinterpret_cast<const float4*>(s) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    xin[pi][4 * c4] = v.x; xin[pi][4 * c4 + 1] = v.y; xin[pi][4 * c4 + 2] = v.z; xin[pi][4 * c4 + 3] = v.w;
                 }
+            } else {
+#pragma unroll
+                for (int c = 0; c < CIN; ++c) xin[pi][c] = ok ? __ldg(s + c) : 0.f;
             }
+        }
+        const float4* wt = reinterpret_cast<const float4*>(ws + tap * CIN * CO);
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
+            const float a0 = xin[0][c], a1 = xin[1][c];
+#pragma unroll
+            for (int j4 = 0; j4 < CO / 4; ++j4) {
+                const float4 w = wt[c * (CO / 4) + j4];
+                acc[0][4 * j4] = fmaf(a0, w.x, acc[0][4 * j4]); acc[0][4 * j4 + 1] = fmaf(a0, w.y, acc[0][4 * j4 + 1]);
+                acc[0][4 * j4 + 2] = fmaf(a0, w.z, acc[0][4 * j4 + 2]); acc[0][4 * j4 + 3] = fmaf(a0, w.w, acc[0][4 * j4 + 3]);
+                acc[1][4 * j4] = fmaf(a1, w.x, acc[1][4 * j4]); acc[1][4 * j4 + 1] = fmaf(a1, w.y, acc[1][4 * j4 + 1]);
+                acc[1][4 * j4 + 2] = fmaf(a1, w.z, acc[1][4 * j4 + 2]); acc[1][4 * j4 + 3] = fmaf(a1, w.w, acc[1][4 * j4 + 3]);
+            }
+        }
     }
     const bool vec = (p.y.cs & 3) == 0 && al16s(p.y.p);
 #pragma unroll
     for (int pi = 0; pi < 2; ++pi) {
         const int ox = ox0 + pi;
         if (ox >= p.y.w) break;
-        float* yrow = p.y.p + ((size_t)(img * p.y.h + oy) * p.y.w + ox) * p.y.cs;
+        const size_t pix = (size_t)(img * p.y.h + oy) * p.y.w + ox;
+        float* yrow = p.y.p + pix * p.y.cs;
 #pragma unroll
-        for (int j = 0; j < CO; ++j) acc[pi][j] = fmaxf(p.alpha * acc[pi][j], acc[pi][j]);
+        for (int j = 0; j < CO; ++j) {                       // same epilogue order as conv_gemm_kernel / conv_tc
+            float t = fmaxf(p.alpha * acc[pi][j], acc[pi][j]);
+            if (p.res) t += p.res[pix * p.res_cs + j];
+            if (p.accumulate) t += yrow[j];
+            if (p.mask) t *= (p.mask[pix * p.mask_cs + j] > 0.f) ? 1.f : p.mask_alpha;
+            acc[pi][j] = t;
+        }
         if (vec) {
 #pragma unroll
             for (int j = 0; j < CO; j += 4)
@@ -94,16 +105,21 @@ __global__ void __launch_bounds__(C3_NT) conv_c3_fwd_kernel(ConvGemm p, int pair
 }
 
 bool conv_small_fwd_supported(const ConvGemm& p) {
-    return p.x.c == 3 && p.y.c == 16 && p.kh == 3 && p.kw == 3 && p.div == 1 && p.mul >= 1 && p.step >= 1 && !p.mask &&
-           !p.res && !p.accumulate && p.alpha <= 1.f && p.alpha >= 0.f && p.x.n == p.y.n;
+    if (p.kh != 3 || p.kw != 3 || p.div != 1 || p.mul < 1 || p.x.n != p.y.n || p.alpha > 1.f || p.alpha < 0.f) return false;
+    if (p.x.c == 3 && p.y.c == 16) return true;
+    if (p.x.c == 16 && (p.y.c == 16 || p.y.c == 32)) return (p.x.cs & 3) == 0 && al16s(p.x.p);
+    return false;
 }
 
 int conv_small_fwd(const ConvGemm& p, cudaStream_t st) {
     const int pairs_per_row = cdiv(p.y.w, 2);
     const size_t total = (size_t)p.y.n * p.y.h * pairs_per_row;
     MS_REQUIRE(total < (1u << 30), "conv_small_fwd: too many output pixels");
-    conv_c3_fwd_kernel<16><<<(unsigned)cdivz(total, C3_NT), C3_NT, 0, st>>>(p, pairs_per_row, (int)total);
-    return check_launch("conv_c3_fwd");
+    const unsigned grid = (unsigned)cdivz(total, CS_NT);
+    if (p.x.c == 3) conv_small_fwd_kernel<3, 16><<<grid, CS_NT, 0, st>>>(p, pairs_per_row, (int)total);
+    else if (p.y.c == 16) conv_small_fwd_kernel<16, 16><<<grid, CS_NT, 0, st>>>(p, pairs_per_row, (int)total);
+    else conv_small_fwd_kernel<16, 32><<<grid, CS_NT, 0, st>>>(p, pairs_per_row, (int)total);
+    return check_launch("conv_small_fwd");
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -154,7 +154,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 for (int e = 0; e < 4; ++e) {
                     const int idx = st_tid + e * SPLIT_THREADS;
                     float4 h, l;
-                    h.x = tf32_rna(v[e].x); h.y = tf32_rna(v[e].y); h.z = tf32_rna(v[e].z); h.w = tf32_rna(v[e].w);
+                    h.x = tf32_hi(v[e].x); h.y = tf32_hi(v[e].y); h.z = tf32_hi(v[e].z); h.w = tf32_hi(v[e].w);
                     l.x = v[e].x - h.x; l.y = v[e].y - h.y; l.z = v[e].z - h.z; l.w = v[e].w - h.w;
                     ahi[idx] = h; alo[idx] = l;
                 }
@@ -163,11 +163,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     const bool two = i1 < b_f4;
                     float4 w0 = bhi[i0], w1 = two ? bhi[i1] : make_float4(0.f, 0.f, 0.f, 0.f);
                     float4 h, l;
-                    h.x = tf32_rna(w0.x); h.y = tf32_rna(w0.y); h.z = tf32_rna(w0.z); h.w = tf32_rna(w0.w);
+                    h.x = tf32_hi(w0.x); h.y = tf32_hi(w0.y); h.z = tf32_hi(w0.z); h.w = tf32_hi(w0.w);
                     l.x = w0.x - h.x; l.y = w0.y - h.y; l.z = w0.z - h.z; l.w = w0.w - h.w;
                     bhi[i0] = h; blo[i0] = l;
                     if (two) {
-                        h.x = tf32_rna(w1.x); h.y = tf32_rna(w1.y); h.z = tf32_rna(w1.z); h.w = tf32_rna(w1.w);
+                        h.x = tf32_hi(w1.x); h.y = tf32_hi(w1.y); h.z = tf32_hi(w1.z); h.w = tf32_hi(w1.w);
                         l.x = w1.x - h.x; l.y = w1.y - h.y; l.z = w1.z - h.z; l.w = w1.w - h.w;
                         bhi[i1] = h; blo[i1] = l;
                     }
@@ -191,14 +191,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const bool vec = ((p.ycs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
         const int chunks = p.BN / 16, half = (chunks + 1) / 2;
         const int cbeg = (warp < 6 ? 0 : half) * 16, cend = (warp < 6 ? half : chunks) * 16;   // warps 2-5 | 6-9
+        const bool plain = vec && !p.res && !p.accumulate && !p.mask;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         for (int c0 = cbeg; c0 < cend; c0 += 16) {
-            float v[16];
-            tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            for (int a = 1; a <= p.n_main; ++a) {
-                float u[16];
-                tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.acc_stride + c0), u);
+            uint32_t r0[16], r1[16], r2[16], r3[16];
+            float bb[16];
+            const bool fast = plain && c0 + 16 <= p.N;
+            if (fast) {                                  // bias loads overlap the TMEM reads
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] += u[j];
+                for (int j = 0; j < 16; ++j) bb[j] = p.bias ? __ldg(p.bias + c0 + j) : 0.f;
+            }
+            tc_ld16_nowait(tmem + lane_base + (uint32_t)c0, r0);
+            tc_ld16_nowait(tmem + lane_base + (uint32_t)(p.acc_stride + c0), r1);
+            if (p.n_main > 1) tc_ld16_nowait(tmem + lane_base + (uint32_t)(2 * p.acc_stride + c0), r2);
+            if (p.n_main > 2) tc_ld16_nowait(tmem + lane_base + (uint32_t)(3 * p.acc_stride + c0), r3);
+            tc_wait_ld();
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float t = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+                if (p.n_main > 1) t += __uint_as_float(r2[j]);
+                if (p.n_main > 2) t += __uint_as_float(r3[j]);
+                v[j] = t;
+            }
+            if (valid && fast) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { const float t = v[j] + bb[j]; v[j] = fmaxf(p.alpha * t, t); }
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(yrow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                continue;
             }
             if (!valid) continue;
 #pragma unroll
@@ -390,7 +412,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_const
                         const int row = idx >> 3, ch = idx & 7;
                         const int d = row * 8 + (ch ^ (row & 7));
                         float4 h, l;
-                        h.x = tf32_rna(v[e].x); h.y = tf32_rna(v[e].y); h.z = tf32_rna(v[e].z); h.w = tf32_rna(v[e].w);
+                        h.x = tf32_hi(v[e].x); h.y = tf32_hi(v[e].y); h.z = tf32_hi(v[e].z); h.w = tf32_hi(v[e].w);
                         l.x = v[e].x - h.x; l.y = v[e].y - h.y; l.z = v[e].z - h.z; l.w = v[e].w - h.w;
                         ahi[d] = h; alo[d] = l;
                     }
@@ -400,11 +422,11 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_const
                         const bool two = i1 < b_f4;
                         float4 w0 = braw[i0], w1 = two ? braw[i1] : make_float4(0.f, 0.f, 0.f, 0.f);
                         float4 h, l;
-                        h.x = tf32_rna(w0.x); h.y = tf32_rna(w0.y); h.z = tf32_rna(w0.z); h.w = tf32_rna(w0.w);
+                        h.x = tf32_hi(w0.x); h.y = tf32_hi(w0.y); h.z = tf32_hi(w0.z); h.w = tf32_hi(w0.w);
                         l.x = w0.x - h.x; l.y = w0.y - h.y; l.z = w0.z - h.z; l.w = w0.w - h.w;
                         bhi[i0] = h; blo[i0] = l;
                         if (two) {
-                            h.x = tf32_rna(w1.x); h.y = tf32_rna(w1.y); h.z = tf32_rna(w1.z); h.w = tf32_rna(w1.w);
+                            h.x = tf32_hi(w1.x); h.y = tf32_hi(w1.y); h.z = tf32_hi(w1.z); h.w = tf32_hi(w1.w);
                             l.x = w1.x - h.x; l.y = w1.y - h.y; l.z = w1.z - h.z; l.w = w1.w - h.w;
                             bhi[i1] = h; blo[i1] = l;
                         }
@@ -485,6 +507,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_const
 // (weight split) + 48 KB (B operand reads) instead of 192 KB, and the freed 64 KB deepen the weight ring.
 //   TMEM columns: [0, (n_main+1)*acc_stride) accumulators | then 2 stages x {32 hi, 32 lo} columns of A
 // ------------------------------------------------------------------------------------------------
+#define TSP_T0() const long long _t0 = PROF ? clock64() : 0
+#define TSP_ADD(slot, cond) do { if (PROF && (cond)) g_tc_prof[slot] += (unsigned long long)(clock64() - _t0); } while (0)
+template <bool PROF>      // PROF: per-role clock64 counters + MS_TC_DEBUG kill switches (timing experiments only)
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapB,
                   const ConvTCHaloParams hp) {
@@ -510,11 +535,12 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
     const int img = bid / p.tiles_y;
     const int x0 = tx * p.TW, y0 = ty * p.TH;
     const int taps = p.kh * p.kw;
-    const int kb0 = (int)(((long)blockIdx.y * p.kblocks) / p.ksplit), kb1 = (int)(((long)(blockIdx.y + 1) * p.kblocks) / p.ksplit);
-    const int nkb = kb1 - kb0;
-    const int total = taps * nkb;
-    const bool prof = (p.dbg & 8) && blockIdx.x == 0;
-    const long long t_start = clock64();
+    // split-K unit = one (channel block, tap) iteration; this CTA owns global iterations [g0, g1), kb-major / tap-minor
+    const int total_all = taps * p.kblocks;
+    const int g0 = (int)(((long)blockIdx.y * total_all) / p.ksplit), g1 = (int)(((long)(blockIdx.y + 1) * total_all) / p.ksplit);
+    const int total = g1 - g0;
+    const bool prof = PROF && (p.dbg & 8) && blockIdx.x == 0;
+    const long long t_start = PROF ? clock64() : 0;
     long long t_epi = 0;
 
     if (threadIdx.x == 0) {
@@ -537,24 +563,30 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
 
     if (warp == 0) {
         if (lane == 0) {
-            auto load_patch = [&](int kl) {           // kl = local channel-block index
+            int kl = 0;                               // local patch counter (slot = kl & 1)
+            auto load_patch = [&](int kb) {
                 const int pb = kl & 1;
                 mb_wait(&pempty[pb], (((uint32_t)kl >> 1) & 1u) ^ 1u);
                 mb_expect_tx(&pfull[pb], hp.patch_bytes);
-                tma_load_4d(gbase + patch_off + (size_t)pb * patch_stride, &mapP, &pfull[pb], (kb0 + kl) * 32, x0 + hp.minx, y0 + hp.miny, img);
+                tma_load_4d(gbase + patch_off + (size_t)pb * patch_stride, &mapP, &pfull[pb], kb * 32, x0 + hp.minx, y0 + hp.miny, img);
+                ++kl;
             };
-            load_patch(0);
             int slot = 0;
             uint32_t bph = 0;
             const int ahead = min(NB, taps) - 1;
-            for (int kb = 0; kb < nkb; ++kb) {
-                for (int tap = 0; tap < taps; ++tap) {
-                    { TCP_T0(); mb_wait(&bempty[slot], bph ^ 1u); TCP_ADD(0, prof); }
-                    mb_expect_tx(&bfull[slot], b_bytes);
-                    tma_load_3d(gbase + braw_off + (size_t)slot * b_bytes, &mapB, &bfull[slot], (kb0 + kb) * 32, 0, tap);
-                    if (++slot == NB) { slot = 0; bph ^= 1u; }
-                    if (tap == ahead && kb + 1 < nkb) load_patch(kb + 1);
+            int next_patch_g = g0;                    // first iteration that needs a patch not requested yet
+            int kb = g0 / taps, tap = g0 - kb * taps;
+            for (int g = g0; g < g1; ++g) {
+                while (next_patch_g < g1 && next_patch_g <= g + ahead) {
+                    const int kbn = next_patch_g / taps;
+                    load_patch(kbn);
+                    next_patch_g = (kbn + 1) * taps;
                 }
+                { TSP_T0(); mb_wait(&bempty[slot], bph ^ 1u); TSP_ADD(0, prof); }
+                mb_expect_tx(&bfull[slot], b_bytes);
+                tma_load_3d(gbase + braw_off + (size_t)slot * b_bytes, &mapB, &bfull[slot], kb * 32, 0, tap);
+                if (++slot == NB) { slot = 0; bph ^= 1u; }
+                if (++tap == taps) { tap = 0; ++kb; }
             }
         }
     } else if (warp == 1) {
@@ -562,12 +594,13 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
             for (int it = 0; it < total; ++it) {
                 const int s = it & 1;
-                { TCP_T0(); mb_wait(&ready_bar[s], ((uint32_t)it >> 1) & 1u); TCP_ADD(1, prof); }
-                const long long t_issue = clock64();
+                { TSP_T0(); mb_wait(&ready_bar[s], ((uint32_t)it >> 1) & 1u); TSP_ADD(1, prof); }
+                const long long t_issue = PROF ? clock64() : 0;
                 tc_fence_after();
                 const uint32_t sb = base + (uint32_t)s * op_bytes;
                 const uint64_t b_hi = umma_desc_sw128(sb), b_lo = umma_desc_sw128(sb + b_bytes);
                 const uint32_t a_hi = tmem + a_col0 + (uint32_t)s * 64u, a_lo = a_hi + 32u;
+                if (!(PROF && (p.dbg & 64)))        // timing experiments only (MS_TC_DEBUG): 64 = no MMAs, 16 = no A split, 32 = no B split
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const uint64_t o = (uint64_t)(j * 2);
@@ -579,7 +612,7 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
                     tc_mma_tf32_ts(dmain, a_hi + ao, b_hi + o, idesc, g >= p.n_main ? 1u : 0u);
                 }
                 tc_commit(&free_bar[s]);
-                if (prof) g_tc_prof[2] += (unsigned long long)(clock64() - t_issue);
+                if (PROF && prof) g_tc_prof[2] += (unsigned long long)(clock64() - t_issue);
             }
             tc_commit(&accum_bar);
         }
@@ -596,65 +629,75 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
             int slot = 0;
             uint32_t bph = 0;
             int it = 0;
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int pb = kb & 1;
-                const bool sp = prof && threadIdx.x == 64;
-                { TCP_T0(); mb_wait(&pfull[pb], ((uint32_t)kb >> 1) & 1u); TCP_ADD(3, sp); }
-                const unsigned char* patch = gbase + patch_off + (size_t)pb * patch_stride;
-                for (int tap = 0; tap < taps; ++tap, ++it) {
+            int kl = -1, cur_kb = -1, pb = 0;
+            const unsigned char* patch = nullptr;
+            const bool sp = prof && threadIdx.x == 64;
+            int kb = g0 / taps, tap = g0 - kb * taps;
+            int tr = tap / p.kw, ts = tap - tr * p.kw;
+            const int pp_base = (my + p.off_y - hp.miny) * hp.PW + (mx + p.off_x - hp.minx);
+            for (int g = g0; g < g1; ++g, ++it) {
+                {
+                    if (kb != cur_kb) {                 // entering a new channel block: release the old patch, wait for the new one
+                        if (cur_kb >= 0) { __syncwarp(); if (lane == 0) mb_arrive(&pempty[pb]); }
+                        cur_kb = kb; ++kl; pb = kl & 1;
+                        { TSP_T0(); mb_wait(&pfull[pb], ((uint32_t)kl >> 1) & 1u); TSP_ADD(3, sp); }
+                        patch = gbase + patch_off + (size_t)pb * patch_stride;
+                    }
                     const int s = it & 1;
-                    { TCP_T0(); mb_wait(&free_bar[s], (((uint32_t)it >> 1) & 1u) ^ 1u); TCP_ADD(4, sp); }
-                    { TCP_T0(); mb_wait(&bfull[slot], bph); TCP_ADD(5, sp); }
-                    const long long t_work = clock64();
+                    { TSP_T0(); mb_wait(&free_bar[s], (((uint32_t)it >> 1) & 1u) ^ 1u); TSP_ADD(4, sp); }
+                    { TSP_T0(); mb_wait(&bfull[slot], bph); TSP_ADD(5, sp); }
+                    const long long t_work = PROF ? clock64() : 0;
                     // ---- A: this thread's pixel, 16 channels -> tf32 hi / lo -> TMEM
-                    const int tr = tap / p.kw, ts = tap - tr * p.kw;
-                    const int pp = (my + p.off_y + tr * p.step - hp.miny) * hp.PW + (mx + p.off_x + ts * p.step - hp.minx);
+                    const int pp = pp_base + (tr * hp.PW + ts) * p.step;
                     const unsigned char* prow = patch + (size_t)pp * 128;
                     float hi[16], lo[16];
+                    if (!(PROF && (p.dbg & 16))) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int ch = hsel * 4 + e;
                         const float4 v = *reinterpret_cast<const float4*>(prow + ((ch ^ (pp & 7)) * 16));
-                        hi[4 * e] = tf32_rna(v.x); hi[4 * e + 1] = tf32_rna(v.y); hi[4 * e + 2] = tf32_rna(v.z); hi[4 * e + 3] = tf32_rna(v.w);
+                        hi[4 * e] = tf32_hi(v.x); hi[4 * e + 1] = tf32_hi(v.y); hi[4 * e + 2] = tf32_hi(v.z); hi[4 * e + 3] = tf32_hi(v.w);
                         lo[4 * e] = v.x - hi[4 * e]; lo[4 * e + 1] = v.y - hi[4 * e + 1];
                         lo[4 * e + 2] = v.z - hi[4 * e + 2]; lo[4 * e + 3] = v.w - hi[4 * e + 3];
                     }
                     const uint32_t acol = tmem + lane_base + a_col0 + (uint32_t)s * 64u + (uint32_t)hsel * 16u;
                     tc_st16(acol, hi);
                     tc_st16(acol + 32u, lo);
+                    }
                     // ---- B: elementwise split raw -> hi / lo (layout already swizzled by TMA)
                     unsigned char* stg = gbase + (size_t)s * op_bytes;
                     float4* __restrict__ bhi = reinterpret_cast<float4*>(stg);
                     float4* __restrict__ blo = reinterpret_cast<float4*>(stg + b_bytes);
                     const float4* __restrict__ braw = reinterpret_cast<const float4*>(gbase + braw_off + (size_t)slot * b_bytes);
+                    if (!(PROF && (p.dbg & 32)))
                     for (int i0 = st_tid; i0 < b_f4; i0 += 2 * SPLIT_THREADS) {
                         const int i1 = i0 + SPLIT_THREADS;
                         const bool two = i1 < b_f4;
                         float4 w0 = braw[i0], w1 = two ? braw[i1] : make_float4(0.f, 0.f, 0.f, 0.f);
                         float4 h, l;
-                        h.x = tf32_rna(w0.x); h.y = tf32_rna(w0.y); h.z = tf32_rna(w0.z); h.w = tf32_rna(w0.w);
+                        h.x = tf32_hi(w0.x); h.y = tf32_hi(w0.y); h.z = tf32_hi(w0.z); h.w = tf32_hi(w0.w);
                         l.x = w0.x - h.x; l.y = w0.y - h.y; l.z = w0.z - h.z; l.w = w0.w - h.w;
                         bhi[i0] = h; blo[i0] = l;
                         if (two) {
-                            h.x = tf32_rna(w1.x); h.y = tf32_rna(w1.y); h.z = tf32_rna(w1.z); h.w = tf32_rna(w1.w);
+                            h.x = tf32_hi(w1.x); h.y = tf32_hi(w1.y); h.z = tf32_hi(w1.z); h.w = tf32_hi(w1.w);
                             l.x = w1.x - h.x; l.y = w1.y - h.y; l.z = w1.z - h.z; l.w = w1.w - h.w;
                             bhi[i1] = h; blo[i1] = l;
                         }
                     }
-                    if (sp) g_tc_prof[6] += (unsigned long long)(clock64() - t_work);
-                    { TCP_T0(); tc_wait_st(); fence_async_smem(); tc_fence_before(); TCP_ADD(7, sp); }
+                    if (PROF && sp) g_tc_prof[6] += (unsigned long long)(clock64() - t_work);
+                    { TSP_T0(); tc_wait_st(); fence_async_smem(); tc_fence_before(); TSP_ADD(7, sp); }
                     __syncwarp();
                     if (lane == 0) { mb_arrive(&ready_bar[s]); mb_arrive(&bempty[slot]); }
                     if (++slot == NB) { slot = 0; bph ^= 1u; }
+                    if (++ts == p.kw) { ts = 0; ++tr; }
+                    if (++tap == taps) { tap = 0; tr = 0; ts = 0; ++kb; }
                 }
-                __syncwarp();
-                if (lane == 0) mb_arrive(&pempty[pb]);
             }
         }
         // ================= epilogue =================
-        t_epi = clock64();
+        if (PROF) t_epi = clock64();
         mb_wait(&accum_bar, 0);
-        if (prof && threadIdx.x == 64) g_tc_prof[11] += (unsigned long long)(clock64() - t_epi);
+        if (PROF && prof && threadIdx.x == 64) g_tc_prof[11] += (unsigned long long)(clock64() - t_epi);
         tc_fence_after();
         const int py = y0 + my, px = x0 + mx;
         const bool valid = (py < p.H) && (px < p.W);
@@ -663,8 +706,15 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
         const bool vec = ((p.ycs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
         const int chunks = p.BN / 16, half = (chunks + 1) / 2;
         const int cbeg = (warp < 6 ? 0 : half) * 16, cend = (warp < 6 ? half : chunks) * 16;
+        const bool plain = vec && !p.res && !p.accumulate && !p.mask && p.ksplit == 1;
         for (int c0 = cbeg; c0 < cend; c0 += 16) {
             uint32_t r0[16], r1[16], r2[16], r3[16];
+            float bb[16];
+            const bool fast = plain && c0 + 16 <= p.N;
+            if (fast) {                                  // bias loads overlap the TMEM reads
+#pragma unroll
+                for (int j = 0; j < 16; ++j) bb[j] = p.bias ? __ldg(p.bias + c0 + j) : 0.f;
+            }
             tc_ld16_nowait(tmem + lane_base + (uint32_t)c0, r0);
             tc_ld16_nowait(tmem + lane_base + (uint32_t)(p.acc_stride + c0), r1);
             if (p.n_main > 1) tc_ld16_nowait(tmem + lane_base + (uint32_t)(2 * p.acc_stride + c0), r2);
@@ -679,6 +729,14 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
                 v[j] = t;
             }
             if (!valid) continue;
+            if (fast) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { const float t = v[j] + bb[j]; v[j] = fmaxf(p.alpha * t, t); }
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(yrow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                continue;
+            }
             if (p.ksplit > 1) {                     // raw partial sums; bias / activation happen in tc_splitk_reduce
                 float* prow = p.part + ((size_t)blockIdx.y * ((size_t)p.NB * p.H * p.W) + pix) * p.BN + c0;
 #pragma unroll
@@ -710,7 +768,7 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
             }
         }
     }
-    if (prof && threadIdx.x == 64) { g_tc_prof[8] += (unsigned long long)(clock64() - t_epi); g_tc_prof[9] += (unsigned long long)(t_epi - t_start); g_tc_prof[10] += 1; }
+    if (PROF && prof && threadIdx.x == 64) { g_tc_prof[8] += (unsigned long long)(clock64() - t_epi); g_tc_prof[9] += (unsigned long long)(t_epi - t_start); g_tc_prof[10] += 1; }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -848,7 +906,8 @@ int conv_tc_init() {
     if (done) return 0;
     MS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
     MS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-    MS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    MS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    MS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
     done = true;
     return 0;
 }
@@ -928,12 +987,17 @@ int conv_tc(const ConvGemm& g, const float* bw, cudaStream_t st, float* part) {
                     // small maps leave most SMs idle while each CTA walks the whole K loop: split K over channel blocks
                     const size_t npix = (size_t)p.NB * p.H * p.W;
                     int ksplit = 1;
-                    if (part && grid <= 74 && kblocks > 1) {
-                        ksplit = std::min(kblocks, std::max(1, 148 / grid));
+                    static int tapsplit = -1;
+                    if (tapsplit < 0) { const char* e = getenv("MS_TC_TAPSPLIT"); tapsplit = (e && e[0] == '0') ? 0 : 1; }
+                    const int units = tapsplit ? taps * kblocks : kblocks;       // split-K granularity: (kb, tap) iterations
+                    if (part && grid <= 74 && units > 1) {
+                        ksplit = std::min(units, std::max(1, 148 / grid));
+                        if (!tapsplit) ksplit = std::min(ksplit, kblocks);
                         if ((size_t)ksplit * npix * BN > conv_tc_part_floats()) ksplit = 1;
                     }
                     hp.c.ksplit = ksplit; hp.c.part = part;
-                    conv_tc_ts_kernel<<<dim3(grid, ksplit), TC_THREADS, smem2, st>>>(*mapP, *mapB, hp);
+                    if (p.dbg & 8) conv_tc_ts_kernel<true><<<dim3(grid, ksplit), TC_THREADS, smem2, st>>>(*mapP, *mapB, hp);
+                    else conv_tc_ts_kernel<false><<<dim3(grid, ksplit), TC_THREADS, smem2, st>>>(*mapP, *mapB, hp);
                     if (ksplit > 1) {
                         tc_splitk_reduce_kernel<<<(unsigned)cdivz(npix * p.N, 256), 256, 0, st>>>(hp.c, npix);
                         return check_launch("conv_tc_ts+reduce", 2);

@@ -36,16 +36,29 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// shared-memory byte address of row r of a swizzled tile, pre-XORed so that chunk q sits at rowkey(..) ^ (q << 4):
+// the row base is 128-byte aligned and the swizzled chunk offset is < 128, so OR == ADD and the XOR distributes.
+__device__ __forceinline__ uint32_t rowkey(uint32_t tile_s, int r) { return (tile_s + (uint32_t)r * 128u) | (((uint32_t)r & 7u) << 4); }
+
 struct Corr4Params {
     CorrFwd p;
     int TW, WB, RB, ncb;     // tile width, RW rows (>= TW+4), raw right window rows, 32-channel blocks
     int store_o, store_o2;   // left -> concat copy by TMA store
+    float invC;
 };
 
 // float4 index of chunk q of row r in 32-channel block cb of a [ncb][rows][8] swizzled tile
 __device__ __forceinline__ int t4(int cb, int rows, int r, int q) { return ((cb * rows + r) << 3) + (q ^ (r & 7)); }
 
-template <int LP>
+template <int LP, int NCB_CT>     // NCB_CT > 0: number of 32-channel blocks known at compile time (loops unroll)
 __global__ void __launch_bounds__(256) corr_fwd4_kernel(const __grid_constant__ CUtensorMap mapL,
                                                         const __grid_constant__ CUtensorMap mapR,
                                                         const __grid_constant__ CUtensorMap mapO,
@@ -56,7 +69,7 @@ __global__ void __launch_bounds__(256) corr_fwd4_kernel(const __grid_constant__ 
     __shared__ __align__(8) uint64_t barL, barR;
     __shared__ int s_lo, s_hi;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
-    const int TW = k.TW, WB = k.WB, RB = k.RB, ncb = k.ncb;
+    const int TW = k.TW, WB = k.WB, RB = k.RB, ncb = NCB_CT > 0 ? NCB_CT : k.ncb;
     const int w = p.w;
     const bool warped = p.u != nullptr;
     const int row = blockIdx.y, x0 = blockIdx.x * TW;
@@ -67,6 +80,7 @@ __global__ void __launch_bounds__(256) corr_fwd4_kernel(const __grid_constant__ 
     float4* RWs = Ls + (size_t)ncb * TW * 8;                           // [ncb][WB][8]
     float4* Rs = RWs + (size_t)ncb * WB * 8;                           // [ncb][RB][8]   (warped only)
     Tap* taps = reinterpret_cast<Tap*>(Rs + (warped ? (size_t)ncb * RB * 8 : 0));   // [WB]
+    const uint32_t Ls_s = base, RWs_s = Ls_s + (uint32_t)(ncb * TW) * 128u, Rs_s = RWs_s + (uint32_t)(ncb * WB) * 128u;
 
     const float* rrow = p.right + (size_t)row * w * p.rcs;
     float* orow = p.out + (size_t)row * w * p.ocs;
@@ -139,21 +153,39 @@ __global__ void __launch_bounds__(256) corr_fwd4_kernel(const __grid_constant__ 
     // ---- RW[t] = w0 * R[i0] + w1 * R[i1]
     if (warped) {
         if (rhi > rlo) mb_wait(&barR, 0);
+        const uint32_t subk = (uint32_t)q0 << 4;
         for (int t = pl; t < NW; t += npl) {
             const Tap tp = taps[t];
             const int r0 = tp.i0 - rlo, r1 = tp.i1 - rlo;
             const bool in0 = r0 >= 0 && tp.i0 < rhi, in1 = r1 >= 0 && tp.i1 < rhi;
             const bool z0 = tp.w0 == 0.f, z1 = tp.w1 == 0.f;
-            for (int cb = 0; cb < ncb; ++cb) {
+            uint32_t dk = rowkey(RWs_s, t) ^ subk;
+            if (!z0 && !z1 && in0 && in1) {                  // common case: both taps staged
+                uint32_t ak = rowkey(Rs_s, r0) ^ subk, bk = rowkey(Rs_s, r1) ^ subk;
 #pragma unroll
-                for (int qq = 0; qq < QPL; ++qq) {
-                    const int q = q0 + qq;
-                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-                    if (!z0) a = in0 ? Rs[t4(cb, RB, r0, q)] : *reinterpret_cast<const float4*>(rrow + (size_t)tp.i0 * p.rcs + cb * 32 + q * 4);
-                    if (!z1) b = in1 ? Rs[t4(cb, RB, r1, q)] : *reinterpret_cast<const float4*>(rrow + (size_t)tp.i1 * p.rcs + cb * 32 + q * 4);
-                    a.x = tp.w0 * a.x + tp.w1 * b.x; a.y = tp.w0 * a.y + tp.w1 * b.y;
-                    a.z = tp.w0 * a.z + tp.w1 * b.z; a.w = tp.w0 * a.w + tp.w1 * b.w;
-                    RWs[t4(cb, WB, t, q)] = a;
+                for (int cb = 0; cb < ncb; ++cb) {
+#pragma unroll
+                    for (int qq = 0; qq < QPL; ++qq) {
+                        float4 a = lds128(ak ^ (uint32_t)(qq << 4));
+                        const float4 b = lds128(bk ^ (uint32_t)(qq << 4));
+                        a.x = tp.w0 * a.x + tp.w1 * b.x; a.y = tp.w0 * a.y + tp.w1 * b.y;
+                        a.z = tp.w0 * a.z + tp.w1 * b.z; a.w = tp.w0 * a.w + tp.w1 * b.w;
+                        sts128(dk ^ (uint32_t)(qq << 4), a);
+                    }
+                    ak += (uint32_t)RB * 128u; bk += (uint32_t)RB * 128u; dk += (uint32_t)WB * 128u;
+                }
+            } else {                                         // border columns (zero weights) / taps outside the staged window
+                for (int cb = 0; cb < ncb; ++cb) {
+#pragma unroll
+                    for (int qq = 0; qq < QPL; ++qq) {
+                        const int q = q0 + qq;
+                        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+                        if (!z0) a = in0 ? Rs[t4(cb, RB, r0, q)] : *reinterpret_cast<const float4*>(rrow + (size_t)tp.i0 * p.rcs + cb * 32 + q * 4);
+                        if (!z1) b = in1 ? Rs[t4(cb, RB, r1, q)] : *reinterpret_cast<const float4*>(rrow + (size_t)tp.i1 * p.rcs + cb * 32 + q * 4);
+                        a.x = tp.w0 * a.x + tp.w1 * b.x; a.y = tp.w0 * a.y + tp.w1 * b.y;
+                        a.z = tp.w0 * a.z + tp.w1 * b.z; a.w = tp.w0 * a.w + tp.w1 * b.w;
+                        RWs[t4(cb, WB, t, q)] = a;
+                    }
                 }
             }
         }
@@ -168,20 +200,30 @@ __global__ void __launch_bounds__(256) corr_fwd4_kernel(const __grid_constant__ 
         float acc[ND];
 #pragma unroll
         for (int i = 0; i < ND; ++i) acc[i] = 0.f;
-        for (int cb = 0; cb < ncb; ++cb) {
+        {
+            const uint32_t subk = (uint32_t)q0 << 4;
+            uint32_t lk = rowkey(Ls_s, j) ^ subk;
+            uint32_t rk[ND];
 #pragma unroll
-            for (int qq = 0; qq < QPL; ++qq) {
-                const int q = q0 + qq;
-                const float4 l = Ls[t4(cb, TW, j, q)];
+            for (int i = 0; i < ND; ++i) rk[i] = rowkey(RWs_s, j + i) ^ subk;
 #pragma unroll
-                for (int i = 0; i < ND; ++i) {
-                    const float4 a = RWs[t4(cb, WB, j + i, q)];
-                    acc[i] = fmaf(l.x, a.x, acc[i]); acc[i] = fmaf(l.y, a.y, acc[i]);
-                    acc[i] = fmaf(l.z, a.z, acc[i]); acc[i] = fmaf(l.w, a.w, acc[i]);
+            for (int cb = 0; cb < ncb; ++cb) {
+#pragma unroll
+                for (int qq = 0; qq < QPL; ++qq) {
+                    const float4 l = lds128(lk ^ (uint32_t)(qq << 4));
+#pragma unroll
+                    for (int i = 0; i < ND; ++i) {
+                        const float4 a = lds128(rk[i] ^ (uint32_t)(qq << 4));
+                        acc[i] = fmaf(l.x, a.x, acc[i]); acc[i] = fmaf(l.y, a.y, acc[i]);
+                        acc[i] = fmaf(l.z, a.z, acc[i]); acc[i] = fmaf(l.w, a.w, acc[i]);
+                    }
                 }
+                lk += (uint32_t)TW * 128u;
+#pragma unroll
+                for (int i = 0; i < ND; ++i) rk[i] += (uint32_t)WB * 128u;
             }
         }
-        const float invC = 1.f / (float)p.C;
+        const float invC = k.invC;
 #pragma unroll
         for (int i = 0; i < ND; ++i) {
             if (LP == 2) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 1);
@@ -228,20 +270,25 @@ int corr_fwd4(const CorrFwd& p, cudaStream_t st) {
     if (p.stride != 1 || p.max_disp != 2 || p.C % 32 != 0 || p.C > 256 || p.w < 8) return 1;
     if ((p.lcs & 3) || (p.rcs & 3) || !al16(p.left) || !al16(p.right) || !al16(p.out)) return 1;
     if (p.copy_left && (p.ocs & 3)) return 1;
-    static int tw_env = -2, lp_env, st_env;
-    if (tw_env == -2) { lp_env = env_int("MS_CORR4_LP", 2); st_env = env_int("MS_CORR4_ST", 1); tw_env = env_int("MS_CORR4_TW", 0); }
+    static int tw_env = -2, lp_env, st_env, slack_env;
+    if (tw_env == -2) {
+        lp_env = env_int("MS_CORR4_LP", 2); st_env = env_int("MS_CORR4_ST", 1); slack_env = env_int("MS_CORR4_SLACK", 16);
+        tw_env = env_int("MS_CORR4_TW", 0);
+    }
     const int LP = lp_env == 1 ? 1 : 2;
     const int ncb = p.C / 32;
-    int TW = tw_env > 0 ? tw_env : std::max(32, (128 / ncb + 7) / 8 * 8);
+    // measured (profiles/r1_corr_v4_ab.log): 64-pixel tiles (7 CTAs per SM at C=32) beat 128; slack 16 beats 32
+    int TW = tw_env > 0 ? tw_env : std::max(32, std::min(64, (128 / ncb + 7) / 8 * 8));
     TW = std::min(TW, 256 / LP);
     TW = std::min(TW, (p.w + 7) / 8 * 8);
     TW = std::max(8, TW / 8 * 8);
     const int WB = (TW + 4 + 7) / 8 * 8;
-    const int RB = warped ? std::min(256, (TW + 4 + 32 + 7) / 8 * 8) : 0;
+    const int RB = warped ? std::min(256, (TW + 4 + std::max(8, slack_env) + 7) / 8 * 8) : 0;
     const size_t smem = (size_t)ncb * (TW + WB + RB) * 128 + (size_t)WB * sizeof(Tap) + 1024 + 64;
     if (smem > 200 * 1024) return 1;
 
     Corr4Params k;
+    k.invC = 1.f / (float)p.C;
     k.p = p; k.TW = TW; k.WB = WB; k.RB = RB; k.ncb = ncb;
     k.store_o = (p.copy_left && st_env) ? 1 : 0;
     k.store_o2 = (p.copy_left && p.out2 && st_env && (p.o2cs & 3) == 0 && al16(p.out2)) ? 1 : 0;
@@ -255,14 +302,18 @@ int corr_fwd4(const CorrFwd& p, cudaStream_t st) {
 
     static bool attr = false;
     if (!attr) {
-        MS_CHECK_CUDA(cudaFuncSetAttribute(corr_fwd4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-        MS_CHECK_CUDA(cudaFuncSetAttribute(corr_fwd4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+        MS_CHECK_CUDA(cudaFuncSetAttribute(corr_fwd4_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+        MS_CHECK_CUDA(cudaFuncSetAttribute(corr_fwd4_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+        MS_CHECK_CUDA(cudaFuncSetAttribute(corr_fwd4_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+        MS_CHECK_CUDA(cudaFuncSetAttribute(corr_fwd4_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
         attr = true;
     }
     const dim3 grid(cdiv(p.w, TW), rows);
     const int threads = (TW * LP + 31) / 32 * 32;
-    if (LP == 1) corr_fwd4_kernel<1><<<grid, threads, smem, st>>>(mL, mR, mO, mO2, k);
-    else corr_fwd4_kernel<2><<<grid, threads, smem, st>>>(mL, mR, mO, mO2, k);
+    if (LP == 1) corr_fwd4_kernel<1, 0><<<grid, threads, smem, st>>>(mL, mR, mO, mO2, k);
+    else if (ncb == 1) corr_fwd4_kernel<2, 1><<<grid, threads, smem, st>>>(mL, mR, mO, mO2, k);
+    else if (ncb == 2) corr_fwd4_kernel<2, 2><<<grid, threads, smem, st>>>(mL, mR, mO, mO2, k);
+    else corr_fwd4_kernel<2, 0><<<grid, threads, smem, st>>>(mL, mR, mO, mO2, k);
     return check_launch("corr_fwd4");
 }
 

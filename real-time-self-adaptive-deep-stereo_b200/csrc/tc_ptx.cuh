@@ -102,6 +102,11 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_byte_addr) {
     return (uint64_t)((smem_byte_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// tf32 "hi" half by truncation: the top 19 bits of x (exactly representable in tf32 whatever rounding the tensor core
+// applies to its inputs); lo = x - hi is then exact in fp32 with |lo| < 2^-10 |x|.  One LOP3 instead of the 4-5
+// instruction sequence cvt.rna.tf32.f32 expands to -- ncu showed the splitter loop to be instruction-latency bound
+// (349 instructions per warp per K step, 128 of them from the 32 cvt.rna).
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 __device__ __forceinline__ float tf32_rna(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));

@@ -141,7 +141,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
                     const float v = xs[(hsel * 16 + e) * 128];
-                    hi[e] = tf32_rna(v);
+                    hi[e] = tf32_hi(v);
                     lo[e] = v - hi[e];
                 }
                 const uint32_t acol = tmem + lane_base + a_col0 + (uint32_t)s * 64u + (uint32_t)hsel * 16u;
@@ -157,11 +157,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                     const bool two = i1 < b_f4;
                     float4 w0 = braw[i0], w1 = two ? braw[i1] : make_float4(0.f, 0.f, 0.f, 0.f);
                     float4 h, l;
-                    h.x = tf32_rna(w0.x); h.y = tf32_rna(w0.y); h.z = tf32_rna(w0.z); h.w = tf32_rna(w0.w);
+                    h.x = tf32_hi(w0.x); h.y = tf32_hi(w0.y); h.z = tf32_hi(w0.z); h.w = tf32_hi(w0.w);
                     l.x = w0.x - h.x; l.y = w0.y - h.y; l.z = w0.z - h.z; l.w = w0.w - h.w;
                     bhi[i0] = h; blo[i0] = l;
                     if (two) {
-                        h.x = tf32_rna(w1.x); h.y = tf32_rna(w1.y); h.z = tf32_rna(w1.z); h.w = tf32_rna(w1.w);
+                        h.x = tf32_hi(w1.x); h.y = tf32_hi(w1.y); h.z = tf32_hi(w1.z); h.w = tf32_hi(w1.w);
                         l.x = w1.x - h.x; l.y = w1.y - h.y; l.z = w1.z - h.z; l.w = w1.w - h.w;
                         bhi[i1] = h; blo[i1] = l;
                     }
