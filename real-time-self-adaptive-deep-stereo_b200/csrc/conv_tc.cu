@@ -273,6 +273,7 @@ struct ConvTCHaloParams {
     int minx, miny;        // patch origin relative to the tile origin
     int nb_slots;          // weight ring depth
     uint32_t patch_bytes;
+    int ns;                // operand stages (TS kernel): {A hi/lo in TMEM, B hi/lo in smem} in flight between splitter and MMA
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -515,7 +516,7 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
                   const ConvTCHaloParams hp) {
     const ConvTCParams& p = hp.c;
     extern __shared__ unsigned char smem_dyn[];
-    __shared__ __align__(8) uint64_t pfull[2], pempty[2], bfull[8], bempty[8], ready_bar[2], free_bar[2], accum_bar;
+    __shared__ __align__(8) uint64_t pfull[2], pempty[2], bfull[8], bempty[8], ready_bar[4], free_bar[4], accum_bar;
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -523,7 +524,8 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
     unsigned char* gbase = smem_dyn + (base - s_addr(smem_dyn));
     const uint32_t b_bytes = (uint32_t)p.BN * 128u;
     const uint32_t op_bytes = 2u * b_bytes;                       // B_hi, B_lo
-    const uint32_t braw_off = 2u * op_bytes;
+    const int NS = hp.ns;
+    const uint32_t braw_off = (uint32_t)NS * op_bytes;
     const uint32_t patch_stride = (hp.patch_bytes + 1023u) & ~1023u;
     const uint32_t patch_off = braw_off + (uint32_t)hp.nb_slots * b_bytes;
     const int NB = hp.nb_slots;
@@ -544,10 +546,8 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
     long long t_epi = 0;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) {
-            mb_init(&pfull[i], 1); mb_init(&pempty[i], SPLIT_THREADS / 32);
-            mb_init(&ready_bar[i], SPLIT_THREADS / 32); mb_init(&free_bar[i], 1);
-        }
+        for (int i = 0; i < 2; ++i) { mb_init(&pfull[i], 1); mb_init(&pempty[i], SPLIT_THREADS / 32); }
+        for (int i = 0; i < NS; ++i) { mb_init(&ready_bar[i], SPLIT_THREADS / 32); mb_init(&free_bar[i], 1); }
         for (int i = 0; i < NB; ++i) { mb_init(&bfull[i], 1); mb_init(&bempty[i], SPLIT_THREADS / 32); }
         mb_init(&accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -592,9 +592,10 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+            int s = 0, rot = 0, gcount = 0;
+            uint32_t ph = 0;
             for (int it = 0; it < total; ++it) {
-                const int s = it & 1;
-                { TSP_T0(); mb_wait(&ready_bar[s], ((uint32_t)it >> 1) & 1u); TSP_ADD(1, prof); }
+                { TSP_T0(); mb_wait(&ready_bar[s], ph); TSP_ADD(1, prof); }
                 const long long t_issue = PROF ? clock64() : 0;
                 tc_fence_after();
                 const uint32_t sb = base + (uint32_t)s * op_bytes;
@@ -605,14 +606,16 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
                 for (int j = 0; j < 4; ++j) {
                     const uint64_t o = (uint64_t)(j * 2);
                     const uint32_t ao = (uint32_t)(j * 8);
-                    const int g = it * 4 + j;
-                    tc_mma_tf32_ts(tmem, a_lo + ao, b_hi + o, idesc, g > 0 ? 1u : 0u);
+                    tc_mma_tf32_ts(tmem, a_lo + ao, b_hi + o, idesc, gcount > 0 ? 1u : 0u);
                     tc_mma_tf32_ts(tmem, a_hi + ao, b_lo + o, idesc, 1u);
-                    const uint32_t dmain = tmem + (uint32_t)((1 + g % p.n_main) * p.acc_stride);
-                    tc_mma_tf32_ts(dmain, a_hi + ao, b_hi + o, idesc, g >= p.n_main ? 1u : 0u);
+                    const uint32_t dmain = tmem + (uint32_t)((1 + rot) * p.acc_stride);
+                    tc_mma_tf32_ts(dmain, a_hi + ao, b_hi + o, idesc, gcount >= p.n_main ? 1u : 0u);
+                    ++gcount;
+                    if (++rot == p.n_main) rot = 0;
                 }
                 tc_commit(&free_bar[s]);
                 if (PROF && prof) g_tc_prof[2] += (unsigned long long)(clock64() - t_issue);
+                if (++s == NS) { s = 0; ph ^= 1u; }
             }
             tc_commit(&accum_bar);
         }
@@ -630,6 +633,8 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
             uint32_t bph = 0;
             int it = 0;
             int kl = -1, cur_kb = -1, pb = 0;
+            int s = 0;
+            uint32_t sph = 0;
             const unsigned char* patch = nullptr;
             const bool sp = prof && threadIdx.x == 64;
             int kb = g0 / taps, tap = g0 - kb * taps;
@@ -643,8 +648,7 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
                         { TSP_T0(); mb_wait(&pfull[pb], ((uint32_t)kl >> 1) & 1u); TSP_ADD(3, sp); }
                         patch = gbase + patch_off + (size_t)pb * patch_stride;
                     }
-                    const int s = it & 1;
-                    { TSP_T0(); mb_wait(&free_bar[s], (((uint32_t)it >> 1) & 1u) ^ 1u); TSP_ADD(4, sp); }
+                    { TSP_T0(); mb_wait(&free_bar[s], sph ^ 1u); TSP_ADD(4, sp); }
                     { TSP_T0(); mb_wait(&bfull[slot], bph); TSP_ADD(5, sp); }
                     const long long t_work = PROF ? clock64() : 0;
                     // ---- A: this thread's pixel, 16 channels -> tf32 hi / lo -> TMEM
@@ -689,6 +693,7 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constan
                     __syncwarp();
                     if (lane == 0) { mb_arrive(&ready_bar[s]); mb_arrive(&bempty[slot]); }
                     if (++slot == NB) { slot = 0; bph ^= 1u; }
+                    if (++s == NS) { s = 0; sph ^= 1u; }
                     if (++ts == p.kw) { ts = 0; ++tr; }
                     if (++tap == taps) { tap = 0; tr = 0; ts = 0; ++kb; }
                 }
@@ -963,8 +968,16 @@ int conv_tc(const ConvGemm& g, const float* bw, cudaStream_t st, float* part) {
             // ---- v3: A operand in tensor memory
             ConvTCHaloParams hp{};
             ConvTCParams pt = p;
-            pt.n_main = std::max(1, std::min(3, (512 - 128) / pt.acc_stride - 1));
-            const int need = (pt.n_main + 1) * pt.acc_stride + 128;
+            // operand stages between splitter and MMA (64 TMEM columns + 2*BN*128 bytes each).  Measured
+            // (profiles/r1_tc_stage_depth.log): 2 / 3 / 4 stages run the 128->128 layer in 77.8 / 77.8 / 75.8 us, and a
+            // third stage costs cout=128 layers their second hi*hi accumulator (truncation bias -8e-6 instead of -4e-6),
+            // so 2 is the default; MS_TC_NS overrides.
+            static int ns_env = -1;
+            if (ns_env < 0) { const char* e = getenv("MS_TC_NS"); ns_env = e ? atoi(e) : 2; }
+            int NS = std::max(2, std::min(4, ns_env));
+            while (NS > 2 && 2 * pt.acc_stride + NS * 64 > 512) --NS;
+            pt.n_main = std::max(1, std::min(3, (512 - NS * 64) / pt.acc_stride - 1));
+            const int need = (pt.n_main + 1) * pt.acc_stride + NS * 64;
             if (need <= 512) {
                 pt.tmem_cols = need <= 256 ? 256 : 512;
                 hp.c = pt;
@@ -974,7 +987,9 @@ int conv_tc(const ConvGemm& g, const float* bw, cudaStream_t st, float* part) {
                 hp.patch_bytes = (uint32_t)hp.PW * hp.PH * 128u;
                 const size_t b_bytes = (size_t)BN * 128, op_bytes = 2 * b_bytes;
                 const size_t patch_stride = (hp.patch_bytes + 1023) & ~(size_t)1023;
-                const size_t fixed = 2 * op_bytes + 2 * patch_stride + 1024;
+                size_t fixed = NS * op_bytes + 2 * patch_stride + 1024;
+                while (NS > 2 && fixed + 3 * b_bytes > 224 * 1024) { --NS; fixed = NS * op_bytes + 2 * patch_stride + 1024; }
+                hp.ns = NS;
                 int nb = fixed + 2 * b_bytes <= 224 * 1024 ? (int)std::min<size_t>(8, (224 * 1024 - fixed) / b_bytes) : 0;
                 if (nb >= 2) {
                     hp.nb_slots = nb;

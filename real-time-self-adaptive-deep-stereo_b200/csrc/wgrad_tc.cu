@@ -30,6 +30,7 @@ struct WgradTCParams {
     int nchunks, chunk_per_split;
     int ci, co, BN, mblocks;
     int n_main, acc_stride, tmem_cols, nslots;
+    int nop;                      // operand stages between splitter and MMA (64 TMEM columns + 2*BN*128 B each)
     float* part;                  // [split][tap][ci][co]
 };
 
@@ -40,7 +41,7 @@ constexpr int X_TILE_BYTES = 32 * 128 * 4;      // 32 pixels x 128 channels
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapD, const WgradTCParams p) {
     extern __shared__ unsigned char smem_dyn[];
-    __shared__ __align__(8) uint64_t full_bar[6], empty_bar[6], ready_bar[2], free_bar[2], accum_bar;
+    __shared__ __align__(8) uint64_t full_bar[6], empty_bar[6], ready_bar[4], free_bar[4], accum_bar;
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -48,7 +49,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
     unsigned char* gbase = smem_dyn + (base - s_addr(smem_dyn));
     const uint32_t b_bytes = (uint32_t)p.BN * 128u;
     const uint32_t op_bytes = 2u * b_bytes;                         // B_hi, B_lo
-    const uint32_t ring_off = 2u * op_bytes;
+    const int NOP = p.nop;
+    const uint32_t ring_off = (uint32_t)NOP * op_bytes;
     const uint32_t slot_bytes = (uint32_t)X_TILE_BYTES + b_bytes;   // X tile | raw dY^T tile
     const int NS = p.nslots;
     const uint32_t a_col0 = (uint32_t)((p.n_main + 1) * p.acc_stride);
@@ -62,7 +64,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NS; ++i) { mb_init(&full_bar[i], 1); mb_init(&empty_bar[i], WG_SPLIT / 32); }
-        for (int i = 0; i < 2; ++i) { mb_init(&ready_bar[i], WG_SPLIT / 32); mb_init(&free_bar[i], 1); }
+        for (int i = 0; i < NOP; ++i) { mb_init(&ready_bar[i], WG_SPLIT / 32); mb_init(&free_bar[i], 1); }
         mb_init(&accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -98,9 +100,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
         // ================= MMA issuer (TS mode: A from tensor memory) =================
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+            int s = 0, rot = 0, gcount = 0;
+            uint32_t oph = 0;
             for (int it = 0; it < total; ++it) {
-                const int s = it & 1;
-                mb_wait(&ready_bar[s], ((uint32_t)it >> 1) & 1u);
+                mb_wait(&ready_bar[s], oph);
                 tc_fence_after();
                 const uint32_t sb = base + (uint32_t)s * op_bytes;
                 const uint64_t b_hi = umma_desc_sw128(sb), b_lo = umma_desc_sw128(sb + b_bytes);
@@ -109,13 +112,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                 for (int j = 0; j < 4; ++j) {
                     const uint64_t o = (uint64_t)(j * 2);
                     const uint32_t ao = (uint32_t)(j * 8);
-                    const int g = it * 4 + j;
-                    tc_mma_tf32_ts(tmem, a_lo + ao, b_hi + o, idesc, g > 0 ? 1u : 0u);
+                    tc_mma_tf32_ts(tmem, a_lo + ao, b_hi + o, idesc, gcount > 0 ? 1u : 0u);
                     tc_mma_tf32_ts(tmem, a_hi + ao, b_lo + o, idesc, 1u);
-                    const uint32_t dmain = tmem + (uint32_t)((1 + g % p.n_main) * p.acc_stride);
-                    tc_mma_tf32_ts(dmain, a_hi + ao, b_hi + o, idesc, g >= p.n_main ? 1u : 0u);
+                    const uint32_t dmain = tmem + (uint32_t)((1 + rot) * p.acc_stride);
+                    tc_mma_tf32_ts(dmain, a_hi + ao, b_hi + o, idesc, gcount >= p.n_main ? 1u : 0u);
+                    ++gcount;
+                    if (++rot == p.n_main) rot = 0;
                 }
                 tc_commit(&free_bar[s]);
+                if (++s == NOP) { s = 0; oph ^= 1u; }
             }
             tc_commit(&accum_bar);
         }
@@ -128,11 +133,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
         const int m = q * 32 + lane;                   // channel inside the 128-block
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         {
-            int slot = 0;
-            uint32_t ph = 0;
+            int slot = 0, s = 0;
+            uint32_t ph = 0, oph = 0;
             for (int it = 0; it < total; ++it) {
-                const int s = it & 1;
-                mb_wait(&free_bar[s], (((uint32_t)it >> 1) & 1u) ^ 1u);
+                mb_wait(&free_bar[s], oph ^ 1u);
                 mb_wait(&full_bar[slot], ph);
                 const unsigned char* sl = gbase + ring_off + (size_t)slot * slot_bytes;
                 // ---- A: X^T. pixel k of the chunk sits at k*512 bytes, channel m at +4m  (conflict-free across lanes)
@@ -172,6 +176,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                 __syncwarp();
                 if (lane == 0) { mb_arrive(&ready_bar[s]); mb_arrive(&empty_bar[slot]); }
                 if (++slot == NS) { slot = 0; ph ^= 1u; }
+                if (++s == NOP) { s = 0; oph ^= 1u; }
             }
         }
         // ================= epilogue: raw partial sums [ci][co] =================
@@ -296,8 +301,13 @@ int wgrad_tc(const ConvWgrad& q, cudaStream_t st) {
     p.nchunks = n * p.chunks_x * p.chunks_y;
     p.ci = ci; p.co = co; p.BN = (co + 15) / 16 * 16; p.mblocks = cdiv(ci, 128);
     p.acc_stride = (p.BN + 31) / 32 * 32;
-    p.n_main = std::max(1, std::min(3, (512 - 128) / p.acc_stride - 1));
-    const int need = (p.n_main + 1) * p.acc_stride + 128;
+    static int nop_env = -1;
+    if (nop_env < 0) { const char* e = getenv("MS_WG_NS"); nop_env = e ? atoi(e) : 2; }     // measured: 3 stages gain nothing and cost an accumulator
+    int nop = std::max(2, std::min(4, nop_env));
+    while (nop > 2 && 2 * p.acc_stride + nop * 64 > 512) --nop;
+    p.nop = nop;
+    p.n_main = std::max(1, std::min(3, (512 - nop * 64) / p.acc_stride - 1));
+    const int need = (p.n_main + 1) * p.acc_stride + nop * 64;
     MS_REQUIRE(need <= 512, "wgrad_tc: accumulators do not fit tensor memory");
     p.tmem_cols = need <= 256 ? 256 : 512;
     const int split = wg_splits(taps * p.mblocks, p.nchunks);
@@ -308,7 +318,7 @@ int wgrad_tc(const ConvWgrad& q, cudaStream_t st) {
     float* dyt = q.workspace;
     p.part = q.workspace + dyt_floats;
     const size_t b_bytes = (size_t)p.BN * 128, op_bytes = 2 * b_bytes, slot_bytes = X_TILE_BYTES + b_bytes;
-    const size_t fixed = 2 * op_bytes + 1024;
+    const size_t fixed = (size_t)p.nop * op_bytes + 1024;
     int ns = (int)std::min<size_t>(6, (224 * 1024 - fixed) / slot_bytes);
     MS_REQUIRE(ns >= 2, "wgrad_tc: tiles do not fit shared memory");
     p.nslots = ns;
