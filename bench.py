@@ -120,6 +120,39 @@ def corr_large_shapes(dev):
     return out
 
 
+def conv_dominant_layer(dev):
+    """The layer shape that dominates the step (128->128 3x3 at 96x320: estimator-2 / context net)
+    timed alone through the operator-level C ABI (weight preparation kernel included), L2 flushed between repetitions."""
+    import torch
+    from ctypes import c_void_p
+    from madstereo._lib import lib, check
+    n, h, w, cin, cout = 1, 96, 320, 128, 128
+    x = torch.randn(n, h, w, cin, device=dev); wt = torch.randn(3, 3, cin, cout, device=dev) * 0.05
+    b = torch.zeros(cout, device=dev); y = torch.empty(n, h, w, cout, device=dev)
+    ns = lib().ms_conv2d_tc_scratch(3, 3, cin, cout); scratch = torch.empty(ns, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    st = c_void_p(torch.cuda.current_stream().cuda_stream)
+    def run():
+        check(lib().ms_conv2d_fwd_tc(c_void_p(x.data_ptr()), n, h, w, cin, cin, c_void_p(wt.data_ptr()), c_void_p(b.data_ptr()),
+                                     c_void_p(y.data_ptr()), cout, cout, 3, 3, 1, 0.2, c_void_p(scratch.data_ptr()), ns, st), 'tc')
+    for _ in range(3):
+        run()
+    ts = []
+    for _ in range(9):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); run(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    us = ts[len(ts) // 2] * 1e3
+    flops = 2.0 * n * h * w * 9 * cin * cout
+    return {'shape': '128->128 3x3 @96x320', 'us': us, 'useful_tflops': flops / us / 1e6,
+            'traffic': 16362752, 'traffic_src': 'dram__bytes_read+write per launch, profiles/r1_ncu_conv_tc_ts_final_128x128_96x320.txt '
+                                                '(algorithmic: 15.7 MB input + 0.6 MB weights; the 15.7 MB output stays in L2)',
+            'note': 'conv_tc_ts_kernel + weight-prep kernel; each useful FLOP costs 3 tf32 tensor FLOPs (3xTF32), '
+                    'tf32 dense peak = bf16 peak / 2'}
+
+
 def make_inputs(n_pairs, rank):
     from madstereo.synthetic import make_pair
     return [make_pair(H, W, seed=100 * rank + i)[:2] for i in range(n_pairs)]
@@ -212,15 +245,22 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(src, steps, warmup):
+    def timed(src, steps, warmup, pipelined=False):
+        # pipelined: the host->device copy of frame i+1 is issued (side stream) while frame i computes; every frame's
+        # copy is still inside the timed region
+        def one(i):
+            if pipelined:
+                ad.step(*src[i % n_pairs], prefetch=src[(i + 1) % n_pairs])
+            else:
+                ad.step(*src[i % n_pairs])
         for i in range(warmup):
-            ad.step(*src[i % n_pairs])
+            one(i)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = eng.launch_count()
         e0.record()
         for i in range(steps):
-            ad.step(*src[i % n_pairs])
+            one(warmup + i)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -235,7 +275,13 @@ def run_ours(args):
     if clk:
         clk.start()
     ms_dev, launches = timed(dev_pairs, args.steps, args.warmup)
-    ms_e2e, _ = timed(host_pairs, args.steps, 1)
+    ms_e2e_serial, _ = timed(host_pairs, args.steps, 1)
+    try:
+        ms_e2e, _ = timed(host_pairs, args.steps, 2, pipelined=True)
+        e2e_mode = 'pipelined: H2D of frame i+1 on a side stream while frame i computes (OnlineAdaptation.step(prefetch=...))'
+    except Exception as ex:                        # keep the serial number rather than no number
+        print('pipelined e2e failed: %r' % (ex,), file=sys.stderr)
+        ms_e2e, e2e_mode = ms_e2e_serial, 'serial (pipelined path failed: %r)' % (ex,)
     if clk:
         clk.stop_flag = True
         clk.join(timeout=2)
@@ -257,6 +303,9 @@ def run_ours(args):
 
     pk = peaks()
     corr_large = corr_large_shapes(dev)
+    dom = conv_dominant_layer(dev)
+    dom['frac_of_bf16_peak'] = dom['useful_tflops'] / pk['bf16_tflops']
+    dom['tensor_flops_frac_of_tf32_peak'] = 3.0 * dom['useful_tflops'] / (pk['bf16_tflops'] / 2.0)
     fps = world * args.steps / (ms_dev / 1e3)
     fps_e2e = world * args.steps / (ms_e2e / 1e3)
     conv_ms = sum(prof[c]['ms'] for c in ('conv_fwd', 'conv_dgrad', 'conv_wgrad'))
@@ -276,18 +325,22 @@ def run_ours(args):
                          '%d distinct pairs' % (L2_MB, n_pairs),
                    'step': 'set_input, forward, full-res loss, module loss+backward, all-reduce(N>1), momentum update, '
                            'loss D2H (host reward policy needs it every frame)'},
-        'e2e': {'value': fps_e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': 2 * H * W * 3 * 4, 'd2h_bytes_per_step': 16},
+        'e2e': {'value': fps_e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': 2 * H * W * 3 * 4, 'd2h_bytes_per_step': 16,
+                'mode': e2e_mode, 'serial_value': world * args.steps / (ms_e2e_serial / 1e3)},
         'gpu_launches': int(launches),
         'roofline': {'bound': 'tensor', 'kernel': 'conv stack: conv_tc_ts/conv_tc kernels (tcgen05 3xTF32 implicit GEMM, stride-1 fwd+dgrad) + wgrad_tc_kernel (tcgen05 stride-1 wgrad) + conv_gemm/conv_wgrad (fp32 CUDA-core: stride-2, cin=3 and cout=1 layers); useful FLOPs = 2*MACs, the 3x tf32 passes are not counted',
                      'achieved': conv_tflops, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
                      'frac': conv_tflops / pk['bf16_tflops_sustained'], 'peak_src': pk['src'] + ' bf16 sustained (kernels timed inside a long step)',
                      'traffic': None, 'avg_launch_us': 1e3 * conv_ms / max(conv_calls, 1),
-                     'share_of_step': conv_ms / prof_total if prof_total else None},
+                     'share_of_step': conv_ms / prof_total if prof_total else None,
+                     'dominant_layer': dom},
         'corr_kernel': {'bound': 'hbm', 'achieved': corr_gbs, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
                         'frac': corr_gbs / pk['hbm_gbs'],
                         'note': 'in-step number: all 5 MADNet levels at 1280x384 (<=8.5 MB each: L2-resident, launch-latency bound); '
                                 'algorithmic bytes B*h*w*(2C+5)*4',
-                        'large': {k: dict(v, frac=v['gbs'] / pk['hbm_gbs']) for k, v in corr_large.items()}},
+                        'large': {k: dict(v, frac=v['gbs'] / pk['hbm_gbs']) for k, v in corr_large.items()},
+                        'traffic': {'madnet_L2_1920x1088_B8': 289069312,
+                                    'src': 'dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_ncu_corr_fwd4_L2_1920x1088_B8.txt'}},
         'profile_ms_per_step': {k: v['ms'] / 10.0 for k, v in prof.items()},
         'clocks': clk.summary() if clk else None,
     }

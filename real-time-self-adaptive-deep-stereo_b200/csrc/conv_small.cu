@@ -7,12 +7,14 @@
 // 27 MB: it should be a ~10 us HBM-bound kernel) and 319 + 271 us for the conv1 / conv2 weight gradients (432 / 2304
 // outputs reduced over 245 760 pixels: a 16 x 16 output tile leaves the GEMM kernel with 9 CTAs per K split).
 //   forward  : one thread computes two adjacent output pixels x all output channels; the weights sit in shared memory
-//              and are read as broadcast float4 (also used for conv2 forward / dgrad and conv3 forward: 16 -> 16 | 32).
+//              and are read as broadcast float4.  105 -> 30 us for conv1.  (16 -> 16 | 32 instantiations exist but are
+//              opt-in: without a staged input patch they are slower than the gather GEMM, see conv_small_fwd_supported.)
 //   wgrad    : a thread owns one input channel ("role") and keeps all 9 taps x 16 output channels = 144 partial sums
 //              in registers while it walks its share of the pixels (9 input loads + 16 dY loads per 144 FMAs, next
 //              pixel prefetched); lanes of equal role are combined by shuffles, warps through shared memory, CTAs by
 //              the fixed-order wgrad_reduce pass (deterministic).
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -107,7 +109,12 @@ __global__ void __launch_bounds__(CS_NT) conv_small_fwd_kernel(ConvGemm p, int p
 bool conv_small_fwd_supported(const ConvGemm& p) {
     if (p.kh != 3 || p.kw != 3 || p.div != 1 || p.mul < 1 || p.x.n != p.y.n || p.alpha > 1.f || p.alpha < 0.f) return false;
     if (p.x.c == 3 && p.y.c == 16) return true;
-    if (p.x.c == 16 && (p.y.c == 16 || p.y.c == 32)) return (p.x.cs & 3) == 0 && al16s(p.x.p);
+    // The 16-channel instantiations are opt-in (MS_CONV_SMALL16=1): measured 86 us (16->16) and 36 us (16->32 stride 2)
+    // against 71 / 32 us for the gather GEMM -- one thread reading its pixels' 64-byte channel rows straight from
+    // global memory is LSU-bound (32 cache lines per load instruction); they need a shared-memory staged patch first.
+    static int small16 = -1;
+    if (small16 < 0) { const char* e = getenv("MS_CONV_SMALL16"); small16 = (e && e[0] == '1') ? 1 : 0; }
+    if (small16 && p.x.c == 16 && (p.y.c == 16 || p.y.c == 32)) return (p.x.cs & 3) == 0 && al16s(p.x.p);
     return false;
 }
 

@@ -62,6 +62,8 @@ class OnlineAdaptation(object):
         self.reset_counter = 0
         self.step_count = 0
         self._snapshot = None
+        self._stage = None          # device staging buffers + side stream for prefetch()
+        self._staged_for = None
 
     # ---- weights -----------------------------------------------------------------------------------
     def load_weights(self, params):
@@ -81,7 +83,41 @@ class OnlineAdaptation(object):
         if self.world > 1:
             torch.distributed.all_reduce(t, group=self.pg)
 
-    def step(self, left, right, gt=None, want_disp_mask=0):
+    def prefetch(self, left, right):
+        """Start the host->device copy of the NEXT frame on a side stream while the current frame computes (the
+        reference overlaps input decoding with sess.run through its tf.data pipeline, Data_utils/data_reader.py).
+        The step() call that receives these same tensor objects then only does a device-to-device copy."""
+        eng = self.engine
+        if self._stage is None:
+            shape = (eng.B, eng.H, eng.W, 3)
+            self._stage = [torch.empty(shape, dtype=torch.float32, device=eng.device) for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(device=eng.device)
+            self._stage_ready = torch.cuda.Event()
+            self._stage_free = torch.cuda.Event()
+            self._stage_free.record(torch.cuda.current_stream(eng.device))
+        l, r = eng._as_f32(left), eng._as_f32(right)
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._stage_free)      # the previous frame's staging -> input copy is done
+            self._stage[0].copy_(l, non_blocking=True)
+            self._stage[1].copy_(r, non_blocking=True)
+            self._stage_ready.record(self._copy_stream)
+        self._staged_for = (left, right, l, r)
+
+    def _set_input(self, left, right):
+        eng = self.engine
+        st = self._staged_for
+        if st is not None and left is st[0] and right is st[1]:
+            cur = torch.cuda.current_stream(eng.device)
+            cur.wait_event(self._stage_ready)
+            eng.set_input(self._stage[0], self._stage[1])
+            self._stage_free.record(cur)
+            self._staged_for = None
+        else:
+            eng.set_input(left, right)
+
+    def step(self, left, right, gt=None, want_disp_mask=0, prefetch=None):
+        """One frame == one sess.run of the reference loop (Stereo_Online_Adaptation.py:176-253).
+        prefetch=(next_left, next_right): start copying the next frame's host buffers while this frame computes."""
         eng = self.engine
         step = self.step_count
         if self.mode == 'MAD' and step % self.sample_frequency == 0:
@@ -98,7 +134,9 @@ class OnlineAdaptation(object):
             for l in blocks:
                 self.fetch_counter[l] += 1
 
-        eng.set_input(left, right)
+        self._set_input(left, right)
+        if prefetch is not None:
+            self.prefetch(*prefetch)
         if gt is not None:
             eng.set_gt(gt)
         mask = want_disp_mask

@@ -234,3 +234,32 @@ def test_sequential_sampler_and_reward_bookkeeping():
     assert seen == [0, 1, 2, 3, 4, 0, 1]
     assert ad.fetch_counter == [2, 2, 1, 1, 1]
     assert ad.sample_distribution.shape == (5,) and np.isfinite(ad.sample_distribution).all()
+
+
+def test_prefetch_pipeline_matches_serial_input_path():
+    """step(prefetch=next) stages the next frame's host buffers on a side stream while the current frame computes;
+    the sequence of losses and the adapted weights must be identical to the serial path (same kernels, same order)."""
+    from madstereo.synthetic import make_pair
+    import Nets
+    from madstereo.adaptation import OnlineAdaptation
+    from oracle.madnet import init_params
+    frames = [make_pair(64, 128, seed=10 + i)[:2] for i in range(3)]
+    host = [(torch.from_numpy(l).pin_memory(), torch.from_numpy(r).pin_memory()) for l, r in frames]
+    cfg = json.load(open(os.path.join(PKG, 'block_config', 'MadNet_full.json')))
+
+    def run(pipelined):
+        net = Nets.get_stereo_net('MADNet', dict(left_img=host[0][0].cuda(), right_img=host[0][1].cuda(), split_layers=[None],
+                                                 sequence=True, train_portion='BEGIN', bulkhead=True))
+        ad = OnlineAdaptation(net, mode='MAD', train_config=cfg, sample_mode='SEQUENTIAL')
+        ad.load_weights(init_params(seed=42))
+        losses = []
+        for i in range(6):
+            cur, nxt = host[i % 3], host[(i + 1) % 3]
+            out = ad.step(*cur, prefetch=nxt) if pipelined else ad.step(*cur)
+            losses.append((out['loss'], out['train_loss']))
+        return losses, net.engine.weights.clone().cpu().numpy()
+
+    l0, w0 = run(False)
+    l1, w1 = run(True)
+    assert l0 == l1
+    assert np.array_equal(w0, w1)
