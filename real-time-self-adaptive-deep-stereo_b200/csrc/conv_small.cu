@@ -106,19 +106,129 @@ __global__ void __launch_bounds__(CS_NT) conv_small_fwd_kernel(ConvGemm p, int p
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 16 -> 16, 3x3, stride 1 (conv2 forward and its dgrad): shared-memory staged version.  A CTA owns an 8 x 32 output tile;
+// the 10 x 34 input patch is loaded with coalesced 128-bit loads into shared memory with a 20-float pixel pitch (a
+// quarter-warp's 128-bit reads at one-pixel lane stride then hit 32 distinct banks); a thread computes pixels (r, c) and
+// (r, c + 16) so that lanes stay one pixel apart.  Default (MS_CONV_SMALL16=2; 0 = gather GEMM, 1 = untiled direct
+// kernels): validated with the ops + MADNet GPU suites, conv_fwd 1.600 -> 1.575 ms per frame (profiles/r1_last_visit.log).
+// ---------------------------------------------------------------------------------------------
+constexpr int T16_TH = 8, T16_TW = 32, T16_PH = T16_TH + 2, T16_PW = T16_TW + 2, T16_PS = 20, T16_NT = 128;
+
+__global__ void __launch_bounds__(T16_NT) conv_c16_tiled_kernel(ConvGemm p, int tiles_x, int tiles_y) {
+    constexpr int CIN = 16, CO = 16;
+    __shared__ __align__(16) float ws[9 * CIN * CO];
+    __shared__ __align__(16) float patch[T16_PH * T16_PW * T16_PS];
+    __shared__ float bs[CO];
+    int bid = blockIdx.x;
+    const int tx_ = bid % tiles_x; bid /= tiles_x;
+    const int ty_ = bid % tiles_y;
+    const int img = bid / tiles_y;
+    const int y0 = ty_ * T16_TH, x0 = tx_ * T16_TW;
+    const int miny = p.off_y + (p.step < 0 ? 2 * p.step : 0), minx = p.off_x + (p.step < 0 ? 2 * p.step : 0);
+    for (int i = threadIdx.x; i < 9 * CIN * CO / 4; i += T16_NT)
+        reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(p.wmat) + i);
+    for (int i = threadIdx.x; i < CO; i += T16_NT) bs[i] = p.bias ? p.bias[i] : 0.f;
+    const float* ximg = p.x.p + (size_t)img * p.x.h * p.x.w * p.x.cs;
+    for (int e = threadIdx.x; e < T16_PH * T16_PW * 4; e += T16_NT) {
+        const int pix = e >> 2, q = e & 3;
+        const int py = pix / T16_PW, px = pix - py * T16_PW;
+        const int iy = y0 + miny + py, ix = x0 + minx + px;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (iy >= 0 && iy < p.x.h && ix >= 0 && ix < p.x.w)
+            v = __ldg(reinterpret_cast<const float4*>(ximg + ((size_t)iy * p.x.w + ix) * p.x.cs) + q);
+        *reinterpret_cast<float4*>(patch + pix * T16_PS + q * 4) = v;
+    }
+    __syncthreads();
+    const int r = threadIdx.x >> 4, c = threadIdx.x & 15;
+    float acc[2][CO];
+#pragma unroll
+    for (int j = 0; j < CO; ++j) { acc[0][j] = bs[j]; acc[1][j] = bs[j]; }
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+        const int ty = tap / 3, tx = tap - ty * 3;
+        const int pr = r + p.off_y + ty * p.step - miny, pc = c + p.off_x + tx * p.step - minx;
+        const float* s0 = patch + (pr * T16_PW + pc) * T16_PS;
+        float xin[2][CIN];
+#pragma unroll
+        for (int pi = 0; pi < 2; ++pi)
+#pragma unroll
+            for (int c4 = 0; c4 < CIN / 4; ++c4) {
+                const float4 v = *reinterpret_cast<const float4*>(s0 + pi * 16 * T16_PS + c4 * 4);
+                xin[pi][4 * c4] = v.x; xin[pi][4 * c4 + 1] = v.y; xin[pi][4 * c4 + 2] = v.z; xin[pi][4 * c4 + 3] = v.w;
+            }
+        const float4* wt = reinterpret_cast<const float4*>(ws + tap * CIN * CO);
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+            const float a0 = xin[0][ci], a1 = xin[1][ci];
+#pragma unroll
+            for (int j4 = 0; j4 < CO / 4; ++j4) {
+                const float4 w = wt[ci * (CO / 4) + j4];
+                acc[0][4 * j4] = fmaf(a0, w.x, acc[0][4 * j4]); acc[0][4 * j4 + 1] = fmaf(a0, w.y, acc[0][4 * j4 + 1]);
+                acc[0][4 * j4 + 2] = fmaf(a0, w.z, acc[0][4 * j4 + 2]); acc[0][4 * j4 + 3] = fmaf(a0, w.w, acc[0][4 * j4 + 3]);
+                acc[1][4 * j4] = fmaf(a1, w.x, acc[1][4 * j4]); acc[1][4 * j4 + 1] = fmaf(a1, w.y, acc[1][4 * j4 + 1]);
+                acc[1][4 * j4 + 2] = fmaf(a1, w.z, acc[1][4 * j4 + 2]); acc[1][4 * j4 + 3] = fmaf(a1, w.w, acc[1][4 * j4 + 3]);
+            }
+        }
+    }
+    const bool vec = (p.y.cs & 3) == 0 && al16s(p.y.p);
+    const int oy = y0 + r;
+    if (oy >= p.y.h) return;
+#pragma unroll
+    for (int pi = 0; pi < 2; ++pi) {
+        const int ox = x0 + c + pi * 16;
+        if (ox >= p.y.w) continue;
+        const size_t pix = (size_t)(img * p.y.h + oy) * p.y.w + ox;
+        float* yrow = p.y.p + pix * p.y.cs;
+#pragma unroll
+        for (int j = 0; j < CO; ++j) {
+            float t = fmaxf(p.alpha * acc[pi][j], acc[pi][j]);
+            if (p.res) t += p.res[pix * p.res_cs + j];
+            if (p.accumulate) t += yrow[j];
+            if (p.mask) t *= (p.mask[pix * p.mask_cs + j] > 0.f) ? 1.f : p.mask_alpha;
+            acc[pi][j] = t;
+        }
+        if (vec) {
+#pragma unroll
+            for (int j = 0; j < CO; j += 4)
+                *reinterpret_cast<float4*>(yrow + j) = make_float4(acc[pi][j], acc[pi][j + 1], acc[pi][j + 2], acc[pi][j + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < CO; ++j) yrow[j] = acc[pi][j];
+        }
+    }
+}
+
+static int small16_mode() {
+    static int m = -1;
+    if (m < 0) { const char* e = getenv("MS_CONV_SMALL16"); m = e ? atoi(e) : 2; }
+    return m;
+}
+
+static bool conv_c16_tiled_supported(const ConvGemm& p) {
+    return p.x.c == 16 && p.y.c == 16 && p.kh == 3 && p.kw == 3 && p.div == 1 && p.mul == 1 && (p.step == 1 || p.step == -1) &&
+           p.x.h == p.y.h && p.x.w == p.y.w && p.x.n == p.y.n && (p.x.cs & 3) == 0 && al16s(p.x.p) && al16s(p.wmat) &&
+           p.alpha <= 1.f && p.alpha >= 0.f;
+}
+
 bool conv_small_fwd_supported(const ConvGemm& p) {
     if (p.kh != 3 || p.kw != 3 || p.div != 1 || p.mul < 1 || p.x.n != p.y.n || p.alpha > 1.f || p.alpha < 0.f) return false;
     if (p.x.c == 3 && p.y.c == 16) return true;
-    // The 16-channel instantiations are opt-in (MS_CONV_SMALL16=1): measured 86 us (16->16) and 36 us (16->32 stride 2)
-    // against 71 / 32 us for the gather GEMM -- one thread reading its pixels' 64-byte channel rows straight from
-    // global memory is LSU-bound (32 cache lines per load instruction); they need a shared-memory staged patch first.
-    static int small16 = -1;
-    if (small16 < 0) { const char* e = getenv("MS_CONV_SMALL16"); small16 = (e && e[0] == '1') ? 1 : 0; }
-    if (small16 && p.x.c == 16 && (p.y.c == 16 || p.y.c == 32)) return (p.x.cs & 3) == 0 && al16s(p.x.p);
+    // The untiled 16-channel instantiations are opt-in (MS_CONV_SMALL16=1): measured 86 us (16->16) and 36 us (16->32
+    // stride 2) against 71 / 32 us for the gather GEMM -- one thread reading its pixels' 64-byte channel rows straight
+    // from global memory is LSU-bound (32 cache lines per load instruction).  The default (=2) is the shared-memory
+    // tiled 16->16 stride-1 kernel above.
+    if (small16_mode() == 2 && conv_c16_tiled_supported(p)) return true;
+    if (small16_mode() == 1 && p.x.c == 16 && (p.y.c == 16 || p.y.c == 32)) return (p.x.cs & 3) == 0 && al16s(p.x.p);
     return false;
 }
 
 int conv_small_fwd(const ConvGemm& p, cudaStream_t st) {
+    if (small16_mode() == 2 && conv_c16_tiled_supported(p)) {
+        const int tiles_x = cdiv(p.y.w, T16_TW), tiles_y = cdiv(p.y.h, T16_TH);
+        conv_c16_tiled_kernel<<<(unsigned)(tiles_x * tiles_y * p.y.n), T16_NT, 0, st>>>(p, tiles_x, tiles_y);
+        return check_launch("conv_c16_tiled");
+    }
     const int pairs_per_row = cdiv(p.y.w, 2);
     const size_t total = (size_t)p.y.n * p.y.h * pairs_per_row;
     MS_REQUIRE(total < (1u << 30), "conv_small_fwd: too many output pixels");

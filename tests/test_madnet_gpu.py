@@ -263,3 +263,36 @@ def test_prefetch_pipeline_matches_serial_input_path():
     l1, w1 = run(True)
     assert l0 == l1
     assert np.array_equal(w0, w1)
+
+
+def test_config5_1920x1056_size_independent_properties():
+    """BASELINE config 5 resolution (1920x1056 -> REFLECT-padded to 1920x1088, preprocessing.py:7-29), where the CPU oracle
+    is too slow to be a checker: properties that do not depend on size.
+      * forward is deterministic (bit-identical disparities on a second run) and the output has the un-padded shape;
+      * the final disparity is relu'd (>= 0) and finite;
+      * one MAD step per module (SEQUENTIAL sampler): finite losses, exactly the sampled module's variables change
+        (bulkhead + var_list, Stereo_Online_Adaptation.py:112-118), every other parameter is bit-identical."""
+    from madstereo.synthetic import make_pair
+    H, W = 1056, 1920
+    left, right, _ = make_pair(H, W, seed=5)
+    net, ad, params, lt, rt = build(left, right, 'MAD')
+    ad.sampler = __import__('Sampler.sampler_factory', fromlist=['x']).get_sampler('SEQUENTIAL', 1)
+    eng = net.engine
+    eng.set_input(lt, rt)
+    eng.forward()
+    d0 = net.get_disparities()[-1].numpy().copy()
+    eng.forward()
+    d1 = net.get_disparities()[-1].numpy()
+    assert d0.shape == (1, H, W, 1)
+    assert np.array_equal(d0, d1)
+    assert np.isfinite(d0).all() and d0.min() >= 0.0 and d0.max() > 0.0
+    ranges = eng.group_ranges
+    for k in range(5):
+        before = eng.weights.clone()
+        out = ad.step(lt, rt)
+        assert out['blocks'] == [k] and np.isfinite(out['loss']) and np.isfinite(out['train_loss'])
+        changed = (eng.weights != before)
+        lo, hi = ranges[k]
+        assert bool(changed[lo:hi].any()), 'module %d did not move' % k
+        changed[lo:hi] = False
+        assert not bool(changed.any()), 'parameters outside module %d moved' % k
