@@ -30,6 +30,10 @@ METRIC = 'stereo FPS (fwd+MAD backprop) @1280x384'
 L2_MB = 126
 
 
+WORKLOAD = ('MADNet MAD adaptation (block_config/MadNet_full.json, SEQUENTIAL sampler => uniform mix of the 5 modules), '
+            '1280x384, 1 frame per GPU per step')
+
+
 def peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -190,8 +194,8 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus,
             'steps': steps, 'warmup': warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'MADNet MAD adaptation (block_config/MadNet_full.json, SEQUENTIAL sampler), '
-                                   '1280x384, 1 frame/step, CPU'},
+            'config': {'workload': WORKLOAD, 'arm': 'reference path on the host cores (oracle port; TF1 cannot run here), '
+                                                     'one frame stream whatever N'},
             'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
@@ -318,8 +322,7 @@ def run_ours(args):
         'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'MADNet MAD adaptation (block_config/MadNet_full.json, SEQUENTIAL sampler => uniform '
-                               'mix of the 5 modules), 1280x384, 1 frame per GPU per step',
+        'config': {'workload': WORKLOAD,
                    'parallelism': 'dp%d' % world, 'global_batch': world,
                    'l2': 'no flush: per-step activation+gradient working set ~0.5 GB >> %d MB L2; inputs rotate over '
                          '%d distinct pairs' % (L2_MB, n_pairs),
