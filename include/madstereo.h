@@ -149,6 +149,9 @@ int ms_engine_profile(void* e, int enable);
 int ms_engine_profile_read(void* e, double* ms7, double* macs7, double* bytes7, long long* calls7);
 /* Kernels launched by this library in this process so far. */
 long long ms_launch_count(void);
+/* Diagnostic (no reference counterpart): per-role clock64 counters of the tcgen05 conv kernel, filled only when the
+ * environment selects its profiling build (MS_TC_DEBUG=8, scripts/tc_prof.py). out32: 32 counters; reset != 0 clears. */
+int ms_debug_tc_prof(unsigned long long* out32, int reset);
 int ms_engine_num_tensors(void* e);
 int ms_engine_tensor_name(void* e, int i, char* name, int cap);
 /* dims: n,h,w,c,cs */

@@ -333,7 +333,7 @@ int ms_engine_profile_read(void* h, double* ms7, double* macs7, double* bytes7, 
     return 0;
 }
 long long ms_launch_count(void) { return ms::launch_count(); }
-__attribute__((visibility("default"))) int ms_debug_tc_prof(unsigned long long* out32, int reset) { return ms::conv_tc_read_prof(out32, reset); }
+int ms_debug_tc_prof(unsigned long long* out32, int reset) { return ms::conv_tc_read_prof(out32, reset); }
 int ms_engine_num_tensors(void* h) { return (int)static_cast<Engine*>(h)->tensors.size(); }
 int ms_engine_tensor_name(void* h, int i, char* name, int cap) {
     Engine* e = static_cast<Engine*>(h);
