@@ -1,4 +1,7 @@
-"""CPU oracle — DispNet-C forward restated from Nets/DispNet.py (TEST INFRASTRUCTURE, parity unpinned).
+"""CPU oracle — DispNet-C forward restated from Nets/DispNet.py (TEST INFRASTRUCTURE).
+
+Pinned against the reference's own Nets/DispNet.py executed over oracle/tf1_shim.py (tests/golden/reference_graph_dispnet_64x128.npz);
+TF's conv-padding / resize kernels themselves stay unpinned (see oracle/tf1_ops.py).
 
 Follows /root/reference/Nets/DispNet.py:39-43 (_make_disp), :45-57 (_upsampling_block), :59-73 (_preprocess_inputs),
 :75-152 (_build_network, correlation=True branch).  Activations: sharedLayers.conv2d default leaky 0.1

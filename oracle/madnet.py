@@ -1,4 +1,7 @@
-"""CPU oracle — MADNet forward restated from Nets/MadNet.py (TEST INFRASTRUCTURE, parity unpinned).
+"""CPU oracle — MADNet forward restated from Nets/MadNet.py (TEST INFRASTRUCTURE).
+
+Pinned against the reference's own Nets/MadNet.py executed over oracle/tf1_shim.py (tests/golden/reference_graph_madnet_64x128.npz,
+tests/test_oracle_cpu.py); TF's conv-padding / resize kernels themselves stay unpinned (see oracle/tf1_ops.py).
 
 Follows /root/reference/Nets/MadNet.py:56-71 (_preprocess_inputs, _make_disp), :73-120 (estimator),
 :122-171 (context net), :173-249 (pyramid), :251-364 (_build_network), :370-375 (cost volume).

@@ -1,9 +1,11 @@
 """CPU oracle — TF1-semantics op restatements (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
 
-PARITY UNPINNED: the reference (TF 1.12 graph code) cannot be imported or run in this
-environment and ships no tests / golden vectors, so these functions restate the documented
-TF 1.x behaviour of the ops the reference calls.  Each function cites the reference call
-site it follows (paths relative to /root/reference).
+PARITY: TensorFlow 1.12 cannot be installed here and the reference ships no tests / golden vectors, so these
+functions restate the documented TF 1.x behaviour of the ops the reference calls; each cites the reference call site it
+follows (paths relative to /root/reference).  The restatement as a whole is pinned to the reference's own Python graph
+code executed over oracle/tf1_shim.py (oracle/run_reference_graph.py -> tests/golden/reference_graph_*.npz); the
+SAME-padding conv family, legacy resize and crop_or_pad kernels are shared with that shim and stay UNPINNED w.r.t.
+TensorFlow's own kernels.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 import this package.  The product path (real-time-self-adaptive-deep-stereo_b200/) never does.

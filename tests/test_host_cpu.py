@@ -127,3 +127,22 @@ def test_reward_recurrence_matches_transcription():
         last = b; l2, l1 = l1, L
         assert np.allclose(tr.h, h)
     assert np.allclose(softmax(h).sum(), 1.0)
+
+
+def test_sampler_and_block_configs_match_reference_golden_vectors():
+    """Vectors produced by the reference's OWN Sampler/sampler_factory.py and block_config/*.json (imported in the build
+    container by tests/golden/make_reference_golden.py): the mirror must reproduce every draw with the same numpy seed."""
+    import json
+    g = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'reference_sampler.json')))
+    assert sorted(sampler_factory.AVAILABLE_SAMPLER) == g['available_sampler']
+    for c in g['cases']:
+        d = np.array(c['distribution'])
+        np.random.seed(c['seed'])
+        s = sampler_factory.get_sampler(c['name'], c['blocks'], fixed_id=2)
+        draws = [[int(v) for v in s.sample(d)] for _ in range(len(c['draws']))]
+        if c['name'] == 'ARGMAX':
+            draws = [sorted(v) for v in draws]
+        assert draws == c['draws'], (c['name'], c['blocks'], c['seed'])
+    pkg = os.path.join(ROOT, 'real-time-self-adaptive-deep-stereo_b200', 'block_config')
+    for fn, ref_cfg in g['block_config'].items():
+        assert json.load(open(os.path.join(pkg, fn))) == ref_cfg, fn

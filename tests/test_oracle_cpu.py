@@ -126,3 +126,82 @@ def test_fp64_cross_check():
     d64, _ = MadNetOracle(params, dtype=torch.float64).forward(left, right)
     for a, b in zip(d32, d64):
         assert float((a.double() - b).abs().max()) <= 1e-4 * max(1.0, float(b.abs().max()))
+
+
+# ---------------------------------------------------------------------------------------------------
+# vectors produced by the REFERENCE'S OWN graph code (Nets/*.py, Losses/loss_factory.py, Data_utils/preprocessing.py
+# imported unmodified from /root/reference and executed over oracle/tf1_shim.py by oracle/run_reference_graph.py in the
+# build container; fixtures committed under tests/golden/).  They pin the oracle's wiring, warps, losses, variable
+# naming and MAD variable lists to the reference; conv SAME padding / legacy resize / crop_or_pad kernels are shared
+# with the shim and therefore NOT independently pinned.
+# ---------------------------------------------------------------------------------------------------
+REF_MADNET = os.path.join(os.path.dirname(__file__), 'golden', 'reference_graph_madnet_64x128.npz')
+REF_DISPNET = os.path.join(os.path.dirname(__file__), 'golden', 'reference_graph_dispnet_64x128.npz')
+
+
+def _sub(a, n=4096):
+    a = np.asarray(a).ravel()                       # same deterministic subsample as oracle/run_reference_graph.py:sub
+    return a[::max(1, a.size // n)]
+
+
+def _rel(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def test_oracle_forward_matches_reference_graph_madnet():
+    import json
+    g = np.load(REF_MADNET)
+    left = g['left'].astype(np.float32); right = g['right'].astype(np.float32)
+    params = init_params(seed=42)
+    assert list(g['variable_names']) == list(param_shapes().keys())            # creation order == checkpoint order
+    assert [tuple(json.loads(s)) for s in g['variable_shapes']] == [tuple(v) for v in param_shapes().values()]
+    disps, layers = MadNetOracle(params).forward(left, right)
+    assert len(disps) == 6
+    for i, d in enumerate(disps):
+        assert d.shape == g['disp%d' % i].shape
+        assert _rel(d.numpy(), g['disp%d' % i]) < 5e-5, i
+    for k in [k for k in g.files if k.startswith('layer:')]:
+        assert _rel(layers[k[6:]].numpy(), g[k]) < 5e-5, k
+    loss = float(T.reprojection_loss(disps[-1], torch.tensor(left), torch.tensor(right)))
+    assert abs(loss - float(g['full_loss'])) < 2e-6
+    # what StereoNet.get_variables returns in the reference (captured when the layer is created, Stereo_net.py:63-67)
+    gv = json.loads(str(g['get_variables']))
+    assert gv['left/conv1'] == ['model/gc-read-pyramid/conv1/weights:0', 'model/gc-read-pyramid/conv1/biases:0']
+    assert gv['right/conv1'] == [] and gv['rescaled_prediction'] == []
+    assert len(gv['final_disp']) == 98
+
+
+def test_oracle_mad_and_full_steps_match_reference_graph():
+    g = np.load(REF_MADNET)
+    left = g['left'].astype(np.float32); right = g['right'].astype(np.float32)
+    params = init_params(seed=42)
+    groups = mad_groups_full()
+    for k in range(5):
+        out = OracleAdapter(params, mode='MAD', lr=1e-4).step(left, right, k)
+        assert abs(out['train_loss'] - float(g['mad%d_loss' % k])) < 2e-6, k
+        ref_vars = set(g['mad%d_vars' % k]) - set(g['mad%d_none' % k])
+        assert set(out['grads']) == ref_vars, k                                 # the reference's var_list for module k
+        assert set(groups[k]) == ref_vars, k
+        for key in [x for x in g.files if x.startswith('mad%d_grad:' % k)]:
+            assert _rel(_sub(out['grads'][key.split(':', 1)[1]]), g[key]) < 2e-4, key
+    out = OracleAdapter(params, mode='FULL', lr=1e-4).step(left, right, 0)
+    assert abs(out['train_loss'] - float(g['full_mode_loss'])) < 2e-6
+    for key in [x for x in g.files if x.startswith('full_grad:')]:
+        assert _rel(_sub(out['grads'][key.split(':', 1)[1]]), g[key]) < 2e-4, key
+
+
+def test_oracle_dispnet_matches_reference_graph():
+    from oracle.dispnet import DispNetOracle, DispNetAdapter, init_params as dinit, param_shapes as dshapes
+    g = np.load(REF_DISPNET)
+    left = g['left'].astype(np.float32); right = g['right'].astype(np.float32)
+    p = dinit(seed=7)
+    assert list(g['variable_names']) == list(dshapes().keys())
+    disps, _ = DispNetOracle(p).forward(left, right)
+    assert len(disps) == 7
+    for i, d in enumerate(disps):
+        assert _rel(d.numpy(), g['disp%d' % i]) < 5e-5, i
+    out = DispNetAdapter(p, mode='FULL').step(left, right)
+    assert abs(out['train_loss'] - float(g['full_loss'])) < 2e-6
+    for key in [x for x in g.files if x.startswith('full_grad:')]:
+        assert _rel(_sub(out['grads'][key.split(':', 1)[1]]), g[key]) < 2e-4, key
