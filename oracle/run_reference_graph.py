@@ -171,8 +171,30 @@ def run_dispnet(out_path, h=64, w=128):
     print('wrote', out_path, '(%d arrays)' % len(out))
 
 
+def run_madnet_padded(out_path, h=100, w=200):
+    """A size that is not a multiple of 64: exercises preprocessing.pad_image (REFLECT, :7-29) and the crop back to the
+    input size in _make_disp / rescaled_prediction (MadNet.py:68-71,362-363).  Forward + losses only (small fixture)."""
+    from madstereo.synthetic import make_pair
+    from oracle.madnet import init_params
+    left, right, _ = make_pair(h, w, seed=11)
+    left = left.astype(np.float16).astype(np.float32); right = right.astype(np.float16).astype(np.float32)
+    params = {k: np.asarray(v) for k, v in init_params(seed=42).items()}
+    cfg = json.load(open(os.path.join(REF, 'block_config', 'MadNet_full.json')))
+    out = {'left': left.astype(np.float16), 'right': right.astype(np.float16)}
+    tf, net, preds, full_loss, inputs, lf, pp = build('MADNet', 'MAD', left, right, params)
+    for i, d in enumerate(preds):
+        out['disp%d' % i] = d.numpy().astype(np.float32)
+    out['layer:final_disp'] = net['final_disp'].numpy()
+    out['full_loss'] = np.float32(float(full_loss))
+    for k, (loss, _vars) in enumerate(mad_train_ops(tf, net, preds, inputs, lf, pp, cfg)):
+        out['mad%d_loss' % k] = np.float32(float(loss))
+    np.savez_compressed(out_path, **out)
+    print('wrote', out_path, '(%d arrays)' % len(out))
+
+
 if __name__ == '__main__':
     torch.set_num_threads(1)
     gold = os.path.join(ROOT, 'tests', 'golden')
     run_madnet(os.path.join(gold, 'reference_graph_madnet_64x128.npz'))
+    run_madnet_padded(os.path.join(gold, 'reference_graph_madnet_100x200.npz'))
     run_dispnet(os.path.join(gold, 'reference_graph_dispnet_64x128.npz'))

@@ -205,3 +205,19 @@ def test_oracle_dispnet_matches_reference_graph():
     assert abs(out['train_loss'] - float(g['full_loss'])) < 2e-6
     for key in [x for x in g.files if x.startswith('full_grad:')]:
         assert _rel(_sub(out['grads'][key.split(':', 1)[1]]), g[key]) < 2e-4, key
+
+
+def test_oracle_matches_reference_graph_at_padded_size():
+    """100x200 is not a multiple of 64: the reference's pad_image (REFLECT) and the crop back in _make_disp run as written."""
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'reference_graph_madnet_100x200.npz'))
+    left = g['left'].astype(np.float32); right = g['right'].astype(np.float32)
+    params = init_params(seed=42)
+    disps, layers = MadNetOracle(params).forward(left, right)
+    for i, d in enumerate(disps):
+        assert tuple(d.shape) == (1, 100, 200, 1)
+        assert _rel(d.numpy(), g['disp%d' % i]) < 5e-5, i
+    assert _rel(layers['final_disp'].numpy(), g['layer:final_disp']) < 5e-5
+    assert abs(float(T.reprojection_loss(disps[-1], torch.tensor(left), torch.tensor(right))) - float(g['full_loss'])) < 2e-6
+    for k in range(5):
+        out = OracleAdapter(params, mode='MAD', lr=1e-4).step(left, right, k)
+        assert abs(out['train_loss'] - float(g['mad%d_loss' % k])) < 2e-6, k
