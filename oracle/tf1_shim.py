@@ -30,7 +30,12 @@ from . import tf1_ops as T
 
 float32 = 'float32'
 int32 = 'int32'
-_DT = {'float32': torch.float32, 'int32': torch.int32, 'float64': torch.float64, 'int64': torch.int64}
+uint8 = 'uint8'
+uint16 = 'uint16'
+float64 = 'float64'
+int64 = 'int64'
+_DT = {'float32': torch.float32, 'int32': torch.int32, 'float64': torch.float64, 'int64': torch.int64,
+       'uint8': torch.uint8, 'uint16': torch.int32}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -66,10 +66,21 @@ class OnlineAdaptation(object):
         self._staged_for = None
 
     # ---- weights -----------------------------------------------------------------------------------
-    def load_weights(self, params):
-        """params: dict TF-variable-name -> array (HWIO).  Also becomes the snapshot used by the reset."""
-        self.engine.load_params(params)
+    def load_weights(self, params, strict=True):
+        """params: dict TF-variable-name -> array (HWIO).  Also becomes the snapshot used by the reset.
+        strict=False keeps the current value of every variable `params` does not name (partial restore)."""
+        self.engine.load_params(params, strict)
         self._snapshot = self.engine.weights.clone()
+
+    def get_variable_names(self):
+        """TF variable names (without ':0') in checkpoint order, e.g. model/gc-read-pyramid/conv1/weights."""
+        return list(self.engine.param_views().keys())
+
+    def save_weights(self, prefix):
+        """Write the current weights as a TensorFlow V2 checkpoint (<prefix>.index / .data-00000-of-00001) that the
+        reference's tf.train.Saver can restore: same variable names, HWIO fp32."""
+        from .tf_checkpoint import write_checkpoint
+        write_checkpoint(prefix, self.engine.export_params())
 
     def restore(self):
         """restorer.restore(sess, weights) (:242-244): weights only; momentum slots are left untouched."""

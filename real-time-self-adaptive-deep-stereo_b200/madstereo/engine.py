@@ -110,11 +110,15 @@ class StereoEngine:
             out[l.scope + '/' + l.bias_name] = arena[bo:bo + l.cout]
         return out
 
-    def load_params(self, params):
+    def load_params(self, params, strict=True):
+        """strict=False: parameters absent from `params` keep their current values (tf.train.Saver with a partial
+        var_list, Data_utils/weights_utils.py:27-37)."""
         views = self.param_views()
         for k, v in views.items():
             if k not in params:
-                raise MadStereoError('missing parameter %s' % k)
+                if strict:
+                    raise MadStereoError('missing parameter %s' % k)
+                continue
             v.copy_(torch.as_tensor(np.asarray(params[k]), dtype=torch.float32).to(self.device).reshape(v.shape))
         self.weights_changed()
 

@@ -58,3 +58,62 @@ def main():
 
 if __name__ == '__main__':
     main()
+
+
+def driver_cli():
+    """The argparse definition of the reference's Stereo_Online_Adaptation.py, captured by running the script as __main__
+    with `tensorflow` replaced by the eager shim and `parse_args` intercepted (nothing else of the script executes)."""
+    import argparse
+    import runpy
+    import sys
+    import types
+    root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    sys.path.insert(0, root)
+    from oracle import tf1_shim
+    sys.modules['tensorflow'] = tf1_shim.as_module()
+    mpl = types.ModuleType('matplotlib'); mpl.cm = types.ModuleType('matplotlib.cm'); mpl.pyplot = types.ModuleType('matplotlib.pyplot')
+    for k, v in (('matplotlib', mpl), ('matplotlib.cm', mpl.cm), ('matplotlib.pyplot', mpl.pyplot)):
+        sys.modules.setdefault(k, v)
+    for k in [k for k in sys.modules if k.split('.')[0] in ('Nets', 'Losses', 'Data_utils', 'Sampler')]:
+        del sys.modules[k]
+    captured = {}
+
+    class Stop(Exception):
+        pass
+
+    def fake_parse(self, *a, **k):
+        captured['parser'] = self
+        raise Stop()
+
+    orig = argparse.ArgumentParser.parse_args
+    argparse.ArgumentParser.parse_args = fake_parse
+    sys.path.insert(0, REF)
+    old_argv = sys.argv
+    try:
+        sys.argv = ['Stereo_Online_Adaptation.py']
+        runpy.run_path(os.path.join(REF, 'Stereo_Online_Adaptation.py'), run_name='__main__')
+    except Stop:
+        pass
+    finally:
+        sys.argv = old_argv
+        argparse.ArgumentParser.parse_args = orig
+        sys.path.remove(REF)
+    acts = []
+    for a in captured['parser']._actions:
+        if a.dest == 'help':
+            continue
+        acts.append({'flags': list(a.option_strings), 'dest': a.dest, 'required': bool(a.required), 'default': a.default,
+                     'type': getattr(a.type, '__name__', None), 'nargs': a.nargs, 'choices': sorted(a.choices) if a.choices else None,
+                     'store_true': isinstance(a, argparse._StoreTrueAction)})
+    return acts
+
+
+def main_cli():
+    out_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'reference_driver_cli.json')
+    json.dump({'source': 'CVLAB-Unibo/Real-time-self-adaptive-deep-stereo: Stereo_Online_Adaptation.py (argparse actions)',
+               'actions': driver_cli()}, open(out_path, 'w'), indent=1)
+    print('wrote', out_path)
+
+
+if __name__ == '__main__':
+    main_cli()

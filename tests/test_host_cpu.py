@@ -146,3 +146,13 @@ def test_sampler_and_block_configs_match_reference_golden_vectors():
     pkg = os.path.join(ROOT, 'real-time-self-adaptive-deep-stereo_b200', 'block_config')
     for fn, ref_cfg in g['block_config'].items():
         assert json.load(open(os.path.join(pkg, fn))) == ref_cfg, fn
+
+
+def test_loss_factory_entry_point_errors_like_the_reference():
+    from Losses import loss_factory
+    with pytest.raises(Exception, match='Unknown loss function selected'):
+        loss_factory.get_reprojection_loss('no_such_loss')
+    with pytest.raises(NotImplementedError):
+        loss_factory.get_reprojection_loss('mean_l1')
+    assert callable(loss_factory.get_reprojection_loss('mean_SSIM_l1', reduced=True))
+    assert set(loss_factory.ALL_LOSSES) >= {'mean_SSIM_l1', 'ssim_l1', 'ZNCC'}

@@ -1,0 +1,257 @@
+"""Host-side I/O next to the hot path: TF V2 checkpoint import/export without TensorFlow, the
+reference's checkpoint-key matching rules, the list-file / image reader and the driver's output files."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, 'real-time-self-adaptive-deep-stereo_b200')
+sys.path.insert(0, ROOT)
+sys.path.insert(0, PKG)
+
+from madstereo import tf_checkpoint as tfc  # noqa: E402
+from Data_utils import weights_utils  # noqa: E402
+
+
+def test_crc32c_known_answers_and_masking():
+    assert tfc.crc32c(b'123456789') == 0xE3069283               # the standard CRC-32C check value
+    assert tfc.crc32c(b'') == 0
+    assert tfc.crc32c(bytes(32)) == 0x8A9136AA                   # RFC 3720 B.4: 32 zero bytes
+    for v in (0, 1, 0xE3069283, 0xFFFFFFFF):
+        assert tfc.unmask_crc(tfc.mask_crc(v)) == v
+
+
+def _tensors(seed=0):
+    rng = np.random.default_rng(seed)
+    t = {'model/gc-read-pyramid/conv%d/weights' % i: rng.standard_normal((3, 3, 4, 5)).astype(np.float32) for i in range(1, 40)}
+    t['model/gc-read-pyramid/conv1/biases'] = rng.standard_normal(5).astype(np.float32)
+    t['model/G6/fgc-volume-filtering-6/disp-1/weights/Momentum'] = rng.standard_normal((3, 3, 2, 2)).astype(np.float32)
+    t['global_step'] = np.array(1234, dtype=np.int64)
+    t['empty'] = np.zeros((0, 3), dtype=np.float32)
+    return t
+
+
+def test_checkpoint_round_trip_multi_block(tmp_path):
+    t = _tensors()
+    prefix = str(tmp_path / 'model.ckpt-100')
+    tfc.write_checkpoint(prefix, t, block_size=512)             # small blocks: several data blocks + a real index block
+    assert os.path.exists(prefix + '.index') and os.path.exists(prefix + '.data-00000-of-00001')
+    r = tfc.CheckpointReader(prefix, verify=True)                # verifies block and tensor CRC32C
+    shapes = r.get_variable_to_shape_map()
+    assert set(shapes) == set(t)
+    assert shapes['global_step'] == [] and shapes['empty'] == [0, 3]
+    for k, v in t.items():
+        got = r.get_tensor(k)
+        assert got.dtype == v.dtype and got.shape == v.shape and np.array_equal(got, v), k
+    assert r.get_variable_to_dtype_map()['global_step'] == np.int64
+    assert not r.has_tensor('nope')
+    with pytest.raises(tfc.CheckpointError):
+        r.get_tensor('nope')
+
+
+def test_checkpoint_rejects_foreign_and_corrupt_files(tmp_path):
+    p = str(tmp_path / 'x')
+    open(p + '.index', 'wb').write(b'not a table' * 10)
+    with pytest.raises(tfc.CheckpointError):
+        tfc.CheckpointReader(p)
+    with pytest.raises(tfc.CheckpointError):
+        tfc.CheckpointReader(str(tmp_path / 'missing'))
+    prefix = str(tmp_path / 'c')
+    tfc.write_checkpoint(prefix, {'a': np.arange(100, dtype=np.float32)})
+    raw = bytearray(open(prefix + '.data-00000-of-00001', 'rb').read())
+    raw[17] ^= 0x40
+    open(prefix + '.data-00000-of-00001', 'wb').write(bytes(raw))
+    assert tfc.CheckpointReader(prefix).get_tensor('a').shape == (100,)          # unverified read still works
+    with pytest.raises(tfc.CheckpointError):
+        tfc.CheckpointReader(prefix, verify=True).get_tensor('a')                # checksum catches the flipped bit
+
+
+def test_restore_list_follows_reference_matching_rules(tmp_path):
+    """Data_utils/weights_utils.py:4-38 -- mask skips model variables, ignore_list strips substrings from checkpoint keys,
+    prefix is prepended before the lookup; optimizer slots and unknown keys are ignored."""
+    t = _tensors()
+    prefix = str(tmp_path / 'm')
+    tfc.write_checkpoint(prefix, t)
+    variables = ['model/gc-read-pyramid/conv1/weights:0', 'model/gc-read-pyramid/conv1/biases:0',
+                 'model/gc-read-pyramid/conv2/weights:0', 'model/context-1/weights:0']
+    m = weights_utils.get_var_to_restore_list(prefix, variables=variables)
+    assert m == {'model/gc-read-pyramid/conv1/weights': 'model/gc-read-pyramid/conv1/weights',
+                 'model/gc-read-pyramid/conv1/biases': 'model/gc-read-pyramid/conv1/biases',
+                 'model/gc-read-pyramid/conv2/weights': 'model/gc-read-pyramid/conv2/weights'}
+    m = weights_utils.get_var_to_restore_list(prefix, mask=['conv2'], variables=variables)
+    assert 'model/gc-read-pyramid/conv2/weights' not in m and len(m) == 2
+    stripped = ['gc-read-pyramid/conv1/weights', 'gc-read-pyramid/conv1/biases']
+    m = weights_utils.get_var_to_restore_list(prefix, ignore_list=['model/'], variables=stripped)
+    assert m == {'model/gc-read-pyramid/conv1/weights': stripped[0], 'model/gc-read-pyramid/conv1/biases': stripped[1]}
+    m = weights_utils.get_var_to_restore_list(prefix, prefix='net/', variables=['net/model/gc-read-pyramid/conv3/weights'])
+    assert m == {'model/gc-read-pyramid/conv3/weights': 'net/model/gc-read-pyramid/conv3/weights'}
+    w = weights_utils.load_weights(prefix, variables)
+    assert set(w) == set(v[:-2] for v in variables[:3]) and np.array_equal(w[variables[0][:-2]], t[variables[0][:-2]])
+    # an .npz archive of name -> array is accepted wherever a checkpoint prefix is
+    np.savez(str(tmp_path / 'w.npz'), **{k: v for k, v in t.items() if 'conv1/' in k})
+    assert set(weights_utils.load_weights(str(tmp_path / 'w.npz'), variables)) == {variables[0][:-2], variables[1][:-2]}
+
+
+class _Model:
+    def __init__(self, names):
+        self.names, self.loaded = names, None
+
+    def get_variable_names(self):
+        return self.names
+
+    def load_weights(self, w, strict=True):
+        self.loaded, self.strict = w, strict
+
+
+def test_check_for_weights_or_restore_them(tmp_path):
+    t = _tensors()
+    names = ['model/gc-read-pyramid/conv1/weights', 'model/gc-read-pyramid/conv1/biases']
+    logdir = tmp_path / 'log'; logdir.mkdir()
+    init = tmp_path / 'init'; init.mkdir()
+    tfc.write_checkpoint(str(init / 'weights.ckpt'), t)
+    open(str(init / 'checkpoint'), 'w').write('model_checkpoint_path: "weights.ckpt"\nall_model_checkpoint_paths: "weights.ckpt"\n')
+    m = _Model(names)
+    assert weights_utils.check_for_weights_or_restore_them(str(logdir), m) == (False, 0) and m.loaded is None
+    assert weights_utils.check_for_weights_or_restore_them(str(logdir), m, initial_weights=str(init)) == (True, 0)
+    assert set(m.loaded) == set(names) and m.strict is False
+    tfc.write_checkpoint(str(logdir / 'model.ckpt-4200'), t)
+    open(str(logdir / 'checkpoint'), 'w').write('model_checkpoint_path: "model.ckpt-4200"\n')
+    assert weights_utils.check_for_weights_or_restore_them(str(logdir), _Model(names), initial_weights=str(init)) == (True, 4200)
+    assert weights_utils.check_for_weights_or_restore_them(str(logdir), _Model(['zzz']), initial_weights=None)[0] is True
+
+
+# ---------------------------------------------------------------------------------------------------
+# input pipeline
+# ---------------------------------------------------------------------------------------------------
+def _write_dataset(tmp_path, n=5, h=20, w=30, gt16=True):
+    import cv2
+    from Data_utils import data_reader as dr  # noqa: F401
+    rng = np.random.default_rng(3)
+    lines, frames = ['# left;right;gt', ''], []
+    for i in range(n):
+        l = rng.integers(0, 256, (h, w, 3), dtype=np.uint8); r = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        g = rng.integers(0, 40 * 256, (h, w + 4), dtype=np.uint16) if gt16 else rng.integers(0, 200, (h, w + 4), dtype=np.uint8)
+        pl, pr, pg = (str(tmp_path / ('%s_%d.png' % (k, i))) for k in 'lrg')
+        cv2.imwrite(pl, l[:, :, ::-1]); cv2.imwrite(pr, r[:, :, ::-1]); cv2.imwrite(pg, g)      # cv2 writes BGR
+        lines.append('%s;%s,%s' % (pl, pr, pg))                                                   # both separators
+        frames.append((l, r, g))
+    lst = str(tmp_path / 'list.csv')
+    open(lst, 'w').write('\n'.join(lines) + '\n')
+    return lst, frames
+
+
+def test_list_file_and_image_decoding(tmp_path):
+    from Data_utils import data_reader as dr
+    lst, frames = _write_dataset(tmp_path)
+    left, right, gt, conf = dr.read_list_file(lst)
+    assert len(left) == len(right) == len(gt) == 5 and conf == []
+    img = dr.read_image_from_disc(left[0])
+    assert img.dtype == np.float32 and np.array_equal(img, frames[0][0].astype(np.float32))      # RGB order, 0..255
+    g = dr.read_gt_from_disc(gt[0])
+    assert g.shape == (20, 34, 1) and np.allclose(g[..., 0], frames[0][2] / 256.0)                 # 16-bit PNG / 256
+    with pytest.raises(Exception):
+        dr.dataset(str(tmp_path / 'missing.csv'))
+
+
+def test_crop_or_pad_matches_oracle_restatement():
+    import torch
+    from Data_utils import data_reader as dr
+    from oracle import tf1_ops as T
+    rng = np.random.default_rng(0)
+    for (h, w, th, tw) in [(10, 13, 7, 9), (7, 9, 10, 13), (10, 9, 7, 13), (5, 5, 5, 5), (11, 12, 6, 17), (1, 1, 4, 3)]:
+        x = rng.standard_normal((h, w, 3)).astype(np.float32)
+        assert np.array_equal(dr.resize_image_with_crop_or_pad(x, th, tw), T.crop_or_pad(torch.tensor(x)[None], th, tw)[0].numpy())
+
+
+def test_dataset_batches_in_order_with_prefetch_thread(tmp_path):
+    from Data_utils import data_reader as dr
+    lst, frames = _write_dataset(tmp_path, n=5, h=20, w=30)
+    ds = dr.dataset(lst, batch_size=2, crop_shape=[16, 36], num_epochs=1, augment=False, is_training=False, shuffle=False, prefetch=2)
+    assert len(ds) == 5 and ds.get_max_steps() == 2                                               # drop_remainder
+    batches = list(ds)
+    assert len(batches) == 2
+    l, r, g = batches[1]
+    assert l.shape == (2, 16, 36, 3) and g.shape == (2, 16, 36, 1) and l.dtype == np.float32
+    want = dr.resize_image_with_crop_or_pad(frames[2][0].astype(np.float32), 16, 36)             # centre crop rows, zero-pad cols
+    assert np.array_equal(l[0], want)
+    gt_cropped = (frames[3][2][:, :30, None] / 256.0).astype(np.float32)                           # gt cut to the image width first
+    assert np.allclose(g[1], dr.resize_image_with_crop_or_pad(gt_cropped, 16, 36))
+    with pytest.raises(NotImplementedError):
+        dr.dataset(lst, augment=True)
+
+
+def test_pfm_reader(tmp_path):
+    from Data_utils import data_reader as dr
+    a = np.arange(12, dtype=np.float32).reshape(3, 4)
+    p = str(tmp_path / 'd.pfm')
+    with open(p, 'wb') as f:
+        f.write(b'Pf\n4 3\n-1.0\n'); f.write(np.flipud(a).astype('<f4').tobytes())
+    d, scale = dr.readPFM(p)
+    assert scale == 1.0 and d.shape == (3, 4, 1) and np.array_equal(d[..., 0], a)
+    assert np.array_equal(dr.read_gt_from_disc(p)[..., 0], a)
+
+
+# ---------------------------------------------------------------------------------------------------
+# driver: command line and output files
+# ---------------------------------------------------------------------------------------------------
+def _driver():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('soa_driver', os.path.join(PKG, 'Stereo_Online_Adaptation.py'))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_driver_command_line_equals_the_reference(tmp_path):
+    """tests/golden/reference_driver_cli.json holds the argparse actions of the reference's Stereo_Online_Adaptation.py
+    (captured by tests/golden/make_reference_golden.py running that script under the TF shim)."""
+    import argparse
+    import json
+    g = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'reference_driver_cli.json')))['actions']
+    mine = []
+    for a in _driver().build_parser()._actions:
+        if a.dest == 'help':
+            continue
+        mine.append({'flags': list(a.option_strings), 'dest': a.dest, 'required': bool(a.required), 'default': a.default,
+                     'type': getattr(a.type, '__name__', None), 'nargs': a.nargs, 'choices': sorted(a.choices) if a.choices else None,
+                     'store_true': isinstance(a, argparse._StoreTrueAction)})
+    assert mine == g
+
+
+class _FakeAdapt:
+    def __init__(self):
+        self.calls, self.reset_counter, self.fetch_counter, self.sample_distribution = [], 1, [2, 1, 0, 0, 0], np.array([0.5, 0, 0, 0, -0.25])
+
+    def step(self, left, right, gt=None, want_disp_mask=0, prefetch=None):
+        self.calls.append((float(left.mean()), want_disp_mask, prefetch is not None))
+        k = len(self.calls)
+        return {'loss': 0.1 * k, 'train_loss': 0.0, 'epe': 1.0 * k, 'bad3': 0.01 * k, 'blocks': [0], 'reset': False}
+
+
+def test_driver_loop_and_output_files(tmp_path):
+    import argparse
+    import cv2
+    d = _driver()
+    out = tmp_path / 'out'; (out / 'disparities').mkdir(parents=True)
+    args = argparse.Namespace(logDispStep=2, output=str(out))
+    frames = [(np.full((1, 4, 6, 3), float(i), np.float32), np.zeros((1, 4, 6, 3), np.float32), np.zeros((1, 4, 6, 1), np.float32)) for i in range(3)]
+    ad = _FakeAdapt()
+    disp = np.linspace(0, 300, 24, dtype=np.float32).reshape(1, 4, 6, 1)
+    epe, bad3, exec_time, step = d.run_loop(ad, frames, args, max_steps=3, get_disparity=lambda: disp, log=lambda s: None)
+    assert step == 3 and epe == [1.0, 2.0, 3.0] and bad3 == [0.01, 0.02, 0.03]
+    assert [c[0] for c in ad.calls] == [0.0, 1.0, 2.0]                                      # frames in order
+    assert [c[1] for c in ad.calls] == [0b100000, 0, 0b100000]                             # disparity fetched on logDispStep
+    assert [c[2] for c in ad.calls] == [True, True, False]                                 # next frame prefetched except at the end
+    png = cv2.imread(str(out / 'disparities' / 'disparity_2.png'), cv2.IMREAD_UNCHANGED)
+    assert png.dtype == np.uint16 and png.shape == (4, 6)
+    assert np.array_equal(png, (np.clip(disp[0, ..., 0], 0, 256) * 256.0).astype(np.uint16))   # x256, clipped at MAX_DISP
+    d.write_stats(str(out / 'stats.csv'), epe, bad3, 0.5, step, ad.reset_counter, 5, ad.fetch_counter, ad.sample_distribution)
+    d.write_series(str(out / 'series.csv'), epe, bad3, 0.5, step)
+    lines = open(str(out / 'stats.csv')).read().splitlines()
+    assert lines[0] == 'Metrics,cumulative,average' and lines[1] == 'EPE,6.0,2.0'
+    assert lines[3].startswith('time,0.5,') and lines[4].startswith('FPS,6.0') and lines[5] == '#resets,1'
+    assert lines[6] == 'Blocks,0,1,2,3,4,final' and lines[7] == 'fetch_counter,2,1,0,0,0' and lines[8] == ',0.5,0.0,0.0,0.0,-0.25'
+    s = open(str(out / 'series.csv')).read().splitlines()
+    assert s[0] == 'Iteration,Time,EPE,bad3' and s[1] == '0,0.0,1.0,0.01' and s[3].startswith('2,0.3333')

@@ -219,3 +219,16 @@ def test_pad_reflect(ops):
     ref = T.pad_reflect_to_multiple(torch.tensor(x), 64)
     out = ops.pad_reflect(cu(x), 64)
     assert out.shape == ref.shape and torch.equal(out.cpu(), ref)
+
+
+def test_zz_loss_factory_operator_form(ops):
+    """Losses.loss_factory.get_reprojection_loss('mean_SSIM_l1') -- the reference's public entry point
+    (Losses/loss_factory.py:353-395) -- on the device vs the oracle.  (Last test of the last file on purpose.)"""
+    T = _oracle()
+    from Losses import loss_factory
+    from madstereo.synthetic import make_pair
+    left, right, gt = make_pair(48, 96, seed=4, batch=1)
+    disp = gt.astype(np.float32)
+    ref = float(T.reprojection_loss(torch.tensor(disp), torch.tensor(left), torch.tensor(right)))
+    got = loss_factory.get_reprojection_loss('mean_SSIM_l1', reduced=True)([cu(disp)], {'left': cu(left), 'right': cu(right)})
+    assert abs(float(got.cpu()) - ref) < 2e-6 + 1e-5 * abs(ref)
