@@ -128,30 +128,39 @@ def run_loop(adapt, frames, args, max_steps, get_disparity=None, log=print):
     return epe_accumulator, bad3_accumulator, exec_time, step
 
 
-def main(args):
+def build_model(args, train_config):
+    """Network + adaptation object on the current CUDA device (graph construction of the reference, :54-128)."""
     import torch
     from madstereo.adaptation import OnlineAdaptation
-    with open(args.blockConfig) as json_data:
-        train_config = json.load(json_data)
-
-    data_set = data_reader.dataset(args.list, batch_size=1, crop_shape=args.imageShape, num_epochs=1, augment=False,
-                                   is_training=False, shuffle=False, pin_memory=True)
+    if not torch.cuda.is_available():
+        raise SystemExit('Stereo_Online_Adaptation.py needs a CUDA device (there is no CPU fallback)')
     h, w = args.imageShape
     dev = torch.device('cuda', torch.cuda.current_device())
     left_buf = torch.zeros(1, h, w, 3, device=dev); right_buf = torch.zeros(1, h, w, 3, device=dev)
-
     net_args = {'left_img': left_buf, 'right_img': right_buf, 'split_layers': [None], 'sequence': True,
                 'train_portion': 'BEGIN', 'bulkhead': True if args.mode == 'MAD' else False}
     stereo_net = Nets.get_stereo_net(args.modelName, net_args)
     print('Stereo Prediction Model:\n', stereo_net)
-    predictions = stereo_net.get_disparities()
     if args.mode == 'MAD':
-        assert (len(predictions[:-1]) == len(train_config))
-    if args.reprojectionScale != 1:
-        raise SystemExit('--reprojectionScale != 1 is not supported: the engine computes every loss at full resolution')
+        assert (len(stereo_net.get_disparities()[:-1]) == len(train_config))
     adapt = OnlineAdaptation(stereo_net, mode=args.mode, train_config=train_config, lr=args.lr, sample_mode=args.sampleMode,
                              num_blocks=args.numBlocks, fixed_id=args.fixedID, sample_frequency=args.sampleFrequency,
                              ssim_th=args.SSIMTh)
+    return stereo_net, adapt
+
+
+def main(args, build=build_model):
+    with open(args.blockConfig) as json_data:
+        train_config = json.load(json_data)
+    if args.reprojectionScale != 1:
+        raise SystemExit('--reprojectionScale != 1 is not supported: the engine computes every loss at full resolution')
+    if len(args.imageShape) != 2:
+        raise SystemExit('--imageShape takes two integers: height width')
+
+    data_set = data_reader.dataset(args.list, batch_size=1, crop_shape=args.imageShape, num_epochs=1, augment=False,
+                                   is_training=False, shuffle=False, pin_memory=(build is build_model))
+    stereo_net, adapt = build(args, train_config)
+    predictions = stereo_net.get_disparities()
 
     # restore disparity inference weights (:150-154)
     weights = args.weights

@@ -255,3 +255,67 @@ def test_driver_loop_and_output_files(tmp_path):
     assert lines[6] == 'Blocks,0,1,2,3,4,final' and lines[7] == 'fetch_counter,2,1,0,0,0' and lines[8] == ',0.5,0.0,0.0,0.0,-0.25'
     s = open(str(out / 'series.csv')).read().splitlines()
     assert s[0] == 'Iteration,Time,EPE,bad3' and s[1] == '0,0.0,1.0,0.01' and s[3].startswith('2,0.3333')
+
+
+class _FakeHandle:
+    def __init__(self, h, w):
+        self._h, self._w = h, w
+
+    def numpy(self):
+        return np.full((1, self._h, self._w, 1), 7.5, np.float32)
+
+
+class _FakeNet:
+    def __init__(self, h, w):
+        self._d = [_FakeHandle(h, w) for _ in range(6)]
+
+    def get_disparities(self):
+        return self._d
+
+
+class _FakeAdapt2(_FakeAdapt):
+    def __init__(self, names):
+        super().__init__()
+        self.names, self.loaded = names, None
+
+    def get_variable_names(self):
+        return self.names
+
+    def load_weights(self, w, strict=True):
+        self.loaded, self.strict = dict(w), strict
+
+
+def test_driver_main_end_to_end_with_a_stub_engine(tmp_path):
+    """Everything of the driver except the CUDA engine: list file -> decoded, cropped frames -> checkpoint restore through the
+    TF-free reader -> loop -> stats.csv / series.csv / disparity PNGs."""
+    import cv2
+    d = _driver()
+    lst, frames = _write_dataset(tmp_path, n=4, h=20, w=30)
+    names = ['model/gc-read-pyramid/conv1/weights', 'model/gc-read-pyramid/conv1/biases', 'model/context-1/weights']
+    tfc.write_checkpoint(str(tmp_path / 'w.ckpt'), {k: v for k, v in _tensors().items() if 'conv1/' in k})
+    out = tmp_path / 'run'; (out / 'disparities').mkdir(parents=True)
+    cfg = os.path.join(PKG, 'block_config', 'MadNet_full.json')
+    args = d.build_parser().parse_args(['-l', lst, '-o', str(out), '--weights', str(tmp_path / 'w.ckpt'), '--modelName', 'MADNet',
+                                        '--blockConfig', cfg, '--mode', 'MAD', '--sampleMode', 'SEQUENTIAL', '--imageShape', '16', '32',
+                                        '--logDispStep', '3'])
+    made = {}
+
+    def build(a, train_config):
+        assert len(train_config) == 5 and a.imageShape == [16, 32]
+        made['adapt'] = _FakeAdapt2(names)
+        return _FakeNet(16, 32), made['adapt']
+
+    d.main(args, build=build)
+    ad = made['adapt']
+    assert set(ad.loaded) == set(names[:2]) and ad.strict is False                 # only what the checkpoint holds
+    assert len(ad.calls) == 4
+    want0 = float(np.asarray(__import__('Data_utils.data_reader', fromlist=['x']).resize_image_with_crop_or_pad(
+        frames[0][0].astype(np.float32), 16, 32)).mean())
+    assert abs(ad.calls[0][0] - want0) < 1e-3
+    stats = open(str(out / 'stats.csv')).read().splitlines()
+    assert stats[1].startswith('EPE,10.0,2.5') and stats[6] == 'Blocks,0,1,2,3,4,final'
+    assert len(open(str(out / 'series.csv')).read().splitlines()) == 5
+    png = cv2.imread(str(out / 'disparities' / 'disparity_3.png'), cv2.IMREAD_UNCHANGED)
+    assert png.shape == (16, 32) and int(png[0, 0]) == int(7.5 * 256)
+    with pytest.raises(SystemExit):
+        d.main(d.build_parser().parse_args(['-l', lst, '-o', str(out), '--weights', 'x', '--blockConfig', cfg, '--reprojectionScale', '2']), build=build)
