@@ -867,7 +867,16 @@ static int get_map(const CUtensorMap** out, void* addr, int rank, const cuuint64
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r)); return -1; }
-        if (c.size() > 4096) c.clear();
+        if (c.size() >= 4096) {
+            // cache full (callers that keep passing fresh pointers): do not evict -- pointers handed out earlier in the same
+            // launch sequence must stay valid -- but serve this descriptor from a small ring of uncached slots
+            static thread_local CUtensorMap spill[16];
+            static thread_local unsigned spill_i = 0;
+            CUtensorMap* slot = &spill[spill_i++ & 15u];
+            *slot = m;
+            *out = slot;
+            return 0;
+        }
         it = c.emplace(k, m).first;
     }
     *out = &it->second;
