@@ -54,114 +54,118 @@ class LayerHandle(object):
         return "<Layer '%s' shape=%s>" % (self.name, self.shape)
 
 
+def _accessor(attr, doc, as_list=False):
+    """Build one of the trivial public getters of the reference class (Nets/Stereo_net.py:166-211)."""
+    def get(self):
+        value = getattr(self, attr)
+        return list(value.keys()) if as_list else value
+    get.__doc__ = doc
+    return get
+
+
 class StereoNet(object):
+    """Base class of the two networks.  Construction protocol, printed banner, `WARNING:` lines for defaulted arguments,
+    `str(net)` layout and the getter names are those of the reference (the drivers rely on them:
+    Stereo_Online_Adaptation.py:62-65,114); the body is a table-driven restatement."""
     __metaclass__ = abc.ABCMeta
-    _valid_args = [
+
+    _netName = "stereoNet"
+    _ARG_DOC = OrderedDict([
         ("split_layer", "name of the layer where the network will be splitted"),
         ("sequence", "flag to use network on a video sequence instead of on single images"),
         ("train_portion", "one among 'BEGIN' or 'END' specify which portion of the network will be trained"),
         ("is_training", "boolean or placeholder to specify if the network is in train or inference mode"),
-    ]
-    _netName = "stereoNet"
+    ])
+    _valid_args = list(_ARG_DOC.items())
+    # (argument, value used when absent, message printed when absent) -- Nets/Stereo_net.py:131-163
+    _COMMON_DEFAULTS = (
+        ('split_layers', [None], 'WARNING: no split points selected, the network will flow without interruption'),
+        ('train_portion', None, 'WARNING: train_portion not specified, using default END'),
+        ('sequence', False, 'WARNING: sequence flag not setted, configuring the network for single image adaptation'),
+        ('is_training', False, 'WARNING: flag for trainign not setted, using default False'),
+    )
+    _RULE = '=' * 50
 
     @classmethod
     def getPossibleArsg(cls):
         return cls._valid_args
 
     def __init__(self, **kwargs):
-        self._layers = OrderedDict()
-        self._disparities = []
-        self._placeholders = []
-        self._trainable_variables = OrderedDict()
-        self._layer_to_var = {}
+        self._layers, self._trainable_variables = OrderedDict(), OrderedDict()
+        self._disparities, self._placeholders, self._layer_to_var = [], [], {}
         self.engine = None
-        print('=' * 50)
-        print('Starting Creation of {}'.format(self._netName))
-        print('=' * 50)
-        args = self._validate_args(kwargs)
-        print('Args Validated, setting up graph')
-        self._preprocess_inputs(args)
-        print('Meta op to preprocess data created')
-        self._build_network(args)
-        print('Network ready')
-        print('=' * 50)
+        stages = ((self._validate_args, 'Args Validated, setting up graph'),
+                  (self._preprocess_inputs, 'Meta op to preprocess data created'),
+                  (self._build_network, 'Network ready'))
+        for line in (self._RULE, 'Starting Creation of {}'.format(self._netName), self._RULE):
+            print(line)
+        args = kwargs
+        for index, (stage, done) in enumerate(stages):
+            result = stage(args)
+            if index == 0:                      # _validate_args returns the completed argument dict
+                args = result
+            print(done)
+        print(self._RULE)
 
     # -- helpers used by subclasses ---------------------------------------------------------------
     def _add_to_layers(self, name, handle, variables=()):
+        """Register a layer and the variables created with it (the reference captures the variable list at creation time,
+        Stereo_net.py:63-67).  With split_layers == [None] every variable is trainable (:73-76)."""
+        owned = list(variables)
         self._layers[name] = handle
-        self._layer_to_var[name] = list(variables)
+        self._layer_to_var[name] = owned
         if self._train_beginning or self._split_layers_list != [None]:
-            for v in variables:
-                self._trainable_variables[v] = True
+            self._trainable_variables.update((v, True) for v in owned)
 
     def __str__(self):
-        ss = ""
-        for k, l in self._layers.items():
-            if l in self._disparities:
-                ss += "Prediction Layer {}: {}\n".format(k, str(l.shape))
-            else:
-                ss += "Layer {}: {}\n".format(k, str(l.shape))
-        return ss
+        tag = lambda layer: "Prediction Layer" if layer in self._disparities else "Layer"   # noqa: E731
+        return "".join("{} {}: {}\n".format(tag(l), k, str(l.shape)) for k, l in self._layers.items())
 
-    def __repr__(self):
-        return self.__str__()
+    __repr__ = __str__
 
     def __getitem__(self, key):
         return self._layers[key]
 
     @abc.abstractmethod
     def _preprocess_inputs(self, args):
-        pass
+        """Subclasses bind the input buffers here."""
 
     @abc.abstractmethod
     def _build_network(self, args):
-        pass
+        """Subclasses create the engine and register layers / disparities here."""
 
     @abc.abstractmethod
     def _validate_args(self, args):
-        portion_options = ['BEGIN', 'END']
-        if 'split_layers' not in args:
-            print('WARNING: no split points selected, the network will flow without interruption')
-            args['split_layers'] = [None]
-        if 'train_portion' not in args:
-            print('WARNING: train_portion not specified, using default END')
-            args['train_portion'] = 'END' if args['split_layers'] != [None] else 'BEGIN'
-        elif args['train_portion'] not in portion_options:
+        """Common arguments; subclasses call this first, add their own defaults and return `args`."""
+        for key, default, message in self._COMMON_DEFAULTS:
+            if key in args:
+                continue
+            print(message)
+            if key == 'train_portion':
+                default = 'END' if args['split_layers'] != [None] else 'BEGIN'
+            args[key] = default
+        if args['train_portion'] not in ('BEGIN', 'END'):
             raise Exception('Invalid portion options {}'.format(args['train_portion']))
-        if 'sequence' not in args:
-            print('WARNING: sequence flag not setted, configuring the network for single image adaptation')
-            args['sequence'] = False
-        if 'is_training' not in args:
-            print('WARNING: flag for trainign not setted, using default False')
-            args['is_training'] = False
         if args['split_layers'] != [None]:
             raise Exception('split_layers other than [None] is not supported by the B200 engine '
                             '(the adaptation drivers always pass [None], Stereo_Online_Adaptation.py:57)')
         self._split_layers_list = args['split_layers']
-        self._train_beginning = (args['train_portion'] == 'BEGIN')
+        self._train_beginning = args['train_portion'] == 'BEGIN'
         self._sequence = args['sequence']
         self._isTraining = False
 
     # -- public API (Nets/Stereo_net.py:166-222) ----------------------------------------------------
-    def get_placeholders(self):
-        return self._placeholders
-
-    def get_placeholder(self, name):
-        raise Exception('Unable to find placeholder for layer {}'.format(name + '_placeholder'))
-
-    def get_all_layers(self):
-        return self._layers
+    get_placeholders = _accessor('_placeholders', 'placeholders of split layers (always empty: sequence mode only)')
+    get_all_layers = _accessor('_layers', 'OrderedDict layer name -> handle')
+    get_disparities = _accessor('_disparities', 'disparity handles, coarse to fine, last = full resolution')
+    get_trainable_variables = _accessor('_trainable_variables', 'list of trainable variables', as_list=True)
 
     def get_layers_names(self):
         return self._layers.keys()
 
-    def get_disparities(self):
-        return self._disparities
-
-    def get_trainable_variables(self):
-        return list(self._trainable_variables.keys())
+    def get_placeholder(self, name):
+        raise Exception('Unable to find placeholder for layer {}'.format(name + '_placeholder'))
 
     def get_variables(self, layer_name):
-        if layer_name in self._layers and layer_name not in self._layer_to_var:
-            return []
-        return self._layer_to_var[layer_name]
+        """Variables created together with `layer_name`; a layer registered without variables yields []."""
+        return self._layer_to_var.get(layer_name, []) if layer_name in self._layers else self._layer_to_var[layer_name]

@@ -1,14 +1,15 @@
-"""Drop-in for the reference `Nets` package (Nets/__init__.py:1-13): same factory, same names."""
+"""Drop-in for the reference `Nets` package (Nets/__init__.py:1-13): same factory name, keys and error."""
 from Nets import DispNet as _DispNet
 from Nets import MadNet as _MadNet
 
-STEREO_FACTORY = {
-    _DispNet.DispNet._netName: _DispNet.DispNet,
-    _MadNet.MadNet._netName: _MadNet.MadNet,
-}
+# keyed by the class's _netName, like the reference: 'Dispnet', 'MADNet' (argparse choices of the drivers)
+STEREO_FACTORY = {cls._netName: cls for cls in (_DispNet.DispNet, _MadNet.MadNet)}
 
 
 def get_stereo_net(name, args):
-    if name not in STEREO_FACTORY:
+    """Build the network called `name` from the argument dict the drivers assemble (Stereo_Online_Adaptation.py:55-62)."""
+    try:
+        builder = STEREO_FACTORY[name]
+    except KeyError:
         raise Exception('Unrecognized network name: {}'.format(name))
-    return STEREO_FACTORY[name](**args)
+    return builder(**args)

@@ -156,3 +156,60 @@ def test_loss_factory_entry_point_errors_like_the_reference():
         loss_factory.get_reprojection_loss('mean_l1')
     assert callable(loss_factory.get_reprojection_loss('mean_SSIM_l1', reduced=True))
     assert set(loss_factory.ALL_LOSSES) >= {'mean_SSIM_l1', 'ssim_l1', 'ZNCC'}
+
+
+def test_stereonet_base_class_protocol(capsys):
+    """The construction protocol, printed lines, defaults and getters of Nets.Stereo_net.StereoNet (reference
+    Nets/Stereo_net.py:26-46, 99-107, 131-222) on a network without an engine."""
+    from Nets import Stereo_net
+
+    class Shape(object):
+        def __init__(self, shape): self.shape = shape
+
+    class Toy(Stereo_net.StereoNet):
+        _netName = 'Toy'
+
+        def _validate_args(self, args):
+            super(Toy, self)._validate_args(args)
+            return args
+
+        def _preprocess_inputs(self, args):
+            self.seen = dict(args)
+
+        def _build_network(self, args):
+            a, b, d = Shape((1, 4, 8, 16)), Shape((1, 2, 4, 32)), Shape((1, 4, 8, 1))
+            self._add_to_layers('left/conv1', a, ['w1:0', 'b1:0'])
+            self._add_to_layers('right/conv1', b)
+            self._add_to_layers('final_disp', d, ['w1:0', 'b1:0', 'w2:0'])
+            self._layers['rescaled_prediction'] = d
+            self._disparities.append(d)
+
+    net = Toy(left_img=0, right_img=0)
+    out = capsys.readouterr().out.splitlines()
+    assert out[0] == '=' * 50 and out[1] == 'Starting Creation of Toy' and out[2] == '=' * 50
+    assert [l for l in out if l.startswith('WARNING')] == [
+        'WARNING: no split points selected, the network will flow without interruption',
+        'WARNING: train_portion not specified, using default END',
+        'WARNING: sequence flag not setted, configuring the network for single image adaptation',
+        'WARNING: flag for trainign not setted, using default False']
+    assert out[-4:] == ['Args Validated, setting up graph', 'Meta op to preprocess data created', 'Network ready', '=' * 50]
+    assert net.seen['split_layers'] == [None] and net.seen['train_portion'] == 'BEGIN' and net.seen['sequence'] is False
+    assert str(net) == ('Layer left/conv1: (1, 4, 8, 16)\nLayer right/conv1: (1, 2, 4, 32)\n'
+                        'Prediction Layer final_disp: (1, 4, 8, 1)\nPrediction Layer rescaled_prediction: (1, 4, 8, 1)\n')
+    assert repr(net) == str(net)
+    assert list(net.get_layers_names()) == ['left/conv1', 'right/conv1', 'final_disp', 'rescaled_prediction']
+    assert net.get_variables('left/conv1') == ['w1:0', 'b1:0'] and net.get_variables('right/conv1') == []
+    assert net.get_variables('rescaled_prediction') == [] and len(net.get_variables('final_disp')) == 3
+    assert net.get_trainable_variables() == ['w1:0', 'b1:0', 'w2:0']
+    assert net.get_disparities() == [net['final_disp']] and net.get_all_layers() is net._layers and net.get_placeholders() == []
+    with pytest.raises(KeyError):
+        net.get_variables('nope')
+    with pytest.raises(Exception, match='Unable to find placeholder'):
+        net.get_placeholder('x')
+    with pytest.raises(Exception, match='Invalid portion'):
+        Toy(left_img=0, right_img=0, train_portion='MIDDLE')
+    with pytest.raises(Exception, match='split_layers'):
+        Toy(left_img=0, right_img=0, split_layers=['left/conv1'])
+    quiet = Toy(left_img=0, right_img=0, split_layers=[None], sequence=True, train_portion='BEGIN', is_training=False)
+    assert quiet.seen['sequence'] is True
+    assert dict(Toy.getPossibleArsg())['sequence'].startswith('flag to use network')
