@@ -213,3 +213,48 @@ def test_stereonet_base_class_protocol(capsys):
     quiet = Toy(left_img=0, right_img=0, split_layers=[None], sequence=True, train_portion='BEGIN', is_training=False)
     assert quiet.seen['sequence'] is True
     assert dict(Toy.getPossibleArsg())['sequence'].startswith('flag to use network')
+
+
+class _NoCudaCtx(object):
+    def __init__(self, *_a, **_k): pass
+    def __enter__(self): return self
+    def __exit__(self, *_a): return False
+
+
+class _Buf(object):
+    """What the drivers pass as left_img / right_img: only .shape (and optionally .device) is consulted at build time."""
+    def __init__(self, shape): self.shape = shape
+
+
+def _build_mirror_on_cpu(monkeypatch, name, h, w):
+    import torch
+    import Nets
+    monkeypatch.setattr(torch.cuda, 'is_available', lambda: True)
+    monkeypatch.setattr(torch.cuda, 'current_device', lambda: 0)
+    monkeypatch.setattr(torch.cuda, 'device', _NoCudaCtx)
+    return Nets.get_stereo_net(name, dict(left_img=_Buf((1, h, w, 3)), right_img=_Buf((1, h, w, 3)), split_layers=[None],
+                                          sequence=True, train_portion='BEGIN', bulkhead=True))
+
+
+def test_madnet_mirror_matches_reference_graph_layers_and_variable_lists(monkeypatch, capsys):
+    """The host mirror built without a device (engine handle only, nothing bound) against what the reference's own
+    Nets/MadNet.py produced over the TF shim: layer names in order, `str(net)`, the variable list of every layer a
+    block_config names, trainable-variable order."""
+    import json
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'reference_graph_madnet_64x128.npz'))
+    net = _build_mirror_on_cpu(monkeypatch, 'MADNet', 64, 128)
+    assert list(net.get_layers_names()) == [str(s) for s in g['layer_names']]
+    assert str(net) == str(g['str_net'])
+    ref_vars = json.loads(str(g['get_variables']))
+    for layer, names in ref_vars.items():
+        assert [v.name for v in net.get_variables(layer)] == names, layer
+    assert [v.name[:-2] for v in net.get_trainable_variables()] == [str(s) for s in g['variable_names']]
+    assert len(net.get_disparities()) == 6 and net.get_disparities()[-1] is net['rescaled_prediction']
+
+
+def test_dispnet_mirror_matches_reference_graph_layers(monkeypatch, capsys):
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'reference_graph_dispnet_64x128.npz'))
+    net = _build_mirror_on_cpu(monkeypatch, 'Dispnet', 64, 128)
+    assert list(net.get_layers_names()) == [str(s) for s in g['layer_names']]
+    assert [v.name[:-2] for v in net.get_trainable_variables()] == [str(s) for s in g['variable_names']]
+    assert len(net.get_disparities()) == 7
