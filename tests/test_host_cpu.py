@@ -258,3 +258,26 @@ def test_dispnet_mirror_matches_reference_graph_layers(monkeypatch, capsys):
     assert list(net.get_layers_names()) == [str(s) for s in g['layer_names']]
     assert [v.name[:-2] for v in net.get_trainable_variables()] == [str(s) for s in g['variable_names']]
     assert len(net.get_disparities()) == 7
+
+
+def test_mad_groups_of_the_product_equal_the_reference_var_lists(monkeypatch, capsys):
+    """OnlineAdaptation resolves block_config/MadNet_full.json through net.get_variables() exactly like
+    Stereo_Online_Adaptation.py:109-118; the layer sets it hands to the engine must own the variables the reference's own
+    train ops got (tests/golden/reference_graph_madnet_64x128.npz: mad<k>_vars)."""
+    import json
+    from madstereo import engine as eng_mod
+    from madstereo.adaptation import OnlineAdaptation
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'reference_graph_madnet_64x128.npz'))
+    net = _build_mirror_on_cpu(monkeypatch, 'MADNet', 64, 128)
+    monkeypatch.setattr(eng_mod.StereoEngine, 'bind', lambda self: None)
+    cfg = json.load(open(os.path.join(ROOT, 'real-time-self-adaptive-deep-stereo_b200', 'block_config', 'MadNet_full.json')))
+    ad = OnlineAdaptation(net, mode='MAD', train_config=cfg, sample_mode='SEQUENTIAL')
+    assert len(ad.groups) == 5 and ad.num_actions == 5
+    layers = net.engine.layers
+    for k, idxs in enumerate(ad.groups):
+        mine = set()
+        for i in idxs:
+            mine |= {layers[i].scope + '/weights', layers[i].scope + '/' + layers[i].bias_name}
+        assert mine == set(str(s) for s in g['mad%d_vars' % k]), k
+    flat = [i for idxs in ad.groups for i in idxs]
+    assert len(flat) == len(set(flat)) == len(layers)            # a partition of the 49 conv layers
