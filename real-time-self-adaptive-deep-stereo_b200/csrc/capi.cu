@@ -114,6 +114,43 @@ int ms_conv2d_dgrad_tc(const float* dy, int n, int h, int w, int cout, int dy_cs
     if (!conv_tc_supported(p)) { set_error("ms_conv2d_dgrad_tc: shape not supported by the tcgen05 path"); return -3; }
     return conv_tc_oneshot(p, 1, scratch, scratch_floats, S(stream));
 }
+int ms_conv2d_fwd_bf(const float* x, int n, int h, int w, int cin, int x_cs, const float* weights, const float* bias,
+                     float* y, int cout, int y_cs, int kh, int kw, int stride, int dilation, float alpha, void* scratch,
+                     size_t scratch_bytes, void* stream) {
+    int oh, ow, pt, pl;
+    same_pad_c(h, kh, stride, dilation, oh, pt);
+    same_pad_c(w, kw, stride, dilation, ow, pl);
+    ConvGemm p{};
+    p.x = view(const_cast<float*>(x), n, h, w, cin, x_cs);
+    p.y = view(y, n, oh, ow, cout, y_cs);
+    p.wmat = weights; p.bias = bias; p.kh = kh; p.kw = kw;
+    p.mul = stride; p.off_y = -pt; p.off_x = -pl; p.step = dilation; p.div = 1;
+    p.alpha = alpha; p.mask = nullptr; p.mask_alpha = 1.f; p.res = nullptr; p.accumulate = 0;
+    if (!conv_bf_supported(p)) { set_error("ms_conv2d_fwd_bf: shape not supported by the split-bf16 tcgen05 path"); return -3; }
+    return conv_bf_oneshot(p, 0, scratch, scratch_bytes, S(stream));
+}
+int ms_conv2d_dgrad_bf(const float* dy, int n, int h, int w, int cout, int dy_cs, const float* weights, float* dx,
+                       int cin, int dx_cs, int kh, int kw, int dilation, void* scratch, size_t scratch_bytes,
+                       void* stream) {
+    int oh, ow, pt, pl;
+    same_pad_c(h, kh, 1, dilation, oh, pt);
+    same_pad_c(w, kw, 1, dilation, ow, pl);
+    ConvGemm p{};
+    p.x = view(const_cast<float*>(dy), n, h, w, cout, dy_cs);
+    p.y = view(dx, n, h, w, cin, dx_cs);
+    p.wmat = weights; p.bias = nullptr; p.kh = kh; p.kw = kw;
+    p.mul = 1; p.off_y = pt; p.off_x = pl; p.step = -dilation; p.div = 1;
+    p.alpha = 1.f; p.mask = nullptr; p.mask_alpha = 1.f; p.res = nullptr; p.accumulate = 0;
+    if (!conv_bf_supported(p)) { set_error("ms_conv2d_dgrad_bf: shape not supported by the split-bf16 tcgen05 path"); return -3; }
+    return conv_bf_oneshot(p, 1, scratch, scratch_bytes, S(stream));
+}
+size_t ms_conv2d_bf_scratch(int n, int h, int w, int kh, int kw, int cin, int cout) {
+    ConvGemm a{}, b{};
+    a.x = view(nullptr, n, h, w, cin, cin); a.y = view(nullptr, n, h, w, cout, cout); a.kh = kh; a.kw = kw;
+    b.x = view(nullptr, n, h, w, cout, cout); b.y = view(nullptr, n, h, w, cin, cin); b.kh = kh; b.kw = kw;
+    size_t sa = conv_bf_oneshot_scratch_bytes(a), sb = conv_bf_oneshot_scratch_bytes(b);
+    return sa > sb ? sa : sb;
+}
 size_t ms_conv2d_tc_scratch(int kh, int kw, int cin, int cout) {
     size_t a = conv_tc_scratch_floats(kh * kw, cout, cin), b = conv_tc_scratch_floats(kh * kw, cin, cout);
     return a > b ? a : b;

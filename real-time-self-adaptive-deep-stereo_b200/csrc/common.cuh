@@ -176,3 +176,25 @@ int wgrad_tc_init();
 int wgrad_tc(const ConvWgrad& q, cudaStream_t st);
 int conv_tc_read_prof(unsigned long long* out32, int reset);
 }  // namespace ms
+
+namespace ms {
+// split-bf16 tcgen05 path (conv_bf.cu): every activation that feeds a convolution also lives as two bf16 planes
+// (hi = bf16(x), lo = bf16(x - hi)), NHWC with channel stride `cs` (bf16 elements, multiple of 8).
+struct ActPlanes { void* hi; void* lo; int cs; };
+struct BfPrepJob {
+    const float* src; void* hi; void* lo;
+    int taps, M, K, Mpad, Kpad, transposed_src;
+};
+bool conv_bf_supported(const ConvGemm& g);
+void conv_bf_weight_dims(int M, int K, int& Mpad, int& Kpad);
+size_t conv_bf_weight_halfs(int taps, int M, int K);
+size_t conv_bf_part_floats();
+size_t conv_bf_ticket_words();
+int conv_bf_init();
+int bf_prep_weights(const BfPrepJob* jobs_dev, int njobs, size_t max_total, cudaStream_t st);
+int split_planes(const TView& x, const ActPlanes& pl, cudaStream_t st);
+int conv_bf(const ConvGemm& g, const ActPlanes& xp, const void* wh, const void* wl, const ActPlanes* yp, float* part,
+            unsigned int* tickets, cudaStream_t st);
+size_t conv_bf_oneshot_scratch_bytes(const ConvGemm& g);
+int conv_bf_oneshot(const ConvGemm& g, int wmat_is_mk, void* scratch, size_t scratch_bytes, cudaStream_t st);
+}  // namespace ms

@@ -1,0 +1,607 @@
+// conv_bf: tcgen05 implicit-GEMM convolution on split-bf16 operands -- the default tensor-core path of the conv stacks.
+//
+// Replaces the cuDNN calls behind tf.nn.conv2d / tf.nn.atrous_conv2d (reference Nets/sharedLayers.py:58,72) and their
+// input gradients for the estimator / context / pyramid layers of MADNet (Nets/MadNet.py:73-171,173-249) and the
+// DispNet encoder / refinement convs (Nets/DispNet.py:77-140).
+//
+// Why a second tensor-core generation (round-2 findings): the 3xTF32 kernels (conv_tc.cu) split
+// fp32 activations inside the main loop (splitter warps, three-party mbarrier hand-shakes) and every 128-pixel CTA
+// re-streams the whole weight set: 10x L2->SM amplification, tensor pipe < 50 %.  Here
+//   * operands are PRE-SPLIT: every activation tensor that feeds a convolution also exists as two bf16 planes
+//     (hi = bf16(x), lo = bf16(x - hi); x ~= hi + lo to 2^-16), written by the producing kernel's epilogue; weights are
+//     split once per update.  The main loop is the canonical TMA -> tcgen05.mma -> epilogue pipeline, no splitter.
+//   * three kind::f16 MMAs per K step (w_lo*x_hi + w_hi*x_lo into one accumulator, w_hi*x_hi into another) give
+//     ~2^-16 relative product error at half the tensor time of 3xTF32 (bf16 runs at twice the tf32 rate).
+//   * the GEMM is transposed ("swap AB"): M = output channels (128 TMEM lanes), N = up to 256 output pixels per CTA,
+//     K = 32 input channels per step.  One weight tile now serves 256 pixels, per-MMA shared-memory reads drop from
+//     128 to 96 B/clk, and the epilogue thread <-> channel mapping makes every NHWC store a coalesced 128-byte line.
+//   * A tile's pixels are `TW` wide and N/TW high.  For each filter column the kernel loads ONE halo patch
+//     (N/TW + (kh-1)*dilation rows) per 32-channel block; the kh taps of that column are row offsets into the patch
+//     (patch rows are TW*64 bytes = whole SWIZZLE_64B atoms, so a tap is just a different UMMA descriptor start address).
+//     Stride-2 convolutions use TMA element strides {1,2,2,1}: a patch then holds every second pixel / row.
+//   * split-K over (channel block, patch) units for small maps; the last-arriving CTA of a tile reduces the partial
+//     sums in fixed order (deterministic) and runs the epilogue -- no separate reduce launch.
+//
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace ms {
+
+constexpr int BF_THREADS = 320;
+constexpr int BF_MAX_PATCH = 16;
+constexpr int BF_MAX_TAPS = 49;
+constexpr uint32_t BF_W_TILE = 128u * 64u;      // one weight tile: 128 rows x 32 bf16
+
+struct BfPatch { short dx, dy, ntaps, tap0; };
+struct BfTap { short row_off, widx; };
+
+struct ConvBfParams {
+    int H, W, NB;                 // output map
+    int TW, tw_shift, N;          // pixel tile: TW wide (power of two), N pixels
+    int tiles_x, tiles_y;
+    int sx;                       // input coordinate = out * sx + patch.d
+    int kblocks, n_patches;
+    uint32_t slot_bytes;          // bytes of one patch plane in shared memory
+    int NP, NW;
+    int nacc;                     // accumulators: 2 = cross terms and hi*hi separately, 1 = everything in one
+    int nprod;                    // 3 = bf16x3, 1 = plain bf16 (hi*hi only; accuracy experiments)
+    int tmem_cols;
+    int cout;
+    int ksplit;
+    float* part; unsigned int* tickets;
+    float* y; int ycs;
+    const float* bias; float alpha;
+    const float* res; int res_cs;
+    const float* mask; int mask_cs; float mask_alpha;
+    int accumulate;
+    __nv_bfloat16* ohi; __nv_bfloat16* olo; int ocs;
+    BfPatch patch[BF_MAX_PATCH];
+    BfTap tap[BF_MAX_TAPS];
+};
+
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// K-major SWIZZLE_64B shared-memory matrix descriptor: rows of 64 bytes, 8-row atoms of 512 bytes (SBO), version 1,
+// layout_type 4 (cute::UMMA::LayoutType::SWIZZLE_64B).  The start address must be a multiple of 512 bytes.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_byte_addr) {
+    return (uint64_t)((smem_byte_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+}
+__device__ __forceinline__ void bf_split(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(v);
+    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+__global__ void __launch_bounds__(BF_THREADS, 1)
+conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl,
+               const __grid_constant__ CUtensorMap mapWh, const __grid_constant__ CUtensorMap mapWl,
+               const __grid_constant__ ConvBfParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t pfull[4], pempty[4], wfull[8], wempty[8], accum_bar;
+    __shared__ uint32_t tmem_slot;
+    __shared__ int last_flag;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t base = (s_addr(smem_dyn) + 1023u) & ~1023u;
+    unsigned char* gbase = smem_dyn + (base - s_addr(smem_dyn));
+    const uint32_t pslot = 2u * p.slot_bytes;                 // hi plane | lo plane
+    const uint32_t w_off = (uint32_t)p.NP * pslot;
+    const uint32_t wslot = 2u * BF_W_TILE;
+
+    int bid = blockIdx.x;
+    const int tx = bid % p.tiles_x; bid /= p.tiles_x;
+    const int ty = bid % p.tiles_y;
+    const int img = bid / p.tiles_y;
+    const int TH = p.N >> p.tw_shift;
+    const int x0 = tx * p.TW, y0 = ty * TH;
+    const int units = p.kblocks * p.n_patches;
+    const int u0 = (int)(((long)blockIdx.z * units) / p.ksplit), u1 = (int)(((long)(blockIdx.z + 1) * units) / p.ksplit);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.NP; ++i) { mb_init(&pfull[i], 1); mb_init(&pempty[i], 1); }
+        for (int i = 0; i < p.NW; ++i) { mb_init(&wfull[i], 1); mb_init(&wempty[i], 1); }
+        mb_init(&accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_addr(&tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer: halo patches (per channel block x filter column) + weight tiles (per tap) ===
+        if (lane == 0) {
+            int ps = 0, ws = 0;
+            uint32_t pph = 0, wph = 0;
+            const int mrow = blockIdx.y * 128;
+            int kb = u0 / p.n_patches, pi = u0 - kb * p.n_patches;
+            for (int u = u0; u < u1; ++u) {
+                const BfPatch pt = p.patch[pi];
+                mb_wait(&pempty[ps], pph ^ 1u);
+                mb_expect_tx(&pfull[ps], pslot);
+                unsigned char* dst = gbase + (size_t)ps * pslot;
+                tma_load_4d(dst, &mapXh, &pfull[ps], kb * 32, x0 * p.sx + pt.dx, y0 * p.sx + pt.dy, img);
+                tma_load_4d(dst + p.slot_bytes, &mapXl, &pfull[ps], kb * 32, x0 * p.sx + pt.dx, y0 * p.sx + pt.dy, img);
+                if (++ps == p.NP) { ps = 0; pph ^= 1u; }
+                for (int t = pt.tap0; t < pt.tap0 + pt.ntaps; ++t) {
+                    mb_wait(&wempty[ws], wph ^ 1u);
+                    mb_expect_tx(&wfull[ws], wslot);
+                    unsigned char* wd = gbase + w_off + (size_t)ws * wslot;
+                    const int widx = p.tap[t].widx;
+                    tma_load_3d(wd, &mapWh, &wfull[ws], kb * 32, mrow, widx);
+                    tma_load_3d(wd + BF_W_TILE, &mapWl, &wfull[ws], kb * 32, mrow, widx);
+                    if (++ws == p.NW) { ws = 0; wph ^= 1u; }
+                }
+                if (++pi == p.n_patches) { pi = 0; ++kb; }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (bit 4), A=B=bf16 (1<<7, 1<<10), both K-major,
+            // N>>3 at bit 17, M>>4 at bit 24
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t acc_main = tmem + (p.nacc == 2 ? (uint32_t)p.N : 0u);
+            int ps = 0, ws = 0;
+            uint32_t pph = 0, wph = 0;
+            uint32_t started_cross = 0, started_main = 0;
+            int pi = u0 % p.n_patches;
+            const uint32_t row_bytes = (uint32_t)p.TW * 64u;
+            for (int u = u0; u < u1; ++u) {
+                const BfPatch pt = p.patch[pi];
+                mb_wait(&pfull[ps], pph);
+                const uint32_t pb = base + (uint32_t)ps * pslot;
+                for (int t = pt.tap0; t < pt.tap0 + pt.ntaps; ++t) {
+                    mb_wait(&wfull[ws], wph);
+                    tc_fence_after();
+                    const uint32_t boff = (uint32_t)p.tap[t].row_off * row_bytes;
+                    const uint64_t xh = umma_desc_sw64(pb + boff), xl = umma_desc_sw64(pb + p.slot_bytes + boff);
+                    const uint32_t wb = base + w_off + (uint32_t)ws * wslot;
+                    const uint64_t wh = umma_desc_sw64(wb), wl = umma_desc_sw64(wb + BF_W_TILE);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {               // 2 x (K = 16 bf16 = 32 bytes) inside the 64-byte swizzle row
+                        const uint64_t o = (uint64_t)(j * 2);
+                        if (p.nprod == 3) {
+                            tc_mma_f16(tmem, wl + o, xh + o, idesc, started_cross);
+                            tc_mma_f16(tmem, wh + o, xl + o, idesc, 1u);
+                            started_cross = 1u;
+                            if (p.nacc == 1) started_main = 1u;
+                        }
+                        tc_mma_f16(acc_main, wh + o, xh + o, idesc, started_main);
+                        started_main = 1u;
+                        if (p.nacc == 1) started_cross = 1u;
+                    }
+                    tc_commit(&wempty[ws]);
+                    if (++ws == p.NW) { ws = 0; wph ^= 1u; }
+                }
+                tc_commit(&pempty[ps]);
+                if (++ps == p.NP) { ps = 0; pph ^= 1u; }
+                if (++pi == p.n_patches) pi = 0;
+            }
+            tc_commit(&accum_bar);
+        }
+    } else {
+        // ================= epilogue (warps 2..9): thread <-> output channel, columns <-> pixels =================
+        const int q = warp & 3;                         // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;               // which half of the pixel columns
+        const int ch = blockIdx.y * 128 + q * 32 + lane;
+        const bool chv = ch < p.cout;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const float bias = (chv && p.bias) ? __ldg(p.bias + ch) : 0.f;
+        const int cbeg = half * (p.N >> 1), cend = cbeg + (p.N >> 1);
+        const bool two = (p.nacc == 2) && (p.nprod == 3);
+        const int tile_lin = blockIdx.x * gridDim.y + blockIdx.y;
+
+        auto finish = [&](int col, float t) {
+            const int yy = y0 + (col >> p.tw_shift), xx = x0 + (col & (p.TW - 1));
+            if (yy < p.H && xx < p.W && chv) {
+                const size_t pix = ((size_t)img * p.H + yy) * p.W + xx;
+                t += bias;
+                t = fmaxf(p.alpha * t, t);
+                if (p.res) t += p.res[pix * p.res_cs + ch];
+                if (p.accumulate) t += p.y[pix * p.ycs + ch];
+                if (p.mask) t *= (p.mask[pix * p.mask_cs + ch] > 0.f) ? 1.f : p.mask_alpha;
+                p.y[pix * p.ycs + ch] = t;
+                if (p.ohi) {
+                    __nv_bfloat16 h, l;
+                    bf_split(t, h, l);
+                    p.ohi[pix * p.ocs + ch] = h;
+                    p.olo[pix * p.ocs + ch] = l;
+                }
+            }
+        };
+
+        mb_wait(&accum_bar, 0);
+        tc_fence_after();
+        if (p.ksplit == 1) {
+            for (int c0 = cbeg; c0 < cend; c0 += 16) {
+                uint32_t r0[16], r1[16];
+                tc_ld16_nowait(tmem + lane_base + (uint32_t)c0, r0);
+                if (two) tc_ld16_nowait(tmem + lane_base + (uint32_t)(p.N + c0), r1);
+                tc_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float t = __uint_as_float(r0[j]);
+                    if (two) t += __uint_as_float(r1[j]);
+                    finish(c0 + j, t);
+                }
+            }
+        } else {
+            // raw partial sums: part[(z * n_tiles + tile) * N + col][128 channels]
+            const size_t n_tiles = (size_t)gridDim.x * gridDim.y;
+            float* mine = p.part + (((size_t)blockIdx.z * n_tiles + tile_lin) * p.N) * 128 + q * 32 + lane;
+            for (int c0 = cbeg; c0 < cend; c0 += 16) {
+                uint32_t r0[16], r1[16];
+                tc_ld16_nowait(tmem + lane_base + (uint32_t)c0, r0);
+                if (two) tc_ld16_nowait(tmem + lane_base + (uint32_t)(p.N + c0), r1);
+                tc_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float t = __uint_as_float(r0[j]);
+                    if (two) t += __uint_as_float(r1[j]);
+                    mine[(size_t)(c0 + j) * 128] = t;
+                }
+            }
+            __threadfence();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (threadIdx.x == 64) {
+                const unsigned int old = atomicAdd(p.tickets + tile_lin, 1u);
+                const int last = (old == (unsigned int)(p.ksplit - 1)) ? 1 : 0;
+                if (last) p.tickets[tile_lin] = 0u;        // self-resetting for the next launch
+                last_flag = last;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (last_flag) {
+                __threadfence();
+                const float* col0 = p.part + ((size_t)tile_lin * p.N) * 128 + q * 32 + lane;
+                const size_t zstride = n_tiles * (size_t)p.N * 128;
+                for (int col = cbeg; col < cend; ++col) {
+                    float t = 0.f;
+                    for (int z = 0; z < p.ksplit; ++z) t += __ldcg(col0 + (size_t)z * zstride + (size_t)col * 128);
+                    finish(col, t);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bf16 planes of an fp32 NHWC view (producers that are not conv_bf epilogues: correlation, resize, loss seeds ...)
+// ------------------------------------------------------------------------------------------------
+__global__ void split_planes_kernel(const float* __restrict__ x, int xcs, int C, size_t pixels,
+                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int pcs) {
+    const int cq = (C + 3) >> 2;
+    const size_t total = pixels * cq;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t pix = i / cq;
+        const int c = (int)(i - pix * cq) * 4;
+        const float* src = x + pix * xcs + c;
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float v = (c + j < C) ? src[j] : 0.f;
+            bf_split(v, h[j], l[j]);
+        }
+        __nv_bfloat16* dh = hi + pix * pcs + c;
+        __nv_bfloat16* dl = lo + pix * pcs + c;
+        if (c + 4 <= pcs) {
+            *reinterpret_cast<uint2*>(dh) = *reinterpret_cast<const uint2*>(h);
+            *reinterpret_cast<uint2*>(dl) = *reinterpret_cast<const uint2*>(l);
+        } else {
+            for (int j = 0; j < 4 && c + j < pcs; ++j) { dh[j] = h[j]; dl[j] = l[j]; }
+        }
+    }
+}
+
+int split_planes(const TView& x, const ActPlanes& pl, cudaStream_t st) {
+    MS_REQUIRE(pl.hi && pl.lo && pl.cs >= x.c && (pl.cs & 7) == 0, "split_planes: bad plane buffers");
+    const size_t total = x.pixels() * ((x.c + 3) / 4);
+    const unsigned grid = (unsigned)std::min<size_t>(cdivz(total, 256), 148 * 16);
+    split_planes_kernel<<<grid, 256, 0, st>>>(x.p, x.cs, x.c, x.pixels(), reinterpret_cast<__nv_bfloat16*>(pl.hi),
+                                              reinterpret_cast<__nv_bfloat16*>(pl.lo), pl.cs);
+    return check_launch("split_planes");
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight preparation: dst[term][tap][m (Mpad rows)][k (Kpad)] bf16 hi / lo from canonical fp32 HWIO, batched over layers
+//   transposed_src = 1 : src is [tap][K][M]  (forward conv: K = cin, M = cout)
+//   transposed_src = 0 : src is [tap][M][K]  (dgrad: M = cin, K = cout)
+// ------------------------------------------------------------------------------------------------
+__global__ void bf_prep_weights_kernel(const BfPrepJob* __restrict__ jobs) {
+    const BfPrepJob j = jobs[blockIdx.y];
+    const size_t total = (size_t)j.taps * j.Mpad * j.Kpad;
+    __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(j.hi);
+    __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(j.lo);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % j.Kpad);
+        const size_t q = i / j.Kpad;
+        const int m = (int)(q % j.Mpad);
+        const int t = (int)(q / j.Mpad);
+        float v = 0.f;
+        if (m < j.M && k < j.K)
+            v = j.transposed_src ? j.src[((size_t)t * j.K + k) * j.M + m] : j.src[((size_t)t * j.M + m) * j.K + k];
+        __nv_bfloat16 h, l;
+        bf_split(v, h, l);
+        hi[i] = h; lo[i] = l;
+    }
+}
+
+int bf_prep_weights(const BfPrepJob* jobs_dev, int njobs, size_t max_total, cudaStream_t st) {
+    if (njobs <= 0) return 0;
+    const unsigned gx = (unsigned)std::min<size_t>(cdivz(max_total, 256), 512);
+    bf_prep_weights_kernel<<<dim3(gx, njobs), 256, 0, st>>>(jobs_dev);
+    return check_launch("bf_prep_weights");
+}
+
+void conv_bf_weight_dims(int M, int K, int& Mpad, int& Kpad) { Mpad = (M + 127) / 128 * 128; Kpad = (K + 31) / 32 * 32; }
+size_t conv_bf_weight_halfs(int taps, int M, int K) {       // bf16 elements per plane
+    int Mpad, Kpad; conv_bf_weight_dims(M, K, Mpad, Kpad);
+    return (size_t)taps * Mpad * Kpad;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tensor maps (bf16, SWIZZLE_64B, zero OOB fill, optional element strides), cached
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn bf_get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* q = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(q);
+    }
+    return fn;
+}
+struct BfMapKey {
+    uintptr_t addr; int rank; uint64_t d[4]; uint64_t s[3]; uint32_t b[4]; uint32_t es[4];
+    bool operator<(const BfMapKey& o) const { return memcmp(this, &o, sizeof(BfMapKey)) < 0; }
+};
+static int bf_get_map(const CUtensorMap** out, void* addr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                      const cuuint32_t* box, const cuuint32_t* estr) {
+    static std::map<BfMapKey, CUtensorMap> cache;
+    BfMapKey k;
+    memset(&k, 0, sizeof k);
+    k.addr = reinterpret_cast<uintptr_t>(addr); k.rank = rank;
+    for (int i = 0; i < rank; ++i) { k.d[i] = dims[i]; k.b[i] = box[i]; k.es[i] = estr[i]; }
+    for (int i = 0; i + 1 < rank; ++i) k.s[i] = strides_bytes[i];
+    auto it = cache.find(k);
+    if (it == cache.end()) {
+        EncodeTiledFn enc = bf_get_encode();
+        MS_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+        CUtensorMap m;
+        CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, addr, dims, strides_bytes, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (bf16) failed with code " + std::to_string((int)r)); return -1; }
+        if (cache.size() >= 8192) {
+            static thread_local CUtensorMap spill[16];
+            static thread_local unsigned spill_i = 0;
+            CUtensorMap* slot = &spill[spill_i++ & 15u];
+            *slot = m;
+            *out = slot;
+            return 0;
+        }
+        it = cache.emplace(k, m).first;
+    }
+    *out = &it->second;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+bool conv_bf_supported(const ConvGemm& g) {
+    if (g.div != 1) return false;                                       // no fractionally-strided gathers
+    if (g.mul != 1 && g.mul != 2) return false;
+    if (g.mul == 2 && g.step < 0) return false;
+    if (g.x.c < 8 || g.y.c < 8) return false;
+    if (g.kh * g.kw > BF_MAX_TAPS) return false;
+    if (g.y.h * g.y.w < 32) return false;
+    return true;
+}
+
+int conv_bf_init() {
+    static bool done = false;
+    if (done) return 0;
+    MS_CHECK_CUDA(cudaFuncSetAttribute(conv_bf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    done = true;
+    return 0;
+}
+
+size_t conv_bf_part_floats() { return (size_t)8 << 20; }    // 32 MB of split-K partial sums
+size_t conv_bf_ticket_words() { return 4096; }
+
+// xp: bf16 planes of g.x;  wh/wl: prepared weights [tap][Mpad][Kpad];  yp: optional planes of g.y (written by the epilogue)
+int conv_bf(const ConvGemm& g, const ActPlanes& xp, const void* wh, const void* wl, const ActPlanes* yp,
+            float* part, unsigned int* tickets, cudaStream_t st) {
+    MS_REQUIRE(conv_bf_supported(g), "conv_bf: unsupported geometry");
+    MS_REQUIRE(xp.hi && xp.lo && (xp.cs & 7) == 0 && xp.cs >= g.x.c, "conv_bf: input planes missing");
+    if (conv_bf_init()) return -1;
+    const int K = g.x.c, M = g.y.c;
+    int Mpad, Kpad; conv_bf_weight_dims(M, K, Mpad, Kpad);
+    const int taps = g.kh * g.kw;
+
+    static ConvBfParams p;          // large (tables): filled in place, passed by value to the launch
+    memset(&p, 0, sizeof p);
+    p.H = g.y.h; p.W = g.y.w; p.NB = g.y.n; p.sx = g.mul;
+    p.kblocks = Kpad / 32; p.cout = M;
+    // ---- pixel tile: the largest N in {256,128,64} that still gives ~100 CTAs; wide maps use 8-pixel rows
+    const int mblocks = Mpad / 128;
+    static int force_n = -1;
+    if (force_n < 0) { const char* e = getenv("MS_BF_N"); force_n = e ? atoi(e) : 0; }
+    int N = 64, TW = 8;
+    {
+        const int cand_n[3] = {256, 128, 64};
+        for (int ci = 0; ci < 3; ++ci) {
+            const int n = cand_n[ci];
+            int tw = 8;
+            if (n == 256 && (g.y.h % 32) != 0 && (g.y.h % 16) == 0) tw = 16;
+            const int th = n / tw;
+            const long tiles = (long)g.y.n * cdiv(g.y.w, tw) * cdiv(g.y.h, th) * mblocks;
+            const bool take = force_n ? (n == force_n || ci == 2) : (tiles >= 100 || ci == 2);
+            if (take) { N = n; TW = tw; break; }
+        }
+    }
+    const int TH = N / TW;
+    p.TW = TW; p.tw_shift = TW == 8 ? 3 : 4; p.N = N;
+    p.tiles_x = cdiv(p.W, TW); p.tiles_y = cdiv(p.H, TH);
+    // ---- patches: taps grouped by filter column (and by row parity for stride 2); row offsets inside the halo patch
+    const int astep = std::abs(g.step);
+    int max_off = 0, np = 0, nt = 0;
+    const int sy = g.mul;
+    for (int s = 0; s < g.kw; ++s) {
+        for (int par = 0; par < sy; ++par) {
+            // rows r of this column whose (r * step) has parity `par` relative to the stride lattice
+            int first_dy = 0, cnt = 0;
+            for (int r = 0; r < g.kh; ++r) {
+                const int dyr = g.off_y + r * g.step;
+                if (((r * astep) % sy) != par) continue;
+                if (cnt == 0 || dyr < first_dy) first_dy = dyr;
+                ++cnt;
+            }
+            if (!cnt) continue;
+            MS_REQUIRE(np < BF_MAX_PATCH, "conv_bf: too many patches");
+            BfPatch& pt = p.patch[np];
+            pt.dx = (short)(g.off_x + s * g.step); pt.dy = (short)first_dy; pt.tap0 = (short)nt; pt.ntaps = (short)cnt;
+            for (int r = 0; r < g.kh; ++r) {
+                const int dyr = g.off_y + r * g.step;
+                if (((r * astep) % sy) != par) continue;
+                const int off = (dyr - first_dy) / sy;
+                p.tap[nt].row_off = (short)off; p.tap[nt].widx = (short)(r * g.kw + s);
+                max_off = std::max(max_off, off);
+                ++nt;
+            }
+            ++np;
+        }
+    }
+    MS_REQUIRE(nt == taps, "conv_bf: tap table mismatch");
+    p.n_patches = np;
+    int rows = TH + max_off;
+    // a tall halo (large dilation) that costs more than one box per tap: fall back to one patch per tap
+    if ((size_t)rows * TW * 64 * 2 * 2 + 4 * 2 * BF_W_TILE > 200 * 1024 || (sy == 1 && max_off >= (g.kh - 1) * TH && g.kh > 1)) {
+        np = 0; nt = 0;
+        for (int s = 0; s < g.kw; ++s)
+            for (int r = 0; r < g.kh; ++r) {
+                MS_REQUIRE(np < BF_MAX_PATCH, "conv_bf: too many per-tap patches");
+                BfPatch& pt = p.patch[np];
+                pt.dx = (short)(g.off_x + s * g.step); pt.dy = (short)(g.off_y + r * g.step); pt.tap0 = (short)nt; pt.ntaps = 1;
+                p.tap[nt].row_off = 0; p.tap[nt].widx = (short)(r * g.kw + s);
+                ++nt; ++np;
+            }
+        p.n_patches = np;
+        rows = TH;
+    }
+    MS_REQUIRE(rows * sy <= 256, "conv_bf: patch too tall for one TMA box");
+    p.slot_bytes = (uint32_t)rows * TW * 64u;
+    const size_t pslot = 2 * (size_t)p.slot_bytes, wslot = 2 * (size_t)BF_W_TILE;
+    const size_t budget = 220 * 1024;
+    int NW = 4, NP = (int)std::min<size_t>(4, (budget - NW * wslot) / pslot);
+    if (NP < 2) { NW = 3; NP = (int)std::min<size_t>(4, (budget - NW * wslot) / pslot); }
+    MS_REQUIRE(NP >= 2, "conv_bf: patch does not fit shared memory");
+    NW = (int)std::min<size_t>(8, (budget - NP * pslot) / wslot);
+    p.NP = NP; p.NW = NW;
+    static int nacc_env = -1, nprod_env = -1;
+    if (nacc_env < 0) { const char* e = getenv("MS_BF_NACC"); nacc_env = e ? atoi(e) : 2; }
+    if (nprod_env < 0) { const char* e = getenv("MS_BF_NPROD"); nprod_env = e ? atoi(e) : 3; }
+    p.nprod = nprod_env == 1 ? 1 : 3;
+    p.nacc = (nacc_env == 1 || p.nprod == 1) ? 1 : 2;
+    {
+        const int need = p.nacc * N;
+        p.tmem_cols = need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : (need <= 256 ? 256 : 512)));
+    }
+    p.y = g.y.p; p.ycs = g.y.cs; p.bias = g.bias; p.alpha = g.alpha;
+    p.res = g.res; p.res_cs = g.res_cs; p.mask = g.mask; p.mask_cs = g.mask_cs; p.mask_alpha = g.mask_alpha;
+    p.accumulate = g.accumulate;
+    if (yp && yp->hi) {
+        MS_REQUIRE(yp->cs >= M && (yp->cs & 7) == 0, "conv_bf: bad output planes");
+        p.ohi = reinterpret_cast<__nv_bfloat16*>(yp->hi); p.olo = reinterpret_cast<__nv_bfloat16*>(yp->lo); p.ocs = yp->cs;
+    }
+    // ---- split K over (channel block, patch) units when the map is too small to fill the GPU
+    const int grid_tiles = p.NB * p.tiles_x * p.tiles_y;
+    const int units = p.kblocks * p.n_patches;
+    int ksplit = 1;
+    if (part && tickets && (long)grid_tiles * mblocks <= 74 && units > 1) {
+        ksplit = std::min(units, std::max(1, 148 / (grid_tiles * mblocks)));
+        while (ksplit > 1 && (size_t)ksplit * grid_tiles * mblocks * N * 128 > conv_bf_part_floats()) --ksplit;
+        if ((size_t)grid_tiles * mblocks > conv_bf_ticket_words()) ksplit = 1;
+    }
+    p.ksplit = ksplit; p.part = part; p.tickets = tickets;
+
+    const CUtensorMap *mXh, *mXl, *mWh, *mWl;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)g.x.c, (cuuint64_t)g.x.w, (cuuint64_t)g.x.h, (cuuint64_t)g.x.n};
+        cuuint64_t strides[3] = {(cuuint64_t)xp.cs * 2, (cuuint64_t)g.x.w * xp.cs * 2, (cuuint64_t)g.x.h * g.x.w * xp.cs * 2};
+        cuuint32_t box[4] = {32, (cuuint32_t)(TW * sy), (cuuint32_t)(rows * sy), 1};
+        cuuint32_t es[4] = {1, (cuuint32_t)sy, (cuuint32_t)sy, 1};
+        if (bf_get_map(&mXh, xp.hi, 4, dims, strides, box, es)) return -1;
+        if (bf_get_map(&mXl, xp.lo, 4, dims, strides, box, es)) return -1;
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)Kpad, (cuuint64_t)Mpad, (cuuint64_t)taps};
+        cuuint64_t strides[2] = {(cuuint64_t)Kpad * 2, (cuuint64_t)Mpad * Kpad * 2};
+        cuuint32_t box[3] = {32, 128, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        if (bf_get_map(&mWh, const_cast<void*>(wh), 3, dims, strides, box, es)) return -1;
+        if (bf_get_map(&mWl, const_cast<void*>(wl), 3, dims, strides, box, es)) return -1;
+    }
+    const size_t smem = (size_t)NP * pslot + (size_t)NW * wslot + 1024;
+    conv_bf_kernel<<<dim3(grid_tiles, mblocks, ksplit), BF_THREADS, smem, st>>>(*mXh, *mXl, *mWh, *mWl, p);
+    return check_launch("conv_bf");
+}
+
+// one-shot convenience (operator-level C ABI / tests): splits the input, prepares the weights, runs the conv.
+//   scratch layout (bytes): [x hi | x lo | w hi | w lo | job | tickets | split-K partials]
+size_t conv_bf_oneshot_scratch_bytes(const ConvGemm& g) {
+    const size_t xe = g.x.pixels() * ((g.x.c + 7) / 8 * 8);
+    const size_t we = conv_bf_weight_halfs(g.kh * g.kw, g.y.c, g.x.c);
+    return 2 * (xe * 2 + 256) + 2 * (we * 2 + 256) + 1024 + conv_bf_ticket_words() * 4 + conv_bf_part_floats() * 4 + 4096;
+}
+
+int conv_bf_oneshot(const ConvGemm& g, int wmat_is_mk, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+    MS_REQUIRE(conv_bf_supported(g), "conv_bf: unsupported geometry");
+    MS_REQUIRE(scratch_bytes >= conv_bf_oneshot_scratch_bytes(g), "conv_bf: scratch too small");
+    MS_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, "conv_bf: scratch must be 256B aligned");
+    unsigned char* b = reinterpret_cast<unsigned char*>(scratch);
+    auto take = [&](size_t bytes) { unsigned char* r = b; b += (bytes + 255) / 256 * 256; return r; };
+    const int pcs = (g.x.c + 7) / 8 * 8;
+    const size_t xe = g.x.pixels() * pcs;
+    const size_t we = conv_bf_weight_halfs(g.kh * g.kw, g.y.c, g.x.c);
+    ActPlanes xp; xp.hi = take(xe * 2); xp.lo = take(xe * 2); xp.cs = pcs;
+    void* wh = take(we * 2); void* wl = take(we * 2);
+    BfPrepJob* jd = reinterpret_cast<BfPrepJob*>(take(1024));
+    unsigned int* tickets = reinterpret_cast<unsigned int*>(take(conv_bf_ticket_words() * 4));
+    float* part = reinterpret_cast<float*>(take(conv_bf_part_floats() * 4));
+    int Mpad, Kpad; conv_bf_weight_dims(g.y.c, g.x.c, Mpad, Kpad);
+    BfPrepJob job{g.wmat, wh, wl, g.kh * g.kw, g.y.c, g.x.c, Mpad, Kpad, wmat_is_mk ? 0 : 1};
+    MS_CHECK_CUDA(cudaMemcpyAsync(jd, &job, sizeof job, cudaMemcpyHostToDevice, st));
+    MS_CHECK_CUDA(cudaMemsetAsync(tickets, 0, conv_bf_ticket_words() * 4, st));
+    if (bf_prep_weights(jd, 1, we, st)) return -1;
+    if (split_planes(g.x, xp, st)) return -1;
+    return conv_bf(g, xp, wh, wl, nullptr, part, tickets, st);
+}
+
+}  // namespace ms

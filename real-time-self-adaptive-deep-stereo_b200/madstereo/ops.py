@@ -104,6 +104,31 @@ def conv2d_dgrad_tc(dy, w, dilation=1):
     return dx
 
 
+def conv2d_bf(x, w, b, stride=1, dilation=1, alpha=1.0):
+    """split-bf16 tcgen05 forward conv (csrc/conv_bf.cu; same semantics as conv2d, stride 1 or 2)."""
+    n, h, wd, cin = x.shape
+    kh, kw, _, cout = w.shape
+    y = torch.empty(n, same_out(h, stride), same_out(wd, stride), cout, device=x.device, dtype=torch.float32)
+    ns = lib().ms_conv2d_bf_scratch(n, h, wd, kh, kw, cin, cout)
+    scratch = torch.empty(ns + 256, device=x.device, dtype=torch.uint8)
+    off = (-scratch.data_ptr()) % 256
+    check(lib().ms_conv2d_fwd_bf(_p(x), n, h, wd, cin, cin, _p(w), _p(b), _p(y), cout, cout, kh, kw, stride, dilation,
+                                 float(alpha), c_void_p(scratch.data_ptr() + off), ns, _s()), 'ms_conv2d_fwd_bf')
+    return y
+
+
+def conv2d_dgrad_bf(dy, w, dilation=1):
+    n, h, wd, cout = dy.shape
+    kh, kw, cin, _ = w.shape
+    dx = torch.empty(n, h, wd, cin, device=dy.device, dtype=torch.float32)
+    ns = lib().ms_conv2d_bf_scratch(n, h, wd, kh, kw, cin, cout)
+    scratch = torch.empty(ns + 256, device=dy.device, dtype=torch.uint8)
+    off = (-scratch.data_ptr()) % 256
+    check(lib().ms_conv2d_dgrad_bf(_p(dy), n, h, wd, cout, cout, _p(w), _p(dx), cin, cin, kh, kw, dilation,
+                                   c_void_p(scratch.data_ptr() + off), ns, _s()), 'ms_conv2d_dgrad_bf')
+    return dx
+
+
 def conv2d_dgrad(dy, w, in_hw, stride=1, dilation=1):
     n, oh, ow, cout = dy.shape
     kh, kw, cin, _ = w.shape

@@ -1,0 +1,77 @@
+"""GPU parity of the split-bf16 tcgen05 convolution (csrc/conv_bf.cu) vs the CPU oracle.
+
+Three kind::f16 MMAs per K step on bf16 hi/lo planes: per-product relative error <= ~3 * 2^-16, accumulated in fp32.
+Tolerance: 1e-4 relative L-inf of the output (typical measured 1e-5 .. 3e-5), stated here and in DESIGN.md section 7.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def rel_linf(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def cu(x):
+    return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32)).cuda()
+
+
+CASES = [
+    # n, h, w, cin, cout, k, stride, dil, alpha
+    (1, 32, 8, 32, 32, 3, 1, 1, 0.2),           # exactly one 8x32 tile
+    (1, 16, 32, 64, 64, 3, 1, 1, 0.2),
+    (2, 24, 40, 128, 128, 3, 1, 1, 0.2),        # partial tiles, batch 2
+    (1, 24, 48, 128, 96, 3, 1, 4, 0.2),         # dilated (context net)
+    (1, 24, 48, 96, 64, 3, 1, 16, 0.2),         # dilation > tile height: one patch per tap
+    (1, 96, 320, 96, 64, 3, 1, 16, 0.2),        # dilation 16 on a full level-2 map (N = 256, halo patch)
+    (1, 12, 40, 136, 128, 3, 1, 1, 0.2),        # K not a multiple of 32 (TMA zero-fills the channels)
+    (1, 6, 20, 192, 192, 3, 1, 1, 0.2),         # level 6: two M blocks, split-K
+    (1, 12, 40, 133, 128, 3, 1, 1, 0.2),        # level 5 estimator input (odd channel count), split-K
+    (2, 20, 36, 16, 16, 3, 1, 1, 0.2),
+    (1, 16, 16, 128, 64, 1, 1, 1, 0.1),         # 1x1 (DispNet conv_redir)
+    (1, 96, 320, 128, 128, 3, 1, 1, 0.2),       # the dominant MADNet layer shape (N = 256 tiles, 120 CTAs)
+    (1, 96, 320, 38, 128, 3, 1, 1, 0.2),        # estimator-2 disp-1
+    (1, 48, 160, 70, 128, 3, 1, 1, 0.2),        # estimator-3 disp-1
+    (2, 192, 640, 16, 32, 3, 2, 1, 0.2),        # pyramid conv3: stride 2 through TMA element strides
+    (2, 48, 160, 64, 96, 3, 2, 1, 0.2),         # pyramid conv7
+    (1, 24, 80, 96, 128, 3, 2, 1, 0.2),         # pyramid conv9
+    (1, 96, 320, 64, 128, 5, 2, 1, 0.1),        # DispNet conv2 (5x5 stride 2)
+    (1, 24, 80, 256, 512, 3, 2, 1, 0.1),        # DispNet conv4: 4 M blocks
+]
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_conv_bf_forward(case):
+    from madstereo import ops
+    from oracle import tf1_ops as T
+    n, h, w, cin, cout, k, stride, dil, alpha = case
+    rng = np.random.default_rng(sum(case[:8]))
+    x = rng.standard_normal((n, h, w, cin)).astype(np.float32)
+    wt = (rng.standard_normal((k, k, cin, cout)) / np.sqrt(k * k * cin)).astype(np.float32)
+    b = rng.uniform(-0.1, 0.1, cout).astype(np.float32)
+    ref = T.conv2d(torch.tensor(x), torch.tensor(wt), torch.tensor(b), stride=stride, dilation=dil, alpha=alpha)
+    out = ops.conv2d_bf(cu(x), cu(wt), cu(b), stride, dil, alpha)
+    torch.cuda.synchronize()
+    assert out.shape == tuple(ref.shape)
+    assert rel_linf(out.cpu().numpy(), ref.numpy()) < TOL
+
+
+@pytest.mark.parametrize('case', [c for c in CASES if c[6] == 1])
+def test_conv_bf_dgrad(case):
+    from madstereo import ops
+    from oracle import tf1_ops as T
+    n, h, w, cin, cout, k, stride, dil, alpha = case
+    rng = np.random.default_rng(sum(case[:8]) + 1)
+    x = rng.standard_normal((n, h, w, cin)).astype(np.float32)
+    wt = (rng.standard_normal((k, k, cin, cout)) / np.sqrt(k * k * cin)).astype(np.float32)
+    xt = torch.tensor(x, requires_grad=True)
+    pre = T.conv2d(xt, torch.tensor(wt), torch.zeros(cout), stride=1, dilation=dil, alpha=None)
+    g = rng.standard_normal(pre.shape).astype(np.float32)
+    (gx,) = torch.autograd.grad(pre, xt, grad_outputs=torch.tensor(g))
+    dx = ops.conv2d_dgrad_bf(cu(g), cu(wt), dil)
+    torch.cuda.synchronize()
+    assert rel_linf(dx.cpu().numpy(), gx.numpy()) < TOL
