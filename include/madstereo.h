@@ -67,13 +67,13 @@ size_t ms_conv2d_tc_scratch(int kh, int kw, int cin, int cout);
  * the 3xTF32 kernels above): operands as bf16 hi/lo planes, three kind::f16 MMAs per K step (~2^-16 relative product
  * error), GEMM transposed so that M = output channels and N = up to 256 pixels, halo patches by TMA, stride 1 or 2
  * (TMA element strides), any dilation, split-K reduced by the last-arriving CTA.  Same semantics as ms_conv2d_fwd /
- * ms_conv2d_dgrad (stride-1 dgrad only).  scratch: ms_conv2d_bf_scratch() BYTES, 256-byte aligned.  -3 = not eligible. */
+ * ms_conv2d_dgrad (a stride-2 dgrad runs as four dense parity-class launches).  scratch: ms_conv2d_bf_scratch() BYTES, 256-byte aligned.  -3 = not eligible. */
 int ms_conv2d_fwd_bf(const float* x, int n, int h, int w, int cin, int x_cs, const float* weights /*HWIO*/,
                      const float* bias, float* y, int cout, int y_cs, int kh, int kw, int stride, int dilation,
                      float alpha, void* scratch, size_t scratch_bytes, void* stream);
-int ms_conv2d_dgrad_bf(const float* dy, int n, int h, int w, int cout, int dy_cs, const float* weights /*HWIO*/,
-                       float* dx, int cin, int dx_cs, int kh, int kw, int dilation, void* scratch,
-                       size_t scratch_bytes, void* stream);
+int ms_conv2d_dgrad_bf(const float* dy, int n, int oh, int ow, int cout, int dy_cs, const float* weights /*HWIO*/,
+                       float* dx, int h, int w, int cin, int dx_cs, int kh, int kw, int stride, int dilation,
+                       void* scratch, size_t scratch_bytes, void* stream);
 size_t ms_conv2d_bf_scratch(int n, int h, int w, int kh, int kw, int cin, int cout);
 /* tcgen05 weight gradient of a stride-1 conv (same outputs as ms_conv2d_wgrad); workspace from ..._workspace(). */
 int ms_conv2d_wgrad_tc(const float* x, int n, int h, int w, int cin, int x_cs, const float* dy, int cout, int dy_cs,

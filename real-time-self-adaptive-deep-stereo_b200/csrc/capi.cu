@@ -129,17 +129,18 @@ int ms_conv2d_fwd_bf(const float* x, int n, int h, int w, int cin, int x_cs, con
     if (!conv_bf_supported(p)) { set_error("ms_conv2d_fwd_bf: shape not supported by the split-bf16 tcgen05 path"); return -3; }
     return conv_bf_oneshot(p, 0, scratch, scratch_bytes, S(stream));
 }
-int ms_conv2d_dgrad_bf(const float* dy, int n, int h, int w, int cout, int dy_cs, const float* weights, float* dx,
-                       int cin, int dx_cs, int kh, int kw, int dilation, void* scratch, size_t scratch_bytes,
-                       void* stream) {
-    int oh, ow, pt, pl;
-    same_pad_c(h, kh, 1, dilation, oh, pt);
-    same_pad_c(w, kw, 1, dilation, ow, pl);
+int ms_conv2d_dgrad_bf(const float* dy, int n, int oh, int ow, int cout, int dy_cs, const float* weights, float* dx,
+                       int h, int w, int cin, int dx_cs, int kh, int kw, int stride, int dilation, void* scratch,
+                       size_t scratch_bytes, void* stream) {
+    int oh2, ow2, pt, pl;
+    same_pad_c(h, kh, stride, dilation, oh2, pt);
+    same_pad_c(w, kw, stride, dilation, ow2, pl);
+    if (oh2 != oh || ow2 != ow) { set_error("ms_conv2d_dgrad_bf: shape mismatch"); return -2; }
     ConvGemm p{};
-    p.x = view(const_cast<float*>(dy), n, h, w, cout, dy_cs);
+    p.x = view(const_cast<float*>(dy), n, oh, ow, cout, dy_cs);
     p.y = view(dx, n, h, w, cin, dx_cs);
     p.wmat = weights; p.bias = nullptr; p.kh = kh; p.kw = kw;
-    p.mul = 1; p.off_y = pt; p.off_x = pl; p.step = -dilation; p.div = 1;
+    p.mul = 1; p.off_y = pt; p.off_x = pl; p.step = -dilation; p.div = stride;
     p.alpha = 1.f; p.mask = nullptr; p.mask_alpha = 1.f; p.res = nullptr; p.accumulate = 0;
     if (!conv_bf_supported(p)) { set_error("ms_conv2d_dgrad_bf: shape not supported by the split-bf16 tcgen05 path"); return -3; }
     return conv_bf_oneshot(p, 1, scratch, scratch_bytes, S(stream));
@@ -307,6 +308,9 @@ int ms_engine_bind(void* h, float* weights, float* grads, float* momentum, float
     MS_CHECK_CUDA(cudaMemsetAsync(grads, 0, e->n_params * sizeof(float), S(stream)));
     if (!e->prep_jobs.empty())
         MS_CHECK_CUDA(cudaMemcpyAsync(e->prep_jobs_dev, e->prep_jobs.data(), e->prep_jobs.size() * sizeof(TcPrepJob),
+                                      cudaMemcpyHostToDevice, S(stream)));
+    if (!e->bf_jobs.empty())
+        MS_CHECK_CUDA(cudaMemcpyAsync(e->bf_jobs_dev, e->bf_jobs.data(), e->bf_jobs.size() * sizeof(BfPrepJob),
                                       cudaMemcpyHostToDevice, S(stream)));
     MS_CHECK_CUDA(cudaStreamSynchronize(S(stream)));   // the host job table must outlive the copy
     e->weights_dirty = true;

@@ -44,7 +44,8 @@ struct BfPatch { short dx, dy, ntaps, tap0; };
 struct BfTap { short row_off, widx; };
 
 struct ConvBfParams {
-    int H, W, NB;                 // output map
+    int H, W, NB;                 // output lattice handled by this launch (tile validity)
+    int Hout, Wout, os, oy0, ox0; // output tensor; lattice point (j) is output pixel j * os + o0
     int TW, tw_shift, N;          // pixel tile: TW wide (power of two), N pixels
     int tiles_x, tiles_y;
     int sx;                       // input coordinate = out * sx + patch.d
@@ -211,7 +212,7 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
         auto finish = [&](int col, float t) {
             const int yy = y0 + (col >> p.tw_shift), xx = x0 + (col & (p.TW - 1));
             if (yy < p.H && xx < p.W && chv) {
-                const size_t pix = ((size_t)img * p.H + yy) * p.W + xx;
+                const size_t pix = ((size_t)img * p.Hout + (yy * p.os + p.oy0)) * p.Wout + (xx * p.os + p.ox0);
                 t += bias;
                 t = fmaxf(p.alpha * t, t);
                 if (p.res) t += p.res[pix * p.res_cs + ch];
@@ -415,9 +416,10 @@ static int bf_get_map(const CUtensorMap** out, void* addr, int rank, const cuuin
 
 // ------------------------------------------------------------------------------------------------
 bool conv_bf_supported(const ConvGemm& g) {
-    if (g.div != 1) return false;                                       // no fractionally-strided gathers
+    if (g.div != 1 && !(g.div == 2 && g.mul == 1)) return false;       // forward (stride 1/2), dgrad / transposed (stride 1/2)
     if (g.mul != 1 && g.mul != 2) return false;
-    if (g.mul == 2 && g.step < 0) return false;
+    if (g.mul == 2 && g.step != 1) return false;
+    if (g.div == 2 && std::abs(g.step) != 1) return false;
     if (g.x.c < 8 || g.y.c < 8) return false;
     if (g.kh * g.kw > BF_MAX_TAPS) return false;
     if (g.y.h * g.y.w < 32) return false;
@@ -435,21 +437,20 @@ int conv_bf_init() {
 size_t conv_bf_part_floats() { return (size_t)8 << 20; }    // 32 MB of split-K partial sums
 size_t conv_bf_ticket_words() { return 4096; }
 
-// xp: bf16 planes of g.x;  wh/wl: prepared weights [tap][Mpad][Kpad];  yp: optional planes of g.y (written by the epilogue)
-int conv_bf(const ConvGemm& g, const ActPlanes& xp, const void* wh, const void* wl, const ActPlanes* yp,
-            float* part, unsigned int* tickets, cudaStream_t st) {
-    MS_REQUIRE(conv_bf_supported(g), "conv_bf: unsupported geometry");
-    MS_REQUIRE(xp.hi && xp.lo && (xp.cs & 7) == 0 && xp.cs >= g.x.c, "conv_bf: input planes missing");
-    if (conv_bf_init()) return -1;
+struct BfTapSpec { int dy, dx, widx; };     // input pixel = out_lattice * sx + (dy, dx); weight tap index
+
+// One launch: output lattice [Hj x Wj] (output pixel = j * os + o0), gather taps `taps`, input lattice stride sx.
+static int conv_bf_launch(const ConvGemm& g, const ActPlanes& xp, const void* wh, const void* wl, const ActPlanes* yp,
+                          float* part, unsigned int* tickets, int Hj, int Wj, int os, int oy0, int ox0, int sx,
+                          const BfTapSpec* taps, int ntaps, int taps_total, cudaStream_t st) {
     const int K = g.x.c, M = g.y.c;
     int Mpad, Kpad; conv_bf_weight_dims(M, K, Mpad, Kpad);
-    const int taps = g.kh * g.kw;
-
     static ConvBfParams p;          // large (tables): filled in place, passed by value to the launch
     memset(&p, 0, sizeof p);
-    p.H = g.y.h; p.W = g.y.w; p.NB = g.y.n; p.sx = g.mul;
+    p.H = Hj; p.W = Wj; p.NB = g.y.n; p.sx = sx;
+    p.Hout = g.y.h; p.Wout = g.y.w; p.os = os; p.oy0 = oy0; p.ox0 = ox0;
     p.kblocks = Kpad / 32; p.cout = M;
-    // ---- pixel tile: the largest N in {256,128,64} that still gives ~100 CTAs; wide maps use 8-pixel rows
+    // ---- pixel tile: the largest N in {256,128,64} that still gives ~100 CTAs; 8-pixel rows unless that wastes a tile row
     const int mblocks = Mpad / 128;
     static int force_n = -1;
     if (force_n < 0) { const char* e = getenv("MS_BF_N"); force_n = e ? atoi(e) : 0; }
@@ -459,63 +460,53 @@ int conv_bf(const ConvGemm& g, const ActPlanes& xp, const void* wh, const void* 
         for (int ci = 0; ci < 3; ++ci) {
             const int n = cand_n[ci];
             int tw = 8;
-            if (n == 256 && (g.y.h % 32) != 0 && (g.y.h % 16) == 0) tw = 16;
+            if (n == 256 && (Hj % 32) != 0 && (Hj % 16) == 0) tw = 16;
             const int th = n / tw;
-            const long tiles = (long)g.y.n * cdiv(g.y.w, tw) * cdiv(g.y.h, th) * mblocks;
+            const long tiles = (long)g.y.n * cdiv(Wj, tw) * cdiv(Hj, th) * mblocks;
             const bool take = force_n ? (n == force_n || ci == 2) : (tiles >= 100 || ci == 2);
             if (take) { N = n; TW = tw; break; }
         }
     }
     const int TH = N / TW;
     p.TW = TW; p.tw_shift = TW == 8 ? 3 : 4; p.N = N;
-    p.tiles_x = cdiv(p.W, TW); p.tiles_y = cdiv(p.H, TH);
-    // ---- patches: taps grouped by filter column (and by row parity for stride 2); row offsets inside the halo patch
-    const int astep = std::abs(g.step);
-    int max_off = 0, np = 0, nt = 0;
-    const int sy = g.mul;
-    for (int s = 0; s < g.kw; ++s) {
-        for (int par = 0; par < sy; ++par) {
-            // rows r of this column whose (r * step) has parity `par` relative to the stride lattice
-            int first_dy = 0, cnt = 0;
-            for (int r = 0; r < g.kh; ++r) {
-                const int dyr = g.off_y + r * g.step;
-                if (((r * astep) % sy) != par) continue;
-                if (cnt == 0 || dyr < first_dy) first_dy = dyr;
-                ++cnt;
-            }
-            if (!cnt) continue;
-            MS_REQUIRE(np < BF_MAX_PATCH, "conv_bf: too many patches");
-            BfPatch& pt = p.patch[np];
-            pt.dx = (short)(g.off_x + s * g.step); pt.dy = (short)first_dy; pt.tap0 = (short)nt; pt.ntaps = (short)cnt;
-            for (int r = 0; r < g.kh; ++r) {
-                const int dyr = g.off_y + r * g.step;
-                if (((r * astep) % sy) != par) continue;
-                const int off = (dyr - first_dy) / sy;
-                p.tap[nt].row_off = (short)off; p.tap[nt].widx = (short)(r * g.kw + s);
-                max_off = std::max(max_off, off);
-                ++nt;
-            }
-            ++np;
+    p.tiles_x = cdiv(Wj, TW); p.tiles_y = cdiv(Hj, TH);
+    // ---- patches: taps of one filter column (same dx; same row parity for an input lattice of stride 2) share a halo
+    //      patch; a tap is a row offset into it
+    auto posmod = [](int a, int m) { return ((a % m) + m) % m; };
+    bool used[BF_MAX_TAPS] = {false};
+    int np = 0, nt = 0, max_off = 0;
+    for (int i = 0; i < ntaps; ++i) {
+        if (used[i]) continue;
+        int first_dy = taps[i].dy;
+        for (int j = i; j < ntaps; ++j)
+            if (!used[j] && taps[j].dx == taps[i].dx && posmod(taps[j].dy - taps[i].dy, sx) == 0) first_dy = std::min(first_dy, taps[j].dy);
+        MS_REQUIRE(np < BF_MAX_PATCH, "conv_bf: too many patches");
+        BfPatch& pt = p.patch[np];
+        pt.dx = (short)taps[i].dx; pt.dy = (short)first_dy; pt.tap0 = (short)nt; pt.ntaps = 0;
+        for (int j = i; j < ntaps; ++j) {
+            if (used[j] || taps[j].dx != taps[i].dx || posmod(taps[j].dy - taps[i].dy, sx) != 0) continue;
+            used[j] = true;
+            const int off = (taps[j].dy - first_dy) / sx;
+            p.tap[nt].row_off = (short)off; p.tap[nt].widx = (short)taps[j].widx;
+            max_off = std::max(max_off, off);
+            ++nt; ++pt.ntaps;
         }
+        ++np;
     }
-    MS_REQUIRE(nt == taps, "conv_bf: tap table mismatch");
     p.n_patches = np;
     int rows = TH + max_off;
-    // a tall halo (large dilation) that costs more than one box per tap: fall back to one patch per tap
-    if ((size_t)rows * TW * 64 * 2 * 2 + 4 * 2 * BF_W_TILE > 200 * 1024 || (sy == 1 && max_off >= (g.kh - 1) * TH && g.kh > 1)) {
-        np = 0; nt = 0;
-        for (int s = 0; s < g.kw; ++s)
-            for (int r = 0; r < g.kh; ++r) {
-                MS_REQUIRE(np < BF_MAX_PATCH, "conv_bf: too many per-tap patches");
-                BfPatch& pt = p.patch[np];
-                pt.dx = (short)(g.off_x + s * g.step); pt.dy = (short)(g.off_y + r * g.step); pt.tap0 = (short)nt; pt.ntaps = 1;
-                p.tap[nt].row_off = 0; p.tap[nt].widx = (short)(r * g.kw + s);
-                ++nt; ++np;
-            }
-        p.n_patches = np;
+    // a tall halo (large dilation) costs more than one box per tap, or does not fit: one patch per tap instead
+    if (max_off > 0 && ((size_t)rows * TW * 64 * 2 * 2 + 4 * 2 * BF_W_TILE > 200 * 1024 || rows * np >= TH * ntaps)) {
+        MS_REQUIRE(ntaps <= BF_MAX_PATCH, "conv_bf: too many per-tap patches");
+        for (int i = 0; i < ntaps; ++i) {
+            BfPatch& pt = p.patch[i];
+            pt.dx = (short)taps[i].dx; pt.dy = (short)taps[i].dy; pt.tap0 = (short)i; pt.ntaps = 1;
+            p.tap[i].row_off = 0; p.tap[i].widx = (short)taps[i].widx;
+        }
+        p.n_patches = ntaps;
         rows = TH;
     }
-    MS_REQUIRE(rows * sy <= 256, "conv_bf: patch too tall for one TMA box");
+    MS_REQUIRE(rows * sx <= 256 && TW * sx <= 256, "conv_bf: patch too large for one TMA box");
     p.slot_bytes = (uint32_t)rows * TW * 64u;
     const size_t pslot = 2 * (size_t)p.slot_bytes, wslot = 2 * (size_t)BF_W_TILE;
     const size_t budget = 220 * 1024;
@@ -555,13 +546,13 @@ int conv_bf(const ConvGemm& g, const ActPlanes& xp, const void* wh, const void* 
     {
         cuuint64_t dims[4] = {(cuuint64_t)g.x.c, (cuuint64_t)g.x.w, (cuuint64_t)g.x.h, (cuuint64_t)g.x.n};
         cuuint64_t strides[3] = {(cuuint64_t)xp.cs * 2, (cuuint64_t)g.x.w * xp.cs * 2, (cuuint64_t)g.x.h * g.x.w * xp.cs * 2};
-        cuuint32_t box[4] = {32, (cuuint32_t)(TW * sy), (cuuint32_t)(rows * sy), 1};
-        cuuint32_t es[4] = {1, (cuuint32_t)sy, (cuuint32_t)sy, 1};
+        cuuint32_t box[4] = {32, (cuuint32_t)(TW * sx), (cuuint32_t)(rows * sx), 1};
+        cuuint32_t es[4] = {1, (cuuint32_t)sx, (cuuint32_t)sx, 1};
         if (bf_get_map(&mXh, xp.hi, 4, dims, strides, box, es)) return -1;
         if (bf_get_map(&mXl, xp.lo, 4, dims, strides, box, es)) return -1;
     }
     {
-        cuuint64_t dims[3] = {(cuuint64_t)Kpad, (cuuint64_t)Mpad, (cuuint64_t)taps};
+        cuuint64_t dims[3] = {(cuuint64_t)Kpad, (cuuint64_t)Mpad, (cuuint64_t)taps_total};
         cuuint64_t strides[2] = {(cuuint64_t)Kpad * 2, (cuuint64_t)Mpad * Kpad * 2};
         cuuint32_t box[3] = {32, 128, 1};
         cuuint32_t es[3] = {1, 1, 1};
@@ -571,6 +562,46 @@ int conv_bf(const ConvGemm& g, const ActPlanes& xp, const void* wh, const void* 
     const size_t smem = (size_t)NP * pslot + (size_t)NW * wslot + 1024;
     conv_bf_kernel<<<dim3(grid_tiles, mblocks, ksplit), BF_THREADS, smem, st>>>(*mXh, *mXl, *mWh, *mWl, p);
     return check_launch("conv_bf");
+}
+
+// xp: bf16 planes of g.x;  wh/wl: prepared weights [tap][Mpad][Kpad];  yp: optional planes of g.y (written by the epilogue)
+int conv_bf(const ConvGemm& g, const ActPlanes& xp, const void* wh, const void* wl, const ActPlanes* yp,
+            float* part, unsigned int* tickets, cudaStream_t st) {
+    MS_REQUIRE(conv_bf_supported(g), "conv_bf: unsupported geometry");
+    MS_REQUIRE(xp.hi && xp.lo && (xp.cs & 7) == 0 && xp.cs >= g.x.c, "conv_bf: input planes missing");
+    if (conv_bf_init()) return -1;
+    const int taps_total = g.kh * g.kw;
+    BfTapSpec taps[BF_MAX_TAPS];
+    if (g.div == 1) {
+        // gathered input pixel = out * mul + off + tap * step
+        int n = 0;
+        for (int s = 0; s < g.kw; ++s)
+            for (int r = 0; r < g.kh; ++r) taps[n++] = BfTapSpec{g.off_y + r * g.step, g.off_x + s * g.step, r * g.kw + s};
+        return conv_bf_launch(g, xp, wh, wl, yp, part, tickets, g.y.h, g.y.w, 1, 0, 0, g.mul, taps, n, taps_total, st);
+    }
+    // fractionally strided gather (stride-2 dgrad, conv_transpose): t = out + off + tap*step must be even, input = t / 2.
+    // Output pixels of one parity class (py, px) see a fixed subset of the taps at unit input stride: four dense launches.
+    for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+            const int Hj = (g.y.h - py + 1) / 2, Wj = (g.y.w - px + 1) / 2;
+            if (Hj <= 0 || Wj <= 0) continue;
+            int n = 0;
+            for (int s = 0; s < g.kw; ++s) {
+                const int tx = px + g.off_x + s * g.step;
+                if (tx & 1) continue;
+                for (int r = 0; r < g.kh; ++r) {
+                    const int ty = py + g.off_y + r * g.step;
+                    if (ty & 1) continue;
+                    taps[n++] = BfTapSpec{ty / 2, tx / 2, r * g.kw + s};    // exact: ty, tx even (C++ division truncates toward 0)
+                }
+            }
+            if (n == 0) {
+                // no tap reaches this class: the gradient there is the epilogue of a zero sum; one zero-weight tap keeps it generic
+                set_error("conv_bf: parity class without taps"); return -2;
+            }
+            if (conv_bf_launch(g, xp, wh, wl, yp, part, tickets, Hj, Wj, 2, py, px, 1, taps, n, taps_total, st)) return -1;
+        }
+    return 0;
 }
 
 // one-shot convenience (operator-level C ABI / tests): splits the input, prepares the weights, runs the conv.

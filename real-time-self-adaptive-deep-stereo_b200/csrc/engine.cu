@@ -42,6 +42,33 @@ Engine::Engine()
     { const char* e3 = getenv("MS_TC_WGRAD"); use_tc_wgrad = (e3 && e3[0] == '0') ? 0 : 1; }
     const char* e = getenv("MS_CONV_TC");
     use_tc = (e && e[0] == '0') ? 0 : 1;
+    { const char* e4 = getenv("MS_CONV_IMPL"); conv_impl = (e4 && (!strcmp(e4, "tf32") || !strcmp(e4, "0"))) ? 0 : 1; }
+    if (!use_tc) conv_impl = 0;
+    { const char* e5 = getenv("MS_HEADS"); use_heads = (e5 && e5[0] == '0') ? 0 : 1; }
+    bf_jobs_dev = nullptr; bf_max_total = 0; bf_part = nullptr; bf_tickets = nullptr;
+}
+
+void Engine::add_planes(Bump& A, const TView& v) {
+    if (conv_impl != 1 || planes.count(v.p)) return;
+    ActPlanes pl;
+    pl.cs = (v.c + 7) / 8 * 8;
+    const size_t floats = (v.pixels() * pl.cs + 1) / 2;     // bf16 elements -> floats
+    pl.hi = A.alloc(floats);
+    pl.lo = A.alloc(floats);
+    planes[v.p] = pl;
+}
+const ActPlanes* Engine::planes_of(const TView& v) const {
+    auto it = planes.find(v.p);
+    if (it == planes.end() || !it->second.hi || it->second.cs < v.c) return nullptr;
+    return &it->second;
+}
+int Engine::ensure_planes(const TView& v, cudaStream_t st) {
+    if (fresh.count(v.p)) return 0;
+    const ActPlanes* pl = planes_of(v);
+    MS_REQUIRE(pl != nullptr, "ensure_planes: tensor has no bf16 planes");
+    if (split_planes(v, *pl, st)) return -1;
+    fresh.insert(v.p);
+    return 0;
 }
 
 void Engine::prof_reset() {
@@ -145,6 +172,7 @@ size_t Engine::layout(float* base) {
     auto alloc = [&](size_t n) -> float* { return A.alloc(n); };
     auto tens = [&](int n, int h, int w, int c, int cs = 0) { return A.tens(n, h, w, c, cs); };
     tensors.clear();
+    planes.clear(); fresh.clear();
     char nm[128];
     const int nd = (2 * radius_d) / corr_stride + 1;
     TView raw_l = tens(B, H, W, 3), raw_r = tens(B, H, W, 3);
@@ -166,6 +194,7 @@ size_t Engine::layout(float* base) {
         if (i % 2) { h = (h + 1) / 2; w = (w + 1) / 2; }
         pyr[i] = tens(2 * B, h, w, PYR_CH[i]);
         g_pyr[i] = tens(2 * B, h, w, PYR_CH[i]);
+        add_planes(A, pyr[i]); add_planes(A, g_pyr[i]);
         track(layers[i - 1], (size_t)2 * B * h * w);
         snprintf(nm, sizeof nm, "left/conv%d", i); tensors[nm] = batch(pyr[i], 0, B);
         snprintf(nm, sizeof nm, "right/conv%d", i); tensors[nm] = batch(pyr[i], B, B);
@@ -175,17 +204,20 @@ size_t Engine::layout(float* base) {
     ctxin = tens(B, pyr[4].h, pyr[4].w, PYR_CH[4] + 1, pad4(PYR_CH[4] + 1));
     g_ctxin = tens(B, pyr[4].h, pyr[4].w, PYR_CH[4] + 1, pad4(PYR_CH[4] + 1));
     tensors["ctxin"] = ctxin; tensors["grad/ctxin"] = g_ctxin;
+    add_planes(A, ctxin);
     for (int k = 6; k >= 2; --k) {
         const int f = feat_of(k), C = PYR_CH[f];
         const int hh = pyr[f].h, ww = pyr[f].w;
         const int ct = C + nd + (k < 6 ? 1 : 0);
         cost[k] = tens(B, hh, ww, ct, pad4(ct));
         g_cost[k] = tens(B, hh, ww, ct, pad4(ct));
+        add_planes(A, cost[k]);
         snprintf(nm, sizeof nm, "cost%d", k); tensors[nm] = cost[k];
         snprintf(nm, sizeof nm, "grad/cost%d", k); tensors[nm] = g_cost[k];
         for (int j = 1; j <= 5; ++j) {
             est[k][j] = tens(B, hh, ww, EST_CH[j - 1]);
             g_est[k][j] = tens(B, hh, ww, EST_CH[j - 1]);
+            add_planes(A, est[k][j]); add_planes(A, g_est[k][j]);
             snprintf(nm, sizeof nm, "fgc-volume-filtering-%d/disp%d", k, j); tensors[nm] = est[k][j];
             snprintf(nm, sizeof nm, "grad/fgc-volume-filtering-%d/disp%d", k, j); tensors[nm] = g_est[k][j];
         }
@@ -201,6 +233,7 @@ size_t Engine::layout(float* base) {
     for (int j = 1; j <= 6; ++j) {
         ctx[j] = tens(B, pyr[4].h, pyr[4].w, CTX_CH[j - 1]);
         g_ctx[j] = tens(B, pyr[4].h, pyr[4].w, CTX_CH[j - 1]);
+        add_planes(A, ctx[j]); add_planes(A, g_ctx[j]);
         snprintf(nm, sizeof nm, "context%d", j); tensors[nm] = ctx[j];
         snprintf(nm, sizeof nm, "grad/context%d", j); tensors[nm] = g_ctx[j];
     }
@@ -229,6 +262,7 @@ size_t Engine::layout(float* base) {
         for (size_t li = 0; li < layers.size(); ++li) {
             const ConvLayer& L = layers[li];
             const int lg = L.group < 0 ? n_groups : L.group;
+            if (conv_impl == 1) continue;                       // the split-bf16 path has its own weight copies (below)
             if (lg != gidx || L.transposed || L.stride != 1 || L.cin < 8 || L.cout < 8) continue;
             for (int dir = 0; dir < 2; ++dir) {
                 const int N = dir == 0 ? L.cout : L.cin, K = dir == 0 ? L.cin : L.cout;
@@ -245,6 +279,36 @@ size_t Engine::layout(float* base) {
         }
         job_end[gidx] = (int)prep_jobs.size();
     }
+    // split-bf16 weight planes (hi / lo) per layer and orientation + their batched prep job table
+    bfw[0].assign(layers.size(), BfW{nullptr, nullptr, false});
+    bfw[1].assign(layers.size(), BfW{nullptr, nullptr, false});
+    bf_jobs.clear(); bf_job_begin.assign(n_groups + 1, 0); bf_job_end.assign(n_groups + 1, 0);
+    bf_max_total = 0;
+    for (int gidx = 0; gidx <= n_groups && conv_impl == 1; ++gidx) {
+        bf_job_begin[gidx] = (int)bf_jobs.size();
+        for (size_t li = 0; li < layers.size(); ++li) {
+            const ConvLayer& L = layers[li];
+            const int lg = L.group < 0 ? n_groups : L.group;
+            if (lg != gidx || L.transposed || L.cin < 8 || L.cout < 8 || L.kh * L.kw > 49) continue;
+            for (int dir = 0; dir < 2; ++dir) {
+                if (dir == 0 && L.stride > 2) continue;
+                if (dir == 1 && L.stride > 2) continue;
+                const int M = dir == 0 ? L.cout : L.cin, K = dir == 0 ? L.cin : L.cout;
+                int Mpad, Kpad; conv_bf_weight_dims(M, K, Mpad, Kpad);
+                const size_t halfs = conv_bf_weight_halfs(L.kh * L.kw, M, K);
+                BfW t; t.ok = true;
+                t.hi = alloc((halfs + 1) / 2); t.lo = alloc((halfs + 1) / 2);
+                bfw[dir][li] = t;
+                BfPrepJob j{base ? Wt + L.w_off : nullptr, t.hi, t.lo, L.kh * L.kw, M, K, Mpad, Kpad, dir == 0 ? 1 : 0};
+                bf_jobs.push_back(j);
+                bf_max_total = std::max(bf_max_total, halfs);
+            }
+        }
+        bf_job_end[gidx] = (int)bf_jobs.size();
+    }
+    bf_part = alloc(conv_bf_part_floats());
+    bf_tickets = reinterpret_cast<unsigned int*>(alloc(conv_bf_ticket_words()));
+    bf_jobs_dev = reinterpret_cast<BfPrepJob*>(alloc((bf_jobs.size() + 1) * sizeof(BfPrepJob) / sizeof(float) + 16));
     tc_part = alloc(conv_tc_part_floats());
     prep_jobs_dev = reinterpret_cast<TcPrepJob*>(alloc((prep_jobs.size() + 1) * sizeof(TcPrepJob) / sizeof(float) + 16));
     rs_tmp_floats = (size_t)B * H * Wp; rs_tmp = alloc(rs_tmp_floats);
@@ -285,8 +349,20 @@ int Engine::conv_fwd(const ConvLayer& L, const TView& x, const TView& y, const f
     prof_begin(CAT_CONV_FWD, st);
     int rc;
     const int li = (int)(&L - &layers[0]);
-    if (use_tc && tcw[0][li].ok && conv_tc_profitable(p)) rc = conv_tc(p, tcw[0][li].bh, st, tc_part);
-    else rc = conv_gemm(p, st);
+    const ActPlanes* xpl = (conv_impl == 1 && bfw[0][li].ok && conv_bf_supported(p)) ? planes_of(x) : nullptr;
+    if (use_heads && conv_head_kind(p) == 1) {
+        fresh.erase(y.p);
+        rc = conv_head(p, st);
+    } else if (xpl) {
+        if (ensure_planes(x, st)) return -1;
+        const ActPlanes* ypl = planes_of(y);
+        rc = conv_bf(p, *xpl, bfw[0][li].hi, bfw[0][li].lo, ypl, bf_part, bf_tickets, st);
+        if (ypl) fresh.insert(y.p);
+    } else {
+        fresh.erase(y.p);
+        if (use_tc && tcw[0][li].ok && conv_tc_profitable(p)) rc = conv_tc(p, tcw[0][li].bh, st, tc_part);
+        else rc = conv_gemm(p, st);
+    }
     prof_end(st);
     if (profiling) cat_macs[CAT_CONV_FWD] += (double)y.pixels() * L.kh * L.kw * L.cin * L.cout / (L.transposed ? L.stride * L.stride : 1);
     return rc;
@@ -300,6 +376,7 @@ int Engine::conv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, cons
     same_pad(x.h, L.kh, L.stride, L.dil, oh, pt);
     same_pad(x.w, L.kw, L.stride, L.dil, ow, pl);
     MS_REQUIRE(oh == dpre.h && ow == dpre.w && x.c == L.cin && dpre.c == L.cout, "conv_bwd: shape mismatch");
+    if (net == 1) fresh.clear();    // DispNet's backward mutates gradient tensors in place between convs: always re-split
     if (want_wgrad) {
         ConvWgrad q{};
         q.x = x; q.dy = dpre; q.dw = Gr + L.w_off; q.db = Gr + L.b_off;
@@ -322,9 +399,23 @@ int Engine::conv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, cons
         prof_begin(CAT_CONV_DGRAD, st);
         int rc;
         const int li = (int)(&L - &layers[0]);
-        if (use_tc && tcw[1][li].ok && conv_tc_profitable(p)) {
+        const ActPlanes* xpl = (conv_impl == 1 && bfw[1][li].ok && conv_bf_supported(p)) ? planes_of(dpre) : nullptr;
+        if (use_heads && L.cout == 1 && (p.wmat = Wt + L.w_off, conv_head_kind(p) == 2)) {
+            fresh.erase(dx->p);
+            rc = conv_head(p, st);          // [tap][cin][1] == [tap][1][cin]: the canonical weights serve directly
+        } else if (xpl) {
+            p.wmat = wT;
+            rc = ensure_planes(dpre, st);
+            const ActPlanes* ypl = planes_of(*dx);
+            if (!rc) rc = conv_bf(p, *xpl, bfw[1][li].hi, bfw[1][li].lo, ypl, bf_part, bf_tickets, st);
+            if (ypl) fresh.insert(dx->p);
+        } else if (use_tc && tcw[1][li].ok && conv_tc_profitable(p)) {
+            p.wmat = wT;
+            fresh.erase(dx->p);
             rc = conv_tc(p, tcw[1][li].bh, st, tc_part);
         } else {
+            p.wmat = wT;
+            fresh.erase(dx->p);
             rc = transpose_taps(Wt + L.w_off, wT, L.kh * L.kw, L.cin, L.cout, st);   // -> [tap][cout][cin]
             if (!rc) rc = conv_gemm(p, st);
         }
@@ -354,7 +445,14 @@ int Engine::set_input(const float* left, const float* right, cudaStream_t st) {
 }
 
 int Engine::prep_layers(int group, cudaStream_t st) {
-    if (!use_tc || prep_jobs.empty()) return 0;
+    if (!use_tc) return 0;
+    if (!bf_jobs.empty()) {
+        int b, e;
+        if (group < 0) { b = 0; e = (int)bf_jobs.size(); }
+        else { b = bf_job_begin[group]; e = bf_job_end[group]; }
+        if (bf_prep_weights(bf_jobs_dev + b, e - b, bf_max_total, st)) return -1;
+    }
+    if (prep_jobs.empty()) return 0;
     int b, e;
     if (group < 0) { b = 0; e = (int)prep_jobs.size(); }
     else { b = job_begin[group]; e = job_end[group]; }
@@ -363,6 +461,7 @@ int Engine::prep_layers(int group, cudaStream_t st) {
 
 int Engine::forward(int disp_mask, cudaStream_t st) {
     MS_REQUIRE(bound, "engine not bound");
+    fresh.clear();
     const int nd = (2 * radius_d) / corr_stride + 1;
     {
         TView rl = tensors["raw_left"], rr = tensors["raw_right"];
@@ -460,6 +559,9 @@ int Engine::backward(int mode, int group, cudaStream_t st) {
     }
     MS_REQUIRE(mode == 2 || (mode == 1 && group >= 0 && group < n_groups), "backward: bad mode/group");
     const int nd = (2 * radius_d) / corr_stride + 1;
+    for (int i = 1; i <= 12; ++i) fresh.erase(g_pyr[i].p);     // gradient planes never survive from an earlier pass
+    for (int k = 2; k <= 6; ++k) for (int j = 1; j <= 5; ++j) fresh.erase(g_est[k][j].p);
+    for (int j = 1; j <= 6; ++j) fresh.erase(g_ctx[j].p);
 
     // lowest-index trainable pyramid conv (13 = none)
     int lo_pyr = 13;
@@ -514,6 +616,7 @@ int Engine::backward(int mode, int group, cudaStream_t st) {
         cb.du = (want_du && cb.u) ? g_u[k].p : nullptr; cb.ducs = 1;
         cb.B = B; cb.h = cost[k].h; cb.w = cost[k].w; cb.C = C; cb.max_disp = radius_d; cb.stride = corr_stride;
         cb.add_left_slice = 1; cb.acc_left = 0; cb.acc_right = 0; cb.gcoff = -1;
+        fresh.erase(g_pyr[f].p);
         prof_begin(CAT_CORR_BWD, st);
         int crc = corr_bwd(cb, st);
         prof_end(st);
@@ -523,6 +626,7 @@ int Engine::backward(int mode, int group, cudaStream_t st) {
     // ---- pyramid: g_pyr[top] holds d(post-activation output of conv `top`), complete
     auto pyr_bwd = [&](int top, int lo, bool accumulate_feats) -> int {
         if (lo > top) return 0;
+        fresh.erase(g_pyr[top].p);
         if (leaky_bwd(g_pyr[top].p, g_pyr[top].cs, pyr[top].p, pyr[top].cs, g_pyr[top].pixels(), g_pyr[top].c,
                       MAD_ALPHA, st)) return -1;
         for (int i = top; i >= lo; --i) {
@@ -543,6 +647,7 @@ int Engine::backward(int mode, int group, cudaStream_t st) {
     };
     auto ctx_feat = [&]() -> int {   // g_pyr[4].left += g_ctxin[..., :32]
         TView dL = batch(g_pyr[4], 0, B);
+        fresh.erase(g_pyr[4].p);
         return add_channels(dL.p, dL.cs, g_ctxin.p, g_ctxin.cs, dL.pixels(), PYR_CH[4], 1.f, 1, st);
     };
 
@@ -636,7 +741,7 @@ int Engine::run(int mode, int group, int disp_mask, int with_update, float lr, f
     key.lr = lr; key.mu = mu; key.gs = gscale;
     auto it = graphs.find(key);
     if (it == graphs.end()) {
-        if (conv_tc_init() || corr_init() || wgrad_tc_init()) return -1;
+        if (conv_tc_init() || conv_bf_init() || corr_init() || wgrad_tc_init()) return -1;
         cudaGraph_t graph = nullptr;
         const long long l0 = launch_count();
         MS_CHECK_CUDA(cudaStreamBeginCapture(gstream, cudaStreamCaptureModeThreadLocal));

@@ -4,6 +4,7 @@
 #pragma once
 #include <cstring>
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -80,6 +81,19 @@ struct Engine {
     int run(int mode, int group, int disp_mask, int with_update, float lr, float mu, float gscale, cudaStream_t st);
     int run_eager(int mode, int group, int disp_mask, int with_update, float lr, float mu, float gscale, cudaStream_t st);
     int use_tc;                      // route eligible convs through conv_tc (env MS_CONV_TC, default 1)
+    // ---- split-bf16 tcgen05 path (conv_bf.cu), the default implementation of every eligible conv / dgrad
+    int use_heads;                                 // direct kernels for the 3x3 -> 1 heads (MS_HEADS=0: generic path)
+    int conv_impl;                                 // 1 = split-bf16 (default), 0 = the 3xTF32 kernels (MS_CONV_IMPL=tf32)
+    std::map<const float*, ActPlanes> planes;      // bf16 hi/lo planes of tensors that feed convolutions (key: base pointer)
+    std::set<const float*> fresh;                  // planes already written by a conv_bf epilogue in the current pass
+    struct BfW { void* hi; void* lo; bool ok; };
+    std::vector<BfW> bfw[2];                       // prepared weights per layer and orientation (0 = forward, 1 = dgrad)
+    std::vector<BfPrepJob> bf_jobs; std::vector<int> bf_job_begin, bf_job_end;
+    BfPrepJob* bf_jobs_dev; size_t bf_max_total;
+    float* bf_part; unsigned int* bf_tickets;
+    void add_planes(Bump& A, const TView& v);
+    const ActPlanes* planes_of(const TView& v) const;
+    int ensure_planes(const TView& v, cudaStream_t st);
     float* wg_ws; size_t wg_ws_floats;
     float* rs_tmp; size_t rs_tmp_floats;
     float* loss_ws; size_t loss_ws_floats;

@@ -31,7 +31,7 @@ _SIGS = {
     'ms_conv2d_dgrad_tc': (I, [P, I, I, I, I, I, P, P, I, I, I, I, I, P, Z, P]),
     'ms_conv2d_tc_scratch': (Z, [I, I, I, I]),
     'ms_conv2d_fwd_bf': (I, [P, I, I, I, I, I, P, P, P, I, I, I, I, I, I, F, P, Z, P]),
-    'ms_conv2d_dgrad_bf': (I, [P, I, I, I, I, I, P, P, I, I, I, I, I, P, Z, P]),
+    'ms_conv2d_dgrad_bf': (I, [P, I, I, I, I, I, P, P, I, I, I, I, I, I, I, I, P, Z, P]),
     'ms_conv2d_bf_scratch': (Z, [I, I, I, I, I, I, I]),
     'ms_conv2d_wgrad_tc': (I, [P, I, I, I, I, I, P, I, I, P, P, I, I, I, P, Z, P]),
     'ms_conv2d_wgrad_tc_workspace': (Z, [I, I, I, I, I, I, I]),

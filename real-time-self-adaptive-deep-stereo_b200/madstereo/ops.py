@@ -117,14 +117,15 @@ def conv2d_bf(x, w, b, stride=1, dilation=1, alpha=1.0):
     return y
 
 
-def conv2d_dgrad_bf(dy, w, dilation=1):
-    n, h, wd, cout = dy.shape
+def conv2d_dgrad_bf(dy, w, in_hw=None, stride=1, dilation=1):
+    n, oh, ow, cout = dy.shape
     kh, kw, cin, _ = w.shape
+    h, wd = in_hw if in_hw is not None else (oh, ow)
     dx = torch.empty(n, h, wd, cin, device=dy.device, dtype=torch.float32)
     ns = lib().ms_conv2d_bf_scratch(n, h, wd, kh, kw, cin, cout)
     scratch = torch.empty(ns + 256, device=dy.device, dtype=torch.uint8)
     off = (-scratch.data_ptr()) % 256
-    check(lib().ms_conv2d_dgrad_bf(_p(dy), n, h, wd, cout, cout, _p(w), _p(dx), cin, cin, kh, kw, dilation,
+    check(lib().ms_conv2d_dgrad_bf(_p(dy), n, oh, ow, cout, cout, _p(w), _p(dx), h, wd, cin, cin, kh, kw, stride, dilation,
                                    c_void_p(scratch.data_ptr() + off), ns, _s()), 'ms_conv2d_dgrad_bf')
     return dx
 

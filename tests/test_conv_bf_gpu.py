@@ -60,8 +60,9 @@ def test_conv_bf_forward(case):
     assert rel_linf(out.cpu().numpy(), ref.numpy()) < TOL
 
 
-@pytest.mark.parametrize('case', [c for c in CASES if c[6] == 1])
+@pytest.mark.parametrize('case', CASES)
 def test_conv_bf_dgrad(case):
+    """stride 1: one launch; stride 2: the four output-parity classes as dense launches (conv_bf.cu)."""
     from madstereo import ops
     from oracle import tf1_ops as T
     n, h, w, cin, cout, k, stride, dil, alpha = case
@@ -69,9 +70,9 @@ def test_conv_bf_dgrad(case):
     x = rng.standard_normal((n, h, w, cin)).astype(np.float32)
     wt = (rng.standard_normal((k, k, cin, cout)) / np.sqrt(k * k * cin)).astype(np.float32)
     xt = torch.tensor(x, requires_grad=True)
-    pre = T.conv2d(xt, torch.tensor(wt), torch.zeros(cout), stride=1, dilation=dil, alpha=None)
+    pre = T.conv2d(xt, torch.tensor(wt), torch.zeros(cout), stride=stride, dilation=dil, alpha=None)
     g = rng.standard_normal(pre.shape).astype(np.float32)
     (gx,) = torch.autograd.grad(pre, xt, grad_outputs=torch.tensor(g))
-    dx = ops.conv2d_dgrad_bf(cu(g), cu(wt), dil)
+    dx = ops.conv2d_dgrad_bf(cu(g), cu(wt), (h, w), stride, dil)
     torch.cuda.synchronize()
     assert rel_linf(dx.cpu().numpy(), gx.numpy()) < TOL
