@@ -75,6 +75,33 @@ int ms_conv2d_dgrad_bf(const float* dy, int n, int oh, int ow, int cout, int dy_
                        float* dx, int h, int w, int cin, int dx_cs, int kh, int kw, int stride, int dilation,
                        void* scratch, size_t scratch_bytes, void* stream);
 size_t ms_conv2d_bf_scratch(int n, int h, int w, int kh, int kw, int cin, int cout);
+/* Split-bf16 tcgen05 weight + bias gradient (csrc/wgrad_bf.cu; the engine's default for eligible layers): replaces the
+ * filter / bias gradient sub-graphs of tf.nn.conv2d / atrous_conv2d / bias_add (reference Nets/sharedLayers.py:58-59,
+ * 72-73 under the train ops of Stereo_Online_Adaptation.py:118,128).  x and dy planes feed the UMMA as MN-major
+ * operands straight from NHWC; stride 1 or 2, any dilation.  Same outputs as ms_conv2d_wgrad.
+ * scratch: ms_conv2d_wgrad_bf_scratch() BYTES, 256-byte aligned.  -3 = not eligible. */
+int ms_conv2d_wgrad_bf(const float* x, int n, int h, int w, int cin, int x_cs, const float* dy, int oh, int ow, int cout,
+                       int dy_cs, float* dw /*HWIO*/, float* db, int kh, int kw, int stride, int dilation, void* scratch,
+                       size_t scratch_bytes, void* stream);
+size_t ms_conv2d_wgrad_bf_scratch(int n, int h, int w, int oh, int ow, int kh, int kw, int cin, int cout);
+/* Plane-level entry points of the same path (what the engine issues per layer in steady state: activations are split
+ * by the producing kernel's epilogue, weights once per update).  hi / lo planes: bf16 NHWC, channel stride `*_pcs`
+ * (multiple of 8); weight planes: ms_bf_weight_halfs() bf16 elements each; job_dev: >= 64 bytes of device scratch;
+ * part / tickets: ms_conv2d_bf_part_floats() floats / ms_conv2d_bf_ticket_words() zeroed words (split-K). */
+int ms_bf_split(const float* x, int n, int h, int w, int c, int x_cs, void* hi, void* lo, int plane_cs, void* stream);
+size_t ms_bf_weight_halfs(int taps, int m, int k);
+int ms_bf_prep_weights(const float* weights_hwio, int taps, int cin, int cout, int for_dgrad, void* hi, void* lo,
+                       void* job_dev, void* stream);
+int ms_conv2d_fwd_bf_planes(const void* xhi, const void* xlo, int x_pcs, int n, int h, int w, int cin, const void* whi,
+                            const void* wlo, const float* bias, float* y, int cout, int y_cs, void* yhi, void* ylo, int y_pcs,
+                            int kh, int kw, int stride, int dilation, float alpha, float* part, unsigned int* tickets,
+                            void* stream);
+size_t ms_conv2d_bf_part_floats(void);
+size_t ms_conv2d_bf_ticket_words(void);
+int ms_conv2d_wgrad_bf_planes(const void* xhi, const void* xlo, int x_pcs, int n, int h, int w, int cin, const void* dhi,
+                              const void* dlo, int d_pcs, int oh, int ow, int cout, float* dw, float* db, int kh, int kw,
+                              int stride, int dilation, float* workspace, size_t workspace_floats, void* stream);
+size_t ms_conv2d_wgrad_bf_workspace(int kh, int kw, int cin, int cout);
 /* tcgen05 weight gradient of a stride-1 conv (same outputs as ms_conv2d_wgrad); workspace from ..._workspace(). */
 int ms_conv2d_wgrad_tc(const float* x, int n, int h, int w, int cin, int x_cs, const float* dy, int cout, int dy_cs,
                        float* dw /*HWIO*/, float* db, int kh, int kw, int dilation, float* workspace,

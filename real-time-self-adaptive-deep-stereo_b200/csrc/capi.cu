@@ -152,6 +152,79 @@ size_t ms_conv2d_bf_scratch(int n, int h, int w, int kh, int kw, int cin, int co
     size_t sa = conv_bf_oneshot_scratch_bytes(a), sb = conv_bf_oneshot_scratch_bytes(b);
     return sa > sb ? sa : sb;
 }
+int ms_conv2d_wgrad_bf(const float* x, int n, int h, int w, int cin, int x_cs, const float* dy, int oh, int ow, int cout,
+                       int dy_cs, float* dw, float* db, int kh, int kw, int stride, int dilation, void* scratch,
+                       size_t scratch_bytes, void* stream) {
+    int oh2, ow2, pt, pl;
+    same_pad_c(h, kh, stride, dilation, oh2, pt);
+    same_pad_c(w, kw, stride, dilation, ow2, pl);
+    if (oh2 != oh || ow2 != ow) { set_error("ms_conv2d_wgrad_bf: shape mismatch"); return -2; }
+    ConvWgrad q{};
+    q.x = view(const_cast<float*>(x), n, h, w, cin, x_cs);
+    q.dy = view(const_cast<float*>(dy), n, oh, ow, cout, dy_cs);
+    q.dw = dw; q.db = db; q.kh = kh; q.kw = kw; q.stride = stride; q.dil = dilation; q.pad_t = pt; q.pad_l = pl;
+    q.accumulate = 0;
+    if (!wgrad_bf_supported(q)) { set_error("ms_conv2d_wgrad_bf: shape not supported by the split-bf16 tcgen05 path"); return -3; }
+    return wgrad_bf_oneshot(q, scratch, scratch_bytes, S(stream));
+}
+size_t ms_conv2d_wgrad_bf_scratch(int n, int h, int w, int oh, int ow, int kh, int kw, int cin, int cout) {
+    ConvWgrad q{};
+    q.x = view(nullptr, n, h, w, cin, cin); q.dy = view(nullptr, n, oh, ow, cout, cout); q.kh = kh; q.kw = kw;
+    return wgrad_bf_oneshot_scratch_bytes(q);
+}
+// ---- plane-level entry points of the split-bf16 path: what the engine calls per layer in steady state (operands
+//      already split: activations by the producing epilogue, weights once per update)
+int ms_bf_split(const float* x, int n, int h, int w, int c, int x_cs, void* hi, void* lo, int plane_cs, void* stream) {
+    ActPlanes pl; pl.hi = hi; pl.lo = lo; pl.cs = plane_cs;
+    return split_planes(view(const_cast<float*>(x), n, h, w, c, x_cs), pl, S(stream));
+}
+size_t ms_bf_weight_halfs(int taps, int m, int k) { return conv_bf_weight_halfs(taps, m, k); }
+int ms_bf_prep_weights(const float* weights_hwio, int taps, int cin, int cout, int for_dgrad, void* hi, void* lo,
+                       void* job_dev, void* stream) {
+    const int M = for_dgrad ? cin : cout, K = for_dgrad ? cout : cin;
+    int Mpad, Kpad; conv_bf_weight_dims(M, K, Mpad, Kpad);
+    BfPrepJob job{weights_hwio, hi, lo, taps, M, K, Mpad, Kpad, for_dgrad ? 0 : 1};
+    MS_CHECK_CUDA(cudaMemcpyAsync(job_dev, &job, sizeof job, cudaMemcpyHostToDevice, S(stream)));
+    MS_CHECK_CUDA(cudaStreamSynchronize(S(stream)));
+    return bf_prep_weights(static_cast<const BfPrepJob*>(job_dev), 1, conv_bf_weight_halfs(taps, M, K), S(stream));
+}
+int ms_conv2d_fwd_bf_planes(const void* xhi, const void* xlo, int x_pcs, int n, int h, int w, int cin, const void* whi,
+                            const void* wlo, const float* bias, float* y, int cout, int y_cs, void* yhi, void* ylo, int y_pcs,
+                            int kh, int kw, int stride, int dilation, float alpha, float* part, unsigned int* tickets,
+                            void* stream) {
+    int oh, ow, pt, pl;
+    same_pad_c(h, kh, stride, dilation, oh, pt);
+    same_pad_c(w, kw, stride, dilation, ow, pl);
+    ConvGemm p{};
+    p.x = view(nullptr, n, h, w, cin, cin);
+    p.y = view(y, n, oh, ow, cout, y_cs);
+    p.bias = bias; p.kh = kh; p.kw = kw;
+    p.mul = stride; p.off_y = -pt; p.off_x = -pl; p.step = dilation; p.div = 1;
+    p.alpha = alpha; p.mask_alpha = 1.f;
+    if (!conv_bf_supported(p)) { set_error("ms_conv2d_fwd_bf_planes: shape not supported"); return -3; }
+    ActPlanes xp; xp.hi = const_cast<void*>(xhi); xp.lo = const_cast<void*>(xlo); xp.cs = x_pcs;
+    ActPlanes yp; yp.hi = yhi; yp.lo = ylo; yp.cs = y_pcs;
+    return conv_bf(p, xp, whi, wlo, yhi ? &yp : nullptr, part, tickets, S(stream));
+}
+size_t ms_conv2d_bf_part_floats() { return conv_bf_part_floats(); }
+size_t ms_conv2d_bf_ticket_words() { return conv_bf_ticket_words(); }
+int ms_conv2d_wgrad_bf_planes(const void* xhi, const void* xlo, int x_pcs, int n, int h, int w, int cin, const void* dhi,
+                              const void* dlo, int d_pcs, int oh, int ow, int cout, float* dw, float* db, int kh, int kw,
+                              int stride, int dilation, float* workspace, size_t workspace_floats, void* stream) {
+    int oh2, ow2, pt, pl;
+    same_pad_c(h, kh, stride, dilation, oh2, pt);
+    same_pad_c(w, kw, stride, dilation, ow2, pl);
+    if (oh2 != oh || ow2 != ow) { set_error("ms_conv2d_wgrad_bf_planes: shape mismatch"); return -2; }
+    ConvWgrad q{};
+    q.x = view(nullptr, n, h, w, cin, cin); q.dy = view(nullptr, n, oh, ow, cout, cout);
+    q.dw = dw; q.db = db; q.kh = kh; q.kw = kw; q.stride = stride; q.dil = dilation; q.pad_t = pt; q.pad_l = pl;
+    q.workspace = workspace; q.workspace_floats = workspace_floats;
+    if (!wgrad_bf_supported(q)) { set_error("ms_conv2d_wgrad_bf_planes: shape not supported"); return -3; }
+    ActPlanes xp; xp.hi = const_cast<void*>(xhi); xp.lo = const_cast<void*>(xlo); xp.cs = x_pcs;
+    ActPlanes dp; dp.hi = const_cast<void*>(dhi); dp.lo = const_cast<void*>(dlo); dp.cs = d_pcs;
+    return wgrad_bf(q, xp, dp, S(stream));
+}
+size_t ms_conv2d_wgrad_bf_workspace(int kh, int kw, int cin, int cout) { return wgrad_bf_workspace_floats(kh, kw, cin, cout); }
 size_t ms_conv2d_tc_scratch(int kh, int kw, int cin, int cout) {
     size_t a = conv_tc_scratch_floats(kh * kw, cout, cin), b = conv_tc_scratch_floats(kh * kw, cin, cout);
     return a > b ? a : b;
@@ -303,7 +376,7 @@ int ms_engine_bind(void* h, float* weights, float* grads, float* momentum, float
         set_error("ms_engine_bind: arenas must be 256-byte aligned"); return -2;
     }
     e->Wt = weights; e->Gr = grads; e->Mo = momentum; e->ws = workspace; e->ws_floats = workspace_floats;
-    e->layout(workspace);
+    if (e->layout(workspace) > need) { set_error("ms_engine_bind: layout exceeds the size reported by ms_engine_sizes"); return -2; }
     MS_CHECK_CUDA(cudaMemsetAsync(workspace, 0, need * sizeof(float), S(stream)));
     MS_CHECK_CUDA(cudaMemsetAsync(grads, 0, e->n_params * sizeof(float), S(stream)));
     if (!e->prep_jobs.empty())

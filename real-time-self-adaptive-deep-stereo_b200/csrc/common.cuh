@@ -197,6 +197,13 @@ int bf_prep_weights(const BfPrepJob* jobs_dev, int njobs, size_t max_total, cuda
 int split_planes(const TView& x, const ActPlanes& pl, cudaStream_t st);
 int conv_bf(const ConvGemm& g, const ActPlanes& xp, const void* wh, const void* wl, const ActPlanes* yp, float* part,
             unsigned int* tickets, cudaStream_t st);
+// wgrad_bf.cu: weight + bias gradient on the same planes (MN-major UMMA operands, no transposes)
+bool wgrad_bf_supported(const ConvWgrad& q);
+size_t wgrad_bf_workspace_floats(int kh, int kw, int ci, int co);
+int wgrad_bf_init();
+int wgrad_bf(const ConvWgrad& q, const ActPlanes& xp, const ActPlanes& dp, cudaStream_t st);
+size_t wgrad_bf_oneshot_scratch_bytes(const ConvWgrad& q);
+int wgrad_bf_oneshot(const ConvWgrad& q, void* scratch, size_t scratch_bytes, cudaStream_t st);
 size_t conv_bf_oneshot_scratch_bytes(const ConvGemm& g);
 int conv_bf_oneshot(const ConvGemm& g, int wmat_is_mk, void* scratch, size_t scratch_bytes, cudaStream_t st);
 }  // namespace ms

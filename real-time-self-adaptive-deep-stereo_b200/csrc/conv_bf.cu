@@ -380,15 +380,15 @@ static EncodeTiledFn bf_get_encode() {
     return fn;
 }
 struct BfMapKey {
-    uintptr_t addr; int rank; uint64_t d[4]; uint64_t s[3]; uint32_t b[4]; uint32_t es[4];
+    uintptr_t addr; int rank; int swz; uint64_t d[4]; uint64_t s[3]; uint32_t b[4]; uint32_t es[4];
     bool operator<(const BfMapKey& o) const { return memcmp(this, &o, sizeof(BfMapKey)) < 0; }
 };
-static int bf_get_map(const CUtensorMap** out, void* addr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                      const cuuint32_t* box, const cuuint32_t* estr) {
+int bf_get_map(const CUtensorMap** out, void* addr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+               const cuuint32_t* box, const cuuint32_t* estr, int swizzle_bytes) {
     static std::map<BfMapKey, CUtensorMap> cache;
     BfMapKey k;
     memset(&k, 0, sizeof k);
-    k.addr = reinterpret_cast<uintptr_t>(addr); k.rank = rank;
+    k.addr = reinterpret_cast<uintptr_t>(addr); k.rank = rank; k.swz = swizzle_bytes;
     for (int i = 0; i < rank; ++i) { k.d[i] = dims[i]; k.b[i] = box[i]; k.es[i] = estr[i]; }
     for (int i = 0; i + 1 < rank; ++i) k.s[i] = strides_bytes[i];
     auto it = cache.find(k);
@@ -397,7 +397,8 @@ static int bf_get_map(const CUtensorMap** out, void* addr, int rank, const cuuin
         MS_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
         CUtensorMap m;
         CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, addr, dims, strides_bytes, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (bf16) failed with code " + std::to_string((int)r)); return -1; }
         if (cache.size() >= 8192) {

@@ -45,17 +45,19 @@ Engine::Engine()
     { const char* e4 = getenv("MS_CONV_IMPL"); conv_impl = (e4 && (!strcmp(e4, "tf32") || !strcmp(e4, "0"))) ? 0 : 1; }
     if (!use_tc) conv_impl = 0;
     { const char* e5 = getenv("MS_HEADS"); use_heads = (e5 && e5[0] == '0') ? 0 : 1; }
+    { const char* e6 = getenv("MS_BF_WGRAD"); use_bf_wgrad = (e6 && e6[0] == '0') ? 0 : 1; }
     bf_jobs_dev = nullptr; bf_max_total = 0; bf_part = nullptr; bf_tickets = nullptr;
 }
 
 void Engine::add_planes(Bump& A, const TView& v) {
-    if (conv_impl != 1 || planes.count(v.p)) return;
+    if (conv_impl != 1) return;
+    if (v.p && planes.count(v.p)) return;          // (sizing pass: every pointer is null -- never dedupe there)
     ActPlanes pl;
     pl.cs = (v.c + 7) / 8 * 8;
     const size_t floats = (v.pixels() * pl.cs + 1) / 2;     // bf16 elements -> floats
     pl.hi = A.alloc(floats);
     pl.lo = A.alloc(floats);
-    planes[v.p] = pl;
+    if (v.p) planes[v.p] = pl;
 }
 const ActPlanes* Engine::planes_of(const TView& v) const {
     auto it = planes.find(v.p);
@@ -185,6 +187,8 @@ size_t Engine::layout(float* base) {
         if (L.stride == 1 && L.cout <= 192)   // tcgen05 wgrad: NCHW copy of dY + <=64 split partials + bias partials
             max_wg = std::max(max_wg, pixels * L.cout + 64 * (size_t)L.kh * L.kw * L.cin * L.cout + 128 * (size_t)L.cout + 8192);
         max_wt = std::max(max_wt, (size_t)L.kh * L.kw * L.cin * L.cout);
+        if (conv_impl == 1 && !L.transposed && L.cin >= 16 && L.cout >= 16)
+            max_wg = std::max(max_wg, std::min<size_t>(wgrad_bf_workspace_floats(L.kh, L.kw, L.cin, L.cout), (size_t)48 << 20));
     };
     if (net == 1) {
         layout_dispnet(A, max_wg, max_wt);
@@ -383,7 +387,16 @@ int Engine::conv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, cons
         q.kh = L.kh; q.kw = L.kw; q.stride = L.stride; q.dil = L.dil; q.pad_t = pt; q.pad_l = pl;
         q.workspace = wg_ws; q.workspace_floats = wg_ws_floats; q.accumulate = 0;
         prof_begin(CAT_CONV_WGRAD, st);
-        int rc = (use_tc && use_tc_wgrad && wgrad_tc_supported(q)) ? wgrad_tc(q, st) : conv_wgrad(q, st);
+        int rc;
+        const ActPlanes* wxp = (conv_impl == 1 && use_bf_wgrad && wgrad_bf_supported(q)) ? planes_of(x) : nullptr;
+        const ActPlanes* wdp = wxp ? planes_of(dpre) : nullptr;
+        if (wxp && wdp) {
+            rc = ensure_planes(x, st);
+            if (!rc) rc = ensure_planes(dpre, st);
+            if (!rc) rc = wgrad_bf(q, *wxp, *wdp, st);
+        } else {
+            rc = (use_tc && use_tc_wgrad && wgrad_tc_supported(q)) ? wgrad_tc(q, st) : conv_wgrad(q, st);
+        }
         prof_end(st);
         if (profiling) cat_macs[CAT_CONV_WGRAD] += (double)dpre.pixels() * L.kh * L.kw * L.cin * L.cout;
         if (rc) return -1;
@@ -741,7 +754,7 @@ int Engine::run(int mode, int group, int disp_mask, int with_update, float lr, f
     key.lr = lr; key.mu = mu; key.gs = gscale;
     auto it = graphs.find(key);
     if (it == graphs.end()) {
-        if (conv_tc_init() || conv_bf_init() || corr_init() || wgrad_tc_init()) return -1;
+        if (conv_tc_init() || conv_bf_init() || wgrad_bf_init() || corr_init() || wgrad_tc_init()) return -1;
         cudaGraph_t graph = nullptr;
         const long long l0 = launch_count();
         MS_CHECK_CUDA(cudaStreamBeginCapture(gstream, cudaStreamCaptureModeThreadLocal));

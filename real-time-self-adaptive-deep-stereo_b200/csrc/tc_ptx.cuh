@@ -118,4 +118,8 @@ __device__ __forceinline__ float tf32_rna(float x) {
 int tc_get_map(const CUtensorMap** out, void* addr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                const cuuint32_t* box, bool swizzle128);
 
+// cached cuTensorMapEncodeTiled for bf16 planes (zero OOB fill, element strides); swizzle_bytes 64 or 128.  (conv_bf.cu)
+int bf_get_map(const CUtensorMap** out, void* addr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+               const cuuint32_t* box, const cuuint32_t* estr, int swizzle_bytes = 64);
+
 }  // namespace ms

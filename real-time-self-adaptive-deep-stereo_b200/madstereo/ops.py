@@ -130,6 +130,20 @@ def conv2d_dgrad_bf(dy, w, in_hw=None, stride=1, dilation=1):
     return dx
 
 
+def conv2d_wgrad_bf(x, dy, kh, kw, stride=1, dilation=1):
+    """split-bf16 tcgen05 weight + bias gradient (csrc/wgrad_bf.cu), stride 1 or 2."""
+    n, h, wd, cin = x.shape
+    _, oh, ow, cout = dy.shape
+    dw = torch.empty(kh, kw, cin, cout, device=x.device, dtype=torch.float32)
+    db = torch.empty(cout, device=x.device, dtype=torch.float32)
+    ns = lib().ms_conv2d_wgrad_bf_scratch(n, h, wd, oh, ow, kh, kw, cin, cout)
+    scratch = torch.empty(ns + 256, device=x.device, dtype=torch.uint8)
+    off = (-scratch.data_ptr()) % 256
+    check(lib().ms_conv2d_wgrad_bf(_p(x), n, h, wd, cin, cin, _p(dy), oh, ow, cout, cout, _p(dw), _p(db), kh, kw, stride,
+                                   dilation, c_void_p(scratch.data_ptr() + off), ns, _s()), 'ms_conv2d_wgrad_bf')
+    return dw, db
+
+
 def conv2d_dgrad(dy, w, in_hw, stride=1, dilation=1):
     n, oh, ow, cout = dy.shape
     kh, kw, cin, _ = w.shape

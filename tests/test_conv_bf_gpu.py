@@ -76,3 +76,31 @@ def test_conv_bf_dgrad(case):
     dx = ops.conv2d_dgrad_bf(cu(g), cu(wt), (h, w), stride, dil)
     torch.cuda.synchronize()
     assert rel_linf(dx.cpu().numpy(), gx.numpy()) < TOL
+
+
+WGRAD_CASES = [c for c in CASES if c[3] >= 16 and c[4] >= 16 and c[4] % 4 == 0] + [
+    (1, 6, 20, 197, 128, 3, 1, 1, 0.2),         # estimator-6 disp-1: two ci blocks, odd channel count
+    (2, 6, 20, 192, 192, 3, 1, 1, 0.2),         # pyramid conv12 (both towers): two co blocks
+    (1, 96, 320, 33, 128, 3, 1, 1, 0.2),        # context-1
+    (1, 96, 320, 128, 128, 3, 1, 2, 0.2),       # context-2 (dilation 2: shared halo patch)
+    (1, 96, 320, 128, 96, 3, 1, 8, 0.2),        # context-4 (dilation 8: one box per tap)
+]
+
+
+@pytest.mark.parametrize('case', WGRAD_CASES)
+def test_wgrad_bf(case):
+    """dW, db of csrc/wgrad_bf.cu (MN-major UMMA operands straight from the NHWC planes) vs autograd over the oracle conv."""
+    from madstereo import ops
+    from oracle import tf1_ops as T
+    n, h, w, cin, cout, k, stride, dil, alpha = case
+    rng = np.random.default_rng(sum(case[:8]) + 2)
+    x = rng.standard_normal((n, h, w, cin)).astype(np.float32)
+    wt = torch.tensor((rng.standard_normal((k, k, cin, cout)) / np.sqrt(k * k * cin)).astype(np.float32), requires_grad=True)
+    b = torch.zeros(cout, requires_grad=True)
+    pre = T.conv2d(torch.tensor(x), wt, b, stride=stride, dilation=dil, alpha=None)
+    g = rng.standard_normal(pre.shape).astype(np.float32)
+    gw, gb = torch.autograd.grad(pre, (wt, b), grad_outputs=torch.tensor(g))
+    dw, db = ops.conv2d_wgrad_bf(cu(x), cu(g), k, k, stride, dil)
+    torch.cuda.synchronize()
+    assert rel_linf(dw.cpu().numpy(), gw.numpy()) < TOL
+    assert rel_linf(db.cpu().numpy(), gb.numpy()) < TOL
