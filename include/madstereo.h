@@ -172,8 +172,17 @@ int ms_engine_update(void* e, int group /* -1 = all */, float lr, float mu, floa
 /* One whole frame = what a single sess.run(tf_fetches) executes (Stereo_Online_Adaptation.py:194-208):
  * forward, full-res loss (slot 0), and for mode 1/2 the train op (module loss in slot 1, backward,
  * momentum update if with_update).  After the first call per (mode, group, ...) the sequence is replayed as
- * ONE CUDA graph launch.  with_update=0 leaves the gradients in the arena for a data-parallel all-reduce
- * followed by ms_engine_update. */
+ * ONE CUDA graph launch.  with_update=0 leaves the gradients in the arena for an external all-reduce
+ * followed by ms_engine_update; with_update=2 (after ms_engine_dp_connect) appends the data-parallel exchange to the
+ * same graph: one kernel all-reduces the module's gradient range + the loss scalars over NVLink peer memory and
+ * applies the momentum update with the 1/N mean folded in (csrc/dp.cu). */
+/* Data parallel (new functionality; the reference is single-GPU): one process per GPU.  dp_create allocates
+ * this rank's exchange buffer + flag block and returns their two 64-byte CUDA IPC handles; the caller all-gathers the
+ * 128 bytes of every rank (any transport) and passes world x 128 bytes to dp_connect.  dp_error: 0 ok, 1 peer
+ * timeout, 2 ranks disagreed on the module being adapted. */
+int ms_engine_dp_create(void* e, int rank, int world, unsigned char* handles_out128);
+int ms_engine_dp_connect(void* e, const unsigned char* all_handles);
+int ms_engine_dp_error(void* e, unsigned int* out);
 int ms_engine_run(void* e, int mode, int group, int disp_mask, int with_update, float lr, float mu,
                   float grad_scale, void* stream);
 /* Tell the engine that the weight arena was written from outside (checkpoint load / divergence reset). */

@@ -409,6 +409,11 @@ int ms_engine_backward(void* h, int mode, int group, void* stream) {
 int ms_engine_update(void* h, int group, float lr, float mu, float grad_scale, void* stream) {
     return static_cast<Engine*>(h)->update(group, lr, mu, grad_scale, S(stream));
 }
+int ms_engine_dp_create(void* h, int rank, int world, unsigned char* handles_out128) {
+    return static_cast<Engine*>(h)->dp_create(rank, world, handles_out128);
+}
+int ms_engine_dp_connect(void* h, const unsigned char* all_handles) { return static_cast<Engine*>(h)->dp_connect(all_handles); }
+int ms_engine_dp_error(void* h, unsigned int* out) { return static_cast<Engine*>(h)->dp_error(out); }
 int ms_engine_run(void* h, int mode, int group, int disp_mask, int with_update, float lr, float mu, float grad_scale,
                   void* stream) {
     return static_cast<Engine*>(h)->run(mode, group, disp_mask, with_update, lr, mu, grad_scale, S(stream));

@@ -47,6 +47,7 @@ Engine::Engine()
     { const char* e5 = getenv("MS_HEADS"); use_heads = (e5 && e5[0] == '0') ? 0 : 1; }
     { const char* e6 = getenv("MS_BF_WGRAD"); use_bf_wgrad = (e6 && e6[0] == '0') ? 0 : 1; }
     bf_jobs_dev = nullptr; bf_max_total = 0; bf_part = nullptr; bf_tickets = nullptr;
+    dp_rank = 0; dp_world = 1; dp_connected = false; dp_xbuf = nullptr; dp_state = nullptr; dp_cap_floats = 0;
 }
 
 void Engine::add_planes(Bump& A, const TView& v) {
@@ -727,10 +728,12 @@ int Engine::run_eager(int mode, int group, int disp_mask, int with_update, float
     if (mode == 1) {
         if (loss(group, 1, 1, 1.f, st)) return -1;
         if (backward(1, group, st)) return -1;
-        if (with_update && update(group, lr, mu, gscale, st)) return -1;
+        if (with_update == 1 && update(group, lr, mu, gscale, st)) return -1;
+        if (with_update == 2 && dp_update(group, lr, mu, st)) return -1;       // all-reduce over peer memory + update
     } else if (mode == 2) {
         if (backward(2, 0, st)) return -1;
-        if (with_update && update(-1, lr, mu, gscale, st)) return -1;
+        if (with_update == 1 && update(-1, lr, mu, gscale, st)) return -1;
+        if (with_update == 2 && dp_update(-1, lr, mu, st)) return -1;
     }
     return 0;
 }

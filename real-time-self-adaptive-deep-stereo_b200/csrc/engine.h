@@ -23,6 +23,13 @@ struct ConvLayer {
     int group;            // MAD module index or -1
 };
 
+constexpr int DP_MAX_WORLD = 8;
+struct DpState {               // device-resident exchange state of one rank (IPC-mapped into every peer), csrc/dp.cu
+    unsigned int ready[DP_MAX_WORLD];   // ready[src] = (epoch << 8) | module tag, written by rank src
+    unsigned int done[DP_MAX_WORLD];    // done[src]  = last epoch rank src finished reading this rank's buffer
+    unsigned int epoch, blocks_done, error, pad;
+};
+
 struct Bump {            // workspace bump allocator (sizes only when base == nullptr)
     float* base; size_t off;
     float* alloc(size_t n) { float* p = base ? base + off : nullptr; off += (n + 63) / 64 * 64; return p; }
@@ -95,6 +102,14 @@ struct Engine {
     void add_planes(Bump& A, const TView& v);
     const ActPlanes* planes_of(const TView& v) const;
     int ensure_planes(const TView& v, cudaStream_t st);
+    // ---- data-parallel exchange over NVLink peer memory (csrc/dp.cu)
+    int dp_rank, dp_world; bool dp_connected;
+    float* dp_xbuf; DpState* dp_state; size_t dp_cap_floats;
+    float* dp_peer_xbuf[DP_MAX_WORLD]; DpState* dp_peer_state[DP_MAX_WORLD];
+    int dp_create(int rank, int world, unsigned char* handles_out /* 128 bytes */);
+    int dp_connect(const unsigned char* all_handles /* world x 128 bytes */);
+    int dp_update(int group, float lr, float mu, cudaStream_t st);
+    int dp_error(unsigned int* out);
     float* wg_ws; size_t wg_ws_floats;
     float* rs_tmp; size_t rs_tmp_floats;
     float* loss_ws; size_t loss_ws_floats;

@@ -65,6 +65,9 @@ _SIGS = {
     'ms_engine_bind': (I, [P, P, P, P, P, Z, P]),
     'ms_engine_set_input': (I, [P, P, P, P]),
     'ms_engine_set_gt': (I, [P, P, P]),
+    'ms_engine_dp_create': (I, [P, I, I, P]),
+    'ms_engine_dp_connect': (I, [P, P]),
+    'ms_engine_dp_error': (I, [P, P]),
     'ms_engine_forward': (I, [P, I, P]),
     'ms_engine_loss': (I, [P, I, I, I, F, P]),
     'ms_engine_backward': (I, [P, I, I, P]),

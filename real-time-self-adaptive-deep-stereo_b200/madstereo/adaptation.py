@@ -6,10 +6,15 @@ every variable on the full-resolution loss (:126-128); one momentum slot per var
 Per frame: sample blocks (:181-189) -> one engine step (forward, full-res loss, selected train ops) ->
 reward recurrence (:211-224) -> divergence reset (:242-244).
 
-Data parallel (new functionality): one process per GPU; the adapted module's gradient range and
-the scalar loss are summed with one NCCL all-reduce each and the 1/N is folded into the momentum kernel, so
-N ranks with one frame each equal the reference graph at batch N (every loss is a mean over the batch).
+Data parallel (new functionality): one process per GPU.  The adapted module's gradient range and the
+loss scalars are exchanged by ONE kernel inside the step's CUDA graph: it all-reduces over NVLink peer memory and
+applies the momentum update with the 1/N mean folded in (csrc/dp.cu), so N ranks with one frame each equal the
+reference graph at batch N (every loss is a mean over the batch).  Every rank draws the module from an identically
+seeded private RNG stream and sees the same all-reduced loss, so no per-step broadcast is needed; the exchange
+kernel cross-checks the module id.  If peer mapping is unavailable the torch.distributed all-reduce path remains.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -64,6 +69,37 @@ class OnlineAdaptation(object):
         self._snapshot = None
         self._stage = None          # device staging buffers + side stream for prefetch()
         self._staged_for = None
+        self.dp_peer = False
+        self._dp_rng_state = None
+        if self.world > 1 and hasattr(self.engine, 'dp_setup') and os.environ.get('MS_DP_IMPL', 'peer') == 'peer':
+            self._dp_peer_setup()
+
+    def _dp_peer_setup(self):
+        ok = 1
+        try:
+            self.engine.dp_setup(self.rank, self.world, self.pg)
+        except Exception as ex:                       # e.g. CUDA IPC not permitted in this container
+            print('WARNING: peer-memory gradient exchange unavailable (%r); using torch.distributed all-reduce' % (ex,))
+            ok = 0
+        t = torch.tensor([ok], dtype=torch.int32, device=self.engine.device)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN, group=self.pg)
+        self.dp_peer = bool(int(t.item()))
+        if self.dp_peer:
+            # a private, identically seeded RNG stream for the module sampler on every rank
+            seed = torch.tensor([int(np.random.randint(0, 2 ** 31 - 1))], dtype=torch.int64, device=self.engine.device)
+            torch.distributed.broadcast(seed, 0, group=self.pg)
+            self._dp_rng_state = np.random.RandomState(int(seed.item())).get_state()
+
+    def _sample_blocks(self, distribution):
+        if self._dp_rng_state is None:
+            return [int(b) for b in self.sampler.sample(distribution)]
+        outer = np.random.get_state()
+        np.random.set_state(self._dp_rng_state)
+        try:
+            return [int(b) for b in self.sampler.sample(distribution)]
+        finally:
+            self._dp_rng_state = np.random.get_state()
+            np.random.set_state(outer)
 
     # ---- weights -----------------------------------------------------------------------------------
     def load_weights(self, params, strict=True):
@@ -133,7 +169,9 @@ class OnlineAdaptation(object):
         step = self.step_count
         if self.mode == 'MAD' and step % self.sample_frequency == 0:
             distribution = softmax(self.sample_distribution)
-            if self.world > 1:
+            if self.dp_peer:
+                blocks = self._sample_blocks(distribution)
+            elif self.world > 1:
                 blocks = [int(b) for b in self.sampler.sample(distribution)] if self.rank == 0 else [0] * len(
                     self.blocks_to_train or [0] * self.sampler._blocks_to_fetch)
                 t = torch.tensor(blocks, dtype=torch.int32, device=eng.device)
@@ -156,8 +194,9 @@ class OnlineAdaptation(object):
         if self.mode == 'NONE':
             eng.run(MODE_NONE, 0, mask, False)
         elif self.mode == 'FULL':
-            eng.run(MODE_FULL, 0, mask, solo, self.lr, self.mu, gscale)
-            if not solo:
+            fused = self.dp_peer
+            eng.run(MODE_FULL, 0, mask, 2 if fused else (1 if solo else 0), self.lr, self.mu, gscale)
+            if not solo and not fused:
                 self._allreduce(eng.grads)
                 eng.update(-1, self.lr, self.mu, gscale)
         else:
@@ -166,7 +205,10 @@ class OnlineAdaptation(object):
                     bm = mask
                     for other in self.blocks_to_train[1:]:
                         bm |= 1 << other
-                    eng.run(MODE_MAD, b, bm, solo, self.lr, self.mu, gscale)
+                    fused = self.dp_peer and len(self.blocks_to_train) == 1
+                    eng.run(MODE_MAD, b, bm, 2 if fused else (1 if solo else 0), self.lr, self.mu, gscale)
+                    if fused:
+                        break
                 else:      # further train ops of the same sess.run: same forward, disjoint variables
                     eng.loss(b, True, 1)
                     eng.backward(MODE_MAD, b)
@@ -179,7 +221,12 @@ class OnlineAdaptation(object):
             eng.metrics()
         sc = eng.read_scalars()
         new_loss = sc[0]
-        if self.world > 1:
+        fused_loss = self.dp_peer and (self.mode == 'FULL' or (self.mode == 'MAD' and len(self.blocks_to_train) == 1))
+        if fused_loss:                  # the exchange kernel already wrote the mean over the ranks
+            if new_loss != new_loss:
+                raise MadStereoError('data-parallel exchange failed (code %d: 1 = peer timeout, 2 = ranks adapt '
+                                     'different modules)' % eng.dp_error())
+        elif self.world > 1:
             t = torch.tensor([new_loss], dtype=torch.float64, device=eng.device)
             self._allreduce(t)
             new_loss = float(t.item()) / self.world

@@ -167,8 +167,28 @@ class StereoEngine:
     def run(self, mode, group=0, disp_mask=0, with_update=True, lr=1e-4, mu=0.9, grad_scale=1.0):
         """One whole frame (forward, full-res loss, train op) — replayed as a single CUDA graph."""
         with torch.cuda.device(self.device):
-            check(self._lib.ms_engine_run(self._h, mode, group, disp_mask, 1 if with_update else 0, lr, mu, grad_scale,
+            check(self._lib.ms_engine_run(self._h, mode, group, disp_mask, int(with_update), lr, mu, grad_scale,
                                           _stream()), 'run')
+
+    # ---- data parallel: gradient exchange over NVLink peer memory fused with the update (csrc/dp.cu) ----------
+    def dp_setup(self, rank, world, process_group=None):
+        """Allocate this rank's exchange buffer, all-gather the CUDA IPC handles through torch.distributed (plumbing
+        only) and map every peer.  Afterwards run(..., with_update=2) performs all-reduce + momentum update in-graph."""
+        import torch.distributed as dist
+        mine = (ctypes.c_ubyte * 128)()
+        with torch.cuda.device(self.device):
+            check(self._lib.ms_engine_dp_create(self._h, rank, world, mine), 'dp_create')
+        gathered = [None] * world
+        dist.all_gather_object(gathered, bytes(mine), group=process_group)
+        blob = (ctypes.c_ubyte * (128 * world)).from_buffer_copy(b''.join(gathered))
+        with torch.cuda.device(self.device):
+            check(self._lib.ms_engine_dp_connect(self._h, blob), 'dp_connect')
+        dist.barrier(group=process_group)
+
+    def dp_error(self):
+        out = ctypes.c_uint(0)
+        check(self._lib.ms_engine_dp_error(self._h, byref(out)), 'dp_error')
+        return int(out.value)
 
     def weights_changed(self):
         """Call after writing the weight arena from outside (checkpoint load / reset)."""

@@ -79,7 +79,36 @@ class FakeNet:
         return v.idx
 
 
-def _worker(rank, world, port, out):
+class FakePeerEngine(FakeEngine):
+    """The fused path: run(with_update=2) = backward + in-graph peer-memory all-reduce + update (csrc/dp.cu); here the
+    exchange is emulated with gloo so that the host logic around it (sampler stream, loss handling) runs on CPU."""
+
+    def dp_setup(self, rank, world, pg=None):
+        self.world = world
+
+    def dp_error(self):
+        return 0
+
+    def run(self, mode, group=0, disp_mask=0, with_update=True, lr=1e-4, mu=0.9, grad_scale=1.0):
+        assert int(with_update) == 2
+        lo, hi = self.group_ranges[group]
+        self.grads[lo:hi] = (self.rank + 1) * (group + 1) * torch.ones(hi - lo)
+        dist.all_reduce(self.grads[lo:hi])
+        self.momentum[lo:hi] = mu * self.momentum[lo:hi] + self.grads[lo:hi] / self.world
+        self.weights[lo:hi] -= lr * self.momentum[lo:hi]
+        self.calls.append(('update', group, 1.0 / self.world))
+        t = torch.tensor([0.1 * (self.rank + 1) + 0.01 * self.frame], dtype=torch.float64)
+        dist.all_reduce(t)
+        self._mean_loss = float(t) / self.world
+
+    def update(self, *a, **k):
+        raise AssertionError('fused path must not call update()')
+
+    def read_scalars(self):
+        return [self._mean_loss, 0.0, 0.0, 0.0]
+
+
+def _worker(rank, world, port, out, peer=False):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
@@ -88,6 +117,8 @@ def _worker(rank, world, port, out):
     from madstereo.adaptation import OnlineAdaptation
     np.random.seed(100 + rank)                        # different host RNG per rank: sampling must still agree
     net = FakeNet(rank)
+    if peer:
+        net.engine = FakePeerEngine(rank)
     ad = OnlineAdaptation(net, mode='MAD', train_config=[['g%d' % i] for i in range(5)], lr=0.5,
                           sample_mode='PROBABILITY', num_blocks=1, ssim_th=10.0)
     hist = []
@@ -100,11 +131,12 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_dp_two_ranks_gloo():
+@pytest.mark.parametrize('peer', [False, True])
+def test_dp_two_ranks_gloo(peer):
     s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, peer)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
