@@ -161,6 +161,9 @@ int ms_engine_bind(void* e, float* weights, float* grads, float* momentum, float
                    size_t workspace_floats, void* stream);
 /* left/right: [B,H,W,3] fp32 0..255, host (pinned recommended) or device pointers. */
 int ms_engine_set_input(void* e, const float* left, const float* right, void* stream);
+/* the same with uint8 frames [B,H,W,3] (host or device): what the reference's decode ops deliver before tf.cast
+ * (Data_utils/data_reader.py); converted to fp32 on the device. */
+int ms_engine_set_input_u8(void* e, const unsigned char* left, const unsigned char* right, void* stream);
 int ms_engine_set_gt(void* e, const float* gt, void* stream);
 /* disp_mask bit i => materialise get_disparities()[i] (MADNet: D6,D5,D4,D3,D2ctx,full). */
 int ms_engine_forward(void* e, int disp_mask, void* stream);
@@ -193,7 +196,12 @@ int ms_engine_metrics(void* e, void* stream);
 /* Profiling aid for bench.py (no reference counterpart): CUDA events around kernel groups on the launching
  * stream.  Categories: 0 conv fwd, 1 conv dgrad, 2 conv wgrad, 3 corr fwd, 4 corr bwd, 5 loss, 6 other.
  * Arrays have 7 entries: summed device ms, algorithmic MACs, algorithmic bytes, number of timed calls. */
+/* enable: 0 off; 1 eager steps with CUDA events between launches; 2 = the step still replays as ONE CUDA graph, with
+ * external event-record nodes around every kernel group inside the graph (per-kernel times under the same launch
+ * conditions as the timed replay; ms_engine_run then synchronises once per step to read them). */
 int ms_engine_profile(void* e, int enable);
+/* per layer and direction (0 fwd, 1 dgrad, 2 wgrad): accumulated milliseconds and call counts, arrays of 3 * num_layers */
+int ms_engine_profile_layers(void* e, double* ms3n, long long* calls3n);
 int ms_engine_profile_read(void* e, double* ms7, double* macs7, double* bytes7, long long* calls7);
 /* Kernels launched by this library in this process so far. */
 long long ms_launch_count(void);

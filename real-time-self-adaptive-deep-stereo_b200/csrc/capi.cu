@@ -393,6 +393,9 @@ int ms_engine_bind(void* h, float* weights, float* grads, float* momentum, float
 int ms_engine_set_input(void* h, const float* left, const float* right, void* stream) {
     return static_cast<Engine*>(h)->set_input(left, right, S(stream));
 }
+int ms_engine_set_input_u8(void* h, const unsigned char* left, const unsigned char* right, void* stream) {
+    return static_cast<Engine*>(h)->set_input_u8(left, right, S(stream));
+}
 int ms_engine_set_gt(void* h, const float* gt, void* stream) {
     Engine* e = static_cast<Engine*>(h);
     if (!e->bound) { set_error("engine not bound"); return -2; }
@@ -436,7 +439,7 @@ int ms_engine_read_scalars(void* h, float* host4, void* stream) {
 }
 int ms_engine_profile(void* h, int enable) {
     Engine* e = static_cast<Engine*>(h);
-    e->profiling = enable != 0;
+    e->profiling = enable < 0 ? 0 : (enable > 2 ? 2 : enable);     // 1 = eager events, 2 = event nodes inside the replayed graph
     if (enable) e->prof_reset();
     return 0;
 }
@@ -449,6 +452,17 @@ int ms_engine_profile_read(void* h, double* ms7, double* macs7, double* bytes7, 
         if (bytes7) bytes7[i] = e->cat_bytes[i];
         if (calls7) calls7[i] = e->cat_calls[i];
     }
+    return 0;
+}
+int ms_engine_profile_layers(void* h, double* ms3n, long long* calls3n) {
+    Engine* e = static_cast<Engine*>(h);
+    if (e->prof_collect()) return -1;
+    const size_t n = e->layers.size();
+    for (int d = 0; d < 3; ++d)
+        for (size_t i = 0; i < n; ++i) {
+            ms3n[d * n + i] = i < e->layer_ms[d].size() ? e->layer_ms[d][i] : 0.0;
+            calls3n[d * n + i] = i < e->layer_calls[d].size() ? e->layer_calls[d][i] : 0;
+        }
     return 0;
 }
 long long ms_launch_count(void) { return ms::launch_count(); }

@@ -133,6 +133,7 @@ int leaky_bwd(float* g, int gcs, const float* act, int acs, size_t pixels, int c
 int add_channels(float* dst, int dcs, const float* src, int scs, size_t pixels, int c, float scale,
                  int accumulate, cudaStream_t st);
 int fill(float* p, size_t n, float v, cudaStream_t st);
+int u8_to_f32(const unsigned char* src, float* dst, size_t n, cudaStream_t st);
 
 // loss (loss.cu)
 struct ReprojLoss {

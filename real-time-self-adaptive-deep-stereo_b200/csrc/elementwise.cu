@@ -6,6 +6,7 @@
 //                        relu / x20 / x(-20) scalings of MadNet._make_disp fused in
 //   resize_bilinear_bwd  its transpose (what tf.gradients builds), separable two-pass gather => deterministic
 //   leaky_bwd            gradient of tf.maximum(alpha*x, x)      (Nets/MadNet.py:366-367)
+#include <algorithm>
 #include "common.cuh"
 
 namespace ms {
@@ -222,6 +223,21 @@ int fill(float* p, size_t n, float v, cudaStream_t st) {
     if (n == 0) return 0;
     fill_kernel<<<(unsigned)cdivz(n, 256), 256, 0, st>>>(p, n, v);
     return check_launch("fill");
+}
+
+// uint8 image -> fp32 (what tf.image.decode_* + tf.cast do in the reference input pipeline, Data_utils/data_reader.py)
+__global__ void u8_to_f32_kernel(const uchar4* __restrict__ src, float4* __restrict__ dst, size_t n4) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const uchar4 v = src[i];
+        dst[i] = make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w);
+    }
+}
+int u8_to_f32(const unsigned char* src, float* dst, size_t n, cudaStream_t st) {
+    MS_REQUIRE((n & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0, "u8_to_f32: size / alignment");
+    const size_t n4 = n / 4;
+    u8_to_f32_kernel<<<(unsigned)std::min<size_t>(cdivz(n4, 256), 148 * 8), 256, 0, st>>>(reinterpret_cast<const uchar4*>(src),
+                                                                                       reinterpret_cast<float4*>(dst), n4);
+    return check_launch("u8_to_f32");
 }
 
 }  // namespace ms

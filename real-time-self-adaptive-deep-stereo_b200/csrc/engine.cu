@@ -34,7 +34,7 @@ Engine::Engine()
     : net(0), B(1), H(0), W(0), Hp(0), Wp(0), radius_d(2), corr_stride(1), warping(1), n_groups(0), n_params(0),
       Wt(nullptr), Gr(nullptr), Mo(nullptr), ws(nullptr), ws_floats(0), bound(false), wT(nullptr), wT_floats(0),
       wg_ws(nullptr), wg_ws_floats(0), rs_tmp(nullptr), rs_tmp_floats(0), loss_ws(nullptr), loss_ws_floats(0),
-      scalars(nullptr), gt(nullptr), profiling(false) {
+      scalars(nullptr), gt(nullptr), profiling(0), prof_capturing(false) {
     prof_reset();
     prep_jobs_dev = nullptr; prep_max_total = 0; weights_dirty = true;
     gstream = nullptr; ev_in = nullptr; ev_out = nullptr;
@@ -76,32 +76,44 @@ int Engine::ensure_planes(const TView& v, cudaStream_t st) {
 
 void Engine::prof_reset() {
     for (int i = 0; i < N_CAT; ++i) { cat_ms[i] = 0; cat_macs[i] = 0; cat_bytes[i] = 0; cat_calls[i] = 0; }
+    for (int d = 0; d < 3; ++d) { layer_ms[d].assign(layers.size(), 0.0); layer_calls[d].assign(layers.size(), 0); }
 }
-void Engine::prof_begin(int cat, cudaStream_t st) {
-    if (!profiling) return;
-    Span s; s.cat = cat;
+void Engine::prof_begin(int cat, cudaStream_t st, int layer) {
+    if (!profiling || (profiling == 2 && !prof_capturing)) return;
+    Span s; s.cat = cat; s.layer = layer; s.macs = 0; s.bytes = 0;
     for (cudaEvent_t* e : {&s.a, &s.b}) {
         if (!event_pool.empty()) { *e = event_pool.back(); event_pool.pop_back(); }
         else cudaEventCreate(e);
     }
-    cudaEventRecord(s.a, st);
+    // inside a stream capture the record becomes an EXTERNAL event node: it fires at every replay of the graph
+    if (prof_capturing) cudaEventRecordWithFlags(s.a, st, cudaEventRecordExternal);
+    else cudaEventRecord(s.a, st);
     spans.push_back(s);
 }
 void Engine::prof_end(cudaStream_t st) {
-    if (!profiling || spans.empty()) return;
-    cudaEventRecord(spans.back().b, st);
+    if (!profiling || spans.empty() || (profiling == 2 && !prof_capturing)) return;
+    if (prof_capturing) cudaEventRecordWithFlags(spans.back().b, st, cudaEventRecordExternal);
+    else cudaEventRecord(spans.back().b, st);
 }
-int Engine::prof_collect() {
-    for (auto& s : spans) {
+void Engine::prof_note(double macs, double bytes) {
+    if (!profiling || spans.empty() || (profiling == 2 && !prof_capturing)) return;
+    spans.back().macs += macs; spans.back().bytes += bytes;
+}
+int Engine::prof_fold(std::vector<Span>& v, bool recycle) {
+    for (auto& s : v) {
         MS_CHECK_CUDA(cudaEventSynchronize(s.b));
         float ms = 0.f;
         MS_CHECK_CUDA(cudaEventElapsedTime(&ms, s.a, s.b));
-        cat_ms[s.cat] += ms; cat_calls[s.cat] += 1;
-        event_pool.push_back(s.a); event_pool.push_back(s.b);
+        cat_ms[s.cat] += ms; cat_calls[s.cat] += 1; cat_macs[s.cat] += s.macs; cat_bytes[s.cat] += s.bytes;
+        if (s.layer >= 0 && s.cat <= CAT_CONV_WGRAD && s.layer < (int)layer_ms[s.cat].size()) {
+            layer_ms[s.cat][s.layer] += ms; layer_calls[s.cat][s.layer] += 1;
+        }
+        if (recycle) { event_pool.push_back(s.a); event_pool.push_back(s.b); }
     }
-    spans.clear();
+    if (recycle) v.clear();
     return 0;
 }
+int Engine::prof_collect() { return prof_fold(spans, true); }
 
 int Engine::build_madnet() {
     layers.clear();
@@ -319,6 +331,7 @@ size_t Engine::layout(float* base) {
     rs_tmp_floats = (size_t)B * H * Wp; rs_tmp = alloc(rs_tmp_floats);
     loss_ws_floats = loss_workspace_floats(B, H, W); loss_ws = alloc(loss_ws_floats);
     scalars = alloc(64);
+    u8_stage = reinterpret_cast<unsigned char*>(alloc(((size_t)2 * B * H * W * 3 + 3) / 4 + 64));
     gt = alloc((size_t)B * H * W);
     return A.off;
 }
@@ -351,9 +364,9 @@ int Engine::conv_fwd(const ConvLayer& L, const TView& x, const TView& y, const f
         p.wmat = wT;
         p.mul = 1; p.off_y = pt; p.off_x = pl; p.step = -1; p.div = L.stride;
     }
-    prof_begin(CAT_CONV_FWD, st);
-    int rc;
     const int li = (int)(&L - &layers[0]);
+    prof_begin(CAT_CONV_FWD, st, li);
+    int rc;
     const ActPlanes* xpl = (conv_impl == 1 && bfw[0][li].ok && conv_bf_supported(p)) ? planes_of(x) : nullptr;
     if (use_heads && conv_head_kind(p) == 1) {
         fresh.erase(y.p);
@@ -369,7 +382,7 @@ int Engine::conv_fwd(const ConvLayer& L, const TView& x, const TView& y, const f
         else rc = conv_gemm(p, st);
     }
     prof_end(st);
-    if (profiling) cat_macs[CAT_CONV_FWD] += (double)y.pixels() * L.kh * L.kw * L.cin * L.cout / (L.transposed ? L.stride * L.stride : 1);
+    prof_note((double)y.pixels() * L.kh * L.kw * L.cin * L.cout / (L.transposed ? L.stride * L.stride : 1), 0);
     return rc;
 }
 
@@ -387,7 +400,7 @@ int Engine::conv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, cons
         q.x = x; q.dy = dpre; q.dw = Gr + L.w_off; q.db = Gr + L.b_off;
         q.kh = L.kh; q.kw = L.kw; q.stride = L.stride; q.dil = L.dil; q.pad_t = pt; q.pad_l = pl;
         q.workspace = wg_ws; q.workspace_floats = wg_ws_floats; q.accumulate = 0;
-        prof_begin(CAT_CONV_WGRAD, st);
+        prof_begin(CAT_CONV_WGRAD, st, (int)(&L - &layers[0]));
         int rc;
         const ActPlanes* wxp = (conv_impl == 1 && use_bf_wgrad && wgrad_bf_supported(q)) ? planes_of(x) : nullptr;
         const ActPlanes* wdp = wxp ? planes_of(dpre) : nullptr;
@@ -399,7 +412,7 @@ int Engine::conv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, cons
             rc = (use_tc && use_tc_wgrad && wgrad_tc_supported(q)) ? wgrad_tc(q, st) : conv_wgrad(q, st);
         }
         prof_end(st);
-        if (profiling) cat_macs[CAT_CONV_WGRAD] += (double)dpre.pixels() * L.kh * L.kw * L.cin * L.cout;
+        prof_note((double)dpre.pixels() * L.kh * L.kw * L.cin * L.cout, 0);
         if (rc) return -1;
     }
     if (dx) {
@@ -410,9 +423,9 @@ int Engine::conv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, cons
         p.mask = dx_mask ? dx_mask->p : nullptr; p.mask_cs = dx_mask ? dx_mask->cs : 0; p.mask_alpha = mask_alpha;
         p.res = nullptr; p.res_cs = 0; p.accumulate = dx_acc;
         p.part = tc_part; p.part_floats = conv_tc_part_floats();
-        prof_begin(CAT_CONV_DGRAD, st);
-        int rc;
         const int li = (int)(&L - &layers[0]);
+        prof_begin(CAT_CONV_DGRAD, st, li);
+        int rc;
         const ActPlanes* xpl = (conv_impl == 1 && bfw[1][li].ok && conv_bf_supported(p)) ? planes_of(dpre) : nullptr;
         if (use_heads && L.cout == 1 && (p.wmat = Wt + L.w_off, conv_head_kind(p) == 2)) {
             fresh.erase(dx->p);
@@ -434,7 +447,7 @@ int Engine::conv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, cons
             if (!rc) rc = conv_gemm(p, st);
         }
         prof_end(st);
-        if (profiling) cat_macs[CAT_CONV_DGRAD] += (double)dpre.pixels() * L.kh * L.kw * L.cin * L.cout;
+        prof_note((double)dpre.pixels() * L.kh * L.kw * L.cin * L.cout, 0);
         if (rc) return -1;
     }
     return 0;
@@ -456,6 +469,18 @@ int Engine::set_input(const float* left, const float* right, cudaStream_t st) {
     MS_CHECK_CUDA(cudaMemcpyAsync(rl.p, left, bytes, cudaMemcpyDefault, st));
     MS_CHECK_CUDA(cudaMemcpyAsync(rr.p, right, bytes, cudaMemcpyDefault, st));
     return 0;
+}
+
+// uint8 frames (host or device): 4x fewer bytes over PCIe than fp32; converted on the device
+int Engine::set_input_u8(const unsigned char* left, const unsigned char* right, cudaStream_t st) {
+    MS_REQUIRE(bound, "engine not bound");
+    TView rl = tensors["raw_left"], rr = tensors["raw_right"];
+    const size_t n = (size_t)B * H * W * 3;
+    MS_REQUIRE((n & 3) == 0, "set_input_u8: B*H*W*3 must be a multiple of 4");
+    MS_CHECK_CUDA(cudaMemcpyAsync(u8_stage, left, n, cudaMemcpyDefault, st));
+    MS_CHECK_CUDA(cudaMemcpyAsync(u8_stage + n, right, n, cudaMemcpyDefault, st));
+    if (u8_to_f32(u8_stage, rl.p, n, st)) return -1;
+    return u8_to_f32(u8_stage + n, rr.p, n, st);
 }
 
 int Engine::prep_layers(int group, cudaStream_t st) {
@@ -518,7 +543,7 @@ int Engine::forward(int disp_mask, cudaStream_t st) {
         prof_begin(CAT_CORR_FWD, st);
         int crc = corr_fwd(cf, st);
         prof_end(st);
-        if (profiling) cat_bytes[CAT_CORR_FWD] += (double)B * cf.h * cf.w * (2.0 * C + nd) * 4.0;
+        prof_note(0, (double)B * cf.h * cf.w * (3.0 * C + nd + (cf.u_chan ? 1 : 0) + (cf.out2 ? C : 0)) * 4.0);   // reads L, R(, u); writes corr + the left copy (fused concat)
         if (crc) return -1;
         TView xin = cost[k];
         for (int j = 1; j <= 6; ++j) {
@@ -634,7 +659,7 @@ int Engine::backward(int mode, int group, cudaStream_t st) {
         prof_begin(CAT_CORR_BWD, st);
         int crc = corr_bwd(cb, st);
         prof_end(st);
-        if (profiling) cat_bytes[CAT_CORR_BWD] += (double)B * cb.h * cb.w * (4.0 * C + nd) * 4.0;
+        prof_note(0, (double)B * cb.h * cb.w * (4.0 * C + nd) * 4.0);
         return crc;
     };
     // ---- pyramid: g_pyr[top] holds d(post-activation output of conv `top`), complete
@@ -741,7 +766,7 @@ int Engine::run_eager(int mode, int group, int disp_mask, int with_update, float
 int Engine::run(int mode, int group, int disp_mask, int with_update, float lr, float mu, float gscale, cudaStream_t st) {
     MS_REQUIRE(bound, "engine not bound");
     MS_REQUIRE(mode == 0 || mode == 2 || (mode == 1 && group >= 0 && group < n_groups), "run: bad mode/group");
-    if (!use_graphs || profiling) return run_eager(mode, group, disp_mask, with_update, lr, mu, gscale, st);
+    if (!use_graphs || profiling == 1) return run_eager(mode, group, disp_mask, with_update, lr, mu, gscale, st);
     if (weights_dirty) {                    // load / restore happened: refresh every tf32 copy outside the graph
         if (prep_layers(-1, st)) return -1;
         weights_dirty = false;
@@ -754,21 +779,25 @@ int Engine::run(int mode, int group, int disp_mask, int with_update, float lr, f
     GraphKey key;
     memset(&key, 0, sizeof key);
     key.mode = mode; key.group = mode == 1 ? group : 0; key.mask = disp_mask; key.with_update = with_update;
-    key.lr = lr; key.mu = mu; key.gs = gscale;
+    key.lr = lr; key.mu = mu; key.gs = gscale; key.prof = profiling == 2 ? 1 : 0;
     auto it = graphs.find(key);
     if (it == graphs.end()) {
         if (conv_tc_init() || conv_bf_init() || wgrad_bf_init() || corr_init() || wgrad_tc_init()) return -1;
         cudaGraph_t graph = nullptr;
         const long long l0 = launch_count();
+        if (profiling == 2) { if (prof_collect()) return -1; }
         MS_CHECK_CUDA(cudaStreamBeginCapture(gstream, cudaStreamCaptureModeThreadLocal));
+        prof_capturing = profiling == 2;
         int rc = run_eager(mode, group, disp_mask, with_update, lr, mu, gscale, gstream);
+        prof_capturing = false;
         cudaError_t ce = cudaStreamEndCapture(gstream, &graph);
-        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (rc) { if (graph) cudaGraphDestroy(graph); spans.clear(); return rc; }
         MS_CHECK_CUDA(ce);
         cudaGraphExec_t exec = nullptr;
         MS_CHECK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
         cudaGraphDestroy(graph);
-        GraphRec rec{exec, launch_count() - l0};
+        GraphRec rec{exec, launch_count() - l0, nullptr};
+        if (profiling == 2) { rec.spans = new std::vector<Span>(spans); spans.clear(); }
         add_launches(-rec.kernels);            // counted again at every replay below
         it = graphs.emplace(key, rec).first;
     }
@@ -779,6 +808,10 @@ int Engine::run(int mode, int group, int disp_mask, int with_update, float lr, f
     add_launches(it->second.kernels);
     MS_CHECK_CUDA(cudaEventRecord(ev_out, gstream));
     MS_CHECK_CUDA(cudaStreamWaitEvent(st, ev_out, 0));
+    if (profiling == 2 && it->second.spans) {        // in-graph timing: read the event nodes of THIS replay
+        MS_CHECK_CUDA(cudaStreamSynchronize(gstream));
+        if (prof_fold(*it->second.spans, false)) return -1;
+    }
     return 0;
 }
 

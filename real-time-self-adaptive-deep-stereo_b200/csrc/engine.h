@@ -78,9 +78,10 @@ struct Engine {
     bool weights_dirty;
     int prep_layers(int group, cudaStream_t st); // -1 = all
     // whole-step CUDA graphs keyed by (mode, group, disp_mask, with_update, lr, mu, gscale)
-    struct GraphKey { int mode, group, mask, with_update; float lr, mu, gs;
+    struct GraphKey { int mode, group, mask, with_update, prof; float lr, mu, gs;
                       bool operator<(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) < 0; } };
-    struct GraphRec { cudaGraphExec_t exec; long long kernels; };
+    struct Span;
+    struct GraphRec { cudaGraphExec_t exec; long long kernels; std::vector<Span>* spans; };
     std::map<GraphKey, GraphRec> graphs;
     int use_graphs;
     int use_tc_wgrad;                            // MS_TC_WGRAD (default 1)
@@ -113,18 +114,23 @@ struct Engine {
     float* wg_ws; size_t wg_ws_floats;
     float* rs_tmp; size_t rs_tmp_floats;
     float* loss_ws; size_t loss_ws_floats;
+    unsigned char* u8_stage;         // 2 x B*H*W*3 bytes: uint8 input staging (set_input_u8)
     float* scalars;                  // [0]=full loss, [1]=train loss, [2]=epe, [3]=bad3
     float* gt;                       // optional ground truth [B,H,W,1]
 
     // ---- profiling (off by default): CUDA events around kernel groups on the launching stream
     enum Cat { CAT_CONV_FWD = 0, CAT_CONV_DGRAD, CAT_CONV_WGRAD, CAT_CORR_FWD, CAT_CORR_BWD, CAT_LOSS, CAT_OTHER, N_CAT };
-    struct Span { int cat; cudaEvent_t a, b; };
-    bool profiling;
+    struct Span { int cat, layer; cudaEvent_t a, b; double macs, bytes; };
+    int profiling;                   // 0 off, 1 eager (events between launches), 2 in-graph (external event nodes inside the replayed graph)
+    bool prof_capturing;
     std::vector<Span> spans;
     std::vector<cudaEvent_t> event_pool;
     double cat_ms[N_CAT]; double cat_macs[N_CAT]; double cat_bytes[N_CAT]; long long cat_calls[N_CAT];
-    void prof_begin(int cat, cudaStream_t st);
+    void prof_begin(int cat, cudaStream_t st, int layer = -1);
     void prof_end(cudaStream_t st);
+    void prof_note(double macs, double bytes);   // work of the span just closed
+    int prof_fold(std::vector<Span>& v, bool recycle);
+    std::vector<double> layer_ms[3]; std::vector<long long> layer_calls[3];   // per layer: fwd / dgrad / wgrad
     int prof_collect();      // synchronises; folds spans into cat_ms
     void prof_reset();
 
@@ -143,6 +149,7 @@ struct Engine {
     int finalize_groups(const int* group_of_layer, int n_groups);
 
     int set_input(const float* left, const float* right, cudaStream_t st);
+    int set_input_u8(const unsigned char* left, const unsigned char* right, cudaStream_t st);
     int forward(int disp_mask, cudaStream_t st);
     int loss(int which, int with_grad, int slot, float grad_scale, cudaStream_t st);
     int backward(int mode, int group, cudaStream_t st);     // mode 1 = MAD(group), 2 = FULL

@@ -117,7 +117,7 @@ int Engine::forward_dispnet(int disp_mask, cudaStream_t st) {
         prof_begin(CAT_CORR_FWD, st);
         int rc = corr_fwd(cf, st);
         prof_end(st);
-        if (profiling) cat_bytes[CAT_CORR_FWD] += (double)B * cf.h * cf.w * (2.0 * 128 + nd) * 4.0;
+        prof_note(0, (double)B * cf.h * cf.w * (2.0 * 128 + nd) * 4.0);
         if (rc) return -1;
     }
     TView x = d_cat3;
@@ -169,7 +169,7 @@ int Engine::deconv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, co
         int rc = conv_wgrad(q, st);
         if (!rc) rc = bias_grad(dpre, Gr + L.b_off, wg_ws, wg_ws_floats, st);
         prof_end(st);
-        if (profiling) cat_macs[CAT_CONV_WGRAD] += (double)x.pixels() * L.kh * L.kw * L.cin * L.cout;
+        prof_note((double)x.pixels() * L.kh * L.kw * L.cin * L.cout, 0);
         if (rc) return -1;
     }
     if (dx) {
@@ -181,7 +181,7 @@ int Engine::deconv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, co
         prof_begin(CAT_CONV_DGRAD, st);
         int rc = conv_gemm(p, st);
         prof_end(st);
-        if (profiling) cat_macs[CAT_CONV_DGRAD] += (double)x.pixels() * L.kh * L.kw * L.cin * L.cout;
+        prof_note((double)x.pixels() * L.kh * L.kw * L.cin * L.cout, 0);
         if (rc) return -1;
     }
     return 0;
@@ -249,7 +249,7 @@ int Engine::backward_dispnet(cudaStream_t st) {
         prof_begin(CAT_CORR_BWD, st);
         int rc = corr_bwd(cb, st);
         prof_end(st);
-        if (profiling) cat_bytes[CAT_CORR_BWD] += (double)B * cb.h * cb.w * (4.0 * 128 + nd) * 4.0;
+        prof_note(0, (double)B * cb.h * cb.w * (4.0 * 128 + nd) * 4.0);
         if (rc) return -1;
         TView sl = skip_slice(3);                                                                   // up2 skip = conv2a
         if (add_channels(gc2a.p, gc2a.cs, sl.p, sl.cs, gc2a.pixels(), 128, 1.f, 1, st)) return -1;

@@ -64,6 +64,7 @@ _SIGS = {
     'ms_engine_group_range': (I, [P, I, POINTER(Z), POINTER(Z)]),
     'ms_engine_bind': (I, [P, P, P, P, P, Z, P]),
     'ms_engine_set_input': (I, [P, P, P, P]),
+    'ms_engine_set_input_u8': (I, [P, P, P, P]),
     'ms_engine_set_gt': (I, [P, P, P]),
     'ms_engine_dp_create': (I, [P, I, I, P]),
     'ms_engine_dp_connect': (I, [P, P]),
@@ -78,6 +79,7 @@ _SIGS = {
     'ms_engine_metrics': (I, [P, P]),
     'ms_engine_profile': (I, [P, I]),
     'ms_engine_profile_read': (I, [P, POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(ctypes.c_longlong)]),
+    'ms_engine_profile_layers': (I, [P, P, P]),
     'ms_launch_count': (ctypes.c_longlong, []),
     'ms_debug_tc_prof': (I, [POINTER(ctypes.c_ulonglong), I]),
     'ms_engine_num_tensors': (I, [P]),

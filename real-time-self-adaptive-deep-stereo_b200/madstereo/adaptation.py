@@ -135,14 +135,16 @@ class OnlineAdaptation(object):
         reference overlaps input decoding with sess.run through its tf.data pipeline, Data_utils/data_reader.py).
         The step() call that receives these same tensor objects then only does a device-to-device copy."""
         eng = self.engine
-        if self._stage is None:
+        u8 = eng._is_u8(left) and eng._is_u8(right)
+        dt = torch.uint8 if u8 else torch.float32
+        if self._stage is None or self._stage[0].dtype != dt:
             shape = (eng.B, eng.H, eng.W, 3)
-            self._stage = [torch.empty(shape, dtype=torch.float32, device=eng.device) for _ in range(2)]
+            self._stage = [torch.empty(shape, dtype=dt, device=eng.device) for _ in range(2)]
             self._copy_stream = torch.cuda.Stream(device=eng.device)
             self._stage_ready = torch.cuda.Event()
             self._stage_free = torch.cuda.Event()
             self._stage_free.record(torch.cuda.current_stream(eng.device))
-        l, r = eng._as_f32(left), eng._as_f32(right)
+        l, r = (eng._as_u8(left), eng._as_u8(right)) if u8 else (eng._as_f32(left), eng._as_f32(right))
         with torch.cuda.stream(self._copy_stream):
             self._copy_stream.wait_event(self._stage_free)      # the previous frame's staging -> input copy is done
             self._stage[0].copy_(l, non_blocking=True)

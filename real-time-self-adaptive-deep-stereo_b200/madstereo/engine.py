@@ -128,10 +128,29 @@ class StereoEngine:
     # ---- per-frame calls ---------------------------------------------------------------------
     def set_input(self, left, right):
         """left/right: [B,H,W,3] float32 torch tensors (CUDA, or pinned/pageable CPU) or numpy arrays."""
+        if self._is_u8(left) and self._is_u8(right):
+            l, r = self._as_u8(left), self._as_u8(right)
+            self._keep = [l, r]
+            with torch.cuda.device(self.device):
+                check(self._lib.ms_engine_set_input_u8(self._h, _ptr(l), _ptr(r), _stream()), 'set_input_u8')
+            return
         l, r = self._as_f32(left), self._as_f32(right)
         self._keep = [l, r]
         with torch.cuda.device(self.device):
             check(self._lib.ms_engine_set_input(self._h, _ptr(l), _ptr(r), _stream()), 'set_input')
+
+    @staticmethod
+    def _is_u8(x):
+        return (isinstance(x, np.ndarray) and x.dtype == np.uint8) or (torch.is_tensor(x) and x.dtype == torch.uint8)
+
+    def _as_u8(self, x, c=3):
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x))
+        if not x.is_contiguous():
+            x = x.contiguous()
+        if tuple(x.shape) != (self.B, self.H, self.W, c):
+            raise MadStereoError('input shape %s != %s' % (tuple(x.shape), (self.B, self.H, self.W, c)))
+        return x
 
     def set_gt(self, gt):
         g = self._as_f32(gt, 1)
@@ -208,7 +227,20 @@ class StereoEngine:
     CATEGORIES = ('conv_fwd', 'conv_dgrad', 'conv_wgrad', 'corr_fwd', 'corr_bwd', 'loss', 'other')
 
     def profile(self, enable):
-        check(self._lib.ms_engine_profile(self._h, 1 if enable else 0), 'profile')
+        """False/0 off; True/1 eager events; 2 = event nodes inside the replayed CUDA graph (in-graph kernel times)."""
+        check(self._lib.ms_engine_profile(self._h, int(enable)), 'profile')
+
+    def profile_layers(self):
+        n = len(self.layers)
+        ms = (ctypes.c_double * (3 * n))(); calls = (ctypes.c_longlong * (3 * n))()
+        with torch.cuda.device(self.device):
+            check(self._lib.ms_engine_profile_layers(self._h, ms, calls), 'profile_layers')
+        out = {}
+        for d, name in enumerate(('fwd', 'dgrad', 'wgrad')):
+            for i, l in enumerate(self.layers):
+                if calls[d * n + i]:
+                    out.setdefault(l.name, {})[name] = {'ms': ms[d * n + i], 'calls': calls[d * n + i]}
+        return out
 
     def profile_read(self):
         ms, macs, byts = ((ctypes.c_double * 7)() for _ in range(3))

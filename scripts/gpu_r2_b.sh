@@ -1,6 +1,7 @@
 #!/bin/bash
 # round-2 second visit: conv_bf + wgrad_bf op tests, full GPU suite on the split-bf16 engine, benches, ncu of the dominant layer
 mkdir -p gpurun_out
+make -C real-time-self-adaptive-deep-stereo_b200/csrc -j16 2>&1 | tail -1
 timeout -s KILL 900 python -m pytest tests/test_conv_bf_gpu.py -q --timeout 180 -x > gpurun_out/b_conv_bf.log 2>&1
 echo "conv_bf rc=$?" >> gpurun_out/b_conv_bf.log
 timeout -s KILL 300 python scripts/bf_bench.py > gpurun_out/b_bf_bench.log 2>&1
