@@ -40,6 +40,15 @@ def correlation(x, y, max_disp, stride=1, u=None):
     return out
 
 
+def correlation_into(x, y, max_disp, out, stride=1):
+    """correlation() into a pre-allocated [b,h,w,nd] tensor (no allocation inside a timed region)."""
+    b, h, w, c = x.shape
+    nd = (2 * max_disp) // stride + 1
+    check(lib().ms_corr_fwd(_p(x), c, _p(y), c, c_void_p(0), 1, _p(out), nd, b, h, w, c, max_disp, stride, 0, 0, _s()),
+          'ms_corr_fwd')
+    return out
+
+
 def cost_volume(x, y, max_disp, stride=1, u=None):
     """MadNet._stereo_cost_volume_correlation (+ warp, + u channel): concat([x, corr, u]) padded to 4 channels."""
     b, h, w, c = x.shape

@@ -102,6 +102,57 @@ def test_correlation_matches_reference_native_kernel(ops):
     assert rel_linf(mine.cpu().numpy(), out_nchw.permute(0, 2, 3, 1).cpu().numpy()) < 2e-5
 
 
+def test_correlation_speed_vs_reference_native_kernel(ops):
+    """the reference's own CorrelateData kernel (oracle/_ref, compiled unmodified for sm_100a) is "the kernel
+    to beat" on the same GPU.  Timed on pre-padded inputs, kernel only (its tf.pad / tf.transpose round trips are not
+    charged); ours on the unpadded NHWC tensors.  The table goes to gpurun_out/corr_vs_reference.json."""
+    import json
+    path = os.path.join(ROOT, 'oracle', '_ref', 'libref_shift_corr.so')
+    if not os.path.exists(path):
+        pytest.skip('oracle/_ref not built (reference sources absent at build time)')
+    ref = ctypes.CDLL(path)
+    ref.ref_shift_corr.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 5 + [ctypes.c_void_p]
+    shapes = {'madnet_L6_1280x384': (1, 6, 20, 192, 2), 'madnet_L5': (1, 12, 40, 128, 2), 'madnet_L4': (1, 24, 80, 96, 2),
+              'madnet_L3': (1, 48, 160, 64, 2), 'madnet_L2': (1, 96, 320, 32, 2), 'madnet_L2_1920x1088_B8': (8, 272, 480, 32, 2),
+              'dispnet_1280x384': (1, 96, 320, 128, 40)}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+
+    def timeit(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(7):
+            flush.zero_()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    rows = {}
+    for name, (b, h, w, c, d) in shapes.items():
+        x = torch.randn(b, h, w, c, device='cuda'); y = torch.randn(b, h, w, c, device='cuda')
+        xp = torch.nn.functional.pad(x, (0, 0, d, d)).contiguous(); yp = torch.nn.functional.pad(y, (0, 0, d, d)).contiguous()
+        out_nchw = torch.zeros(b, 2 * d + 1, h, w, device='cuda')
+        mine = torch.empty(b, h, w, 2 * d + 1, device='cuda')
+        # the reference launches on the legacy default stream: make torch's stream the default one for its timing
+        with torch.cuda.stream(torch.cuda.default_stream()):
+            t_ref = timeit(lambda: ref.ref_shift_corr(xp.data_ptr(), yp.data_ptr(), d, b, h, w + 2 * d, c, out_nchw.data_ptr()))
+        t_mine = timeit(lambda: ops.correlation_into(x, y, d, mine))
+        assert rel_linf(mine.cpu().numpy(), out_nchw.permute(0, 2, 3, 1).cpu().numpy()) < 2e-5
+        byts = b * h * w * (2 * c + 2 * d + 1) * 4
+        rows[name] = {'reference_us': t_ref, 'ours_us': t_mine, 'speedup': t_ref / t_mine, 'bytes': byts,
+                      'ours_gbs': byts / t_mine / 1e3, 'reference_gbs': byts / t_ref / 1e3}
+    try:
+        os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+        json.dump(rows, open(os.path.join(ROOT, 'gpurun_out', 'corr_vs_reference.json'), 'w'), indent=1)
+    except OSError:
+        pass
+    assert rows['madnet_L2_1920x1088_B8']['speedup'] > 1.0 and rows['dispnet_1280x384']['speedup'] > 1.0, rows
+
+
 CONV_CASES = [
     # n, h, w, cin, cout, k, stride, dil, alpha
     (2, 32, 64, 3, 16, 3, 2, 1, 0.2), (2, 16, 32, 16, 16, 3, 1, 1, 0.2), (1, 16, 32, 16, 32, 3, 2, 1, 0.2),
