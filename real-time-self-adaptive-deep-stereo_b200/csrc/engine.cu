@@ -4,6 +4,8 @@
 // warp -> correlation -> 6-conv estimator loop :251-351, context network :122-171, outputs :68-71,:362-364;
 // train-op structure Stereo_Online_Adaptation.py:87-128 (MAD: one module per step with gradients cut between
 // levels by `bulkhead`; FULL: everything, gradients also flow through the up-sampled disparities).
+#include <nvtx3/nvToolsExt.h>
+
 #include "engine.h"
 
 #include <algorithm>
@@ -748,15 +750,19 @@ int Engine::run_eager(int mode, int group, int disp_mask, int with_update, float
     const int full = n_disp - 1;
     int mask = disp_mask | (1 << full);
     if (mode == 1) mask |= 1 << group;
-    if (forward(mask, st)) return -1;
-    if (loss(full, mode == 2, 0, 1.f, st)) return -1;
+    // NVTX ranges (tracing): visible in nsys / ncu timelines, free when no tool is attached
+    struct Range { explicit Range(const char* n) { nvtxRangePushA(n); } ~Range() { nvtxRangePop(); } };
+    { Range r("madstereo/forward"); if (forward(mask, st)) return -1; }
+    { Range r("madstereo/loss_full"); if (loss(full, mode == 2, 0, 1.f, st)) return -1; }
     if (mode == 1) {
-        if (loss(group, 1, 1, 1.f, st)) return -1;
-        if (backward(1, group, st)) return -1;
+        { Range r("madstereo/loss_module"); if (loss(group, 1, 1, 1.f, st)) return -1; }
+        { Range r("madstereo/backward_mad"); if (backward(1, group, st)) return -1; }
+        Range r("madstereo/update");
         if (with_update == 1 && update(group, lr, mu, gscale, st)) return -1;
         if (with_update == 2 && dp_update(group, lr, mu, st)) return -1;       // all-reduce over peer memory + update
     } else if (mode == 2) {
-        if (backward(2, 0, st)) return -1;
+        { Range r("madstereo/backward_full"); if (backward(2, 0, st)) return -1; }
+        Range r("madstereo/update");
         if (with_update == 1 && update(-1, lr, mu, gscale, st)) return -1;
         if (with_update == 2 && dp_update(-1, lr, mu, st)) return -1;
     }
