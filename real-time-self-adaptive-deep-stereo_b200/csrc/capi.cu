@@ -127,7 +127,7 @@ int ms_conv2d_fwd_bf(const float* x, int n, int h, int w, int cin, int x_cs, con
     p.mul = stride; p.off_y = -pt; p.off_x = -pl; p.step = dilation; p.div = 1;
     p.alpha = alpha; p.mask = nullptr; p.mask_alpha = 1.f; p.res = nullptr; p.accumulate = 0;
     if (!conv_bf_supported(p)) { set_error("ms_conv2d_fwd_bf: shape not supported by the split-bf16 tcgen05 path"); return -3; }
-    return conv_bf_oneshot(p, 0, scratch, scratch_bytes, S(stream));
+    return conv_bf_oneshot(p, 0, 1, scratch, scratch_bytes, S(stream));      // forward: fp16 planes (x / 16)
 }
 int ms_conv2d_dgrad_bf(const float* dy, int n, int oh, int ow, int cout, int dy_cs, const float* weights, float* dx,
                        int h, int w, int cin, int dx_cs, int kh, int kw, int stride, int dilation, void* scratch,
@@ -143,7 +143,7 @@ int ms_conv2d_dgrad_bf(const float* dy, int n, int oh, int ow, int cout, int dy_
     p.mul = 1; p.off_y = pt; p.off_x = pl; p.step = -dilation; p.div = stride;
     p.alpha = 1.f; p.mask = nullptr; p.mask_alpha = 1.f; p.res = nullptr; p.accumulate = 0;
     if (!conv_bf_supported(p)) { set_error("ms_conv2d_dgrad_bf: shape not supported by the split-bf16 tcgen05 path"); return -3; }
-    return conv_bf_oneshot(p, 1, scratch, scratch_bytes, S(stream));
+    return conv_bf_oneshot(p, 1, 0, scratch, scratch_bytes, S(stream));      // gradients: bf16 planes
 }
 size_t ms_conv2d_bf_scratch(int n, int h, int w, int kh, int kw, int cin, int cout) {
     ConvGemm a{}, b{};
@@ -153,7 +153,7 @@ size_t ms_conv2d_bf_scratch(int n, int h, int w, int kh, int kw, int cin, int co
     return sa > sb ? sa : sb;
 }
 int ms_conv2d_wgrad_bf(const float* x, int n, int h, int w, int cin, int x_cs, const float* dy, int oh, int ow, int cout,
-                       int dy_cs, float* dw, float* db, int kh, int kw, int stride, int dilation, void* scratch,
+                       int dy_cs, float* dw, float* db, int kh, int kw, int stride, int dilation, int x_fmt, void* scratch,
                        size_t scratch_bytes, void* stream) {
     int oh2, ow2, pt, pl;
     same_pad_c(h, kh, stride, dilation, oh2, pt);
@@ -165,7 +165,7 @@ int ms_conv2d_wgrad_bf(const float* x, int n, int h, int w, int cin, int x_cs, c
     q.dw = dw; q.db = db; q.kh = kh; q.kw = kw; q.stride = stride; q.dil = dilation; q.pad_t = pt; q.pad_l = pl;
     q.accumulate = 0;
     if (!wgrad_bf_supported(q)) { set_error("ms_conv2d_wgrad_bf: shape not supported by the split-bf16 tcgen05 path"); return -3; }
-    return wgrad_bf_oneshot(q, scratch, scratch_bytes, S(stream));
+    return wgrad_bf_oneshot(q, x_fmt, 0, scratch, scratch_bytes, S(stream));
 }
 size_t ms_conv2d_wgrad_bf_scratch(int n, int h, int w, int oh, int ow, int kh, int kw, int cin, int cout) {
     ConvWgrad q{};
@@ -174,24 +174,24 @@ size_t ms_conv2d_wgrad_bf_scratch(int n, int h, int w, int oh, int ow, int kh, i
 }
 // ---- plane-level entry points of the split-bf16 path: what the engine calls per layer in steady state (operands
 //      already split: activations by the producing epilogue, weights once per update)
-int ms_bf_split(const float* x, int n, int h, int w, int c, int x_cs, void* hi, void* lo, int plane_cs, void* stream) {
-    ActPlanes pl; pl.hi = hi; pl.lo = lo; pl.cs = plane_cs;
+int ms_bf_split(const float* x, int n, int h, int w, int c, int x_cs, void* hi, void* lo, int plane_cs, int fmt, void* stream) {
+    ActPlanes pl; pl.hi = hi; pl.lo = lo; pl.cs = plane_cs; pl.fmt = fmt;
     return split_planes(view(const_cast<float*>(x), n, h, w, c, x_cs), pl, S(stream));
 }
 size_t ms_bf_weight_halfs(int taps, int m, int k) { return conv_bf_weight_halfs(taps, m, k); }
-int ms_bf_prep_weights(const float* weights_hwio, int taps, int cin, int cout, int for_dgrad, void* hi, void* lo,
+int ms_bf_prep_weights(const float* weights_hwio, int taps, int cin, int cout, int for_dgrad, int fmt, void* tiles,
                        void* job_dev, void* stream) {
     const int M = for_dgrad ? cin : cout, K = for_dgrad ? cout : cin;
     int Mpad, Kpad; conv_bf_weight_dims(M, K, Mpad, Kpad);
-    BfPrepJob job{weights_hwio, hi, lo, taps, M, K, Mpad, Kpad, for_dgrad ? 0 : 1};
+    BfPrepJob job{weights_hwio, tiles, taps, M, K, Mpad, Kpad, for_dgrad ? 0 : 1, fmt};
     MS_CHECK_CUDA(cudaMemcpyAsync(job_dev, &job, sizeof job, cudaMemcpyHostToDevice, S(stream)));
     MS_CHECK_CUDA(cudaStreamSynchronize(S(stream)));
     return bf_prep_weights(static_cast<const BfPrepJob*>(job_dev), 1, conv_bf_weight_halfs(taps, M, K), S(stream));
 }
-int ms_conv2d_fwd_bf_planes(const void* xhi, const void* xlo, int x_pcs, int n, int h, int w, int cin, const void* whi,
-                            const void* wlo, const float* bias, float* y, int cout, int y_cs, void* yhi, void* ylo, int y_pcs,
-                            int kh, int kw, int stride, int dilation, float alpha, float* part, unsigned int* tickets,
-                            void* stream) {
+int ms_conv2d_fwd_bf_planes(const void* xhi, const void* xlo, int x_pcs, int fmt, int n, int h, int w, int cin,
+                            const void* wtiles, const float* bias, float* y, int cout, int y_cs, void* yhi, void* ylo,
+                            int y_pcs, int kh, int kw, int stride, int dilation, float alpha, float* part,
+                            unsigned int* tickets, void* stream) {
     int oh, ow, pt, pl;
     same_pad_c(h, kh, stride, dilation, oh, pt);
     same_pad_c(w, kw, stride, dilation, ow, pl);
@@ -202,15 +202,15 @@ int ms_conv2d_fwd_bf_planes(const void* xhi, const void* xlo, int x_pcs, int n, 
     p.mul = stride; p.off_y = -pt; p.off_x = -pl; p.step = dilation; p.div = 1;
     p.alpha = alpha; p.mask_alpha = 1.f;
     if (!conv_bf_supported(p)) { set_error("ms_conv2d_fwd_bf_planes: shape not supported"); return -3; }
-    ActPlanes xp; xp.hi = const_cast<void*>(xhi); xp.lo = const_cast<void*>(xlo); xp.cs = x_pcs;
-    ActPlanes yp; yp.hi = yhi; yp.lo = ylo; yp.cs = y_pcs;
-    return conv_bf(p, xp, whi, wlo, yhi ? &yp : nullptr, part, tickets, S(stream));
+    ActPlanes xp; xp.hi = const_cast<void*>(xhi); xp.lo = const_cast<void*>(xlo); xp.cs = x_pcs; xp.fmt = fmt;
+    ActPlanes yp; yp.hi = yhi; yp.lo = ylo; yp.cs = y_pcs; yp.fmt = fmt;
+    return conv_bf(p, xp, wtiles, yhi ? &yp : nullptr, part, tickets, S(stream));
 }
 size_t ms_conv2d_bf_part_floats() { return conv_bf_part_floats(); }
 size_t ms_conv2d_bf_ticket_words() { return conv_bf_ticket_words(); }
-int ms_conv2d_wgrad_bf_planes(const void* xhi, const void* xlo, int x_pcs, int n, int h, int w, int cin, const void* dhi,
-                              const void* dlo, int d_pcs, int oh, int ow, int cout, float* dw, float* db, int kh, int kw,
-                              int stride, int dilation, float* workspace, size_t workspace_floats, void* stream) {
+int ms_conv2d_wgrad_bf_planes(const void* xhi, const void* xlo, int x_pcs, int x_fmt, int n, int h, int w, int cin,
+                              const void* dhi, const void* dlo, int d_pcs, int oh, int ow, int cout, float* dw, float* db,
+                              int kh, int kw, int stride, int dilation, float* workspace, size_t workspace_floats, void* stream) {
     int oh2, ow2, pt, pl;
     same_pad_c(h, kh, stride, dilation, oh2, pt);
     same_pad_c(w, kw, stride, dilation, ow2, pl);
@@ -220,8 +220,8 @@ int ms_conv2d_wgrad_bf_planes(const void* xhi, const void* xlo, int x_pcs, int n
     q.dw = dw; q.db = db; q.kh = kh; q.kw = kw; q.stride = stride; q.dil = dilation; q.pad_t = pt; q.pad_l = pl;
     q.workspace = workspace; q.workspace_floats = workspace_floats;
     if (!wgrad_bf_supported(q)) { set_error("ms_conv2d_wgrad_bf_planes: shape not supported"); return -3; }
-    ActPlanes xp; xp.hi = const_cast<void*>(xhi); xp.lo = const_cast<void*>(xlo); xp.cs = x_pcs;
-    ActPlanes dp; dp.hi = const_cast<void*>(dhi); dp.lo = const_cast<void*>(dlo); dp.cs = d_pcs;
+    ActPlanes xp; xp.hi = const_cast<void*>(xhi); xp.lo = const_cast<void*>(xlo); xp.cs = x_pcs; xp.fmt = x_fmt;
+    ActPlanes dp; dp.hi = const_cast<void*>(dhi); dp.lo = const_cast<void*>(dlo); dp.cs = d_pcs; dp.fmt = 0;
     return wgrad_bf(q, xp, dp, S(stream));
 }
 size_t ms_conv2d_wgrad_bf_workspace(int kh, int kw, int cin, int cout) { return wgrad_bf_workspace_floats(kh, kw, cin, cout); }

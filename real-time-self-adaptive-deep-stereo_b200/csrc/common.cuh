@@ -181,10 +181,10 @@ int conv_tc_read_prof(unsigned long long* out32, int reset);
 namespace ms {
 // split-bf16 tcgen05 path (conv_bf.cu): every activation that feeds a convolution also lives as two bf16 planes
 // (hi = bf16(x), lo = bf16(x - hi)), NHWC with channel stride `cs` (bf16 elements, multiple of 8).
-struct ActPlanes { void* hi; void* lo; int cs; };
+struct ActPlanes { void* hi; void* lo; int cs; int fmt; };   // fmt 0 = bf16 (gradients), 1 = fp16 of x/16 (forward activations)
 struct BfPrepJob {
-    const float* src; void* hi; void* lo;
-    int taps, M, K, Mpad, Kpad, transposed_src;
+    const float* src; void* tiles;           // tiles: [M block][tap][K block][hi tile | lo tile], swizzled smem images
+    int taps, M, K, Mpad, Kpad, transposed_src, fmt;
 };
 int conv_head_kind(const ConvGemm& g);      // conv_head.cu: 1 = forward 3x3 -> 1 head, 2 = its dgrad, 0 = no
 int conv_head(const ConvGemm& g, cudaStream_t st);
@@ -196,7 +196,7 @@ size_t conv_bf_ticket_words();
 int conv_bf_init();
 int bf_prep_weights(const BfPrepJob* jobs_dev, int njobs, size_t max_total, cudaStream_t st);
 int split_planes(const TView& x, const ActPlanes& pl, cudaStream_t st);
-int conv_bf(const ConvGemm& g, const ActPlanes& xp, const void* wh, const void* wl, const ActPlanes* yp, float* part,
+int conv_bf(const ConvGemm& g, const ActPlanes& xp, const void* wtiles, const ActPlanes* yp, float* part,
             unsigned int* tickets, cudaStream_t st);
 // wgrad_bf.cu: weight + bias gradient on the same planes (MN-major UMMA operands, no transposes)
 bool wgrad_bf_supported(const ConvWgrad& q);
@@ -204,7 +204,7 @@ size_t wgrad_bf_workspace_floats(int kh, int kw, int ci, int co);
 int wgrad_bf_init();
 int wgrad_bf(const ConvWgrad& q, const ActPlanes& xp, const ActPlanes& dp, cudaStream_t st);
 size_t wgrad_bf_oneshot_scratch_bytes(const ConvWgrad& q);
-int wgrad_bf_oneshot(const ConvWgrad& q, void* scratch, size_t scratch_bytes, cudaStream_t st);
+int wgrad_bf_oneshot(const ConvWgrad& q, int xfmt, int dfmt, void* scratch, size_t scratch_bytes, cudaStream_t st);
 size_t conv_bf_oneshot_scratch_bytes(const ConvGemm& g);
-int conv_bf_oneshot(const ConvGemm& g, int wmat_is_mk, void* scratch, size_t scratch_bytes, cudaStream_t st);
+int conv_bf_oneshot(const ConvGemm& g, int wmat_is_mk, int fmt, void* scratch, size_t scratch_bytes, cudaStream_t st);
 }  // namespace ms

@@ -1,4 +1,4 @@
-// conv_bf: tcgen05 implicit-GEMM convolution on split-bf16 operands -- the default tensor-core path of the conv stacks.
+// conv_bf: tcgen05 implicit-GEMM convolution on split 16-bit operands -- the default tensor-core path of the conv stacks.
 //
 // Replaces the cuDNN calls behind tf.nn.conv2d / tf.nn.atrous_conv2d (reference Nets/sharedLayers.py:58,72) and their
 // input gradients for the estimator / context / pyramid layers of MADNet (Nets/MadNet.py:73-171,173-249) and the
@@ -7,24 +7,34 @@
 // Why a second tensor-core generation (round-2 findings): the 3xTF32 kernels (conv_tc.cu) split
 // fp32 activations inside the main loop (splitter warps, three-party mbarrier hand-shakes) and every 128-pixel CTA
 // re-streams the whole weight set: 10x L2->SM amplification, tensor pipe < 50 %.  Here
-//   * operands are PRE-SPLIT: every activation tensor that feeds a convolution also exists as two bf16 planes
-//     (hi = bf16(x), lo = bf16(x - hi); x ~= hi + lo to 2^-16), written by the producing kernel's epilogue; weights are
-//     split once per update.  The main loop is the canonical TMA -> tcgen05.mma -> epilogue pipeline, no splitter.
-//   * three kind::f16 MMAs per K step (w_lo*x_hi + w_hi*x_lo into one accumulator, w_hi*x_hi into another) give
-//     ~2^-16 relative product error at half the tensor time of 3xTF32 (bf16 runs at twice the tf32 rate).
-//   * the GEMM is transposed ("swap AB"): M = output channels (128 TMEM lanes), N = up to 256 output pixels per CTA,
-//     K = 32 input channels per step.  One weight tile now serves 256 pixels, per-MMA shared-memory reads drop from
-//     128 to 96 B/clk, and the epilogue thread <-> channel mapping makes every NHWC store a coalesced 128-byte line.
+//   * operands are PRE-SPLIT: every tensor that feeds a convolution also exists as two 16-bit planes (x ~= hi + lo),
+//     written by the producing kernel's epilogue; weights are split once per update.  The main loop is the canonical
+//     TMA -> tcgen05.mma -> epilogue pipeline, no splitter.
+//       forward operands : fp16 planes of x/16 and of w  (hi = fp16, lo = fp16 of the remainder: 22 mantissa bits,
+//                          ~2^-22 relative product error -- fp32-grade, so no extra relu / floor / |.| kink flips; the
+//                          1/16 pre-scale keeps |x| <= 1e6 inside the fp16 range, undone exactly in the epilogue)
+//       gradient operands: bf16 planes (hi + lo: 16 mantissa bits, ~2^-16, full fp32 exponent range for 1e-9 gradients)
+//   * three kind::f16 MMAs per K step (w_lo*x_hi + w_hi*x_lo into one accumulator, w_hi*x_hi into another) at the
+//     bf16/fp16 tensor rate (twice the tf32 rate).
+//   * the GEMM is transposed ("swap AB"): M = output channels (128 TMEM lanes), N = up to 256 output pixels per CTA.
+//     One weight tile serves 256 pixels, per-MMA shared-memory reads drop from 128 to 96 B/clk, and the epilogue
+//     thread <-> channel mapping makes every NHWC store a coalesced 128-byte line.
+//   * K blocks of 64 channels (128-byte rows, SWIZZLE_128B) whenever cin > 32: the first version used 32-channel
+//     blocks = 64-byte TMA rows and was bound by the TMA request rate (15.7 k requests per CTA on the dominant layer,
+//     ncu: tensor pipe 35 %, epilogue warps idle on the accumulator barrier for 80 % of the kernel).
+//   * weights are stored PRE-TILED in their shared-memory image (per (M block, tap, K block): hi tile | lo tile,
+//     swizzle applied by the prep kernel) and arrive as ONE 1-D bulk copy per tap instead of 2 x 128 TMA rows.
 //   * A tile's pixels are `TW` wide and N/TW high.  For each filter column the kernel loads ONE halo patch
-//     (N/TW + (kh-1)*dilation rows) per 32-channel block; the kh taps of that column are row offsets into the patch
-//     (patch rows are TW*64 bytes = whole SWIZZLE_64B atoms, so a tap is just a different UMMA descriptor start address).
+//     (N/TW + (kh-1)*dilation rows) per K block; the kh taps of that column are row offsets into the patch
+//     (patch rows are whole swizzle atoms, so a tap is just a different UMMA descriptor start address).
 //     Stride-2 convolutions use TMA element strides {1,2,2,1}: a patch then holds every second pixel / row.
-//   * split-K over (channel block, patch) units for small maps; the last-arriving CTA of a tile reduces the partial
+//   * split-K over (K block, patch) units for small maps; the last-arriving CTA of a tile reduces the partial
 //     sums in fixed order (deterministic) and runs the epilogue -- no separate reduce launch.
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -38,7 +48,6 @@ namespace ms {
 constexpr int BF_THREADS = 320;
 constexpr int BF_MAX_PATCH = 16;
 constexpr int BF_MAX_TAPS = 49;
-constexpr uint32_t BF_W_TILE = 128u * 64u;      // one weight tile: 128 rows x 32 bf16
 
 struct BfPatch { short dx, dy, ntaps, tap0; };
 struct BfTap { short row_off, widx; };
@@ -50,20 +59,26 @@ struct ConvBfParams {
     int tiles_x, tiles_y;
     int sx;                       // input coordinate = out * sx + patch.d
     int kblocks, n_patches;
+    int kch;                      // channels per K block: 32 (64-byte rows, SWIZZLE_64B) or 64 (128-byte rows, SWIZZLE_128B)
+    int taps_total;
     uint32_t slot_bytes;          // bytes of one patch plane in shared memory
+    uint32_t wtile_bytes;         // bytes of one weight tile plane (128 rows x kch x 2)
     int NP, NW;
     int nacc;                     // accumulators: 2 = cross terms and hi*hi separately, 1 = everything in one
-    int nprod;                    // 3 = bf16x3, 1 = plain bf16 (hi*hi only; accuracy experiments)
+    int nprod;                    // 3 = split x3, 1 = hi*hi only (accuracy experiments)
+    int fmt;                      // operand format: 0 = bf16 planes, 1 = fp16 planes (activations pre-scaled by 1/16)
+    float acc_scale;              // multiplies the accumulator (16 undoes the activation pre-scale)
     int tmem_cols;
     int cout;
     int ksplit;
+    const unsigned char* wtiles;  // pre-tiled weights [M block][tap][K block][hi tile | lo tile]
     float* part; unsigned int* tickets;
     float* y; int ycs;
     const float* bias; float alpha;
     const float* res; int res_cs;
     const float* mask; int mask_cs; float mask_alpha;
     int accumulate;
-    __nv_bfloat16* ohi; __nv_bfloat16* olo; int ocs;
+    void* ohi; void* olo; int ocs; int ofmt;     // optional output planes (ofmt as `fmt`)
     BfPatch patch[BF_MAX_PATCH];
     BfTap tap[BF_MAX_TAPS];
 };
@@ -75,19 +90,36 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
         : "memory");
 }
-// K-major SWIZZLE_64B shared-memory matrix descriptor: rows of 64 bytes, 8-row atoms of 512 bytes (SBO), version 1,
-// layout_type 4 (cute::UMMA::LayoutType::SWIZZLE_64B).  The start address must be a multiple of 512 bytes.
-__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_byte_addr) {
-    return (uint64_t)((smem_byte_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+// K-major shared-memory matrix descriptors (cute::UMMA::SmemDescriptor), version 1:
+//   SWIZZLE_64B : rows of 64 bytes, 8-row atoms of 512 bytes (SBO), layout_type 4
+//   SWIZZLE_128B: rows of 128 bytes, 8-row atoms of 1024 bytes (SBO), layout_type 2
+__device__ __forceinline__ uint64_t umma_desc_k(uint32_t smem_byte_addr, bool sw128) {
+    const uint64_t lo = (uint64_t)((smem_byte_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (1ull << 46);
+    return sw128 ? (lo | (64ull << 32) | (2ull << 61)) : (lo | (32ull << 32) | (4ull << 61));
 }
-__device__ __forceinline__ void bf_split(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-    hi = __float2bfloat16_rn(v);
-    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(s_addr(dst)), "l"(src), "r"(bytes), "r"(s_addr(bar)) : "memory");
+}
+
+constexpr float BF_PRESCALE = 0.0625f;            // fp16 activation planes hold x / 16
+// 16-bit split of a float: fmt 0 -> bf16 hi/lo, fmt 1 -> fp16 hi/lo of v * 1/16 (saturating: |v| up to ~2e6 stays finite)
+__device__ __forceinline__ void split16(float v, int fmt, unsigned short& hi, unsigned short& lo) {
+    if (fmt == 0) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+        hi = __bfloat16_as_ushort(h); lo = __bfloat16_as_ushort(l);
+    } else {
+        const float s = v * BF_PRESCALE;
+        const float c = fminf(fmaxf(s, -65504.f), 65504.f);
+        const __half h = __float2half_rn(c);
+        const float r = fminf(fmaxf(s - __half2float(h), -65504.f), 65504.f);
+        hi = __half_as_ushort(h); lo = __half_as_ushort(__float2half_rn(r));
+    }
 }
 
 __global__ void __launch_bounds__(BF_THREADS, 1)
 conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl,
-               const __grid_constant__ CUtensorMap mapWh, const __grid_constant__ CUtensorMap mapWl,
                const __grid_constant__ ConvBfParams p) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t pfull[4], pempty[4], wfull[8], wempty[8], accum_bar;
@@ -99,7 +131,7 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
     unsigned char* gbase = smem_dyn + (base - s_addr(smem_dyn));
     const uint32_t pslot = 2u * p.slot_bytes;                 // hi plane | lo plane
     const uint32_t w_off = (uint32_t)p.NP * pslot;
-    const uint32_t wslot = 2u * BF_W_TILE;
+    const uint32_t wslot = 2u * p.wtile_bytes;                // hi tile | lo tile
 
     int bid = blockIdx.x;
     const int tx = bid % p.tiles_x; bid /= p.tiles_x;
@@ -126,27 +158,24 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
     const uint32_t tmem = tmem_slot;
 
     if (warp == 0) {
-        // ================= TMA producer: halo patches (per channel block x filter column) + weight tiles (per tap) ===
+        // ================= producer: halo patches by TMA (per K block x filter column) + weight tiles by bulk copy (per tap) ===
         if (lane == 0) {
             int ps = 0, ws = 0;
             uint32_t pph = 0, wph = 0;
-            const int mrow = blockIdx.y * 128;
+            const unsigned char* wbase = p.wtiles + (size_t)blockIdx.y * p.taps_total * p.kblocks * wslot;
             int kb = u0 / p.n_patches, pi = u0 - kb * p.n_patches;
             for (int u = u0; u < u1; ++u) {
                 const BfPatch pt = p.patch[pi];
                 mb_wait(&pempty[ps], pph ^ 1u);
                 mb_expect_tx(&pfull[ps], pslot);
                 unsigned char* dst = gbase + (size_t)ps * pslot;
-                tma_load_4d(dst, &mapXh, &pfull[ps], kb * 32, x0 * p.sx + pt.dx, y0 * p.sx + pt.dy, img);
-                tma_load_4d(dst + p.slot_bytes, &mapXl, &pfull[ps], kb * 32, x0 * p.sx + pt.dx, y0 * p.sx + pt.dy, img);
+                tma_load_4d(dst, &mapXh, &pfull[ps], kb * p.kch, x0 * p.sx + pt.dx, y0 * p.sx + pt.dy, img);
+                tma_load_4d(dst + p.slot_bytes, &mapXl, &pfull[ps], kb * p.kch, x0 * p.sx + pt.dx, y0 * p.sx + pt.dy, img);
                 if (++ps == p.NP) { ps = 0; pph ^= 1u; }
                 for (int t = pt.tap0; t < pt.tap0 + pt.ntaps; ++t) {
                     mb_wait(&wempty[ws], wph ^ 1u);
                     mb_expect_tx(&wfull[ws], wslot);
-                    unsigned char* wd = gbase + w_off + (size_t)ws * wslot;
-                    const int widx = p.tap[t].widx;
-                    tma_load_3d(wd, &mapWh, &wfull[ws], kb * 32, mrow, widx);
-                    tma_load_3d(wd + BF_W_TILE, &mapWl, &wfull[ws], kb * 32, mrow, widx);
+                    bulk_load(gbase + w_off + (size_t)ws * wslot, wbase + ((size_t)p.tap[t].widx * p.kblocks + kb) * wslot, wslot, &wfull[ws]);
                     if (++ws == p.NW) { ws = 0; wph ^= 1u; }
                 }
                 if (++pi == p.n_patches) { pi = 0; ++kb; }
@@ -155,15 +184,18 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (bit 4), A=B=bf16 (1<<7, 1<<10), both K-major,
-            // N>>3 at bit 17, M>>4 at bit 24
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (bit 4), A/B format at bits 7 / 10 (0 = f16,
+            // 1 = bf16), both K-major, N>>3 at bit 17, M>>4 at bit 24
+            const uint32_t f = p.fmt == 0 ? 1u : 0u;
+            const uint32_t idesc = (1u << 4) | (f << 7) | (f << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
             const uint32_t acc_main = tmem + (p.nacc == 2 ? (uint32_t)p.N : 0u);
+            const bool sw128 = p.kch == 64;
+            const int k16 = p.kch >> 4;
             int ps = 0, ws = 0;
             uint32_t pph = 0, wph = 0;
             uint32_t started_cross = 0, started_main = 0;
             int pi = u0 % p.n_patches;
-            const uint32_t row_bytes = (uint32_t)p.TW * 64u;
+            const uint32_t row_bytes = (uint32_t)p.TW * (uint32_t)p.kch * 2u;
             for (int u = u0; u < u1; ++u) {
                 const BfPatch pt = p.patch[pi];
                 mb_wait(&pfull[ps], pph);
@@ -172,11 +204,10 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
                     mb_wait(&wfull[ws], wph);
                     tc_fence_after();
                     const uint32_t boff = (uint32_t)p.tap[t].row_off * row_bytes;
-                    const uint64_t xh = umma_desc_sw64(pb + boff), xl = umma_desc_sw64(pb + p.slot_bytes + boff);
+                    const uint64_t xh = umma_desc_k(pb + boff, sw128), xl = umma_desc_k(pb + p.slot_bytes + boff, sw128);
                     const uint32_t wb = base + w_off + (uint32_t)ws * wslot;
-                    const uint64_t wh = umma_desc_sw64(wb), wl = umma_desc_sw64(wb + BF_W_TILE);
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {               // 2 x (K = 16 bf16 = 32 bytes) inside the 64-byte swizzle row
+                    const uint64_t wh = umma_desc_k(wb, sw128), wl = umma_desc_k(wb + p.wtile_bytes, sw128);
+                    for (int j = 0; j < k16; ++j) {               // K = 16 elements = 32 bytes inside the swizzle row
                         const uint64_t o = (uint64_t)(j * 2);
                         if (p.nprod == 3) {
                             tc_mma_f16(tmem, wl + o, xh + o, idesc, started_cross);
@@ -208,22 +239,44 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
         const int cbeg = half * (p.N >> 1), cend = cbeg + (p.N >> 1);
         const bool two = (p.nacc == 2) && (p.nprod == 3);
         const int tile_lin = blockIdx.x * gridDim.y + blockIdx.y;
+        const float acc_scale = p.acc_scale, alpha = p.alpha;
+        const bool has_res = p.res != nullptr, has_mask = p.mask != nullptr, has_acc = p.accumulate != 0, has_pl = p.ohi != nullptr;
+        const int twm = p.TW - 1;
+        const size_t img_pix = (size_t)img * p.Hout;
+        unsigned short* const ohi = reinterpret_cast<unsigned short*>(p.ohi);
+        unsigned short* const olo = reinterpret_cast<unsigned short*>(p.olo);
 
-        auto finish = [&](int col, float t) {
-            const int yy = y0 + (col >> p.tw_shift), xx = x0 + (col & (p.TW - 1));
-            if (yy < p.H && xx < p.W && chv) {
-                const size_t pix = ((size_t)img * p.Hout + (yy * p.os + p.oy0)) * p.Wout + (xx * p.os + p.ox0);
-                t += bias;
-                t = fmaxf(p.alpha * t, t);
-                if (p.res) t += p.res[pix * p.res_cs + ch];
-                if (p.accumulate) t += p.y[pix * p.ycs + ch];
-                if (p.mask) t *= (p.mask[pix * p.mask_cs + ch] > 0.f) ? 1.f : p.mask_alpha;
-                p.y[pix * p.ycs + ch] = t;
-                if (p.ohi) {
-                    __nv_bfloat16 h, l;
-                    bf_split(t, h, l);
-                    p.ohi[pix * p.ocs + ch] = h;
-                    p.olo[pix * p.ocs + ch] = l;
+        // 16 consecutive columns = (TW == 8) two tile rows of 8 pixels, or (TW == 16) one row of 16: hoist the row part
+        auto finish16 = [&](int c0, const float (&v)[16]) {
+            const int r0 = c0 >> p.tw_shift, px0 = c0 & twm;
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow) {
+                const int yy = y0 + r0 + (p.TW == 8 ? hrow : 0);
+                const int jb = p.TW == 8 ? hrow * 8 : hrow * 8;
+                if (yy >= p.H || !chv) continue;
+                const size_t rowpix = (img_pix + (size_t)(yy * p.os + p.oy0)) * p.Wout + p.ox0;
+                float* yrow = p.y + rowpix * p.ycs + ch;
+                const float* rrow = has_res ? p.res + rowpix * p.res_cs + ch : nullptr;
+                const float* mrow = has_mask ? p.mask + rowpix * p.mask_cs + ch : nullptr;
+                unsigned short* hrow_p = has_pl ? ohi + rowpix * p.ocs + ch : nullptr;
+                unsigned short* lrow_p = has_pl ? olo + rowpix * p.ocs + ch : nullptr;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int xx = x0 + (p.TW == 8 ? j : px0 + jb + j);
+                    if (xx >= p.W) continue;
+                    const int xo = xx * p.os;
+                    float t = v[jb + j] * acc_scale + bias;
+                    t = fmaxf(alpha * t, t);
+                    if (has_res) t += rrow[(size_t)xo * p.res_cs];
+                    if (has_acc) t += yrow[(size_t)xo * p.ycs];
+                    if (has_mask) t *= (mrow[(size_t)xo * p.mask_cs] > 0.f) ? 1.f : p.mask_alpha;
+                    yrow[(size_t)xo * p.ycs] = t;
+                    if (has_pl) {
+                        unsigned short h, l;
+                        split16(t, p.ofmt, h, l);
+                        hrow_p[(size_t)xo * p.ocs] = h;
+                        lrow_p[(size_t)xo * p.ocs] = l;
+                    }
                 }
             }
         };
@@ -233,15 +286,13 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
         if (p.ksplit == 1) {
             for (int c0 = cbeg; c0 < cend; c0 += 16) {
                 uint32_t r0[16], r1[16];
+                float v[16];
                 tc_ld16_nowait(tmem + lane_base + (uint32_t)c0, r0);
                 if (two) tc_ld16_nowait(tmem + lane_base + (uint32_t)(p.N + c0), r1);
                 tc_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float t = __uint_as_float(r0[j]);
-                    if (two) t += __uint_as_float(r1[j]);
-                    finish(c0 + j, t);
-                }
+                for (int j = 0; j < 16; ++j) v[j] = two ? __uint_as_float(r0[j]) + __uint_as_float(r1[j]) : __uint_as_float(r0[j]);
+                finish16(c0, v);
             }
         } else {
             // raw partial sums: part[(z * n_tiles + tile) * N + col][128 channels]
@@ -272,10 +323,16 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
                 __threadfence();
                 const float* col0 = p.part + ((size_t)tile_lin * p.N) * 128 + q * 32 + lane;
                 const size_t zstride = n_tiles * (size_t)p.N * 128;
-                for (int col = cbeg; col < cend; ++col) {
-                    float t = 0.f;
-                    for (int z = 0; z < p.ksplit; ++z) t += __ldcg(col0 + (size_t)z * zstride + (size_t)col * 128);
-                    finish(col, t);
+                for (int c0 = cbeg; c0 < cend; c0 += 16) {
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                    for (int z = 0; z < p.ksplit; ++z) {
+                        const float* src = col0 + (size_t)z * zstride + (size_t)c0 * 128;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] += __ldcg(src + (size_t)j * 128);
+                    }
+                    finish16(c0, v);
                 }
             }
         }
@@ -289,24 +346,24 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------
-// bf16 planes of an fp32 NHWC view (producers that are not conv_bf epilogues: correlation, resize, loss seeds ...)
+// 16-bit planes of an fp32 NHWC view (producers that are not conv_bf epilogues: correlation, resize, loss seeds ...)
 // ------------------------------------------------------------------------------------------------
 __global__ void split_planes_kernel(const float* __restrict__ x, int xcs, int C, size_t pixels,
-                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int pcs) {
+                                    unsigned short* __restrict__ hi, unsigned short* __restrict__ lo, int pcs, int fmt) {
     const int cq = (C + 3) >> 2;
     const size_t total = pixels * cq;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t pix = i / cq;
         const int c = (int)(i - pix * cq) * 4;
         const float* src = x + pix * xcs + c;
-        __nv_bfloat16 h[4], l[4];
+        unsigned short h[4], l[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float v = (c + j < C) ? src[j] : 0.f;
-            bf_split(v, h[j], l[j]);
+            split16(v, fmt, h[j], l[j]);
         }
-        __nv_bfloat16* dh = hi + pix * pcs + c;
-        __nv_bfloat16* dl = lo + pix * pcs + c;
+        unsigned short* dh = hi + pix * pcs + c;
+        unsigned short* dl = lo + pix * pcs + c;
         if (c + 4 <= pcs) {
             *reinterpret_cast<uint2*>(dh) = *reinterpret_cast<const uint2*>(h);
             *reinterpret_cast<uint2*>(dl) = *reinterpret_cast<const uint2*>(l);
@@ -320,50 +377,71 @@ int split_planes(const TView& x, const ActPlanes& pl, cudaStream_t st) {
     MS_REQUIRE(pl.hi && pl.lo && pl.cs >= x.c && (pl.cs & 7) == 0, "split_planes: bad plane buffers");
     const size_t total = x.pixels() * ((x.c + 3) / 4);
     const unsigned grid = (unsigned)std::min<size_t>(cdivz(total, 256), 148 * 16);
-    split_planes_kernel<<<grid, 256, 0, st>>>(x.p, x.cs, x.c, x.pixels(), reinterpret_cast<__nv_bfloat16*>(pl.hi),
-                                              reinterpret_cast<__nv_bfloat16*>(pl.lo), pl.cs);
+    split_planes_kernel<<<grid, 256, 0, st>>>(x.p, x.cs, x.c, x.pixels(), reinterpret_cast<unsigned short*>(pl.hi),
+                                              reinterpret_cast<unsigned short*>(pl.lo), pl.cs, pl.fmt);
     return check_launch("split_planes");
 }
 
 // ------------------------------------------------------------------------------------------------
-// weight preparation: dst[term][tap][m (Mpad rows)][k (Kpad)] bf16 hi / lo from canonical fp32 HWIO, batched over layers
+// weight preparation: the shared-memory image of every (M block, tap, K block) tile, hi tile | lo tile, swizzled,
+// from canonical fp32 HWIO, batched over layers
 //   transposed_src = 1 : src is [tap][K][M]  (forward conv: K = cin, M = cout)
 //   transposed_src = 0 : src is [tap][M][K]  (dgrad: M = cin, K = cout)
 // ------------------------------------------------------------------------------------------------
 __global__ void bf_prep_weights_kernel(const BfPrepJob* __restrict__ jobs) {
     const BfPrepJob j = jobs[blockIdx.y];
-    const size_t total = (size_t)j.taps * j.Mpad * j.Kpad;
-    __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(j.hi);
-    __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(j.lo);
+    const int kch = j.Kpad > 32 ? 64 : 32;
+    const int kblocks = j.Kpad / kch, mblocks = j.Mpad / 128;
+    const size_t tile = (size_t)128 * kch;                         // elements per tile plane
+    const size_t total = (size_t)mblocks * j.taps * kblocks * tile;
+    unsigned short* dst = reinterpret_cast<unsigned short*>(j.tiles);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int k = (int)(i % j.Kpad);
-        const size_t q = i / j.Kpad;
-        const int m = (int)(q % j.Mpad);
-        const int t = (int)(q / j.Mpad);
+        const int kk = (int)(i % kch);
+        size_t q = i / kch;
+        const int r = (int)(q % 128); q /= 128;
+        const int kb = (int)(q % kblocks); q /= kblocks;
+        const int t = (int)(q % j.taps);
+        const int mb = (int)(q / j.taps);
+        const int m = mb * 128 + r, k = kb * kch + kk;
         float v = 0.f;
         if (m < j.M && k < j.K)
             v = j.transposed_src ? j.src[((size_t)t * j.K + k) * j.M + m] : j.src[((size_t)t * j.M + m) * j.K + k];
-        __nv_bfloat16 h, l;
-        bf_split(v, h, l);
-        hi[i] = h; lo[i] = l;
+        unsigned short h, l;
+        if (j.fmt == 0) {
+            const __nv_bfloat16 hb = __float2bfloat16_rn(v);
+            h = __bfloat16_as_ushort(hb); l = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(hb)));
+        } else {                                                  // weights are not pre-scaled
+            const __half hh = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+            h = __half_as_ushort(hh); l = __half_as_ushort(__float2half_rn(v - __half2float(hh)));
+        }
+        // swizzled position inside the tile image (K-major rows of kch*2 bytes, 16-byte chunks XOR-ed with the row bits)
+        const int chunk = kk >> 3, e = kk & 7;
+        const int sw = kch == 64 ? (chunk ^ (r & 7)) : (chunk ^ ((r >> 1) & 3));
+        const size_t off = (size_t)r * kch + (size_t)sw * 8 + e;
+        const size_t tbase = ((((size_t)mb * j.taps + t) * kblocks + kb) * 2) * tile;
+        dst[tbase + off] = h;
+        dst[tbase + tile + off] = l;
     }
 }
 
 int bf_prep_weights(const BfPrepJob* jobs_dev, int njobs, size_t max_total, cudaStream_t st) {
     if (njobs <= 0) return 0;
-    const unsigned gx = (unsigned)std::min<size_t>(cdivz(max_total, 256), 512);
+    const unsigned gx = (unsigned)std::min<size_t>(cdivz(max_total / 2, 256), 512);
     bf_prep_weights_kernel<<<dim3(gx, njobs), 256, 0, st>>>(jobs_dev);
     return check_launch("bf_prep_weights");
 }
 
-void conv_bf_weight_dims(int M, int K, int& Mpad, int& Kpad) { Mpad = (M + 127) / 128 * 128; Kpad = (K + 31) / 32 * 32; }
-size_t conv_bf_weight_halfs(int taps, int M, int K) {       // bf16 elements per plane
+void conv_bf_weight_dims(int M, int K, int& Mpad, int& Kpad) {
+    Mpad = (M + 127) / 128 * 128;
+    Kpad = K > 32 ? (K + 63) / 64 * 64 : 32;
+}
+size_t conv_bf_weight_halfs(int taps, int M, int K) {       // 16-bit elements of the tiled image, both planes
     int Mpad, Kpad; conv_bf_weight_dims(M, K, Mpad, Kpad);
-    return (size_t)taps * Mpad * Kpad;
+    return (size_t)2 * taps * Mpad * Kpad;
 }
 
 // ------------------------------------------------------------------------------------------------
-// tensor maps (bf16, SWIZZLE_64B, zero OOB fill, optional element strides), cached
+// tensor maps (16-bit elements, SWIZZLE_64B / 128B, zero OOB fill, optional element strides), cached
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -383,6 +461,7 @@ struct BfMapKey {
     uintptr_t addr; int rank; int swz; uint64_t d[4]; uint64_t s[3]; uint32_t b[4]; uint32_t es[4];
     bool operator<(const BfMapKey& o) const { return memcmp(this, &o, sizeof(BfMapKey)) < 0; }
 };
+// (BFLOAT16 as the element type for fp16 planes too: TMA moves 2-byte elements, the zero fill is format-agnostic)
 int bf_get_map(const CUtensorMap** out, void* addr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                const cuuint32_t* box, const cuuint32_t* estr, int swizzle_bytes) {
     static std::map<BfMapKey, CUtensorMap> cache;
@@ -398,9 +477,8 @@ int bf_get_map(const CUtensorMap** out, void* addr, int rank, const cuuint64_t* 
         CUtensorMap m;
         CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, addr, dims, strides_bytes, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (bf16) failed with code " + std::to_string((int)r)); return -1; }
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (16-bit planes) failed with code " + std::to_string((int)r)); return -1; }
         if (cache.size() >= 8192) {
             static thread_local CUtensorMap spill[16];
             static thread_local unsigned spill_i = 0;
@@ -441,7 +519,7 @@ size_t conv_bf_ticket_words() { return 4096; }
 struct BfTapSpec { int dy, dx, widx; };     // input pixel = out_lattice * sx + (dy, dx); weight tap index
 
 // One launch: output lattice [Hj x Wj] (output pixel = j * os + o0), gather taps `taps`, input lattice stride sx.
-static int conv_bf_launch(const ConvGemm& g, const ActPlanes& xp, const void* wh, const void* wl, const ActPlanes* yp,
+static int conv_bf_launch(const ConvGemm& g, const ActPlanes& xp, const void* wtiles, const ActPlanes* yp,
                           float* part, unsigned int* tickets, int Hj, int Wj, int os, int oy0, int ox0, int sx,
                           const BfTapSpec* taps, int ntaps, int taps_total, cudaStream_t st) {
     const int K = g.x.c, M = g.y.c;
@@ -450,7 +528,11 @@ static int conv_bf_launch(const ConvGemm& g, const ActPlanes& xp, const void* wh
     memset(&p, 0, sizeof p);
     p.H = Hj; p.W = Wj; p.NB = g.y.n; p.sx = sx;
     p.Hout = g.y.h; p.Wout = g.y.w; p.os = os; p.oy0 = oy0; p.ox0 = ox0;
-    p.kblocks = Kpad / 32; p.cout = M;
+    p.kch = Kpad > 32 ? 64 : 32;
+    p.kblocks = Kpad / p.kch; p.cout = M; p.taps_total = taps_total;
+    p.wtile_bytes = 128u * (uint32_t)p.kch * 2u;
+    p.fmt = xp.fmt; p.acc_scale = xp.fmt == 1 ? 16.f : 1.f;
+    const uint32_t row_unit = (uint32_t)p.kch * 2u;                 // bytes of one pixel of a patch plane
     // ---- pixel tile: the largest N in {256,128,64} that still gives ~100 CTAs; 8-pixel rows unless that wastes a tile row
     const int mblocks = Mpad / 128;
     static int force_n = -1;
@@ -496,8 +578,9 @@ static int conv_bf_launch(const ConvGemm& g, const ActPlanes& xp, const void* wh
     }
     p.n_patches = np;
     int rows = TH + max_off;
+    const size_t wslot = 2 * (size_t)p.wtile_bytes;
     // a tall halo (large dilation) costs more than one box per tap, or does not fit: one patch per tap instead
-    if (max_off > 0 && ((size_t)rows * TW * 64 * 2 * 2 + 4 * 2 * BF_W_TILE > 200 * 1024 || rows * np >= TH * ntaps)) {
+    if (max_off > 0 && ((size_t)rows * TW * row_unit * 2 * 2 + 2 * wslot > 220 * 1024 || rows * np >= TH * ntaps)) {
         MS_REQUIRE(ntaps <= BF_MAX_PATCH, "conv_bf: too many per-tap patches");
         for (int i = 0; i < ntaps; ++i) {
             BfPatch& pt = p.patch[i];
@@ -508,13 +591,17 @@ static int conv_bf_launch(const ConvGemm& g, const ActPlanes& xp, const void* wh
         rows = TH;
     }
     MS_REQUIRE(rows * sx <= 256 && TW * sx <= 256, "conv_bf: patch too large for one TMA box");
-    p.slot_bytes = (uint32_t)rows * TW * 64u;
-    const size_t pslot = 2 * (size_t)p.slot_bytes, wslot = 2 * (size_t)BF_W_TILE;
+    p.slot_bytes = (uint32_t)rows * TW * row_unit;
+    const size_t pslot = 2 * (size_t)p.slot_bytes;
     const size_t budget = 220 * 1024;
-    int NW = 4, NP = (int)std::min<size_t>(4, (budget - NW * wslot) / pslot);
-    if (NP < 2) { NW = 3; NP = (int)std::min<size_t>(4, (budget - NW * wslot) / pslot); }
-    MS_REQUIRE(NP >= 2, "conv_bf: patch does not fit shared memory");
-    NW = (int)std::min<size_t>(8, (budget - NP * pslot) / wslot);
+    MS_REQUIRE(2 * pslot + 2 * wslot <= budget, "conv_bf: patch does not fit shared memory");
+    int NP = 2, NW = 2;
+    for (;;) {                                       // grow the two rings alternately while they fit (weights first: smaller)
+        bool grew = false;
+        if (NW < 8 && (size_t)NP * pslot + (size_t)(NW + 1) * wslot <= budget && NW <= 2 * NP) { ++NW; grew = true; }
+        if (NP < 4 && (size_t)(NP + 1) * pslot + (size_t)NW * wslot <= budget) { ++NP; grew = true; }
+        if (!grew) break;
+    }
     p.NP = NP; p.NW = NW;
     static int nacc_env = -1, nprod_env = -1;
     if (nacc_env < 0) { const char* e = getenv("MS_BF_NACC"); nacc_env = e ? atoi(e) : 2; }
@@ -530,43 +617,38 @@ static int conv_bf_launch(const ConvGemm& g, const ActPlanes& xp, const void* wh
     p.accumulate = g.accumulate;
     if (yp && yp->hi) {
         MS_REQUIRE(yp->cs >= M && (yp->cs & 7) == 0, "conv_bf: bad output planes");
-        p.ohi = reinterpret_cast<__nv_bfloat16*>(yp->hi); p.olo = reinterpret_cast<__nv_bfloat16*>(yp->lo); p.ocs = yp->cs;
+        p.ohi = yp->hi; p.olo = yp->lo; p.ocs = yp->cs; p.ofmt = yp->fmt;
     }
-    // ---- split K over (channel block, patch) units when the map is too small to fill the GPU
+    p.wtiles = static_cast<const unsigned char*>(wtiles);
+    // ---- split K over (K block, patch) units when the map is too small to fill the GPU (at most 8 ways: the closing
+    //      CTA reads every partial sum)
     const int grid_tiles = p.NB * p.tiles_x * p.tiles_y;
     const int units = p.kblocks * p.n_patches;
     int ksplit = 1;
     if (part && tickets && (long)grid_tiles * mblocks <= 74 && units > 1) {
-        ksplit = std::min(units, std::max(1, 148 / (grid_tiles * mblocks)));
+        ksplit = std::min(std::min(units, 8), std::max(1, 148 / (grid_tiles * mblocks)));
         while (ksplit > 1 && (size_t)ksplit * grid_tiles * mblocks * N * 128 > conv_bf_part_floats()) --ksplit;
         if ((size_t)grid_tiles * mblocks > conv_bf_ticket_words()) ksplit = 1;
     }
     p.ksplit = ksplit; p.part = part; p.tickets = tickets;
 
-    const CUtensorMap *mXh, *mXl, *mWh, *mWl;
+    const CUtensorMap *mXh, *mXl;
     {
         cuuint64_t dims[4] = {(cuuint64_t)g.x.c, (cuuint64_t)g.x.w, (cuuint64_t)g.x.h, (cuuint64_t)g.x.n};
         cuuint64_t strides[3] = {(cuuint64_t)xp.cs * 2, (cuuint64_t)g.x.w * xp.cs * 2, (cuuint64_t)g.x.h * g.x.w * xp.cs * 2};
-        cuuint32_t box[4] = {32, (cuuint32_t)(TW * sx), (cuuint32_t)(rows * sx), 1};
+        cuuint32_t box[4] = {(cuuint32_t)p.kch, (cuuint32_t)(TW * sx), (cuuint32_t)(rows * sx), 1};
         cuuint32_t es[4] = {1, (cuuint32_t)sx, (cuuint32_t)sx, 1};
-        if (bf_get_map(&mXh, xp.hi, 4, dims, strides, box, es)) return -1;
-        if (bf_get_map(&mXl, xp.lo, 4, dims, strides, box, es)) return -1;
-    }
-    {
-        cuuint64_t dims[3] = {(cuuint64_t)Kpad, (cuuint64_t)Mpad, (cuuint64_t)taps_total};
-        cuuint64_t strides[2] = {(cuuint64_t)Kpad * 2, (cuuint64_t)Mpad * Kpad * 2};
-        cuuint32_t box[3] = {32, 128, 1};
-        cuuint32_t es[3] = {1, 1, 1};
-        if (bf_get_map(&mWh, const_cast<void*>(wh), 3, dims, strides, box, es)) return -1;
-        if (bf_get_map(&mWl, const_cast<void*>(wl), 3, dims, strides, box, es)) return -1;
+        if (bf_get_map(&mXh, xp.hi, 4, dims, strides, box, es, p.kch == 64 ? 128 : 64)) return -1;
+        if (bf_get_map(&mXl, xp.lo, 4, dims, strides, box, es, p.kch == 64 ? 128 : 64)) return -1;
     }
     const size_t smem = (size_t)NP * pslot + (size_t)NW * wslot + 1024;
-    conv_bf_kernel<<<dim3(grid_tiles, mblocks, ksplit), BF_THREADS, smem, st>>>(*mXh, *mXl, *mWh, *mWl, p);
+    conv_bf_kernel<<<dim3(grid_tiles, mblocks, ksplit), BF_THREADS, smem, st>>>(*mXh, *mXl, p);
     return check_launch("conv_bf");
 }
 
-// xp: bf16 planes of g.x;  wh/wl: prepared weights [tap][Mpad][Kpad];  yp: optional planes of g.y (written by the epilogue)
-int conv_bf(const ConvGemm& g, const ActPlanes& xp, const void* wh, const void* wl, const ActPlanes* yp,
+// xp: 16-bit planes of g.x;  wtiles: prepared weight tiles in the SAME format as xp;  yp: optional planes of g.y (written
+// by the epilogue in yp->fmt)
+int conv_bf(const ConvGemm& g, const ActPlanes& xp, const void* wtiles, const ActPlanes* yp,
             float* part, unsigned int* tickets, cudaStream_t st) {
     MS_REQUIRE(conv_bf_supported(g), "conv_bf: unsupported geometry");
     MS_REQUIRE(xp.hi && xp.lo && (xp.cs & 7) == 0 && xp.cs >= g.x.c, "conv_bf: input planes missing");
@@ -578,7 +660,7 @@ int conv_bf(const ConvGemm& g, const ActPlanes& xp, const void* wh, const void* 
         int n = 0;
         for (int s = 0; s < g.kw; ++s)
             for (int r = 0; r < g.kh; ++r) taps[n++] = BfTapSpec{g.off_y + r * g.step, g.off_x + s * g.step, r * g.kw + s};
-        return conv_bf_launch(g, xp, wh, wl, yp, part, tickets, g.y.h, g.y.w, 1, 0, 0, g.mul, taps, n, taps_total, st);
+        return conv_bf_launch(g, xp, wtiles, yp, part, tickets, g.y.h, g.y.w, 1, 0, 0, g.mul, taps, n, taps_total, st);
     }
     // fractionally strided gather (stride-2 dgrad, conv_transpose): t = out + off + tap*step must be even, input = t / 2.
     // Output pixels of one parity class (py, px) see a fixed subset of the taps at unit input stride: four dense launches.
@@ -596,24 +678,22 @@ int conv_bf(const ConvGemm& g, const ActPlanes& xp, const void* wh, const void* 
                     taps[n++] = BfTapSpec{ty / 2, tx / 2, r * g.kw + s};    // exact: ty, tx even (C++ division truncates toward 0)
                 }
             }
-            if (n == 0) {
-                // no tap reaches this class: the gradient there is the epilogue of a zero sum; one zero-weight tap keeps it generic
-                set_error("conv_bf: parity class without taps"); return -2;
-            }
-            if (conv_bf_launch(g, xp, wh, wl, yp, part, tickets, Hj, Wj, 2, py, px, 1, taps, n, taps_total, st)) return -1;
+            if (n == 0) { set_error("conv_bf: parity class without taps"); return -2; }
+            if (conv_bf_launch(g, xp, wtiles, yp, part, tickets, Hj, Wj, 2, py, px, 1, taps, n, taps_total, st)) return -1;
         }
     return 0;
 }
 
 // one-shot convenience (operator-level C ABI / tests): splits the input, prepares the weights, runs the conv.
-//   scratch layout (bytes): [x hi | x lo | w hi | w lo | job | tickets | split-K partials]
+//   fmt: operand format (1 = fp16 forward planes, 0 = bf16 gradient planes)
+//   scratch layout (bytes): [x hi | x lo | weight tiles | job | tickets | split-K partials]
 size_t conv_bf_oneshot_scratch_bytes(const ConvGemm& g) {
     const size_t xe = g.x.pixels() * ((g.x.c + 7) / 8 * 8);
     const size_t we = conv_bf_weight_halfs(g.kh * g.kw, g.y.c, g.x.c);
-    return 2 * (xe * 2 + 256) + 2 * (we * 2 + 256) + 1024 + conv_bf_ticket_words() * 4 + conv_bf_part_floats() * 4 + 4096;
+    return 2 * (xe * 2 + 256) + (we * 2 + 256) + 1024 + conv_bf_ticket_words() * 4 + conv_bf_part_floats() * 4 + 4096;
 }
 
-int conv_bf_oneshot(const ConvGemm& g, int wmat_is_mk, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+int conv_bf_oneshot(const ConvGemm& g, int wmat_is_mk, int fmt, void* scratch, size_t scratch_bytes, cudaStream_t st) {
     MS_REQUIRE(conv_bf_supported(g), "conv_bf: unsupported geometry");
     MS_REQUIRE(scratch_bytes >= conv_bf_oneshot_scratch_bytes(g), "conv_bf: scratch too small");
     MS_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, "conv_bf: scratch must be 256B aligned");
@@ -622,18 +702,18 @@ int conv_bf_oneshot(const ConvGemm& g, int wmat_is_mk, void* scratch, size_t scr
     const int pcs = (g.x.c + 7) / 8 * 8;
     const size_t xe = g.x.pixels() * pcs;
     const size_t we = conv_bf_weight_halfs(g.kh * g.kw, g.y.c, g.x.c);
-    ActPlanes xp; xp.hi = take(xe * 2); xp.lo = take(xe * 2); xp.cs = pcs;
-    void* wh = take(we * 2); void* wl = take(we * 2);
+    ActPlanes xp; xp.hi = take(xe * 2); xp.lo = take(xe * 2); xp.cs = pcs; xp.fmt = fmt;
+    void* wt = take(we * 2);
     BfPrepJob* jd = reinterpret_cast<BfPrepJob*>(take(1024));
     unsigned int* tickets = reinterpret_cast<unsigned int*>(take(conv_bf_ticket_words() * 4));
     float* part = reinterpret_cast<float*>(take(conv_bf_part_floats() * 4));
     int Mpad, Kpad; conv_bf_weight_dims(g.y.c, g.x.c, Mpad, Kpad);
-    BfPrepJob job{g.wmat, wh, wl, g.kh * g.kw, g.y.c, g.x.c, Mpad, Kpad, wmat_is_mk ? 0 : 1};
+    BfPrepJob job{g.wmat, wt, g.kh * g.kw, g.y.c, g.x.c, Mpad, Kpad, wmat_is_mk ? 0 : 1, fmt};
     MS_CHECK_CUDA(cudaMemcpyAsync(jd, &job, sizeof job, cudaMemcpyHostToDevice, st));
     MS_CHECK_CUDA(cudaMemsetAsync(tickets, 0, conv_bf_ticket_words() * 4, st));
     if (bf_prep_weights(jd, 1, we, st)) return -1;
     if (split_planes(g.x, xp, st)) return -1;
-    return conv_bf(g, xp, wh, wl, nullptr, part, tickets, st);
+    return conv_bf(g, xp, wt, nullptr, part, tickets, st);
 }
 
 }  // namespace ms

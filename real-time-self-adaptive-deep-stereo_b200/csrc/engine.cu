@@ -48,14 +48,17 @@ Engine::Engine()
     if (!use_tc) conv_impl = 0;
     { const char* e5 = getenv("MS_HEADS"); use_heads = (e5 && e5[0] == '0') ? 0 : 1; }
     { const char* e6 = getenv("MS_BF_WGRAD"); use_bf_wgrad = (e6 && e6[0] == '0') ? 0 : 1; }
+    { const char* e7 = getenv("MS_WGRAD_MIXED"); wgrad_mixed = (e7 && e7[0] == '1') ? 1 : 0; }
+    wg_xp.hi = wg_xp.lo = nullptr; wg_xp.cs = 0; wg_xp.fmt = 0; wg_xp_halfs = 0;
     bf_jobs_dev = nullptr; bf_max_total = 0; bf_part = nullptr; bf_tickets = nullptr;
     dp_rank = 0; dp_world = 1; dp_connected = false; dp_xbuf = nullptr; dp_state = nullptr; dp_cap_floats = 0;
 }
 
-void Engine::add_planes(Bump& A, const TView& v) {
+void Engine::add_planes(Bump& A, const TView& v, int fmt) {
     if (conv_impl != 1) return;
     if (v.p && planes.count(v.p)) return;          // (sizing pass: every pointer is null -- never dedupe there)
     ActPlanes pl;
+    pl.fmt = fmt;
     pl.cs = (v.c + 7) / 8 * 8;
     const size_t floats = (v.pixels() * pl.cs + 1) / 2;     // bf16 elements -> floats
     pl.hi = A.alloc(floats);
@@ -202,9 +205,12 @@ size_t Engine::layout(float* base) {
         if (L.stride == 1 && L.cout <= 192)   // tcgen05 wgrad: NCHW copy of dY + <=64 split partials + bias partials
             max_wg = std::max(max_wg, pixels * L.cout + 64 * (size_t)L.kh * L.kw * L.cin * L.cout + 128 * (size_t)L.cout + 8192);
         max_wt = std::max(max_wt, (size_t)L.kh * L.kw * L.cin * L.cout);
-        if (conv_impl == 1 && !L.transposed && L.cin >= 16 && L.cout >= 16)
+        if (conv_impl == 1 && !L.transposed && L.cin >= 16 && L.cout >= 16) {
             max_wg = std::max(max_wg, std::min<size_t>(wgrad_bf_workspace_floats(L.kh, L.kw, L.cin, L.cout), (size_t)48 << 20));
+            wg_xp_halfs = std::max(wg_xp_halfs, pixels * L.stride * L.stride * (size_t)((L.cin + 7) / 8 * 8));
+        }
     };
+    wg_xp_halfs = 0;
     if (net == 1) {
         layout_dispnet(A, max_wg, max_wt);
     } else {
@@ -213,7 +219,7 @@ size_t Engine::layout(float* base) {
         if (i % 2) { h = (h + 1) / 2; w = (w + 1) / 2; }
         pyr[i] = tens(2 * B, h, w, PYR_CH[i]);
         g_pyr[i] = tens(2 * B, h, w, PYR_CH[i]);
-        add_planes(A, pyr[i]); add_planes(A, g_pyr[i]);
+        add_planes(A, pyr[i], 1); add_planes(A, g_pyr[i], 0);
         track(layers[i - 1], (size_t)2 * B * h * w);
         snprintf(nm, sizeof nm, "left/conv%d", i); tensors[nm] = batch(pyr[i], 0, B);
         snprintf(nm, sizeof nm, "right/conv%d", i); tensors[nm] = batch(pyr[i], B, B);
@@ -223,20 +229,20 @@ size_t Engine::layout(float* base) {
     ctxin = tens(B, pyr[4].h, pyr[4].w, PYR_CH[4] + 1, pad4(PYR_CH[4] + 1));
     g_ctxin = tens(B, pyr[4].h, pyr[4].w, PYR_CH[4] + 1, pad4(PYR_CH[4] + 1));
     tensors["ctxin"] = ctxin; tensors["grad/ctxin"] = g_ctxin;
-    add_planes(A, ctxin);
+    add_planes(A, ctxin, 1);
     for (int k = 6; k >= 2; --k) {
         const int f = feat_of(k), C = PYR_CH[f];
         const int hh = pyr[f].h, ww = pyr[f].w;
         const int ct = C + nd + (k < 6 ? 1 : 0);
         cost[k] = tens(B, hh, ww, ct, pad4(ct));
         g_cost[k] = tens(B, hh, ww, ct, pad4(ct));
-        add_planes(A, cost[k]);
+        add_planes(A, cost[k], 1);
         snprintf(nm, sizeof nm, "cost%d", k); tensors[nm] = cost[k];
         snprintf(nm, sizeof nm, "grad/cost%d", k); tensors[nm] = g_cost[k];
         for (int j = 1; j <= 5; ++j) {
             est[k][j] = tens(B, hh, ww, EST_CH[j - 1]);
             g_est[k][j] = tens(B, hh, ww, EST_CH[j - 1]);
-            add_planes(A, est[k][j]); add_planes(A, g_est[k][j]);
+            add_planes(A, est[k][j], 1); add_planes(A, g_est[k][j], 0);
             snprintf(nm, sizeof nm, "fgc-volume-filtering-%d/disp%d", k, j); tensors[nm] = est[k][j];
             snprintf(nm, sizeof nm, "grad/fgc-volume-filtering-%d/disp%d", k, j); tensors[nm] = g_est[k][j];
         }
@@ -252,7 +258,7 @@ size_t Engine::layout(float* base) {
     for (int j = 1; j <= 6; ++j) {
         ctx[j] = tens(B, pyr[4].h, pyr[4].w, CTX_CH[j - 1]);
         g_ctx[j] = tens(B, pyr[4].h, pyr[4].w, CTX_CH[j - 1]);
-        add_planes(A, ctx[j]); add_planes(A, g_ctx[j]);
+        add_planes(A, ctx[j], 1); add_planes(A, g_ctx[j], 0);
         snprintf(nm, sizeof nm, "context%d", j); tensors[nm] = ctx[j];
         snprintf(nm, sizeof nm, "grad/context%d", j); tensors[nm] = g_ctx[j];
     }
@@ -298,9 +304,9 @@ size_t Engine::layout(float* base) {
         }
         job_end[gidx] = (int)prep_jobs.size();
     }
-    // split-bf16 weight planes (hi / lo) per layer and orientation + their batched prep job table
-    bfw[0].assign(layers.size(), BfW{nullptr, nullptr, false});
-    bfw[1].assign(layers.size(), BfW{nullptr, nullptr, false});
+    // split 16-bit weight tiles per layer and orientation (forward: fp16, dgrad: bf16) + their batched prep job table
+    bfw[0].assign(layers.size(), BfW{nullptr, false});
+    bfw[1].assign(layers.size(), BfW{nullptr, false});
     bf_jobs.clear(); bf_job_begin.assign(n_groups + 1, 0); bf_job_end.assign(n_groups + 1, 0);
     bf_max_total = 0;
     for (int gidx = 0; gidx <= n_groups && conv_impl == 1; ++gidx) {
@@ -308,22 +314,23 @@ size_t Engine::layout(float* base) {
         for (size_t li = 0; li < layers.size(); ++li) {
             const ConvLayer& L = layers[li];
             const int lg = L.group < 0 ? n_groups : L.group;
-            if (lg != gidx || L.transposed || L.cin < 8 || L.cout < 8 || L.kh * L.kw > 49) continue;
+            if (lg != gidx || L.transposed || L.cin < 8 || L.cout < 8 || L.kh * L.kw > 49 || L.stride > 2) continue;
             for (int dir = 0; dir < 2; ++dir) {
-                if (dir == 0 && L.stride > 2) continue;
-                if (dir == 1 && L.stride > 2) continue;
                 const int M = dir == 0 ? L.cout : L.cin, K = dir == 0 ? L.cin : L.cout;
                 int Mpad, Kpad; conv_bf_weight_dims(M, K, Mpad, Kpad);
                 const size_t halfs = conv_bf_weight_halfs(L.kh * L.kw, M, K);
                 BfW t; t.ok = true;
-                t.hi = alloc((halfs + 1) / 2); t.lo = alloc((halfs + 1) / 2);
+                t.tiles = alloc((halfs + 1) / 2);
                 bfw[dir][li] = t;
-                BfPrepJob j{base ? Wt + L.w_off : nullptr, t.hi, t.lo, L.kh * L.kw, M, K, Mpad, Kpad, dir == 0 ? 1 : 0};
+                BfPrepJob j{base ? Wt + L.w_off : nullptr, t.tiles, L.kh * L.kw, M, K, Mpad, Kpad, dir == 0 ? 1 : 0, dir == 0 ? 1 : 0};
                 bf_jobs.push_back(j);
                 bf_max_total = std::max(bf_max_total, halfs);
             }
         }
         bf_job_end[gidx] = (int)bf_jobs.size();
+    }
+    if (conv_impl == 1 && wg_xp_halfs) {
+        wg_xp.hi = alloc((wg_xp_halfs + 1) / 2); wg_xp.lo = alloc((wg_xp_halfs + 1) / 2); wg_xp.fmt = 0;
     }
     bf_part = alloc(conv_bf_part_floats());
     bf_tickets = reinterpret_cast<unsigned int*>(alloc(conv_bf_ticket_words()));
@@ -376,7 +383,7 @@ int Engine::conv_fwd(const ConvLayer& L, const TView& x, const TView& y, const f
     } else if (xpl) {
         if (ensure_planes(x, st)) return -1;
         const ActPlanes* ypl = planes_of(y);
-        rc = conv_bf(p, *xpl, bfw[0][li].hi, bfw[0][li].lo, ypl, bf_part, bf_tickets, st);
+        rc = conv_bf(p, *xpl, bfw[0][li].tiles, ypl, bf_part, bf_tickets, st);
         if (ypl) fresh.insert(y.p);
     } else {
         fresh.erase(y.p);
@@ -407,9 +414,16 @@ int Engine::conv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, cons
         const ActPlanes* wxp = (conv_impl == 1 && use_bf_wgrad && wgrad_bf_supported(q)) ? planes_of(x) : nullptr;
         const ActPlanes* wdp = wxp ? planes_of(dpre) : nullptr;
         if (wxp && wdp) {
-            rc = ensure_planes(x, st);
-            if (!rc) rc = ensure_planes(dpre, st);
-            if (!rc) rc = wgrad_bf(q, *wxp, *wdp, st);
+            rc = ensure_planes(dpre, st);
+            if (!rc && wgrad_mixed) {                       // fp16 forward planes x bf16 gradient planes in one MMA
+                rc = ensure_planes(x, st);
+                if (!rc) rc = wgrad_bf(q, *wxp, *wdp, st);
+            } else if (!rc) {                               // bf16 copy of the forward activation (scratch planes)
+                ActPlanes xb = wg_xp; xb.cs = (x.c + 7) / 8 * 8;
+                MS_REQUIRE(xb.hi && x.pixels() * (size_t)xb.cs <= wg_xp_halfs, "conv_bwd: wgrad scratch planes too small");
+                rc = split_planes(x, xb, st);
+                if (!rc) rc = wgrad_bf(q, xb, *wdp, st);
+            }
         } else {
             rc = (use_tc && use_tc_wgrad && wgrad_tc_supported(q)) ? wgrad_tc(q, st) : conv_wgrad(q, st);
         }
@@ -436,7 +450,7 @@ int Engine::conv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, cons
             p.wmat = wT;
             rc = ensure_planes(dpre, st);
             const ActPlanes* ypl = planes_of(*dx);
-            if (!rc) rc = conv_bf(p, *xpl, bfw[1][li].hi, bfw[1][li].lo, ypl, bf_part, bf_tickets, st);
+            if (!rc) rc = conv_bf(p, *xpl, bfw[1][li].tiles, ypl, bf_part, bf_tickets, st);
             if (ypl) fresh.insert(dx->p);
         } else if (use_tc && tcw[1][li].ok && conv_tc_profitable(p)) {
             p.wmat = wT;

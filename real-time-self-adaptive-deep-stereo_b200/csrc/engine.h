@@ -95,12 +95,14 @@ struct Engine {
     int conv_impl;                                 // 1 = split-bf16 (default), 0 = the 3xTF32 kernels (MS_CONV_IMPL=tf32)
     std::map<const float*, ActPlanes> planes;      // bf16 hi/lo planes of tensors that feed convolutions (key: base pointer)
     std::set<const float*> fresh;                  // planes already written by a conv_bf epilogue in the current pass
-    struct BfW { void* hi; void* lo; bool ok; };
+    struct BfW { void* tiles; bool ok; };
     std::vector<BfW> bfw[2];                       // prepared weights per layer and orientation (0 = forward, 1 = dgrad)
     std::vector<BfPrepJob> bf_jobs; std::vector<int> bf_job_begin, bf_job_end;
     BfPrepJob* bf_jobs_dev; size_t bf_max_total;
     float* bf_part; unsigned int* bf_tickets;
-    void add_planes(Bump& A, const TView& v);
+    void add_planes(Bump& A, const TView& v, int fmt);      // fmt 1 = forward activation (fp16 of x/16), 0 = gradient (bf16)
+    ActPlanes wg_xp; size_t wg_xp_halfs;              // bf16 scratch planes: forward activations re-split for the weight gradient
+    int wgrad_mixed;                                  // MS_WGRAD_MIXED=1: feed the fp16 forward planes to wgrad_bf directly (f16 x bf16 MMA)
     const ActPlanes* planes_of(const TView& v) const;
     int ensure_planes(const TView& v, cudaStream_t st);
     // ---- data-parallel exchange over NVLink peer memory (csrc/dp.cu)

@@ -54,8 +54,10 @@ void Engine::layout_dispnet(Bump& A, size_t& max_wg, size_t& max_wt) {
         max_wg = std::max(max_wg, conv_wgrad_workspace_floats(L.kh * L.kw, L.cin, L.cout, pixels));
         max_wg = std::max(max_wg, conv_wgrad_workspace_floats(L.kh * L.kw, L.cout, L.cin, pixels));
         max_wt = std::max(max_wt, (size_t)L.kh * L.kw * L.cin * L.cout);
-        if (conv_impl == 1 && !L.transposed && L.cin >= 16 && L.cout >= 16)
+        if (conv_impl == 1 && !L.transposed && L.cin >= 16 && L.cout >= 16) {
             max_wg = std::max(max_wg, std::min<size_t>(wgrad_bf_workspace_floats(L.kh, L.kw, L.cin, L.cout), (size_t)48 << 20));
+            wg_xp_halfs = std::max(wg_xp_halfs, pixels * L.stride * L.stride * (size_t)((L.cin + 7) / 8 * 8));
+        }
         if (L.stride == 1 && !L.transposed && L.cout <= 192)
             max_wg = std::max(max_wg, pixels * L.cout + 64 * (size_t)L.kh * L.kw * L.cin * L.cout + 128 * (size_t)L.cout + 8192);
     };
@@ -63,15 +65,15 @@ void Engine::layout_dispnet(Bump& A, size_t& max_wg, size_t& max_wt) {
     d_c1 = A.tens(2 * B, h2, w2, 64); gd_c1 = A.tens(2 * B, h2, w2, 64);
     d_c2 = A.tens(2 * B, h4, w4, 128); gd_c2 = A.tens(2 * B, h4, w4, 128);
     d_cat3 = A.tens(B, h4, w4, 145, 148); gd_cat3 = A.tens(B, h4, w4, 145, 148);
-    add_planes(A, d_c1); add_planes(A, d_c2); add_planes(A, d_cat3);
-    add_planes(A, gd_c2); add_planes(A, gd_cat3);
+    add_planes(A, d_c1, 1); add_planes(A, d_c2, 1); add_planes(A, d_cat3, 1);
+    add_planes(A, gd_c2, 0); add_planes(A, gd_cat3, 0);
     track(layers[0], (size_t)2 * B * h2 * w2); track(layers[1], (size_t)2 * B * h4 * w4); track(layers[2], (size_t)B * h4 * w4);
     int hh = h4, ww = w4;
     for (int i = 0; i < 8; ++i) {
         const ConvLayer& L = layers[3 + i];
         if (L.stride == 2) { hh /= 2; ww /= 2; }
         d_enc[i] = A.tens(B, hh, ww, L.cout); gd_enc[i] = A.tens(B, hh, ww, L.cout);
-        add_planes(A, d_enc[i]); add_planes(A, gd_enc[i]);
+        add_planes(A, d_enc[i], 1); add_planes(A, gd_enc[i], 0);
         track(L, (size_t)B * hh * ww);
         tensors[L.name] = d_enc[i]; tensors["grad/" + L.name] = gd_enc[i];
     }
@@ -88,7 +90,7 @@ void Engine::layout_dispnet(Bump& A, size_t& max_wg, size_t& max_wt) {
         d_pr[u] = A.tens(B, bh, bw, 1); gd_pr[u] = A.tens(B, bh, bw, 1);
         d_cat[u] = A.tens(B, 2 * bh, 2 * bw, ct, pad4i(ct)); gd_cat[u] = A.tens(B, 2 * bh, 2 * bw, ct, pad4i(ct));
         d_cc[u] = A.tens(B, 2 * bh, 2 * bw, S.cout); gd_cc[u] = A.tens(B, 2 * bh, 2 * bw, S.cout);
-        add_planes(A, d_cat[u]); add_planes(A, d_cc[u]); add_planes(A, gd_cc[u]);
+        add_planes(A, d_cat[u], 1); add_planes(A, d_cc[u], 1); add_planes(A, gd_cc[u], 0);
         for (int j = 0; j < 4; ++j) track(layers[up_layer(u, j)], (size_t)B * 4 * bh * bw);
         std::string n(S.name);
         tensors[n + "/predict"] = d_pr[u];

@@ -56,6 +56,7 @@ struct WgradBfParams {
     uint32_t stage_bytes, x_plane_bytes, d_plane_bytes;
     int tmem_cols;
     int with_bias;
+    int xfmt, dfmt;                // plane formats of X and dY (0 = bf16, 1 = fp16 of value / 16)
     float* part;                   // [split][tap][ci][co]
     float* bpart;                  // [split][co]
 };
@@ -107,7 +108,8 @@ wgrad_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
     }
     if (warp >= 2) {                                    // the all-ones A tile of the bias-gradient MMAs
         uint32_t* ones = reinterpret_cast<uint32_t*>(gbase);
-        for (int i = threadIdx.x - 64; i < (int)(WB_ONES_BYTES / 4); i += WB_THREADS - 64) ones[i] = 0x3F803F80u;
+        const uint32_t one2 = p.dfmt == 0 ? 0x3F803F80u : 0x3C003C00u;      // 1.0 in the format of the dY planes
+        for (int i = threadIdx.x - 64; i < (int)(WB_ONES_BYTES / 4); i += WB_THREADS - 64) ones[i] = one2;
         fence_async_smem();
     }
     tc_fence_before();
@@ -147,8 +149,12 @@ wgrad_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
         // ================= MMA issuer =================
         if (lane == 0 && total > 0) {
             // D = f32, A = B = bf16, both MN-major (bits 15, 16), N >> 3 at bit 17, M >> 4 at bit 24
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+            // A (= X) / B (= dY) element formats follow the planes: 0 = f16, 1 = bf16 in the descriptor
+            const uint32_t fa = p.xfmt == 0 ? 1u : 0u, fb = p.dfmt == 0 ? 1u : 0u;
+            const uint32_t idesc = (1u << 4) | (fa << 7) | (fb << 10) | (1u << 15) | (1u << 16) |
                                    ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc_ones = (1u << 4) | (fb << 7) | (fb << 10) | (1u << 15) | (1u << 16) |
+                                        ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
             const uint32_t lbo_x = p.xblk > 1 ? (uint32_t)p.x_rows * WB_ATOM : 0u;
             const uint32_t lbo_d = (uint32_t)p.TH * WB_ATOM;
             const uint64_t ones = umma_desc_mn_sw128(base, 2048u, 1024u);
@@ -175,8 +181,8 @@ wgrad_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
                         wb_mma_f16(acc, ah, bh, idesc, 1u);
                     }
                     if (do_bias) {
-                        wb_mma_f16(acc_bias, ones, bl, idesc, started);
-                        wb_mma_f16(acc_bias, ones, bh, idesc, 1u);
+                        wb_mma_f16(acc_bias, ones, bl, idesc_ones, started);
+                        wb_mma_f16(acc_bias, ones, bh, idesc_ones, 1u);
                     }
                     started = 1u;
                 }
@@ -257,7 +263,8 @@ wgrad_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
 
 // dw[i] = sum_k part[k][i] (fixed order), db[c] = sum_k bpart[k][c]
 __global__ void wgrad_bf_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, size_t n4, int split,
-                                       const float* __restrict__ bpart, float* __restrict__ db, int co, int accumulate) {
+                                       const float* __restrict__ bpart, float* __restrict__ db, int co, int accumulate,
+                                       float wscale, float bscale) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n4) {
         const float4* src = reinterpret_cast<const float4*>(part) + i;
@@ -266,6 +273,7 @@ __global__ void wgrad_bf_reduce_kernel(const float* __restrict__ part, float* __
             const float4 v = __ldcs(src + (size_t)k * n4);
             a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
         }
+        a.x *= wscale; a.y *= wscale; a.z *= wscale; a.w *= wscale;      // undoes the 1/16 pre-scale of fp16 planes (exact)
         float4* d = reinterpret_cast<float4*>(dw) + i;
         if (accumulate) { const float4 o = *d; a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w; }
         *d = a;
@@ -273,6 +281,7 @@ __global__ void wgrad_bf_reduce_kernel(const float* __restrict__ part, float* __
         const int c = (int)(i - n4);
         float a = 0.f;
         for (int k = 0; k < split; ++k) a += bpart[(size_t)k * co + c];
+        a *= bscale;
         if (accumulate) a += db[c];
         db[c] = a;
     }
@@ -383,6 +392,7 @@ int wgrad_bf(const ConvWgrad& q, const ActPlanes& xp, const ActPlanes& dp, cudaS
     p.nstages = P.nstages; p.stage_bytes = P.stage_bytes; p.x_plane_bytes = P.x_plane_bytes; p.d_plane_bytes = P.d_plane_bytes;
     p.tmem_cols = P.tmem_cols;
     p.with_bias = q.db ? 1 : 0;
+    p.xfmt = xp.fmt; p.dfmt = dp.fmt;
     p.part = q.workspace;
     p.bpart = q.workspace + (size_t)P.splits * wn;
 
@@ -407,7 +417,9 @@ int wgrad_bf(const ConvWgrad& q, const ActPlanes& xp, const ActPlanes& dp, cudaS
     wgrad_bf_kernel<<<dim3(q.kw * P.mblocks * P.nblocks, P.splits), WB_THREADS, smem, st>>>(*mXh, *mXl, *mDh, *mDl, p);
     const size_t n4 = wn / 4;
     const size_t work = n4 + (q.db ? (size_t)co : 0);
-    wgrad_bf_reduce_kernel<<<(unsigned)cdivz(work, 256), 256, 0, st>>>(p.part, q.dw, n4, P.splits, p.bpart, q.db, co, q.accumulate);
+    const float sx16 = xp.fmt == 1 ? 16.f : 1.f, sd16 = dp.fmt == 1 ? 16.f : 1.f;
+    wgrad_bf_reduce_kernel<<<(unsigned)cdivz(work, 256), 256, 0, st>>>(p.part, q.dw, n4, P.splits, p.bpart, q.db, co, q.accumulate,
+                                                                      sx16 * sd16, sd16);
     return check_launch("wgrad_bf", 2);
 }
 
@@ -418,14 +430,14 @@ size_t wgrad_bf_oneshot_scratch_bytes(const ConvWgrad& q) {
     return 2 * (xe * 2 + 256) + 2 * (de * 2 + 256) + wgrad_bf_workspace_floats(q.kh, q.kw, q.x.c, q.dy.c) * 4 + 1024;
 }
 
-int wgrad_bf_oneshot(const ConvWgrad& q0, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+int wgrad_bf_oneshot(const ConvWgrad& q0, int xfmt, int dfmt, void* scratch, size_t scratch_bytes, cudaStream_t st) {
     MS_REQUIRE(wgrad_bf_supported(q0), "wgrad_bf: unsupported geometry");
     MS_REQUIRE(scratch_bytes >= wgrad_bf_oneshot_scratch_bytes(q0), "wgrad_bf: scratch too small");
     MS_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, "wgrad_bf: scratch must be 256B aligned");
     unsigned char* b = reinterpret_cast<unsigned char*>(scratch);
     auto take = [&](size_t bytes) { unsigned char* r = b; b += (bytes + 255) / 256 * 256; return r; };
     ActPlanes xp, dp;
-    xp.cs = (q0.x.c + 7) / 8 * 8; dp.cs = (q0.dy.c + 7) / 8 * 8;
+    xp.cs = (q0.x.c + 7) / 8 * 8; dp.cs = (q0.dy.c + 7) / 8 * 8; xp.fmt = xfmt; dp.fmt = dfmt;
     const size_t xe = q0.x.pixels() * xp.cs, de = q0.dy.pixels() * dp.cs;
     xp.hi = take(xe * 2); xp.lo = take(xe * 2); dp.hi = take(de * 2); dp.lo = take(de * 2);
     ConvWgrad q = q0;

@@ -139,8 +139,9 @@ def conv2d_dgrad_bf(dy, w, in_hw=None, stride=1, dilation=1):
     return dx
 
 
-def conv2d_wgrad_bf(x, dy, kh, kw, stride=1, dilation=1):
-    """split-bf16 tcgen05 weight + bias gradient (csrc/wgrad_bf.cu), stride 1 or 2."""
+def conv2d_wgrad_bf(x, dy, kh, kw, stride=1, dilation=1, x_fmt=0):
+    """tcgen05 weight + bias gradient on 16-bit planes (csrc/wgrad_bf.cu), stride 1 or 2.  x_fmt=1: the x planes are the
+    forward fp16 planes (f16 x bf16 MMA)."""
     n, h, wd, cin = x.shape
     _, oh, ow, cout = dy.shape
     dw = torch.empty(kh, kw, cin, cout, device=x.device, dtype=torch.float32)
@@ -149,7 +150,7 @@ def conv2d_wgrad_bf(x, dy, kh, kw, stride=1, dilation=1):
     scratch = torch.empty(ns + 256, device=x.device, dtype=torch.uint8)
     off = (-scratch.data_ptr()) % 256
     check(lib().ms_conv2d_wgrad_bf(_p(x), n, h, wd, cin, cin, _p(dy), oh, ow, cout, cout, _p(dw), _p(db), kh, kw, stride,
-                                   dilation, c_void_p(scratch.data_ptr() + off), ns, _s()), 'ms_conv2d_wgrad_bf')
+                                   dilation, x_fmt, c_void_p(scratch.data_ptr() + off), ns, _s()), 'ms_conv2d_wgrad_bf')
     return dw, db
 
 

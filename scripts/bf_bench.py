@@ -23,11 +23,11 @@ SHAPES = [  # n, h, w, cin, cout, k, stride, dil
 ]
 
 
-def planes(t, c):
+def planes(t, c, fmt):
     pcs = (c + 7) // 8 * 8
     n, h, w, _ = t.shape
     hi = torch.empty(n * h * w * pcs, dtype=torch.bfloat16, device=dev); lo = torch.empty_like(hi)
-    check(L.ms_bf_split(P(t), n, h, w, c, c, P(hi), P(lo), pcs, st()), 'split')
+    check(L.ms_bf_split(P(t), n, h, w, c, c, P(hi), P(lo), pcs, fmt, st()), 'split')
     return hi, lo, pcs
 
 
@@ -50,24 +50,24 @@ def setup(shape):
     x = torch.randn(n, h, w, cin, device=dev); wt = torch.randn(k, k, cin, cout, device=dev) * 0.05
     b = torch.zeros(cout, device=dev); y = torch.empty(n, oh, ow, cout, device=dev)
     g = torch.randn(n, oh, ow, cout, device=dev)
-    xh, xl, xpcs = planes(x, cin); gh, gl, gpcs = planes(g, cout)
+    xh, xl, xpcs = planes(x, cin, 1); xbh, xbl, _ = planes(x, cin, 0); gh, gl, gpcs = planes(g, cout, 0)
     ypcs = (cout + 7) // 8 * 8
     yh = torch.empty(n * oh * ow * ypcs, dtype=torch.bfloat16, device=dev); yl = torch.empty_like(yh)
     halfs = L.ms_bf_weight_halfs(k * k, cout, cin)
-    wh = torch.empty(halfs, dtype=torch.bfloat16, device=dev); wl = torch.empty_like(wh)
+    wt16 = torch.empty(halfs, dtype=torch.bfloat16, device=dev)
     job = torch.empty(256, dtype=torch.uint8, device=dev)
-    check(L.ms_bf_prep_weights(P(wt), k * k, cin, cout, 0, P(wh), P(wl), P(job), st()), 'prep')
+    check(L.ms_bf_prep_weights(P(wt), k * k, cin, cout, 0, 1, P(wt16), P(job), st()), 'prep')
     part = torch.empty(L.ms_conv2d_bf_part_floats(), device=dev)
     tick = torch.zeros(L.ms_conv2d_bf_ticket_words(), dtype=torch.int32, device=dev)
     nws = L.ms_conv2d_wgrad_bf_workspace(k, k, cin, cout)
     ws = torch.empty(nws, device=dev); dw = torch.empty(k, k, cin, cout, device=dev); db = torch.empty(cout, device=dev)
     def fwd():
-        check(L.ms_conv2d_fwd_bf_planes(P(xh), P(xl), xpcs, n, h, w, cin, P(wh), P(wl), P(b), P(y), cout, cout, P(yh), P(yl), ypcs,
+        check(L.ms_conv2d_fwd_bf_planes(P(xh), P(xl), xpcs, 1, n, h, w, cin, P(wt16), P(b), P(y), cout, cout, P(yh), P(yl), ypcs,
                                         k, k, s, d, 0.2, P(part), P(tick), st()), 'fwd')
     def wgrad():
-        check(L.ms_conv2d_wgrad_bf_planes(P(xh), P(xl), xpcs, n, h, w, cin, P(gh), P(gl), gpcs, oh, ow, cout, P(dw), P(db),
+        check(L.ms_conv2d_wgrad_bf_planes(P(xbh), P(xbl), xpcs, 0, n, h, w, cin, P(gh), P(gl), gpcs, oh, ow, cout, P(dw), P(db),
                                           k, k, s, d, P(ws), nws, st()), 'wgrad')
-    keep = (x, wt, b, y, g, xh, xl, gh, gl, yh, yl, wh, wl, job, part, tick, ws, dw, db)
+    keep = (x, wt, b, y, g, xh, xl, xbh, xbl, gh, gl, yh, yl, wt16, job, part, tick, ws, dw, db)
     return fwd, wgrad, n * oh * ow * k * k * cin * cout, keep
 
 

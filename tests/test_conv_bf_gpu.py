@@ -1,14 +1,29 @@
-"""GPU parity of the split-bf16 tcgen05 convolution (csrc/conv_bf.cu) vs the CPU oracle.
+"""GPU parity of the split-16-bit tcgen05 convolution kernels (csrc/conv_bf.cu, csrc/wgrad_bf.cu) vs the CPU oracle.
 
-Three kind::f16 MMAs per K step on bf16 hi/lo planes: per-product relative error <= ~3 * 2^-16, accumulated in fp32.
-Tolerance: 1e-4 relative L-inf of the output (typical measured 1e-5 .. 3e-5), stated here and in DESIGN.md section 7.
+Three kind::f16 MMAs per K step on hi/lo planes, accumulated in fp32:
+  forward  : fp16 planes (22 mantissa bits)  -> per-product relative error <= ~3 * 2^-22; tolerance 2e-5 relative L-inf
+  gradients: bf16 planes (16 mantissa bits)  -> per-product relative error <= ~3 * 2^-16; tolerance 1e-4 relative L-inf
+Measured errors are appended to gpurun_out/conv_bf_errors.jsonl (DESIGN.md section 7 quotes them).
 """
+import json
+import os
 import numpy as np
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
-TOL = 1e-4
+TOL = 1e-4          # bf16-plane kernels (dgrad, wgrad)
+TOL_FWD = 2e-5      # fp16-plane forward
+_LOG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out', 'conv_bf_errors.jsonl')
+
+
+def _log(rec):
+    try:
+        os.makedirs(os.path.dirname(_LOG), exist_ok=True)
+        with open(_LOG, 'a') as f:
+            f.write(json.dumps(rec) + '\n')
+    except OSError:
+        pass
 
 
 def rel_linf(a, b):
@@ -57,7 +72,9 @@ def test_conv_bf_forward(case):
     out = ops.conv2d_bf(cu(x), cu(wt), cu(b), stride, dil, alpha)
     torch.cuda.synchronize()
     assert out.shape == tuple(ref.shape)
-    assert rel_linf(out.cpu().numpy(), ref.numpy()) < TOL
+    err = rel_linf(out.cpu().numpy(), ref.numpy())
+    _log({'op': 'fwd', 'case': list(case), 'rel_linf': err})
+    assert err < TOL_FWD
 
 
 @pytest.mark.parametrize('case', CASES)
@@ -75,7 +92,9 @@ def test_conv_bf_dgrad(case):
     (gx,) = torch.autograd.grad(pre, xt, grad_outputs=torch.tensor(g))
     dx = ops.conv2d_dgrad_bf(cu(g), cu(wt), (h, w), stride, dil)
     torch.cuda.synchronize()
-    assert rel_linf(dx.cpu().numpy(), gx.numpy()) < TOL
+    err = rel_linf(dx.cpu().numpy(), gx.numpy())
+    _log({'op': 'dgrad', 'case': list(case), 'rel_linf': err})
+    assert err < TOL
 
 
 WGRAD_CASES = [c for c in CASES if c[3] >= 16 and c[4] >= 16 and c[4] % 4 == 0] + [
@@ -102,5 +121,6 @@ def test_wgrad_bf(case):
     gw, gb = torch.autograd.grad(pre, (wt, b), grad_outputs=torch.tensor(g))
     dw, db = ops.conv2d_wgrad_bf(cu(x), cu(g), k, k, stride, dil)
     torch.cuda.synchronize()
-    assert rel_linf(dw.cpu().numpy(), gw.numpy()) < TOL
-    assert rel_linf(db.cpu().numpy(), gb.numpy()) < TOL
+    e1, e2 = rel_linf(dw.cpu().numpy(), gw.numpy()), rel_linf(db.cpu().numpy(), gb.numpy())
+    _log({'op': 'wgrad', 'case': list(case), 'rel_linf_dw': e1, 'rel_linf_db': e2})
+    assert e1 < TOL and e2 < TOL
