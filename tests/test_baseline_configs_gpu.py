@@ -114,7 +114,8 @@ def _oracle_steps(params, mode, left, right, module):
 
 def _check_step(net, ad, params, out, o32, r32, o64, r64, tag):
     assert abs(out['loss'] - r64['full_loss']) < TOL_LOSS
-    assert abs(out['train_loss'] - r64['train_loss']) < TOL_LOSS
+    if tag.startswith('mad'):                       # FULL trains on the full-resolution loss itself (slot 1 unused)
+        assert abs(out['train_loss'] - r64['train_loss']) < TOL_LOSS
     gv = net.engine.param_views(net.engine.grads)
     got = {n: gv[n].cpu().numpy() for n in r64['grads']}
     rep = grad_report(got, r32['grads'], r64['grads'])
