@@ -71,6 +71,7 @@ struct ConvBfParams {
     int tmem_cols;
     int cout;
     int ksplit;
+    int debug;                    // MS_BF_DEBUG kill switches (measurement only): 1 = no MMAs, 2 = no weight loads, 4 = no patch loads, 8 = no epilogue stores
     const unsigned char* wtiles;  // pre-tiled weights [M block][tap][K block][hi tile | lo tile]
     float* part; unsigned int* tickets;
     float* y; int ycs;
@@ -167,15 +168,21 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
             for (int u = u0; u < u1; ++u) {
                 const BfPatch pt = p.patch[pi];
                 mb_wait(&pempty[ps], pph ^ 1u);
-                mb_expect_tx(&pfull[ps], pslot);
                 unsigned char* dst = gbase + (size_t)ps * pslot;
-                tma_load_4d(dst, &mapXh, &pfull[ps], kb * p.kch, x0 * p.sx + pt.dx, y0 * p.sx + pt.dy, img);
-                tma_load_4d(dst + p.slot_bytes, &mapXl, &pfull[ps], kb * p.kch, x0 * p.sx + pt.dx, y0 * p.sx + pt.dy, img);
+                if (p.debug & 4) mb_arrive(&pfull[ps]);
+                else {
+                    mb_expect_tx(&pfull[ps], pslot);
+                    tma_load_4d(dst, &mapXh, &pfull[ps], kb * p.kch, x0 * p.sx + pt.dx, y0 * p.sx + pt.dy, img);
+                    tma_load_4d(dst + p.slot_bytes, &mapXl, &pfull[ps], kb * p.kch, x0 * p.sx + pt.dx, y0 * p.sx + pt.dy, img);
+                }
                 if (++ps == p.NP) { ps = 0; pph ^= 1u; }
                 for (int t = pt.tap0; t < pt.tap0 + pt.ntaps; ++t) {
                     mb_wait(&wempty[ws], wph ^ 1u);
-                    mb_expect_tx(&wfull[ws], wslot);
-                    bulk_load(gbase + w_off + (size_t)ws * wslot, wbase + ((size_t)p.tap[t].widx * p.kblocks + kb) * wslot, wslot, &wfull[ws]);
+                    if (p.debug & 2) mb_arrive(&wfull[ws]);
+                    else {
+                        mb_expect_tx(&wfull[ws], wslot);
+                        bulk_load(gbase + w_off + (size_t)ws * wslot, wbase + ((size_t)p.tap[t].widx * p.kblocks + kb) * wslot, wslot, &wfull[ws]);
+                    }
                     if (++ws == p.NW) { ws = 0; wph ^= 1u; }
                 }
                 if (++pi == p.n_patches) { pi = 0; ++kb; }
@@ -207,7 +214,7 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
                     const uint64_t xh = umma_desc_k(pb + boff, sw128), xl = umma_desc_k(pb + p.slot_bytes + boff, sw128);
                     const uint32_t wb = base + w_off + (uint32_t)ws * wslot;
                     const uint64_t wh = umma_desc_k(wb, sw128), wl = umma_desc_k(wb + p.wtile_bytes, sw128);
-                    for (int j = 0; j < k16; ++j) {               // K = 16 elements = 32 bytes inside the swizzle row
+                    for (int j = 0; j < ((p.debug & 1) ? 0 : k16); ++j) {   // K = 16 elements = 32 bytes inside the swizzle row
                         const uint64_t o = (uint64_t)(j * 2);
                         if (p.nprod == 3) {
                             tc_mma_f16(tmem, wl + o, xh + o, idesc, started_cross);
@@ -270,6 +277,7 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
                     if (has_res) t += rrow[(size_t)xo * p.res_cs];
                     if (has_acc) t += yrow[(size_t)xo * p.ycs];
                     if (has_mask) t *= (mrow[(size_t)xo * p.mask_cs] > 0.f) ? 1.f : p.mask_alpha;
+                    if (p.debug & 8) continue;
                     yrow[(size_t)xo * p.ycs] = t;
                     if (has_pl) {
                         unsigned short h, l;
@@ -631,6 +639,7 @@ static int conv_bf_launch(const ConvGemm& g, const ActPlanes& xp, const void* wt
         if ((size_t)grid_tiles * mblocks > conv_bf_ticket_words()) ksplit = 1;
     }
     p.ksplit = ksplit; p.part = part; p.tickets = tickets;
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MS_BF_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
 
     const CUtensorMap *mXh, *mXl;
     {

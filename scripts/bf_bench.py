@@ -80,7 +80,10 @@ if len(sys.argv) > 2 and sys.argv[1] == 'one':
 
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 rows = []
-for shape in SHAPES:
+sel = [int(a) for a in sys.argv[2:]] if len(sys.argv) > 2 and sys.argv[1] == 'sel' else None
+for si, shape in enumerate(SHAPES):
+    if sel is not None and si not in sel:
+        continue
     fwd, wgrad, macs, keep = setup(shape)
     tf = timeit(fwd, flush); tw = timeit(wgrad, flush)
     rows.append({'shape': shape, 'fwd_us': tf, 'fwd_tflops': 2 * macs / tf / 1e6, 'wgrad_us': tw, 'wgrad_tflops': 2 * macs / tw / 1e6})
