@@ -446,7 +446,8 @@ def run_ours(args, cfg):
                      'share_of_step': conv_ms / prof_total if prof_total else None,
                      'dominant_layer': dom},
         'profile_ms_per_step': dict({k: v['ms'] / n_prof for k, v in prof.items()},
-                                    sum=prof_total / n_prof, instrumented_step_wall_ms=prof_wall_ms),
+                                    sum=prof_total / n_prof, instrumented_step_wall_ms=prof_wall_ms,
+                                    event_node_overhead_us_subtracted_per_span=eng.profile_event_overhead_us()),
         'clocks': clk.summary() if clk else None,
     }
     if cfg['net'] == 'MADNet':

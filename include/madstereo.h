@@ -207,6 +207,8 @@ int ms_engine_metrics(void* e, void* stream);
 int ms_engine_profile(void* e, int enable);
 /* per layer and direction (0 fwd, 1 dgrad, 2 wgrad): accumulated milliseconds and call counts, arrays of 3 * num_layers */
 int ms_engine_profile_layers(void* e, double* ms3n, long long* calls3n);
+/* mode 2: the event-to-event latency of an EMPTY span inside the graph (already subtracted from every reported span) */
+float ms_engine_profile_event_overhead_ms(void* e);
 int ms_engine_profile_read(void* e, double* ms7, double* macs7, double* bytes7, long long* calls7);
 /* Kernels launched by this library in this process so far. */
 long long ms_launch_count(void);

@@ -125,6 +125,7 @@ struct Engine {
     struct Span { int cat, layer; cudaEvent_t a, b; double macs, bytes; };
     int profiling;                   // 0 off, 1 eager (events between launches), 2 in-graph (external event nodes inside the replayed graph)
     bool prof_capturing;
+    float prof_event_overhead_ms;    // in-graph event-to-event latency with nothing in between (calibration)
     std::vector<Span> spans;
     std::vector<cudaEvent_t> event_pool;
     double cat_ms[N_CAT]; double cat_macs[N_CAT]; double cat_bytes[N_CAT]; long long cat_calls[N_CAT];

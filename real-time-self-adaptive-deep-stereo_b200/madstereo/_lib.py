@@ -80,6 +80,7 @@ _SIGS = {
     'ms_engine_profile': (I, [P, I]),
     'ms_engine_profile_read': (I, [P, POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(ctypes.c_longlong)]),
     'ms_engine_profile_layers': (I, [P, P, P]),
+    'ms_engine_profile_event_overhead_ms': (F, [P]),
     'ms_launch_count': (ctypes.c_longlong, []),
     'ms_debug_tc_prof': (I, [POINTER(ctypes.c_ulonglong), I]),
     'ms_engine_num_tensors': (I, [P]),

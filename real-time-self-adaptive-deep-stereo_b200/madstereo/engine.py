@@ -230,6 +230,9 @@ class StereoEngine:
         """False/0 off; True/1 eager events; 2 = event nodes inside the replayed CUDA graph (in-graph kernel times)."""
         check(self._lib.ms_engine_profile(self._h, int(enable)), 'profile')
 
+    def profile_event_overhead_us(self):
+        return 1e3 * float(self._lib.ms_engine_profile_event_overhead_ms(self._h))
+
     def profile_layers(self):
         n = len(self.layers)
         ms = (ctypes.c_double * (3 * n))(); calls = (ctypes.c_longlong * (3 * n))()
