@@ -65,15 +65,16 @@ int ms_conv2d_dgrad_tc(const float* dy, int n, int h, int w, int cout, int dy_cs
 size_t ms_conv2d_tc_scratch(int kh, int kw, int cin, int cout);
 /* Split-16-bit tcgen05 path (csrc/conv_bf.cu; the engine's default for every eligible layer, MS_CONV_IMPL=tf32 selects
  * the 3xTF32 kernels above): operands as two 16-bit planes (x ~= hi + lo), three kind::f16 MMAs per K step at the
- * bf16/fp16 tensor rate.  Forward operands are fp16 planes of x/16 and w (22 mantissa bits, ~2^-22 relative product
- * error, the pre-scale undone exactly in the epilogue); gradient operands are bf16 planes (16 bits, fp32 exponent
+ * bf16/fp16 tensor rate.  Forward operands are fp16 planes of x * act_scale and of w (22 mantissa bits, ~2^-22 relative
+ * product error; the power-of-two scale is undone exactly in the epilogue); gradient operands are bf16 planes (16 bits, fp32 exponent
  * range).  GEMM transposed so that M = output channels and N = up to 256 pixels, halo patches by TMA (64-channel K
  * blocks), pre-tiled weights by 1-D bulk copies, stride 1 or 2 (TMA element strides), any dilation, split-K reduced by
  * the last-arriving CTA.  Same semantics as ms_conv2d_fwd / ms_conv2d_dgrad (a stride-2 dgrad runs as four dense
  * parity-class launches).  scratch: ms_conv2d_bf_scratch() BYTES, 256-byte aligned.  -3 = not eligible. */
 int ms_conv2d_fwd_bf(const float* x, int n, int h, int w, int cin, int x_cs, const float* weights /*HWIO*/,
                      const float* bias, float* y, int cout, int y_cs, int kh, int kw, int stride, int dilation,
-                     float alpha, void* scratch, size_t scratch_bytes, void* stream);
+                     float alpha, float act_scale /* power of two: the fp16 planes hold x * act_scale */, void* scratch,
+                     size_t scratch_bytes, void* stream);
 int ms_conv2d_dgrad_bf(const float* dy, int n, int oh, int ow, int cout, int dy_cs, const float* weights /*HWIO*/,
                        float* dx, int h, int w, int cin, int dx_cs, int kh, int kw, int stride, int dilation,
                        void* scratch, size_t scratch_bytes, void* stream);
@@ -82,28 +83,30 @@ size_t ms_conv2d_bf_scratch(int n, int h, int w, int kh, int kw, int cin, int co
  * replaces the filter / bias gradient sub-graphs of tf.nn.conv2d / atrous_conv2d / bias_add (reference
  * Nets/sharedLayers.py:58-59,72-73 under the train ops of Stereo_Online_Adaptation.py:118,128).  x and dy planes feed
  * the UMMA as MN-major operands straight from NHWC; stride 1 or 2, any dilation.  Same outputs as ms_conv2d_wgrad.
- * x_fmt: format of the x planes (0 = bf16, 1 = fp16 of x/16: the forward planes re-used as they are, an f16 x bf16
- * MMA); dy planes are bf16.  scratch: ms_conv2d_wgrad_bf_scratch() BYTES, 256-byte aligned.  -3 = not eligible. */
+ * Both plane sets are bf16 (tcgen05 kind::f16 rejects an f16 x bf16 operand pair: probed, illegal instruction; the engine
+ * therefore re-splits the forward activation into bf16 scratch planes for this kernel).
+ * scratch: ms_conv2d_wgrad_bf_scratch() BYTES, 256-byte aligned.  -3 = not eligible. */
 int ms_conv2d_wgrad_bf(const float* x, int n, int h, int w, int cin, int x_cs, const float* dy, int oh, int ow, int cout,
-                       int dy_cs, float* dw /*HWIO*/, float* db, int kh, int kw, int stride, int dilation, int x_fmt,
+                       int dy_cs, float* dw /*HWIO*/, float* db, int kh, int kw, int stride, int dilation,
                        void* scratch, size_t scratch_bytes, void* stream);
 size_t ms_conv2d_wgrad_bf_scratch(int n, int h, int w, int oh, int ow, int kh, int kw, int cin, int cout);
 /* Plane-level entry points of the same path (what the engine issues per layer in steady state: activations are split
  * by the producing kernel's epilogue, weights once per update).  hi / lo planes: 16-bit NHWC, channel stride `*_pcs`
- * (multiple of 8), fmt 0 = bf16, 1 = fp16 of value/16; weight tiles: ms_bf_weight_halfs() 16-bit elements (both planes,
+ * (multiple of 8), fmt 0 = bf16, 1 = fp16 of value * scale (scale a power of two); weight tiles: ms_bf_weight_halfs() 16-bit elements (both planes,
  * pre-tiled shared-memory images); job_dev: >= 64 bytes of device scratch; part / tickets:
  * ms_conv2d_bf_part_floats() floats / ms_conv2d_bf_ticket_words() zeroed words (split-K). */
-int ms_bf_split(const float* x, int n, int h, int w, int c, int x_cs, void* hi, void* lo, int plane_cs, int fmt, void* stream);
+int ms_bf_split(const float* x, int n, int h, int w, int c, int x_cs, void* hi, void* lo, int plane_cs, int fmt, float scale,
+                void* stream);
 size_t ms_bf_weight_halfs(int taps, int m, int k);
 int ms_bf_prep_weights(const float* weights_hwio, int taps, int cin, int cout, int for_dgrad, int fmt, void* tiles,
                        void* job_dev, void* stream);
-int ms_conv2d_fwd_bf_planes(const void* xhi, const void* xlo, int x_pcs, int fmt, int n, int h, int w, int cin,
+int ms_conv2d_fwd_bf_planes(const void* xhi, const void* xlo, int x_pcs, int fmt, float scale, int n, int h, int w, int cin,
                             const void* wtiles, const float* bias, float* y, int cout, int y_cs, void* yhi, void* ylo,
                             int y_pcs, int kh, int kw, int stride, int dilation, float alpha, float* part,
                             unsigned int* tickets, void* stream);
 size_t ms_conv2d_bf_part_floats(void);
 size_t ms_conv2d_bf_ticket_words(void);
-int ms_conv2d_wgrad_bf_planes(const void* xhi, const void* xlo, int x_pcs, int x_fmt, int n, int h, int w, int cin,
+int ms_conv2d_wgrad_bf_planes(const void* xhi, const void* xlo, int x_pcs, int n, int h, int w, int cin,
                               const void* dhi, const void* dlo, int d_pcs, int oh, int ow, int cout, float* dw, float* db,
                               int kh, int kw, int stride, int dilation, float* workspace, size_t workspace_floats, void* stream);
 size_t ms_conv2d_wgrad_bf_workspace(int kh, int kw, int cin, int cout);

@@ -115,8 +115,8 @@ int ms_conv2d_dgrad_tc(const float* dy, int n, int h, int w, int cout, int dy_cs
     return conv_tc_oneshot(p, 1, scratch, scratch_floats, S(stream));
 }
 int ms_conv2d_fwd_bf(const float* x, int n, int h, int w, int cin, int x_cs, const float* weights, const float* bias,
-                     float* y, int cout, int y_cs, int kh, int kw, int stride, int dilation, float alpha, void* scratch,
-                     size_t scratch_bytes, void* stream) {
+                     float* y, int cout, int y_cs, int kh, int kw, int stride, int dilation, float alpha, float act_scale,
+                     void* scratch, size_t scratch_bytes, void* stream) {
     int oh, ow, pt, pl;
     same_pad_c(h, kh, stride, dilation, oh, pt);
     same_pad_c(w, kw, stride, dilation, ow, pl);
@@ -127,7 +127,7 @@ int ms_conv2d_fwd_bf(const float* x, int n, int h, int w, int cin, int x_cs, con
     p.mul = stride; p.off_y = -pt; p.off_x = -pl; p.step = dilation; p.div = 1;
     p.alpha = alpha; p.mask = nullptr; p.mask_alpha = 1.f; p.res = nullptr; p.accumulate = 0;
     if (!conv_bf_supported(p)) { set_error("ms_conv2d_fwd_bf: shape not supported by the split-bf16 tcgen05 path"); return -3; }
-    return conv_bf_oneshot(p, 0, 1, scratch, scratch_bytes, S(stream));      // forward: fp16 planes (x / 16)
+    return conv_bf_oneshot(p, 0, 1, act_scale, scratch, scratch_bytes, S(stream));      // forward: fp16 planes of x * act_scale
 }
 int ms_conv2d_dgrad_bf(const float* dy, int n, int oh, int ow, int cout, int dy_cs, const float* weights, float* dx,
                        int h, int w, int cin, int dx_cs, int kh, int kw, int stride, int dilation, void* scratch,
@@ -143,7 +143,7 @@ int ms_conv2d_dgrad_bf(const float* dy, int n, int oh, int ow, int cout, int dy_
     p.mul = 1; p.off_y = pt; p.off_x = pl; p.step = -dilation; p.div = stride;
     p.alpha = 1.f; p.mask = nullptr; p.mask_alpha = 1.f; p.res = nullptr; p.accumulate = 0;
     if (!conv_bf_supported(p)) { set_error("ms_conv2d_dgrad_bf: shape not supported by the split-bf16 tcgen05 path"); return -3; }
-    return conv_bf_oneshot(p, 1, 0, scratch, scratch_bytes, S(stream));      // gradients: bf16 planes
+    return conv_bf_oneshot(p, 1, 0, 1.f, scratch, scratch_bytes, S(stream));      // gradients: bf16 planes
 }
 size_t ms_conv2d_bf_scratch(int n, int h, int w, int kh, int kw, int cin, int cout) {
     ConvGemm a{}, b{};
@@ -153,7 +153,7 @@ size_t ms_conv2d_bf_scratch(int n, int h, int w, int kh, int kw, int cin, int co
     return sa > sb ? sa : sb;
 }
 int ms_conv2d_wgrad_bf(const float* x, int n, int h, int w, int cin, int x_cs, const float* dy, int oh, int ow, int cout,
-                       int dy_cs, float* dw, float* db, int kh, int kw, int stride, int dilation, int x_fmt, void* scratch,
+                       int dy_cs, float* dw, float* db, int kh, int kw, int stride, int dilation, void* scratch,
                        size_t scratch_bytes, void* stream) {
     int oh2, ow2, pt, pl;
     same_pad_c(h, kh, stride, dilation, oh2, pt);
@@ -165,7 +165,7 @@ int ms_conv2d_wgrad_bf(const float* x, int n, int h, int w, int cin, int x_cs, c
     q.dw = dw; q.db = db; q.kh = kh; q.kw = kw; q.stride = stride; q.dil = dilation; q.pad_t = pt; q.pad_l = pl;
     q.accumulate = 0;
     if (!wgrad_bf_supported(q)) { set_error("ms_conv2d_wgrad_bf: shape not supported by the split-bf16 tcgen05 path"); return -3; }
-    return wgrad_bf_oneshot(q, x_fmt, 0, scratch, scratch_bytes, S(stream));
+    return wgrad_bf_oneshot(q, scratch, scratch_bytes, S(stream));
 }
 size_t ms_conv2d_wgrad_bf_scratch(int n, int h, int w, int oh, int ow, int kh, int kw, int cin, int cout) {
     ConvWgrad q{};
@@ -174,8 +174,9 @@ size_t ms_conv2d_wgrad_bf_scratch(int n, int h, int w, int oh, int ow, int kh, i
 }
 // ---- plane-level entry points of the split-bf16 path: what the engine calls per layer in steady state (operands
 //      already split: activations by the producing epilogue, weights once per update)
-int ms_bf_split(const float* x, int n, int h, int w, int c, int x_cs, void* hi, void* lo, int plane_cs, int fmt, void* stream) {
-    ActPlanes pl; pl.hi = hi; pl.lo = lo; pl.cs = plane_cs; pl.fmt = fmt;
+int ms_bf_split(const float* x, int n, int h, int w, int c, int x_cs, void* hi, void* lo, int plane_cs, int fmt, float scale,
+                void* stream) {
+    ActPlanes pl; pl.hi = hi; pl.lo = lo; pl.cs = plane_cs; pl.fmt = fmt; pl.scale = fmt == 1 ? scale : 1.f;
     return split_planes(view(const_cast<float*>(x), n, h, w, c, x_cs), pl, S(stream));
 }
 size_t ms_bf_weight_halfs(int taps, int m, int k) { return conv_bf_weight_halfs(taps, m, k); }
@@ -188,7 +189,7 @@ int ms_bf_prep_weights(const float* weights_hwio, int taps, int cin, int cout, i
     MS_CHECK_CUDA(cudaStreamSynchronize(S(stream)));
     return bf_prep_weights(static_cast<const BfPrepJob*>(job_dev), 1, conv_bf_weight_halfs(taps, M, K), S(stream));
 }
-int ms_conv2d_fwd_bf_planes(const void* xhi, const void* xlo, int x_pcs, int fmt, int n, int h, int w, int cin,
+int ms_conv2d_fwd_bf_planes(const void* xhi, const void* xlo, int x_pcs, int fmt, float scale, int n, int h, int w, int cin,
                             const void* wtiles, const float* bias, float* y, int cout, int y_cs, void* yhi, void* ylo,
                             int y_pcs, int kh, int kw, int stride, int dilation, float alpha, float* part,
                             unsigned int* tickets, void* stream) {
@@ -202,13 +203,13 @@ int ms_conv2d_fwd_bf_planes(const void* xhi, const void* xlo, int x_pcs, int fmt
     p.mul = stride; p.off_y = -pt; p.off_x = -pl; p.step = dilation; p.div = 1;
     p.alpha = alpha; p.mask_alpha = 1.f;
     if (!conv_bf_supported(p)) { set_error("ms_conv2d_fwd_bf_planes: shape not supported"); return -3; }
-    ActPlanes xp; xp.hi = const_cast<void*>(xhi); xp.lo = const_cast<void*>(xlo); xp.cs = x_pcs; xp.fmt = fmt;
-    ActPlanes yp; yp.hi = yhi; yp.lo = ylo; yp.cs = y_pcs; yp.fmt = fmt;
+    ActPlanes xp; xp.hi = const_cast<void*>(xhi); xp.lo = const_cast<void*>(xlo); xp.cs = x_pcs; xp.fmt = fmt; xp.scale = fmt == 1 ? scale : 1.f;
+    ActPlanes yp; yp.hi = yhi; yp.lo = ylo; yp.cs = y_pcs; yp.fmt = fmt; yp.scale = xp.scale;
     return conv_bf(p, xp, wtiles, yhi ? &yp : nullptr, part, tickets, S(stream));
 }
 size_t ms_conv2d_bf_part_floats() { return conv_bf_part_floats(); }
 size_t ms_conv2d_bf_ticket_words() { return conv_bf_ticket_words(); }
-int ms_conv2d_wgrad_bf_planes(const void* xhi, const void* xlo, int x_pcs, int x_fmt, int n, int h, int w, int cin,
+int ms_conv2d_wgrad_bf_planes(const void* xhi, const void* xlo, int x_pcs, int n, int h, int w, int cin,
                               const void* dhi, const void* dlo, int d_pcs, int oh, int ow, int cout, float* dw, float* db,
                               int kh, int kw, int stride, int dilation, float* workspace, size_t workspace_floats, void* stream) {
     int oh2, ow2, pt, pl;
@@ -220,8 +221,8 @@ int ms_conv2d_wgrad_bf_planes(const void* xhi, const void* xlo, int x_pcs, int x
     q.dw = dw; q.db = db; q.kh = kh; q.kw = kw; q.stride = stride; q.dil = dilation; q.pad_t = pt; q.pad_l = pl;
     q.workspace = workspace; q.workspace_floats = workspace_floats;
     if (!wgrad_bf_supported(q)) { set_error("ms_conv2d_wgrad_bf_planes: shape not supported"); return -3; }
-    ActPlanes xp; xp.hi = const_cast<void*>(xhi); xp.lo = const_cast<void*>(xlo); xp.cs = x_pcs; xp.fmt = x_fmt;
-    ActPlanes dp; dp.hi = const_cast<void*>(dhi); dp.lo = const_cast<void*>(dlo); dp.cs = d_pcs; dp.fmt = 0;
+    ActPlanes xp; xp.hi = const_cast<void*>(xhi); xp.lo = const_cast<void*>(xlo); xp.cs = x_pcs; xp.fmt = 0; xp.scale = 1.f;
+    ActPlanes dp; dp.hi = const_cast<void*>(dhi); dp.lo = const_cast<void*>(dlo); dp.cs = d_pcs; dp.fmt = 0; dp.scale = 1.f;
     return wgrad_bf(q, xp, dp, S(stream));
 }
 size_t ms_conv2d_wgrad_bf_workspace(int kh, int kw, int cin, int cout) { return wgrad_bf_workspace_floats(kh, kw, cin, cout); }
@@ -327,6 +328,11 @@ void* ms_engine_create(const char* net_name, int B, int H, int W, int radius_d, 
     e->radius_d = radius_d; e->corr_stride = corr_stride; e->warping = warping;
     if (!strcmp(net_name, "MADNet")) { e->net = 0; e->build_madnet(); }
     else if (!strcmp(net_name, "Dispnet")) { e->net = 1; e->build_dispnet(); }
+    // scale of the fp16 forward planes (stored value = activation * scale, a power of two): MADNet consumes raw 0..255
+    // images (Nets/MadNet.py:56-66) -> activations up to ~1e4, 1/16 keeps |x| <= 1e6 finite; DispNet normalises its input
+    // to [-0.4, 0.6] (Nets/DispNet.py:59-73) -> activations O(1e-3 .. 10), 64 lifts them out of fp16's subnormal range
+    e->act_scale = e->net == 1 ? 64.f : 0.0625f;
+    if (const char* as = getenv("MS_ACT_SCALE")) { const float v = (float)atof(as); if (v > 0.f) e->act_scale = v; }
     else { set_error(std::string("Unrecognized network name: ") + net_name); delete e; return nullptr; }
     e->finalize_groups(nullptr, 0);
     return e;

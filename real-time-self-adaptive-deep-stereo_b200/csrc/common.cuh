@@ -181,7 +181,7 @@ int conv_tc_read_prof(unsigned long long* out32, int reset);
 namespace ms {
 // split-bf16 tcgen05 path (conv_bf.cu): every activation that feeds a convolution also lives as two bf16 planes
 // (hi = bf16(x), lo = bf16(x - hi)), NHWC with channel stride `cs` (bf16 elements, multiple of 8).
-struct ActPlanes { void* hi; void* lo; int cs; int fmt; };   // fmt 0 = bf16 (gradients), 1 = fp16 of x/16 (forward activations)
+struct ActPlanes { void* hi; void* lo; int cs; int fmt; float scale; };   // fmt 0 = bf16 (gradients), 1 = fp16 of x * scale (forward activations; scale a power of two)
 struct BfPrepJob {
     const float* src; void* tiles;           // tiles: [M block][tap][K block][hi tile | lo tile], swizzled smem images
     int taps, M, K, Mpad, Kpad, transposed_src, fmt;
@@ -204,7 +204,7 @@ size_t wgrad_bf_workspace_floats(int kh, int kw, int ci, int co);
 int wgrad_bf_init();
 int wgrad_bf(const ConvWgrad& q, const ActPlanes& xp, const ActPlanes& dp, cudaStream_t st);
 size_t wgrad_bf_oneshot_scratch_bytes(const ConvWgrad& q);
-int wgrad_bf_oneshot(const ConvWgrad& q, int xfmt, int dfmt, void* scratch, size_t scratch_bytes, cudaStream_t st);
+int wgrad_bf_oneshot(const ConvWgrad& q, void* scratch, size_t scratch_bytes, cudaStream_t st);
 size_t conv_bf_oneshot_scratch_bytes(const ConvGemm& g);
-int conv_bf_oneshot(const ConvGemm& g, int wmat_is_mk, int fmt, void* scratch, size_t scratch_bytes, cudaStream_t st);
+int conv_bf_oneshot(const ConvGemm& g, int wmat_is_mk, int fmt, float act_scale, void* scratch, size_t scratch_bytes, cudaStream_t st);
 }  // namespace ms

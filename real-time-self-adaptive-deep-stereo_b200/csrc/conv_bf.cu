@@ -66,8 +66,8 @@ struct ConvBfParams {
     int NP, NW;
     int nacc;                     // accumulators: 2 = cross terms and hi*hi separately, 1 = everything in one
     int nprod;                    // 3 = split x3, 1 = hi*hi only (accuracy experiments)
-    int fmt;                      // operand format: 0 = bf16 planes, 1 = fp16 planes (activations pre-scaled by 1/16)
-    float acc_scale;              // multiplies the accumulator (16 undoes the activation pre-scale)
+    int fmt;                      // operand format: 0 = bf16 planes, 1 = fp16 planes (activation planes hold x * scale)
+    float acc_scale;              // multiplies the accumulator (1 / scale of the input planes, a power of two: exact)
     int tmem_cols;
     int cout;
     int ksplit;
@@ -79,7 +79,7 @@ struct ConvBfParams {
     const float* res; int res_cs;
     const float* mask; int mask_cs; float mask_alpha;
     int accumulate;
-    void* ohi; void* olo; int ocs; int ofmt;     // optional output planes (ofmt as `fmt`)
+    void* ohi; void* olo; int ocs; int ofmt; float oscale;   // optional output planes (format, stored value = t * oscale)
     BfPatch patch[BF_MAX_PATCH];
     BfTap tap[BF_MAX_TAPS];
 };
@@ -103,15 +103,15 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
                  ::"r"(s_addr(dst)), "l"(src), "r"(bytes), "r"(s_addr(bar)) : "memory");
 }
 
-constexpr float BF_PRESCALE = 0.0625f;            // fp16 activation planes hold x / 16
-// 16-bit split of a float: fmt 0 -> bf16 hi/lo, fmt 1 -> fp16 hi/lo of v * 1/16 (saturating: |v| up to ~2e6 stays finite)
-__device__ __forceinline__ void split16(float v, int fmt, unsigned short& hi, unsigned short& lo) {
+// 16-bit split of a float: fmt 0 -> bf16 hi/lo of v (any magnitude), fmt 1 -> fp16 hi/lo of v * scale (22 mantissa bits while
+// |v * scale| stays inside fp16's normal range; saturating, so an out-of-range value degrades instead of becoming inf)
+__device__ __forceinline__ void split16(float v, int fmt, float scale, unsigned short& hi, unsigned short& lo) {
     if (fmt == 0) {
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
         const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
         hi = __bfloat16_as_ushort(h); lo = __bfloat16_as_ushort(l);
     } else {
-        const float s = v * BF_PRESCALE;
+        const float s = v * scale;
         const float c = fminf(fmaxf(s, -65504.f), 65504.f);
         const __half h = __float2half_rn(c);
         const float r = fminf(fmaxf(s - __half2float(h), -65504.f), 65504.f);
@@ -281,7 +281,7 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
                     yrow[(size_t)xo * p.ycs] = t;
                     if (has_pl) {
                         unsigned short h, l;
-                        split16(t, p.ofmt, h, l);
+                        split16(t, p.ofmt, p.oscale, h, l);
                         hrow_p[(size_t)xo * p.ocs] = h;
                         lrow_p[(size_t)xo * p.ocs] = l;
                     }
@@ -357,7 +357,7 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
 // 16-bit planes of an fp32 NHWC view (producers that are not conv_bf epilogues: correlation, resize, loss seeds ...)
 // ------------------------------------------------------------------------------------------------
 __global__ void split_planes_kernel(const float* __restrict__ x, int xcs, int C, size_t pixels,
-                                    unsigned short* __restrict__ hi, unsigned short* __restrict__ lo, int pcs, int fmt) {
+                                    unsigned short* __restrict__ hi, unsigned short* __restrict__ lo, int pcs, int fmt, float scale) {
     const int cq = (C + 3) >> 2;
     const size_t total = pixels * cq;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -368,7 +368,7 @@ __global__ void split_planes_kernel(const float* __restrict__ x, int xcs, int C,
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float v = (c + j < C) ? src[j] : 0.f;
-            split16(v, fmt, h[j], l[j]);
+            split16(v, fmt, scale, h[j], l[j]);
         }
         unsigned short* dh = hi + pix * pcs + c;
         unsigned short* dl = lo + pix * pcs + c;
@@ -386,7 +386,7 @@ int split_planes(const TView& x, const ActPlanes& pl, cudaStream_t st) {
     const size_t total = x.pixels() * ((x.c + 3) / 4);
     const unsigned grid = (unsigned)std::min<size_t>(cdivz(total, 256), 148 * 16);
     split_planes_kernel<<<grid, 256, 0, st>>>(x.p, x.cs, x.c, x.pixels(), reinterpret_cast<unsigned short*>(pl.hi),
-                                              reinterpret_cast<unsigned short*>(pl.lo), pl.cs, pl.fmt);
+                                              reinterpret_cast<unsigned short*>(pl.lo), pl.cs, pl.fmt, pl.fmt == 1 ? pl.scale : 1.f);
     return check_launch("split_planes");
 }
 
@@ -539,7 +539,8 @@ static int conv_bf_launch(const ConvGemm& g, const ActPlanes& xp, const void* wt
     p.kch = Kpad > 32 ? 64 : 32;
     p.kblocks = Kpad / p.kch; p.cout = M; p.taps_total = taps_total;
     p.wtile_bytes = 128u * (uint32_t)p.kch * 2u;
-    p.fmt = xp.fmt; p.acc_scale = xp.fmt == 1 ? 16.f : 1.f;
+    p.fmt = xp.fmt; p.acc_scale = xp.fmt == 1 ? 1.f / xp.scale : 1.f;
+    MS_REQUIRE(xp.fmt == 0 || xp.scale > 0.f, "conv_bf: fp16 planes need a positive scale");
     const uint32_t row_unit = (uint32_t)p.kch * 2u;                 // bytes of one pixel of a patch plane
     // ---- pixel tile: the largest N in {256,128,64} that still gives ~100 CTAs; 8-pixel rows unless that wastes a tile row
     const int mblocks = Mpad / 128;
@@ -625,7 +626,7 @@ static int conv_bf_launch(const ConvGemm& g, const ActPlanes& xp, const void* wt
     p.accumulate = g.accumulate;
     if (yp && yp->hi) {
         MS_REQUIRE(yp->cs >= M && (yp->cs & 7) == 0, "conv_bf: bad output planes");
-        p.ohi = yp->hi; p.olo = yp->lo; p.ocs = yp->cs; p.ofmt = yp->fmt;
+        p.ohi = yp->hi; p.olo = yp->lo; p.ocs = yp->cs; p.ofmt = yp->fmt; p.oscale = yp->fmt == 1 ? yp->scale : 1.f;
     }
     p.wtiles = static_cast<const unsigned char*>(wtiles);
     // ---- split K over (K block, patch) units when the map is too small to fill the GPU (at most 8 ways: the closing
@@ -702,7 +703,7 @@ size_t conv_bf_oneshot_scratch_bytes(const ConvGemm& g) {
     return 2 * (xe * 2 + 256) + (we * 2 + 256) + 1024 + conv_bf_ticket_words() * 4 + conv_bf_part_floats() * 4 + 4096;
 }
 
-int conv_bf_oneshot(const ConvGemm& g, int wmat_is_mk, int fmt, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+int conv_bf_oneshot(const ConvGemm& g, int wmat_is_mk, int fmt, float act_scale, void* scratch, size_t scratch_bytes, cudaStream_t st) {
     MS_REQUIRE(conv_bf_supported(g), "conv_bf: unsupported geometry");
     MS_REQUIRE(scratch_bytes >= conv_bf_oneshot_scratch_bytes(g), "conv_bf: scratch too small");
     MS_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, "conv_bf: scratch must be 256B aligned");
@@ -711,7 +712,7 @@ int conv_bf_oneshot(const ConvGemm& g, int wmat_is_mk, int fmt, void* scratch, s
     const int pcs = (g.x.c + 7) / 8 * 8;
     const size_t xe = g.x.pixels() * pcs;
     const size_t we = conv_bf_weight_halfs(g.kh * g.kw, g.y.c, g.x.c);
-    ActPlanes xp; xp.hi = take(xe * 2); xp.lo = take(xe * 2); xp.cs = pcs; xp.fmt = fmt;
+    ActPlanes xp; xp.hi = take(xe * 2); xp.lo = take(xe * 2); xp.cs = pcs; xp.fmt = fmt; xp.scale = fmt == 1 ? act_scale : 1.f;
     void* wt = take(we * 2);
     BfPrepJob* jd = reinterpret_cast<BfPrepJob*>(take(1024));
     unsigned int* tickets = reinterpret_cast<unsigned int*>(take(conv_bf_ticket_words() * 4));

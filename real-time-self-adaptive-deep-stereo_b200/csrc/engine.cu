@@ -48,8 +48,8 @@ Engine::Engine()
     if (!use_tc) conv_impl = 0;
     { const char* e5 = getenv("MS_HEADS"); use_heads = (e5 && e5[0] == '0') ? 0 : 1; }
     { const char* e6 = getenv("MS_BF_WGRAD"); use_bf_wgrad = (e6 && e6[0] == '0') ? 0 : 1; }
-    { const char* e7 = getenv("MS_WGRAD_MIXED"); wgrad_mixed = (e7 && e7[0] == '1') ? 1 : 0; }
-    wg_xp.hi = wg_xp.lo = nullptr; wg_xp.cs = 0; wg_xp.fmt = 0; wg_xp_halfs = 0;
+    wg_xp.hi = wg_xp.lo = nullptr; wg_xp.cs = 0; wg_xp.fmt = 0; wg_xp.scale = 1.f; wg_xp_halfs = 0;
+    act_scale = 0.f;
     bf_jobs_dev = nullptr; bf_max_total = 0; bf_part = nullptr; bf_tickets = nullptr;
     dp_rank = 0; dp_world = 1; dp_connected = false; dp_xbuf = nullptr; dp_state = nullptr; dp_cap_floats = 0;
 }
@@ -59,6 +59,7 @@ void Engine::add_planes(Bump& A, const TView& v, int fmt) {
     if (v.p && planes.count(v.p)) return;          // (sizing pass: every pointer is null -- never dedupe there)
     ActPlanes pl;
     pl.fmt = fmt;
+    pl.scale = fmt == 1 ? act_scale : 1.f;
     pl.cs = (v.c + 7) / 8 * 8;
     const size_t floats = (v.pixels() * pl.cs + 1) / 2;     // bf16 elements -> floats
     pl.hi = A.alloc(floats);
@@ -426,10 +427,8 @@ int Engine::conv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, cons
         const ActPlanes* wdp = wxp ? planes_of(dpre) : nullptr;
         if (wxp && wdp) {
             rc = ensure_planes(dpre, st);
-            if (!rc && wgrad_mixed) {                       // fp16 forward planes x bf16 gradient planes in one MMA
-                rc = ensure_planes(x, st);
-                if (!rc) rc = wgrad_bf(q, *wxp, *wdp, st);
-            } else if (!rc) {                               // bf16 copy of the forward activation (scratch planes)
+            if (!rc) {      // bf16 copy of the forward activation in scratch planes: kind::f16 MMAs reject f16 x bf16 operand pairs
+                            // (probed on sm_100a: illegal instruction), so the fp16 forward planes cannot serve here
                 ActPlanes xb = wg_xp; xb.cs = (x.c + 7) / 8 * 8;
                 MS_REQUIRE(xb.hi && x.pixels() * (size_t)xb.cs <= wg_xp_halfs, "conv_bwd: wgrad scratch planes too small");
                 rc = split_planes(x, xb, st);

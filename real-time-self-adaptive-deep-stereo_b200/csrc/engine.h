@@ -102,7 +102,7 @@ struct Engine {
     float* bf_part; unsigned int* bf_tickets;
     void add_planes(Bump& A, const TView& v, int fmt);      // fmt 1 = forward activation (fp16 of x/16), 0 = gradient (bf16)
     ActPlanes wg_xp; size_t wg_xp_halfs;              // bf16 scratch planes: forward activations re-split for the weight gradient
-    int wgrad_mixed;                                  // MS_WGRAD_MIXED=1: feed the fp16 forward planes to wgrad_bf directly (f16 x bf16 MMA)
+    float act_scale;                                  // power-of-two scale of the fp16 forward planes (per network, MS_ACT_SCALE overrides)
     const ActPlanes* planes_of(const TView& v) const;
     int ensure_planes(const TView& v, cudaStream_t st);
     // ---- data-parallel exchange over NVLink peer memory (csrc/dp.cu)

@@ -368,6 +368,7 @@ int wgrad_bf(const ConvWgrad& q, const ActPlanes& xp, const ActPlanes& dp, cudaS
         const size_t per = (size_t)q.kh * q.kw * q.x.c * q.dy.c + (size_t)q.dy.c;
         P.splits = (int)std::max<size_t>(1, std::min<size_t>((size_t)P.splits, q.workspace_floats / std::max<size_t>(per, 1)));
     }
+    MS_REQUIRE(xp.fmt == dp.fmt, "wgrad_bf: tcgen05 kind::f16 rejects mixed f16 x bf16 operands (probed: illegal instruction); both plane sets must share a format");
     MS_REQUIRE(xp.hi && xp.lo && dp.hi && dp.lo && (xp.cs & 7) == 0 && (dp.cs & 7) == 0 && xp.cs >= q.x.c && dp.cs >= q.dy.c,
                "wgrad_bf: operand planes missing");
     if (wgrad_bf_init()) return -1;
@@ -417,7 +418,7 @@ int wgrad_bf(const ConvWgrad& q, const ActPlanes& xp, const ActPlanes& dp, cudaS
     wgrad_bf_kernel<<<dim3(q.kw * P.mblocks * P.nblocks, P.splits), WB_THREADS, smem, st>>>(*mXh, *mXl, *mDh, *mDl, p);
     const size_t n4 = wn / 4;
     const size_t work = n4 + (q.db ? (size_t)co : 0);
-    const float sx16 = xp.fmt == 1 ? 16.f : 1.f, sd16 = dp.fmt == 1 ? 16.f : 1.f;
+    const float sx16 = xp.fmt == 1 ? 1.f / xp.scale : 1.f, sd16 = dp.fmt == 1 ? 1.f / dp.scale : 1.f;
     wgrad_bf_reduce_kernel<<<(unsigned)cdivz(work, 256), 256, 0, st>>>(p.part, q.dw, n4, P.splits, p.bpart, q.db, co, q.accumulate,
                                                                       sx16 * sd16, sd16);
     return check_launch("wgrad_bf", 2);
@@ -430,14 +431,14 @@ size_t wgrad_bf_oneshot_scratch_bytes(const ConvWgrad& q) {
     return 2 * (xe * 2 + 256) + 2 * (de * 2 + 256) + wgrad_bf_workspace_floats(q.kh, q.kw, q.x.c, q.dy.c) * 4 + 1024;
 }
 
-int wgrad_bf_oneshot(const ConvWgrad& q0, int xfmt, int dfmt, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+int wgrad_bf_oneshot(const ConvWgrad& q0, void* scratch, size_t scratch_bytes, cudaStream_t st) {
     MS_REQUIRE(wgrad_bf_supported(q0), "wgrad_bf: unsupported geometry");
     MS_REQUIRE(scratch_bytes >= wgrad_bf_oneshot_scratch_bytes(q0), "wgrad_bf: scratch too small");
     MS_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, "wgrad_bf: scratch must be 256B aligned");
     unsigned char* b = reinterpret_cast<unsigned char*>(scratch);
     auto take = [&](size_t bytes) { unsigned char* r = b; b += (bytes + 255) / 256 * 256; return r; };
     ActPlanes xp, dp;
-    xp.cs = (q0.x.c + 7) / 8 * 8; dp.cs = (q0.dy.c + 7) / 8 * 8; xp.fmt = xfmt; dp.fmt = dfmt;
+    xp.cs = (q0.x.c + 7) / 8 * 8; dp.cs = (q0.dy.c + 7) / 8 * 8; xp.fmt = 0; dp.fmt = 0; xp.scale = dp.scale = 1.f;
     const size_t xe = q0.x.pixels() * xp.cs, de = q0.dy.pixels() * dp.cs;
     xp.hi = take(xe * 2); xp.lo = take(xe * 2); dp.hi = take(de * 2); dp.lo = take(de * 2);
     ConvWgrad q = q0;

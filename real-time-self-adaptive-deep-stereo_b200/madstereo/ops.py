@@ -113,7 +113,7 @@ def conv2d_dgrad_tc(dy, w, dilation=1):
     return dx
 
 
-def conv2d_bf(x, w, b, stride=1, dilation=1, alpha=1.0):
+def conv2d_bf(x, w, b, stride=1, dilation=1, alpha=1.0, act_scale=0.0625):
     """split-bf16 tcgen05 forward conv (csrc/conv_bf.cu; same semantics as conv2d, stride 1 or 2)."""
     n, h, wd, cin = x.shape
     kh, kw, _, cout = w.shape
@@ -122,7 +122,7 @@ def conv2d_bf(x, w, b, stride=1, dilation=1, alpha=1.0):
     scratch = torch.empty(ns + 256, device=x.device, dtype=torch.uint8)
     off = (-scratch.data_ptr()) % 256
     check(lib().ms_conv2d_fwd_bf(_p(x), n, h, wd, cin, cin, _p(w), _p(b), _p(y), cout, cout, kh, kw, stride, dilation,
-                                 float(alpha), c_void_p(scratch.data_ptr() + off), ns, _s()), 'ms_conv2d_fwd_bf')
+                                 float(alpha), float(act_scale), c_void_p(scratch.data_ptr() + off), ns, _s()), 'ms_conv2d_fwd_bf')
     return y
 
 
@@ -139,9 +139,8 @@ def conv2d_dgrad_bf(dy, w, in_hw=None, stride=1, dilation=1):
     return dx
 
 
-def conv2d_wgrad_bf(x, dy, kh, kw, stride=1, dilation=1, x_fmt=0):
-    """tcgen05 weight + bias gradient on 16-bit planes (csrc/wgrad_bf.cu), stride 1 or 2.  x_fmt=1: the x planes are the
-    forward fp16 planes (f16 x bf16 MMA)."""
+def conv2d_wgrad_bf(x, dy, kh, kw, stride=1, dilation=1):
+    """tcgen05 weight + bias gradient on bf16 hi/lo planes (csrc/wgrad_bf.cu), stride 1 or 2."""
     n, h, wd, cin = x.shape
     _, oh, ow, cout = dy.shape
     dw = torch.empty(kh, kw, cin, cout, device=x.device, dtype=torch.float32)
@@ -150,7 +149,7 @@ def conv2d_wgrad_bf(x, dy, kh, kw, stride=1, dilation=1, x_fmt=0):
     scratch = torch.empty(ns + 256, device=x.device, dtype=torch.uint8)
     off = (-scratch.data_ptr()) % 256
     check(lib().ms_conv2d_wgrad_bf(_p(x), n, h, wd, cin, cin, _p(dy), oh, ow, cout, cout, _p(dw), _p(db), kh, kw, stride,
-                                   dilation, x_fmt, c_void_p(scratch.data_ptr() + off), ns, _s()), 'ms_conv2d_wgrad_bf')
+                                   dilation, c_void_p(scratch.data_ptr() + off), ns, _s()), 'ms_conv2d_wgrad_bf')
     return dw, db
 
 

@@ -27,7 +27,7 @@ def planes(t, c, fmt):
     pcs = (c + 7) // 8 * 8
     n, h, w, _ = t.shape
     hi = torch.empty(n * h * w * pcs, dtype=torch.bfloat16, device=dev); lo = torch.empty_like(hi)
-    check(L.ms_bf_split(P(t), n, h, w, c, c, P(hi), P(lo), pcs, fmt, st()), 'split')
+    check(L.ms_bf_split(P(t), n, h, w, c, c, P(hi), P(lo), pcs, fmt, 0.0625, st()), 'split')
     return hi, lo, pcs
 
 
@@ -62,10 +62,10 @@ def setup(shape):
     nws = L.ms_conv2d_wgrad_bf_workspace(k, k, cin, cout)
     ws = torch.empty(nws, device=dev); dw = torch.empty(k, k, cin, cout, device=dev); db = torch.empty(cout, device=dev)
     def fwd():
-        check(L.ms_conv2d_fwd_bf_planes(P(xh), P(xl), xpcs, 1, n, h, w, cin, P(wt16), P(b), P(y), cout, cout, P(yh), P(yl), ypcs,
+        check(L.ms_conv2d_fwd_bf_planes(P(xh), P(xl), xpcs, 1, 0.0625, n, h, w, cin, P(wt16), P(b), P(y), cout, cout, P(yh), P(yl), ypcs,
                                         k, k, s, d, 0.2, P(part), P(tick), st()), 'fwd')
     def wgrad():
-        check(L.ms_conv2d_wgrad_bf_planes(P(xbh), P(xbl), xpcs, 0, n, h, w, cin, P(gh), P(gl), gpcs, oh, ow, cout, P(dw), P(db),
+        check(L.ms_conv2d_wgrad_bf_planes(P(xbh), P(xbl), xpcs, n, h, w, cin, P(gh), P(gl), gpcs, oh, ow, cout, P(dw), P(db),
                                           k, k, s, d, P(ws), nws, st()), 'wgrad')
     keep = (x, wt, b, y, g, xh, xl, xbh, xbl, gh, gl, yh, yl, wt16, job, part, tick, ws, dw, db)
     return fwd, wgrad, n * oh * ow * k * k * cin * cout, keep

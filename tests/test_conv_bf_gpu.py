@@ -69,7 +69,7 @@ def test_conv_bf_forward(case):
     wt = (rng.standard_normal((k, k, cin, cout)) / np.sqrt(k * k * cin)).astype(np.float32)
     b = rng.uniform(-0.1, 0.1, cout).astype(np.float32)
     ref = T.conv2d(torch.tensor(x), torch.tensor(wt), torch.tensor(b), stride=stride, dilation=dil, alpha=alpha)
-    out = ops.conv2d_bf(cu(x), cu(wt), cu(b), stride, dil, alpha)
+    out = ops.conv2d_bf(cu(x), cu(wt), cu(b), stride, dil, alpha)           # fp16 planes of x / 16 (the MADNet setting)
     torch.cuda.synchronize()
     assert out.shape == tuple(ref.shape)
     err = rel_linf(out.cpu().numpy(), ref.numpy())
@@ -124,3 +124,24 @@ def test_wgrad_bf(case):
     e1, e2 = rel_linf(dw.cpu().numpy(), gw.numpy()), rel_linf(db.cpu().numpy(), gb.numpy())
     _log({'op': 'wgrad', 'case': list(case), 'rel_linf_dw': e1, 'rel_linf_db': e2})
     assert e1 < TOL and e2 < TOL
+
+
+@pytest.mark.parametrize('mag,scale', [(1e-3, 64.0), (1e-3, 0.0625), (300.0, 0.0625), (2.0e5, 0.0625)])
+def test_conv_bf_forward_activation_range(mag, scale):
+    """fp16 forward planes hold x * act_scale: small activations need a large scale (DispNet: 64), large ones a small one
+    (MADNet: 1/16); out-of-range values saturate (graceful degradation), they never become inf / nan."""
+    from madstereo import ops
+    from oracle import tf1_ops as T
+    n, h, w, cin, cout, k = 1, 24, 40, 64, 64, 3
+    rng = np.random.default_rng(11)
+    x = (rng.standard_normal((n, h, w, cin)) * mag).astype(np.float32)
+    wt = (rng.standard_normal((k, k, cin, cout)) / np.sqrt(k * k * cin)).astype(np.float32)
+    b = np.zeros(cout, np.float32)
+    ref = T.conv2d(torch.tensor(x), torch.tensor(wt), torch.tensor(b), stride=1, dilation=1, alpha=0.2)
+    out = ops.conv2d_bf(cu(x), cu(wt), cu(b), 1, 1, 0.2, act_scale=scale)
+    torch.cuda.synchronize()
+    err = rel_linf(out.cpu().numpy(), ref.numpy())
+    _log({'op': 'fwd_range', 'mag': mag, 'scale': scale, 'rel_linf': err})
+    assert np.isfinite(out.cpu().numpy()).all()
+    good_range = 6e-5 * 64 < mag * scale < 6e4 / 8
+    assert err < (TOL_FWD if good_range else 5e-3), (mag, scale, err)
