@@ -328,12 +328,12 @@ void* ms_engine_create(const char* net_name, int B, int H, int W, int radius_d, 
     e->radius_d = radius_d; e->corr_stride = corr_stride; e->warping = warping;
     if (!strcmp(net_name, "MADNet")) { e->net = 0; e->build_madnet(); }
     else if (!strcmp(net_name, "Dispnet")) { e->net = 1; e->build_dispnet(); }
+    else { set_error(std::string("Unrecognized network name: ") + net_name); delete e; return nullptr; }
     // scale of the fp16 forward planes (stored value = activation * scale, a power of two): MADNet consumes raw 0..255
     // images (Nets/MadNet.py:56-66) -> activations up to ~1e4, 1/16 keeps |x| <= 1e6 finite; DispNet normalises its input
     // to [-0.4, 0.6] (Nets/DispNet.py:59-73) -> activations O(1e-3 .. 10), 64 lifts them out of fp16's subnormal range
     e->act_scale = e->net == 1 ? 64.f : 0.0625f;
     if (const char* as = getenv("MS_ACT_SCALE")) { const float v = (float)atof(as); if (v > 0.f) e->act_scale = v; }
-    else { set_error(std::string("Unrecognized network name: ") + net_name); delete e; return nullptr; }
     e->finalize_groups(nullptr, 0);
     return e;
 }
