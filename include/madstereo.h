@@ -218,6 +218,9 @@ long long ms_launch_count(void);
 /* Diagnostic (no reference counterpart): per-role clock64 counters of the tcgen05 conv kernel, filled only when the
  * environment selects its profiling build (MS_TC_DEBUG=8, scripts/tc_prof.py). out32: 32 counters; reset != 0 clears. */
 int ms_debug_tc_prof(unsigned long long* out32, int reset);
+/* MS_BF_PROF=1: clock64 stamps of the last conv_bf launch, 8 per CTA (entry, setup done, first data, MMAs issued,
+ * accumulator seen, epilogue done, exit, MMA-thread wait cycles); returns the number of CTAs copied */
+int ms_debug_bf_prof(unsigned long long* out, int max_ctas);
 int ms_engine_num_tensors(void* e);
 int ms_engine_tensor_name(void* e, int i, char* name, int cap);
 /* dims: n,h,w,c,cs */

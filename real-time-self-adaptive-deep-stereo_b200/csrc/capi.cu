@@ -474,6 +474,7 @@ int ms_engine_profile_layers(void* h, double* ms3n, long long* calls3n) {
 float ms_engine_profile_event_overhead_ms(void* h) { return static_cast<Engine*>(h)->prof_event_overhead_ms; }
 long long ms_launch_count(void) { return ms::launch_count(); }
 int ms_debug_tc_prof(unsigned long long* out32, int reset) { return ms::conv_tc_read_prof(out32, reset); }
+int ms_debug_bf_prof(unsigned long long* out, int max_ctas) { return ms::conv_bf_read_prof(out, max_ctas); }
 int ms_engine_num_tensors(void* h) { return (int)static_cast<Engine*>(h)->tensors.size(); }
 int ms_engine_tensor_name(void* h, int i, char* name, int cap) {
     Engine* e = static_cast<Engine*>(h);

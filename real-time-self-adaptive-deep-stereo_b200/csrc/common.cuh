@@ -194,6 +194,7 @@ size_t conv_bf_weight_halfs(int taps, int M, int K);
 size_t conv_bf_part_floats();
 size_t conv_bf_ticket_words();
 int conv_bf_init();
+int conv_bf_read_prof(unsigned long long* out, int max_ctas);
 int bf_prep_weights(const BfPrepJob* jobs_dev, int njobs, size_t max_total, cudaStream_t st);
 int split_planes(const TView& x, const ActPlanes& pl, cudaStream_t st);
 int conv_bf(const ConvGemm& g, const ActPlanes& xp, const void* wtiles, const ActPlanes* yp, float* part,

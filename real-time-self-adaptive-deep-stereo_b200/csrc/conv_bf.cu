@@ -71,6 +71,7 @@ struct ConvBfParams {
     int tmem_cols;
     int cout;
     int ksplit;
+    unsigned long long* prof;     // MS_BF_PROF=1: per-CTA clock64 stamps [8] (entry, setup done, first data, MMAs issued, accumulator seen, epilogue done, exit, MMA-thread wait cycles)
     int debug;                    // MS_BF_DEBUG kill switches (measurement only): 1 = no MMAs, 2 = no weight loads, 4 = no patch loads, 8 = no epilogue stores
     const unsigned char* wtiles;  // pre-tiled weights [M block][tap][K block][hi tile | lo tile]
     float* part; unsigned int* tickets;
@@ -142,6 +143,8 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
     const int x0 = tx * p.TW, y0 = ty * TH;
     const int units = p.kblocks * p.n_patches;
     const int u0 = (int)(((long)blockIdx.z * units) / p.ksplit), u1 = (int)(((long)(blockIdx.z + 1) * units) / p.ksplit);
+    unsigned long long* prof = p.prof ? p.prof + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
+    if (prof && threadIdx.x == 0) prof[0] = clock64();
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.NP; ++i) { mb_init(&pfull[i], 1); mb_init(&pempty[i], 1); }
@@ -157,6 +160,7 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
+    if (prof && threadIdx.x == 0) prof[1] = clock64();
 
     if (warp == 0) {
         // ================= producer: halo patches by TMA (per K block x filter column) + weight tiles by bulk copy (per tap) ===
@@ -203,12 +207,17 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
             uint32_t started_cross = 0, started_main = 0;
             int pi = u0 % p.n_patches;
             const uint32_t row_bytes = (uint32_t)p.TW * (uint32_t)p.kch * 2u;
+            long long waited = 0;
             for (int u = u0; u < u1; ++u) {
                 const BfPatch pt = p.patch[pi];
+                long long tw0 = prof ? clock64() : 0;
                 mb_wait(&pfull[ps], pph);
+                if (prof) { const long long tw1 = clock64(); waited += tw1 - tw0; if (u == u0) prof[2] = tw1; }
                 const uint32_t pb = base + (uint32_t)ps * pslot;
                 for (int t = pt.tap0; t < pt.tap0 + pt.ntaps; ++t) {
+                    tw0 = prof ? clock64() : 0;
                     mb_wait(&wfull[ws], wph);
+                    if (prof) waited += clock64() - tw0;
                     tc_fence_after();
                     const uint32_t boff = (uint32_t)p.tap[t].row_off * row_bytes;
                     const uint64_t xh = umma_desc_k(pb + boff, sw128), xl = umma_desc_k(pb + p.slot_bytes + boff, sw128);
@@ -233,6 +242,7 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
                 if (++ps == p.NP) { ps = 0; pph ^= 1u; }
                 if (++pi == p.n_patches) pi = 0;
             }
+            if (prof) { prof[3] = clock64(); prof[7] = (unsigned long long)waited; }
             tc_commit(&accum_bar);
         }
     } else {
@@ -291,6 +301,7 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
 
         mb_wait(&accum_bar, 0);
         tc_fence_after();
+        if (prof && threadIdx.x == 64) prof[4] = clock64();
         if (p.ksplit == 1) {
             for (int c0 = cbeg; c0 < cend; c0 += 16) {
                 uint32_t r0[16], r1[16];
@@ -345,12 +356,25 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
             }
         }
     }
+    if (prof && threadIdx.x == 64) prof[5] = clock64();
     tc_fence_before();
     __syncthreads();
+    if (prof && threadIdx.x == 0) prof[6] = clock64();
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmem_cols) : "memory");
     }
+}
+
+static unsigned long long* g_bf_prof = nullptr;
+static int g_bf_prof_ctas = 0;
+constexpr int BF_PROF_MAX = 8192;
+// last profiled launch: per-CTA stamps (MS_BF_PROF=1); returns the number of CTAs copied
+int conv_bf_read_prof(unsigned long long* out, int max_ctas) {
+    if (!g_bf_prof || g_bf_prof_ctas <= 0) return 0;
+    const int n = std::min(max_ctas, g_bf_prof_ctas);
+    if (cudaMemcpy(out, g_bf_prof, (size_t)n * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return n;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -640,6 +664,16 @@ static int conv_bf_launch(const ConvGemm& g, const ActPlanes& xp, const void* wt
         if ((size_t)grid_tiles * mblocks > conv_bf_ticket_words()) ksplit = 1;
     }
     p.ksplit = ksplit; p.part = part; p.tickets = tickets;
+    {
+        static int prof_env = -1;
+        if (prof_env < 0) { const char* e = getenv("MS_BF_PROF"); prof_env = e ? atoi(e) : 0; }
+        p.prof = nullptr;
+        if (prof_env) {
+            if (!g_bf_prof) cudaMalloc(reinterpret_cast<void**>(&g_bf_prof), (size_t)BF_PROF_MAX * 8 * sizeof(unsigned long long));
+            const int nctas = grid_tiles * mblocks * ksplit;
+            if (g_bf_prof && nctas <= BF_PROF_MAX) { p.prof = g_bf_prof; g_bf_prof_ctas = nctas; }
+        }
+    }
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MS_BF_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
 
     const CUtensorMap *mXh, *mXl;

@@ -83,6 +83,7 @@ _SIGS = {
     'ms_engine_profile_event_overhead_ms': (F, [P]),
     'ms_launch_count': (ctypes.c_longlong, []),
     'ms_debug_tc_prof': (I, [POINTER(ctypes.c_ulonglong), I]),
+    'ms_debug_bf_prof': (I, [P, I]),
     'ms_engine_num_tensors': (I, [P]),
     'ms_engine_tensor_name': (I, [P, I, c_char_p, I]),
     'ms_engine_tensor': (I, [P, c_char_p, POINTER(P), POINTER(I)]),

@@ -71,6 +71,25 @@ def setup(shape):
     return fwd, wgrad, n * oh * ow * k * k * cin * cout, keep
 
 
+if len(sys.argv) > 2 and sys.argv[1] == 'prof':
+    # MS_BF_PROF=1 python scripts/bf_bench.py prof <i>: per-CTA clock64 breakdown of the forward kernel on shape i
+    import ctypes, numpy as np
+    fwd, wgrad, macs, keep = setup(SHAPES[int(sys.argv[2])])
+    for _ in range(5):
+        fwd()
+    torch.cuda.synchronize()
+    buf = (ctypes.c_ulonglong * (8 * 8192))()
+    n = L.ms_debug_bf_prof(buf, 8192)
+    a = np.frombuffer(buf, dtype=np.uint64)[:n * 8].reshape(n, 8).astype(np.int64)
+    names = ['setup', 'first data', 'main loop (issue)', 'drain to accumulator barrier', 'epilogue', 'exit sync']
+    d = np.stack([a[:, 1] - a[:, 0], a[:, 2] - a[:, 1], a[:, 3] - a[:, 2], a[:, 4] - a[:, 3], a[:, 5] - a[:, 4], a[:, 6] - a[:, 5]], 1)
+    print('shape', SHAPES[int(sys.argv[2])], 'CTAs', n)
+    for i, nm in enumerate(names):
+        print('  %-30s mean %8.0f  min %8.0f  max %8.0f cycles' % (nm, d[:, i].mean(), d[:, i].min(), d[:, i].max()))
+    print('  %-30s mean %8.0f cycles (of the main loop)' % ('MMA thread waiting on data', a[:, 7].mean()))
+    print('  %-30s mean %8.0f cycles' % ('CTA lifetime', (a[:, 6] - a[:, 0]).mean()))
+    sys.exit(0)
+
 if len(sys.argv) > 2 and sys.argv[1] == 'one':
     fwd, wgrad, macs, keep = setup(SHAPES[int(sys.argv[2])])
     for _ in range(3):
