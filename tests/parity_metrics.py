@@ -34,10 +34,15 @@ def grad_report(got, g32, g64):
 
 
 def assert_grads(rep, tol_l2, tol_linf, what=''):
+    """Per tensor: error <= max(floor, 2 x that tensor's fp32-oracle noise, the step's noise level).  The step's noise level
+    (the largest fp32-vs-fp64 distance over the trained tensors) covers tensors with a handful of elements -- e.g. the single
+    bias of a disparity head -- whose own noise figure is ONE sample of the kink-flip distribution that moves every tensor
+    of the step, so twice that sample is not a bound."""
     worst = (0.0, None)
+    n2_step = max(v[1] for v in rep.values()); ni_step = max(v[3] for v in rep.values())
     for n, (l2, n2, li, ni) in rep.items():
-        assert l2 <= max(tol_l2, 2.0 * n2), '%s %s: rel L2 %.3e (fp32-oracle noise %.3e, floor %.1e)' % (what, n, l2, n2, tol_l2)
-        assert li <= max(tol_linf, 2.0 * ni), '%s %s: rel Linf %.3e (fp32-oracle noise %.3e, floor %.1e)' % (what, n, li, ni, tol_linf)
+        assert l2 <= max(tol_l2, 2.0 * n2, n2_step), '%s %s: rel L2 %.3e (fp32-oracle noise %.3e, step noise %.3e, floor %.1e)' % (what, n, l2, n2, n2_step, tol_l2)
+        assert li <= max(tol_linf, 2.0 * ni, ni_step), '%s %s: rel Linf %.3e (fp32-oracle noise %.3e, step noise %.3e, floor %.1e)' % (what, n, li, ni, ni_step, tol_linf)
         if l2 > worst[0]:
             worst = (l2, n)
     return worst
