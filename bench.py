@@ -412,6 +412,14 @@ def run_ours(args, cfg):
                       'tensor_flops_frac': 3.0 * 2.0 * macs / us / 1e6 / pk['bf16_tflops']}
         dom['note'] = ('in-graph CUDA-event time of that layer inside the replayed step graph; split-bf16 (3 kind::f16 MMAs per '
                        'product): tensor_flops_frac counts the 3 issued MMAs against the measured bf16 peak')
+    if os.environ.get('MS_BENCH_LAYERS'):       # per-layer in-graph times (diagnosis; not part of the JSON line)
+        try:
+            os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+            with open(os.path.join(ROOT, 'gpurun_out', 'layers_cfg%d.json' % args.config), 'w') as f:
+                json.dump({k: {d: {'us_per_call': v['ms'] / v['calls'] * 1e3, 'calls_per_step': v['calls'] / n_prof}
+                               for d, v in dv.items()} for k, dv in layers.items()}, f, indent=1)
+        except OSError:
+            pass
     corr_large = corr_large_shapes(dev) if not args.no_corr_shapes else {}
     line = {
         'metric': cfg['metric'], 'value': fps, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,

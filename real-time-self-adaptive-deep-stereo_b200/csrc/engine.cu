@@ -392,6 +392,12 @@ int Engine::conv_fwd(const ConvLayer& L, const TView& x, const TView& y, const f
     if (use_heads && conv_head_kind(p) == 1) {
         fresh.erase(y.p);
         rc = conv_head(p, st);
+    } else if (!L.transposed && L.cout <= 16 && conv_small_fwd_supported(p)) {
+        // full-resolution 16-channel layers (conv2: 2 x 192 x 640 x 16): M = cout = 16 would waste 7/8 of the swap-AB
+        // tile's TMEM lanes and epilogue threads (183 us on the split-16-bit path); the shared-memory tiled direct
+        // kernel is bandwidth-shaped
+        fresh.erase(y.p);
+        rc = conv_small_fwd(p, st);
     } else if (xpl) {
         if (ensure_planes(x, st)) return -1;
         const ActPlanes* ypl = planes_of(y);
