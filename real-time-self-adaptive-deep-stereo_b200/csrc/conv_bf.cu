@@ -319,33 +319,41 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
         const int ofmt = p.ofmt;
         auto finish16 = [&](int c0, const float (&v)[16]) {
             if (!vec_ok) { finish16_scalar(c0, v); return; }
+            // pixel addresses of this lane's 4 pixels, and the operands that do not depend on the accumulator (residual,
+            // previous value, mask) requested BEFORE the transpose so that their latency overlaps it
+            size_t pix[4];
+            bool ok[4];
+            float4 rv[4], ov[4], mv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int col = c0 + i * 4 + prow;
+                const int yy = y0 + (col >> p.tw_shift), xx = x0 + (col & twm);
+                ok[i] = yy < p.H && xx < p.W && ch4v;
+                pix[i] = (img_pix + (size_t)(yy * p.os + p.oy0)) * p.Wout + (size_t)(xx * p.os + p.ox0);
+                if (ok[i]) {
+                    if (has_res) rv[i] = *reinterpret_cast<const float4*>(p.res + pix[i] * p.res_cs + ch4);
+                    if (has_acc) ov[i] = *reinterpret_cast<const float4*>(p.y + pix[i] * p.ycs + ch4);
+                    if (has_mask) mv[i] = *reinterpret_cast<const float4*>(p.mask + pix[i] * p.mask_cs + ch4);
+                }
+            }
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 16; ++j) stage[j * 32 + lane] = v[j];
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int px = i * 4 + prow;
-                float4 t = *reinterpret_cast<const float4*>(stage + px * 32 + c4 * 4);
-                const int col = c0 + px;
-                const int yy = y0 + (col >> p.tw_shift), xx = x0 + (col & twm);
-                if (yy >= p.H || xx >= p.W || !ch4v) continue;
-                const size_t pix = (img_pix + (size_t)(yy * p.os + p.oy0)) * p.Wout + (size_t)(xx * p.os + p.ox0);
+                float4 t = *reinterpret_cast<const float4*>(stage + (i * 4 + prow) * 32 + c4 * 4);
+                if (!ok[i]) continue;
                 t.x = t.x * acc_scale + bias4.x; t.y = t.y * acc_scale + bias4.y; t.z = t.z * acc_scale + bias4.z; t.w = t.w * acc_scale + bias4.w;
                 t.x = fmaxf(alpha * t.x, t.x); t.y = fmaxf(alpha * t.y, t.y); t.z = fmaxf(alpha * t.z, t.z); t.w = fmaxf(alpha * t.w, t.w);
-                float4* yp4 = reinterpret_cast<float4*>(p.y + pix * p.ycs + ch4);
-                if (has_res) {
-                    const float4 r = *reinterpret_cast<const float4*>(p.res + pix * p.res_cs + ch4);
-                    t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
-                }
-                if (has_acc) { const float4 o = *yp4; t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w; }
+                if (has_res) { t.x += rv[i].x; t.y += rv[i].y; t.z += rv[i].z; t.w += rv[i].w; }
+                if (has_acc) { t.x += ov[i].x; t.y += ov[i].y; t.z += ov[i].z; t.w += ov[i].w; }
                 if (has_mask) {
-                    const float4 m = *reinterpret_cast<const float4*>(p.mask + pix * p.mask_cs + ch4);
-                    t.x *= m.x > 0.f ? 1.f : mask_alpha; t.y *= m.y > 0.f ? 1.f : mask_alpha;
-                    t.z *= m.z > 0.f ? 1.f : mask_alpha; t.w *= m.w > 0.f ? 1.f : mask_alpha;
+                    t.x *= mv[i].x > 0.f ? 1.f : mask_alpha; t.y *= mv[i].y > 0.f ? 1.f : mask_alpha;
+                    t.z *= mv[i].z > 0.f ? 1.f : mask_alpha; t.w *= mv[i].w > 0.f ? 1.f : mask_alpha;
                 }
                 if (p.debug & 8) continue;
-                *yp4 = t;
+                *reinterpret_cast<float4*>(p.y + pix[i] * p.ycs + ch4) = t;
                 if (has_pl) {
                     unsigned short h[4], l[4];
                     split16(t.x, ofmt, oscale, h[0], l[0]); split16(t.y, ofmt, oscale, h[1], l[1]);
@@ -353,8 +361,8 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
                     uint2 hv, lv;
                     hv.x = (uint32_t)h[0] | ((uint32_t)h[1] << 16); hv.y = (uint32_t)h[2] | ((uint32_t)h[3] << 16);
                     lv.x = (uint32_t)l[0] | ((uint32_t)l[1] << 16); lv.y = (uint32_t)l[2] | ((uint32_t)l[3] << 16);
-                    *reinterpret_cast<uint2*>(ohi + pix * p.ocs + ch4) = hv;
-                    *reinterpret_cast<uint2*>(olo + pix * p.ocs + ch4) = lv;
+                    *reinterpret_cast<uint2*>(ohi + pix[i] * p.ocs + ch4) = hv;
+                    *reinterpret_cast<uint2*>(olo + pix[i] * p.ocs + ch4) = lv;
                 }
             }
         };

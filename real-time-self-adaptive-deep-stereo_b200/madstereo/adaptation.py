@@ -91,7 +91,8 @@ class OnlineAdaptation(object):
             self._dp_rng_state = np.random.RandomState(int(seed.item())).get_state()
 
     def _sample_blocks(self, distribution):
-        if self._dp_rng_state is None:
+        # only the samplers that draw random numbers need the private stream (swapping numpy's global state costs ~50 us)
+        if self._dp_rng_state is None or type(self.sampler).__name__ not in ('random_sampler', 'probabilistic_sampler'):
             return [int(b) for b in self.sampler.sample(distribution)]
         outer = np.random.get_state()
         np.random.set_state(self._dp_rng_state)

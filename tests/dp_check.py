@@ -61,7 +61,9 @@ def main():
             ref = orc.step(bl, br, 3)
             g = net.engine.param_views(net.engine.grads)
             worst = max(rel(g[n].cpu().numpy() / world, gr) for n, gr in ref['grads'].items())
-            worst_l2 = max(rel_l2(g[n].cpu().numpy() / world, gr) for n, gr in ref['grads'].items())
+            per = sorted(((rel_l2(g[n].cpu().numpy() / world, gr), n, float(np.abs(gr).max())) for n, gr in ref['grads'].items()), reverse=True)
+            worst_l2 = per[0][0]
+            print('   worst tensors (rel L2, name, max|ref|):', [(round(a, 4), n, '%.2e' % m) for a, n, m in per[:4]], flush=True)
             wv = net.engine.export_params()
             wworst = max(rel_l2(wv[n] - params[n], orc.net.p[n].detach().numpy() - params[n]) for n in ref['grads'])
             # same bounds as the single-GPU step tests (tests/test_madnet_gpu.py): gradients 1e-2 L-inf, and relative L2
