@@ -609,7 +609,7 @@ bool conv_bf_supported(const ConvGemm& g) {
     if (g.mul != 1 && g.mul != 2) return false;
     if (g.mul == 2 && g.step != 1) return false;
     if (g.div == 2 && std::abs(g.step) != 1) return false;
-    if (g.x.c < 8 || g.y.c < 8) return false;
+    if (g.x.c < 3 || g.y.c < 8) return false;          // (3-channel images: the planes are padded to 8 channels, TMA zero-fills the K block)
     if (g.kh * g.kw > BF_MAX_TAPS) return false;
     if (g.y.h * g.y.w < 32) return false;
     return true;
