@@ -188,6 +188,8 @@ struct BfPrepJob {
 };
 int conv_head_kind(const ConvGemm& g);      // conv_head.cu: 1 = forward 3x3 -> 1 head, 2 = its dgrad, 0 = no
 int conv_head(const ConvGemm& g, cudaStream_t st);
+bool conv_one_channel_supported(const ConvGemm& g);   // conv_head.cu: 1 -> 1 channel gather (any geometry)
+int conv_one_channel(const ConvGemm& g, cudaStream_t st);
 bool conv_bf_supported(const ConvGemm& g);
 void conv_bf_weight_dims(int M, int K, int& Mpad, int& Kpad);
 size_t conv_bf_weight_halfs(int taps, int M, int K);

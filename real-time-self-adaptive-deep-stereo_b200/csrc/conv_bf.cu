@@ -609,7 +609,7 @@ bool conv_bf_supported(const ConvGemm& g) {
     if (g.mul != 1 && g.mul != 2) return false;
     if (g.mul == 2 && g.step != 1) return false;
     if (g.div == 2 && std::abs(g.step) != 1) return false;
-    if (g.x.c < 8 || g.y.c < 8) return false;
+    if (g.x.c < 3 || g.y.c < 8) return false;          // (3-channel images: the planes are padded to 8 channels, TMA zero-fills the K block)
     if (g.kh * g.kw > BF_MAX_TAPS) return false;
     if (g.y.h * g.y.w < 32) return false;
     return true;
@@ -738,6 +738,13 @@ static int conv_bf_launch(const ConvGemm& g, const ActPlanes& xp, const void* wt
     int ksplit = 1;
     if (part && tickets && (long)grid_tiles * mblocks <= 74 && units > 1) {
         ksplit = std::min(std::min(units, 8), std::max(1, 148 / (grid_tiles * mblocks)));
+        // splitting only pays while a CTA's share of the main loop outweighs the partial-sum round trip (write, fence,
+        // ticket, the closing CTA's ordered reduction: ~5 us measured); an N = 64 MMA is 32 cycles, so the small maps of
+        // pyramid levels 4-6 are faster un-split (MMA cycles of the whole K loop: taps x k16 x 3 products x N/2)
+        static int min_cyc = -1;
+        if (min_cyc < 0) { const char* e = getenv("MS_BF_SPLIT_CYCLES"); min_cyc = e ? atoi(e) : 8192; }
+        const long loop_cycles = (long)p.kblocks * nt * (p.kch / 16) * (p.nprod == 1 ? 1 : 3) * (N / 2);
+        ksplit = (int)std::max<long>(1, std::min<long>(ksplit, loop_cycles / std::max(min_cyc, 1)));
         while (ksplit > 1 && (size_t)ksplit * grid_tiles * mblocks * N * 128 > conv_bf_part_floats()) --ksplit;
         if ((size_t)grid_tiles * mblocks > conv_bf_ticket_words()) ksplit = 1;
     }

@@ -99,6 +99,44 @@ conv_head_dgrad_kernel(ConvGemm g, size_t npix) {
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // 1 = forward head (y.c == 1), 2 = head dgrad (x.c == 1), 0 = not a head
+// single-channel gather (1 -> 1 channel, any generic gather geometry): DispNet's `up_predict` 4x4 stride-2 conv_transpose of
+// a disparity map (Nets/DispNet.py:51-53).  One thread per output pixel; the generic fp32 gather GEMM spent 166 us on the
+// 192x640 instance of this 2 MFLOP operation.
+__global__ void __launch_bounds__(256) conv_one_channel_kernel(ConvGemm g, size_t npix) {
+    const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    const int W = g.y.w, H = g.y.h;
+    const int ox = (int)(pix % W);
+    const size_t t = pix / W;
+    const int oy = (int)(t % H);
+    const size_t img = t / H;
+    float acc = g.bias ? g.bias[0] : 0.f;
+    for (int r = 0; r < g.kh; ++r) {
+        int ty = oy * g.mul + g.off_y + r * g.step;
+        if (g.div > 1) { if (ty % g.div) continue; ty /= g.div; }
+        if (ty < 0 || ty >= g.x.h) continue;
+        for (int s = 0; s < g.kw; ++s) {
+            int tx = ox * g.mul + g.off_x + s * g.step;
+            if (g.div > 1) { if (tx % g.div) continue; tx /= g.div; }
+            if (tx < 0 || tx >= g.x.w) continue;
+            acc = fmaf(g.x.p[((img * g.x.h + ty) * g.x.w + tx) * g.x.cs], g.wmat[r * g.kw + s], acc);
+        }
+    }
+    acc = fmaxf(g.alpha * acc, acc);
+    float* yp = g.y.p + pix * g.y.cs;
+    if (g.res) acc += g.res[pix * g.res_cs];
+    if (g.accumulate) acc += *yp;
+    if (g.mask) acc *= (g.mask[pix * g.mask_cs] > 0.f) ? 1.f : g.mask_alpha;
+    *yp = acc;
+}
+bool conv_one_channel_supported(const ConvGemm& g) { return g.x.c == 1 && g.y.c == 1 && g.x.n == g.y.n && g.alpha <= 1.f && g.alpha >= 0.f; }
+int conv_one_channel(const ConvGemm& g, cudaStream_t st) {
+    MS_REQUIRE(conv_one_channel_supported(g), "conv_one_channel: not a 1 -> 1 channel gather");
+    const size_t npix = g.y.pixels();
+    conv_one_channel_kernel<<<(unsigned)cdivz(npix, 256), 256, 0, st>>>(g, npix);
+    return check_launch("conv_one_channel");
+}
+
 int conv_head_kind(const ConvGemm& g) {
     if (g.mul != 1 || g.div != 1) return 0;
     if (g.x.h != g.y.h || g.x.w != g.y.w) return 0;

@@ -211,13 +211,14 @@ size_t Engine::layout(float* base) {
     tensors["raw_left"] = raw_l; tensors["raw_right"] = raw_r;
     img = tens(2 * B, Hp, Wp, 3, 4);
     tensors["img"] = img;
+    if (net == 1) add_planes(A, img, 1);           // DispNet's 7x7 stem runs on the tensor cores
     size_t max_wg = 0, max_wt = 0;
     auto track = [&](const ConvLayer& L, size_t pixels) {
         max_wg = std::max(max_wg, conv_wgrad_workspace_floats(L.kh * L.kw, L.cin, L.cout, pixels));
         if (L.stride == 1 && L.cout <= 192)   // tcgen05 wgrad: NCHW copy of dY + <=64 split partials + bias partials
             max_wg = std::max(max_wg, pixels * L.cout + 64 * (size_t)L.kh * L.kw * L.cin * L.cout + 128 * (size_t)L.cout + 8192);
         max_wt = std::max(max_wt, (size_t)L.kh * L.kw * L.cin * L.cout);
-        if (conv_impl == 1 && !L.transposed && L.cin >= 16 && L.cout >= 16) {
+        if (conv_impl == 1 && !L.transposed && L.cin >= 3 && L.cout >= 16) {
             max_wg = std::max(max_wg, std::min<size_t>(wgrad_bf_workspace_floats(L.kh, L.kw, L.cin, L.cout), (size_t)48 << 20));
             wg_xp_halfs = std::max(wg_xp_halfs, pixels * L.stride * L.stride * (size_t)((L.cin + 7) / 8 * 8));
         }
@@ -326,8 +327,25 @@ size_t Engine::layout(float* base) {
         for (size_t li = 0; li < layers.size(); ++li) {
             const ConvLayer& L = layers[li];
             const int lg = L.group < 0 ? n_groups : L.group;
-            if (lg != gidx || L.transposed || L.cin < 8 || L.cout < 8 || L.kh * L.kw > 49 || L.stride > 2) continue;
+            // (MADNet's 3 -> 16 conv1 stays on its direct kernel; a 3-channel stem with a large filter -- DispNet conv1, 7x7 --
+            //  is 2.3 GMAC and goes to the tensor cores with its K block zero-padded)
+            const bool stem = L.cin >= 3 && L.cin < 8 && L.kh * L.kw >= 25 && L.cout >= 16;
+            if (lg != gidx || (L.cin < 8 && !stem) || L.cout < 8 || L.kh * L.kw > 49 || L.stride > 2) continue;
+            if (L.transposed) {
+                // conv2d_transpose forward = fractionally strided gather: M = cout, K = cin, canonical W is already
+                // [tap][cout][cin] = [tap][M][K].  (Its two gradients still run on the fp32 path.)
+                int Mpad, Kpad; conv_bf_weight_dims(L.cout, L.cin, Mpad, Kpad);
+                const size_t halfs = conv_bf_weight_halfs(L.kh * L.kw, L.cout, L.cin);
+                BfW t; t.ok = true;
+                t.tiles = alloc((halfs + 1) / 2);
+                bfw[0][li] = t;
+                BfPrepJob j{base ? Wt + L.w_off : nullptr, t.tiles, L.kh * L.kw, L.cout, L.cin, Mpad, Kpad, 0, 1};
+                bf_jobs.push_back(j);
+                bf_max_total = std::max(bf_max_total, halfs);
+                continue;
+            }
             for (int dir = 0; dir < 2; ++dir) {
+                if (dir == 1 && stem) continue;                  // no input gradient for the image
                 const int M = dir == 0 ? L.cout : L.cin, K = dir == 0 ? L.cin : L.cout;
                 int Mpad, Kpad; conv_bf_weight_dims(M, K, Mpad, Kpad);
                 const size_t halfs = conv_bf_weight_halfs(L.kh * L.kw, M, K);
@@ -380,10 +398,12 @@ int Engine::conv_fwd(const ConvLayer& L, const TView& x, const TView& y, const f
         same_pad(y.h, L.kh, L.stride, 1, oh, pt);
         same_pad(y.w, L.kw, L.stride, 1, ow, pl);
         MS_REQUIRE(oh == x.h && ow == x.w && x.c == L.cin && y.c == L.cout, "conv_fwd(T): shape mismatch");
-        // canonical W is [tap][cout][cin]; the gather GEMM wants [tap][K=cin][N=cout]
-        if (transpose_taps(Wt + L.w_off, wT, L.kh * L.kw, L.cout, L.cin, st)) return -1;
         p.wmat = wT;
         p.mul = 1; p.off_y = pt; p.off_x = pl; p.step = -1; p.div = L.stride;
+        const int li_t = (int)(&L - &layers[0]);
+        const bool bf_t = conv_impl == 1 && bfw[0][li_t].ok && conv_bf_supported(p) && planes_of(x);
+        // canonical W is [tap][cout][cin]; the gather GEMM wants [tap][K=cin][N=cout] (the tensor-core path has its own tiles)
+        if (!bf_t && transpose_taps(Wt + L.w_off, wT, L.kh * L.kw, L.cout, L.cin, st)) return -1;
     }
     const int li = (int)(&L - &layers[0]);
     prof_begin(CAT_CONV_FWD, st, li);
@@ -392,6 +412,10 @@ int Engine::conv_fwd(const ConvLayer& L, const TView& x, const TView& y, const f
     if (use_heads && conv_head_kind(p) == 1) {
         fresh.erase(y.p);
         rc = conv_head(p, st);
+    } else if (use_heads && L.cin == 1 && L.cout == 1 && conv_one_channel_supported(p)) {
+        fresh.erase(y.p);
+        p.wmat = Wt + L.w_off;                       // [tap][1][1]: canonical weights serve either orientation
+        rc = conv_one_channel(p, st);
     } else if (!L.transposed && L.cout <= 16 && conv_small_fwd_supported(p)) {
         // full-resolution 16-channel layers (conv2: 2 x 192 x 640 x 16): M = cout = 16 would waste 7/8 of the swap-AB
         // tile's TMEM lanes and epilogue threads (183 us on the split-16-bit path); the shared-memory tiled direct

@@ -299,7 +299,7 @@ static WbPlan wb_plan(const ConvWgrad& q) {
     P.ok = false;
     if (q.stride != 1 && q.stride != 2) return P;
     if (kh > WB_MAX_KH || kh * kw > 49) return P;
-    if (ci < 16 || co < 16 || (co & 3)) return P;
+    if (ci < 3 || co < 16 || (co & 3)) return P;
     if ((size_t)q.dy.h * q.dy.w < 32) return P;
     // output-channel blocks: (kh taps + bias) accumulators of BN columns in 512 TMEM columns
     int nbk = 1, BN = 0;

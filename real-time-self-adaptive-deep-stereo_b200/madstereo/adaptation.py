@@ -187,8 +187,6 @@ class OnlineAdaptation(object):
                 self.fetch_counter[l] += 1
 
         self._set_input(left, right)
-        if prefetch is not None:
-            self.prefetch(*prefetch)
         if gt is not None:
             eng.set_gt(gt)
         mask = want_disp_mask
@@ -222,6 +220,8 @@ class OnlineAdaptation(object):
                     eng.update(b, self.lr, self.mu, gscale)
         if gt is not None:
             eng.metrics()
+        if prefetch is not None:         # issued AFTER the step's graph launch: the host work of enqueueing the next frame's
+            self.prefetch(*prefetch)     # copies (side stream) no longer delays this frame's kernels
         sc = eng.read_scalars()
         new_loss = sc[0]
         fused_loss = self.dp_peer and (self.mode == 'FULL' or (self.mode == 'MAD' and len(self.blocks_to_train) == 1))
