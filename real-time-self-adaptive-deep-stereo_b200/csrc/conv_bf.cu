@@ -738,11 +738,12 @@ static int conv_bf_launch(const ConvGemm& g, const ActPlanes& xp, const void* wt
     int ksplit = 1;
     if (part && tickets && (long)grid_tiles * mblocks <= 74 && units > 1) {
         ksplit = std::min(std::min(units, 8), std::max(1, 148 / (grid_tiles * mblocks)));
-        // splitting only pays while a CTA's share of the main loop outweighs the partial-sum round trip (write, fence,
-        // ticket, the closing CTA's ordered reduction: ~5 us measured); an N = 64 MMA is 32 cycles, so the small maps of
-        // pyramid levels 4-6 are faster un-split (MMA cycles of the whole K loop: taps x k16 x 3 products x N/2)
+        // MS_BF_SPLIT_CYCLES = c: split only while a CTA's share of the main loop stays above c MMA cycles (taps x k16 x
+        // 3 products x N/2).  Measured (profiles/r2_split_heuristic.log): un-splitting the small maps (c = 8192) LOSES 5 % of
+        // the step (521 vs 552 FPS) -- the serial K loop of a 3-30 CTA grid costs more than the partial-sum round trip --
+        // so the default keeps every split (c = 1).
         static int min_cyc = -1;
-        if (min_cyc < 0) { const char* e = getenv("MS_BF_SPLIT_CYCLES"); min_cyc = e ? atoi(e) : 8192; }
+        if (min_cyc < 0) { const char* e = getenv("MS_BF_SPLIT_CYCLES"); min_cyc = e ? atoi(e) : 1; }
         const long loop_cycles = (long)p.kblocks * nt * (p.kch / 16) * (p.nprod == 1 ? 1 : 3) * (N / 2);
         ksplit = (int)std::max<long>(1, std::min<long>(ksplit, loop_cycles / std::max(min_cyc, 1)));
         while (ksplit > 1 && (size_t)ksplit * grid_tiles * mblocks * N * 128 > conv_bf_part_floats()) --ksplit;
