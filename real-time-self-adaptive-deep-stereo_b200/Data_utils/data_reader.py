@@ -62,6 +62,9 @@ def _imread(path):
     img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
     if img is None:
         raise Exception('cannot decode image %s' % path)
+    if img.dtype == np.uint16 and img.ndim == 3 and img.shape[2] >= 3:
+        # a 16-bit COLOUR image: tf.image.decode_image(..., dtype=uint8) hands the reference the top 8 bits
+        img = (img >> 8).astype(np.uint8)
     if img.ndim == 2:
         img = img[:, :, None]
     elif img.shape[2] >= 3:                      # OpenCV decodes to BGR(A); TensorFlow to RGB(A)

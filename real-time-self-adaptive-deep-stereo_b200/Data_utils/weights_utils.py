@@ -74,7 +74,10 @@ def check_for_weights_or_restore_them(logdir, model, initial_weights=None, prefi
         return True, step
     elif initial_weights is not None:
         if os.path.isdir(initial_weights):
-            initial_weights = latest_checkpoint(initial_weights)
+            found = latest_checkpoint(initial_weights)
+            if found is None:
+                raise Exception('no usable checkpoint in directory {} (missing `checkpoint` state file or its .index)'.format(initial_weights))
+            initial_weights = found
         w = load_weights(initial_weights, names, [], prefix=prefix, ignore_list=ignore_list)
         print('Found {} variables to restore in {}'.format(len(w), initial_weights))
         if len(w) > 0:

@@ -22,6 +22,8 @@ class fixed_sampler(meta_sampler):
     def __init__(self, blocks_to_fetch, fixed_id):
         super(fixed_sampler, self).__init__(blocks_to_fetch)
         if isinstance(fixed_id, (list, tuple, np.ndarray)):   # argparse nargs='+' quirk, Stereo_Online_Adaptation.py:304
+            if len(fixed_id) > 1:
+                print('WARNING: fixed sampler trains ONE group per frame; using fixedID {} and ignoring {}'.format(fixed_id[0], list(fixed_id[1:])))
             fixed_id = fixed_id[0]
         self._fixed_id = int(fixed_id)
 

@@ -184,6 +184,8 @@ def main(args, build=build_model):
 if __name__ == '__main__':
     parser = build_parser()
     args = parser.parse_args()
+    if args.summary:
+        print('WARNING: --summary is accepted for command-line compatibility, but no TensorBoard summaries are written')
     if not os.path.exists(args.output):
         os.makedirs(args.output)
     if args.logDispStep != -1 and not os.path.exists(os.path.join(args.output, 'disparities')):

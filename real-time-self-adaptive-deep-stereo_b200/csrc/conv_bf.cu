@@ -144,6 +144,9 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
     const int u0 = (int)(((long)blockIdx.z * units) / p.ksplit), u1 = (int)(((long)(blockIdx.z + 1) * units) / p.ksplit);
     unsigned long long* prof = p.prof ? p.prof + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
     if (prof && threadIdx.x == 0) prof[0] = clock64();
+    // programmatic dependent launch (MS_PDL=1): let the next kernel's CTAs become resident as soon as every CTA of this
+    // grid has started; this kernel's own global traffic starts only after `griddepcontrol.wait` below (no-ops otherwise)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.NP; ++i) { mb_init(&pfull[i], 1); mb_init(&pempty[i], 1); }
@@ -159,6 +162,7 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
+    asm volatile("griddepcontrol.wait;" ::: "memory");       // everything above (barriers, TMEM) overlapped the previous kernel's tail
     if (prof && threadIdx.x == 0) prof[1] = clock64();
 
     if (warp == 0) {
@@ -737,12 +741,15 @@ static int conv_bf_launch(const ConvGemm& g, const ActPlanes& xp, const void* wt
     const int units = p.kblocks * p.n_patches;
     int ksplit = 1;
     if (part && tickets && (long)grid_tiles * mblocks <= 74 && units > 1) {
-        ksplit = std::min(std::min(units, 8), std::max(1, 148 / (grid_tiles * mblocks)));
-        // splitting only pays while a CTA's share of the main loop outweighs the partial-sum round trip (write, fence,
-        // ticket, the closing CTA's ordered reduction: ~5 us measured); an N = 64 MMA is 32 cycles, so the small maps of
-        // pyramid levels 4-6 are faster un-split (MMA cycles of the whole K loop: taps x k16 x 3 products x N/2)
+        static int kmax = -1;
+        if (kmax < 0) { const char* e = getenv("MS_BF_KSPLIT_MAX"); kmax = e ? std::max(1, atoi(e)) : 8; }
+        ksplit = std::min(std::min(units, kmax), std::max(1, 148 / (grid_tiles * mblocks)));
+        // MS_BF_SPLIT_CYCLES = c: split only while a CTA's share of the main loop stays above c MMA cycles (taps x k16 x
+        // 3 products x N/2).  Measured (profiles/r2_split_heuristic.log): un-splitting the small maps (c = 8192) LOSES 5 % of
+        // the step (521 vs 552 FPS) -- the serial K loop of a 3-30 CTA grid costs more than the partial-sum round trip --
+        // so the default keeps every split (c = 1).
         static int min_cyc = -1;
-        if (min_cyc < 0) { const char* e = getenv("MS_BF_SPLIT_CYCLES"); min_cyc = e ? atoi(e) : 8192; }
+        if (min_cyc < 0) { const char* e = getenv("MS_BF_SPLIT_CYCLES"); min_cyc = e ? atoi(e) : 1; }
         const long loop_cycles = (long)p.kblocks * nt * (p.kch / 16) * (p.nprod == 1 ? 1 : 3) * (N / 2);
         ksplit = (int)std::max<long>(1, std::min<long>(ksplit, loop_cycles / std::max(min_cyc, 1)));
         while (ksplit > 1 && (size_t)ksplit * grid_tiles * mblocks * N * 128 > conv_bf_part_floats()) --ksplit;
@@ -771,7 +778,19 @@ static int conv_bf_launch(const ConvGemm& g, const ActPlanes& xp, const void* wt
         if (bf_get_map(&mXl, xp.lo, 4, dims, strides, box, es, p.kch == 64 ? 128 : 64)) return -1;
     }
     const size_t smem = (size_t)NP * pslot + (size_t)NW * wslot + 1024;
-    conv_bf_kernel<<<dim3(grid_tiles, mblocks, ksplit), BF_THREADS, smem, st>>>(*mXh, *mXl, p);
+    static int pdl = -1;
+    if (pdl < 0) { const char* e = getenv("MS_PDL"); pdl = e ? atoi(e) : 0; }
+    if (pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid_tiles, mblocks, ksplit); cfg.blockDim = dim3(BF_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        MS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_bf_kernel, *mXh, *mXl, p));
+    } else {
+        conv_bf_kernel<<<dim3(grid_tiles, mblocks, ksplit), BF_THREADS, smem, st>>>(*mXh, *mXl, p);
+    }
     return check_launch("conv_bf");
 }
 

@@ -66,7 +66,7 @@ void Engine::layout_dispnet(Bump& A, size_t& max_wg, size_t& max_wt) {
     d_c2 = A.tens(2 * B, h4, w4, 128); gd_c2 = A.tens(2 * B, h4, w4, 128);
     d_cat3 = A.tens(B, h4, w4, 145, 148); gd_cat3 = A.tens(B, h4, w4, 145, 148);
     add_planes(A, d_c1, 1); add_planes(A, d_c2, 1); add_planes(A, d_cat3, 1);
-    add_planes(A, gd_c2, 0); add_planes(A, gd_cat3, 0);
+    add_planes(A, gd_c1, 0); add_planes(A, gd_c2, 0); add_planes(A, gd_cat3, 0);
     track(layers[0], (size_t)2 * B * h2 * w2); track(layers[1], (size_t)2 * B * h4 * w4); track(layers[2], (size_t)B * h4 * w4);
     int hh = h4, ww = w4;
     for (int i = 0; i < 8; ++i) {

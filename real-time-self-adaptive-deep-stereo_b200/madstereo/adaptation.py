@@ -106,6 +106,11 @@ class OnlineAdaptation(object):
     def load_weights(self, params, strict=True):
         """params: dict TF-variable-name -> array (HWIO).  Also becomes the snapshot used by the reset.
         strict=False keeps the current value of every variable `params` does not name (partial restore)."""
+        if not strict:
+            missing = [k for k in self.engine.param_views() if k not in params]
+            if missing:
+                print('WARNING: %d of %d variables are not in the checkpoint and keep their current values (first: %s); '
+                      'the reference would have left them at their initialiser' % (len(missing), len(missing) + len(params), missing[0]))
         self.engine.load_params(params, strict)
         self._snapshot = self.engine.weights.clone()
 
@@ -248,7 +253,9 @@ class OnlineAdaptation(object):
             self.loss_t_1 = new_loss
 
         did_reset = False
-        if new_loss > self.ssim_th and self._snapshot is not None and self.mode != 'NONE':
+        # (any mode: the reference restores and counts whenever the loss exceeds the threshold, Stereo_Online_Adaptation.py:242-244;
+        #  in NONE the weights never moved, so the restore is a no-op and only #resets in stats.csv is affected)
+        if new_loss > self.ssim_th and self._snapshot is not None:
             self.restore()
             self.reset_counter += 1
             did_reset = True

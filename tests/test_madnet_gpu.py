@@ -143,6 +143,38 @@ def test_mad_step_parity(module, hw):
             assert np.array_equal(v, params[n]), n
 
 
+def test_mad_two_blocks_per_frame():
+    """--numBlocks 2 (Stereo_Online_Adaptation.py:181-189,199: several train ops in ONE sess.run): the first block runs
+    inside the captured step (fused update), the second one eagerly on the same forward.  Both gradients must be those of
+    the PRE-update weights: the groups are disjoint and every u_k is stop-gradiented (bulkhead), which only holds if the
+    first block's backward / update leaves the forward activations and the disparity buffers alone."""
+    from madstereo.adaptation import OnlineAdaptation
+    from madstereo.synthetic import make_pair
+    from oracle.adaptation import OracleAdapter
+    from Sampler import sampler_factory
+    left, right, _ = make_pair(64, 128, seed=3)
+    net, ad, params, lt, rt = build(left, right, 'MAD')
+    ad.sampler = sampler_factory.get_sampler('SEQUENTIAL', 2, 0)      # first draw: blocks [0, 1]
+    out = ad.step(lt, rt)
+    assert sorted(out['blocks']) == [0, 1]
+    gviews = net.engine.param_views(net.engine.grads)
+    wviews = net.engine.export_params()
+    trained = set()
+    for module in out['blocks']:
+        orc = OracleAdapter(params, mode='MAD', lr=1e-4)             # fresh: gradients of the pre-update weights
+        ref = orc.step(left, right, module)
+        if module == out['blocks'][0]:
+            assert abs(out['loss'] - ref['full_loss']) < 2e-5
+        for n, gr in ref['grads'].items():
+            assert rel_linf(gviews[n].cpu().numpy(), gr) < TOL_GRAD, (module, n)
+            dw_ref = orc.net.p[n].detach().numpy() - params[n]
+            assert np.abs((wviews[n] - params[n]) - dw_ref).max() <= TOL_DW * np.abs(dw_ref).max() + 1e-7, (module, n)
+            trained.add(n)
+    for n, v in wviews.items():
+        if n not in trained:
+            assert np.array_equal(v, params[n]), n
+
+
 def test_mad_golden_gradients():
     g = np.load(GOLDEN)
     left = g['left'].astype(np.float32); right = g['right'].astype(np.float32)
