@@ -321,7 +321,10 @@ static WbPlan wb_plan(const ConvWgrad& q) {
         if (TH > 2 && TH >= 2 * q.dy.h) continue;                      // do not pad tiny maps to tall tiles
         const int halo = (kh - 1) * q.dil;
         const bool shared = q.stride == 1 && halo < (kh - 1) * TH && (TH + halo) <= 256;
-        const int nbox = shared ? 1 : kh, box_rows = shared ? TH + halo : TH;
+        // stride 2, dilation 1: taps of equal row parity read the same strided patch (tap r = row r/2 of box r%2)
+        const bool parity = q.stride == 2 && q.dil == 1 && kh > 2;
+        const int nbox = shared ? 1 : (parity ? 2 : kh);
+        const int box_rows = shared ? TH + halo : (parity ? TH + (kh - 1) / 2 : TH);
         const int x_rows = nbox * box_rows;
         const size_t xpb = (size_t)P.xblk * x_rows * WB_ATOM, dpb = (size_t)P.dblk * TH * WB_ATOM;
         const size_t stage = 2 * (xpb + dpb);
@@ -383,11 +386,14 @@ int wgrad_bf(const ConvWgrad& q, const ActPlanes& xp, const ActPlanes& dp, cudaS
     p.kh = q.kh; p.kw = q.kw;
     p.tiles_x = P.tiles_x; p.tiles_y = P.tiles_y; p.ntiles = P.ntiles; p.splits = P.splits;
     p.TH = P.TH; p.sx = q.stride; p.nbox = P.nbox; p.box_rows = P.box_rows; p.x_rows = P.x_rows;
+    const bool parity = q.stride == 2 && q.dil == 1 && q.kh > 2 && P.nbox == 2;
     for (int r = 0; r < q.kh; ++r) {
         if (P.nbox == 1) { p.tap_row[r] = (short)(r * q.dil); }
+        else if (parity) { p.tap_row[r] = (short)((r & 1) * P.box_rows + (r >> 1)); }
         else { p.tap_row[r] = (short)(r * P.TH); p.box_dy[r] = (short)(r * q.dil - q.pad_t); }
     }
     if (P.nbox == 1) p.box_dy[0] = (short)(-q.pad_t);
+    if (parity) { p.box_dy[0] = (short)(-q.pad_t); p.box_dy[1] = (short)(1 - q.pad_t); }
     p.pad_l = q.pad_l; p.dil = q.dil;
     p.ci = ci; p.co = co; p.mblocks = P.mblocks; p.nblocks = P.nblocks; p.BN = P.BN; p.xblk = P.xblk; p.dblk = P.dblk;
     p.nstages = P.nstages; p.stage_bytes = P.stage_bytes; p.x_plane_bytes = P.x_plane_bytes; p.d_plane_bytes = P.d_plane_bytes;
