@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1)
 wgrad_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl,
                 const __grid_constant__ CUtensorMap mapDh, const __grid_constant__ CUtensorMap mapDl,
                 const __grid_constant__ WgradBfParams p) {
+    pdl_prologue();
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], accum_bar;
     __shared__ uint32_t tmem_slot;
@@ -265,6 +266,7 @@ wgrad_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
 __global__ void wgrad_bf_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, size_t n4, int split,
                                        const float* __restrict__ bpart, float* __restrict__ db, int co, int accumulate,
                                        float wscale, float bscale) {
+    pdl_prologue();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n4) {
         const float4* src = reinterpret_cast<const float4*>(part) + i;
@@ -421,11 +423,11 @@ int wgrad_bf(const ConvWgrad& q, const ActPlanes& xp, const ActPlanes& dp, cudaS
         if (bf_get_map(&mDl, dp.lo, 4, dims, strides, box, es, 128)) return -1;
     }
     const size_t smem = WB_ONES_BYTES + (size_t)P.nstages * P.stage_bytes + 1024;
-    wgrad_bf_kernel<<<dim3(q.kw * P.mblocks * P.nblocks, P.splits), WB_THREADS, smem, st>>>(*mXh, *mXl, *mDh, *mDl, p);
+    launch_k(wgrad_bf_kernel, dim3(dim3(q.kw * P.mblocks * P.nblocks, P.splits)), dim3(WB_THREADS), smem, st, *mXh, *mXl, *mDh, *mDl, p);
     const size_t n4 = wn / 4;
     const size_t work = n4 + (q.db ? (size_t)co : 0);
     const float sx16 = xp.fmt == 1 ? 1.f / xp.scale : 1.f, sd16 = dp.fmt == 1 ? 1.f / dp.scale : 1.f;
-    wgrad_bf_reduce_kernel<<<(unsigned)cdivz(work, 256), 256, 0, st>>>(p.part, q.dw, n4, P.splits, p.bpart, q.db, co, q.accumulate,
+    launch_k(wgrad_bf_reduce_kernel, dim3((unsigned)cdivz(work, 256)), dim3(256), 0, st, p.part, q.dw, n4, P.splits, p.bpart, q.db, co, q.accumulate,
                                                                       sx16 * sd16, sd16);
     return check_launch("wgrad_bf", 2);
 }
