@@ -144,9 +144,9 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
     const int u0 = (int)(((long)blockIdx.z * units) / p.ksplit), u1 = (int)(((long)(blockIdx.z + 1) * units) / p.ksplit);
     unsigned long long* prof = p.prof ? p.prof + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
     if (prof && threadIdx.x == 0) prof[0] = clock64();
-    // programmatic dependent launch (MS_PDL=1): let the next kernel's CTAs become resident as soon as every CTA of this
-    // grid has started; this kernel's own global traffic starts only after `griddepcontrol.wait` below (no-ops otherwise)
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // programmatic dependent launch (common.cuh): the next kernel's CTAs may become resident as soon as every CTA of this
+    // grid has started; this kernel's own global traffic starts only after pdl_wait() below
+    pdl_trigger();
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.NP; ++i) { mb_init(&pfull[i], 1); mb_init(&pempty[i], 1); }
@@ -162,7 +162,7 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    asm volatile("griddepcontrol.wait;" ::: "memory");       // everything above (barriers, TMEM) overlapped the previous kernel's tail
+    pdl_wait();                                               // everything above (barriers, TMEM) overlapped the previous kernel's tail
     if (prof && threadIdx.x == 0) prof[1] = clock64();
 
     if (warp == 0) {
@@ -464,6 +464,7 @@ int conv_bf_read_prof(unsigned long long* out, int max_ctas) {
 // ------------------------------------------------------------------------------------------------
 __global__ void split_planes_kernel(const float* __restrict__ x, int xcs, int C, size_t pixels,
                                     unsigned short* __restrict__ hi, unsigned short* __restrict__ lo, int pcs, int fmt, float scale) {
+    pdl_prologue();
     const int cq = (C + 3) >> 2;
     const size_t total = pixels * cq;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -491,7 +492,7 @@ int split_planes(const TView& x, const ActPlanes& pl, cudaStream_t st) {
     MS_REQUIRE(pl.hi && pl.lo && pl.cs >= x.c && (pl.cs & 7) == 0, "split_planes: bad plane buffers");
     const size_t total = x.pixels() * ((x.c + 3) / 4);
     const unsigned grid = (unsigned)std::min<size_t>(cdivz(total, 256), 148 * 16);
-    split_planes_kernel<<<grid, 256, 0, st>>>(x.p, x.cs, x.c, x.pixels(), reinterpret_cast<unsigned short*>(pl.hi),
+    launch_k(split_planes_kernel, dim3(grid), dim3(256), 0, st, x.p, x.cs, x.c, x.pixels(), reinterpret_cast<unsigned short*>(pl.hi),
                                               reinterpret_cast<unsigned short*>(pl.lo), pl.cs, pl.fmt, pl.fmt == 1 ? pl.scale : 1.f);
     return check_launch("split_planes");
 }
@@ -503,6 +504,7 @@ int split_planes(const TView& x, const ActPlanes& pl, cudaStream_t st) {
 //   transposed_src = 0 : src is [tap][M][K]  (dgrad: M = cin, K = cout)
 // ------------------------------------------------------------------------------------------------
 __global__ void bf_prep_weights_kernel(const BfPrepJob* __restrict__ jobs) {
+    pdl_prologue();
     const BfPrepJob j = jobs[blockIdx.y];
     const int kch = j.Kpad > 32 ? 64 : 32;
     const int kblocks = j.Kpad / kch, mblocks = j.Mpad / 128;
@@ -541,7 +543,7 @@ __global__ void bf_prep_weights_kernel(const BfPrepJob* __restrict__ jobs) {
 int bf_prep_weights(const BfPrepJob* jobs_dev, int njobs, size_t max_total, cudaStream_t st) {
     if (njobs <= 0) return 0;
     const unsigned gx = (unsigned)std::min<size_t>(cdivz(max_total / 2, 256), 512);
-    bf_prep_weights_kernel<<<dim3(gx, njobs), 256, 0, st>>>(jobs_dev);
+    launch_k(bf_prep_weights_kernel, dim3(dim3(gx, njobs)), dim3(256), 0, st, jobs_dev);
     return check_launch("bf_prep_weights");
 }
 
@@ -778,19 +780,7 @@ static int conv_bf_launch(const ConvGemm& g, const ActPlanes& xp, const void* wt
         if (bf_get_map(&mXl, xp.lo, 4, dims, strides, box, es, p.kch == 64 ? 128 : 64)) return -1;
     }
     const size_t smem = (size_t)NP * pslot + (size_t)NW * wslot + 1024;
-    static int pdl = -1;
-    if (pdl < 0) { const char* e = getenv("MS_PDL"); pdl = e ? atoi(e) : 0; }
-    if (pdl) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid_tiles, mblocks, ksplit); cfg.blockDim = dim3(BF_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        MS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_bf_kernel, *mXh, *mXl, p));
-    } else {
-        conv_bf_kernel<<<dim3(grid_tiles, mblocks, ksplit), BF_THREADS, smem, st>>>(*mXh, *mXl, p);
-    }
+    launch_k(conv_bf_kernel, dim3(grid_tiles, mblocks, ksplit), dim3(BF_THREADS), smem, st, *mXh, *mXl, p);
     return check_launch("conv_bf");
 }
 

@@ -13,6 +13,7 @@ namespace ms {
 // forward: y[p] = act(sum_{tap,c} x[p + tap][c] * w[tap][c] + b) (+ res[p]); 8 lanes per pixel, 4 channels per lane per step
 __global__ void __launch_bounds__(256)
 conv_head_fwd_kernel(ConvGemm g, size_t npix) {
+    pdl_prologue();
     extern __shared__ float w_s[];                       // [taps][C]
     const int C = g.x.c, taps = g.kh * g.kw;
     for (int i = threadIdx.x; i < taps * C; i += blockDim.x) w_s[i] = g.wmat[i];
@@ -60,6 +61,7 @@ conv_head_fwd_kernel(ConvGemm g, size_t npix) {
 // input gradient of a 1-channel conv: dx[p][c] = sum_tap dy[p + off + tap*step] * w[tap][c]   (then accumulate / mask)
 __global__ void __launch_bounds__(256)
 conv_head_dgrad_kernel(ConvGemm g, size_t npix) {
+    pdl_prologue();
     extern __shared__ float w_s[];                       // [taps][C]
     const int C = g.y.c, taps = g.kh * g.kw, cq = C >> 2;
     for (int i = threadIdx.x; i < taps * C; i += blockDim.x) w_s[i] = g.wmat[i];
@@ -103,6 +105,7 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // a disparity map (Nets/DispNet.py:51-53).  One thread per output pixel; the generic fp32 gather GEMM spent 166 us on the
 // 192x640 instance of this 2 MFLOP operation.
 __global__ void __launch_bounds__(256) conv_one_channel_kernel(ConvGemm g, size_t npix) {
+    pdl_prologue();
     const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= npix) return;
     const int W = g.y.w, H = g.y.h;
@@ -133,7 +136,7 @@ bool conv_one_channel_supported(const ConvGemm& g) { return g.x.c == 1 && g.y.c 
 int conv_one_channel(const ConvGemm& g, cudaStream_t st) {
     MS_REQUIRE(conv_one_channel_supported(g), "conv_one_channel: not a 1 -> 1 channel gather");
     const size_t npix = g.y.pixels();
-    conv_one_channel_kernel<<<(unsigned)cdivz(npix, 256), 256, 0, st>>>(g, npix);
+    launch_k(conv_one_channel_kernel, dim3((unsigned)cdivz(npix, 256)), dim3(256), 0, st, g, npix);
     return check_launch("conv_one_channel");
 }
 
@@ -162,12 +165,12 @@ int conv_head(const ConvGemm& g, cudaStream_t st) {
     const size_t npix = g.y.pixels();
     const size_t smem = (size_t)g.kh * g.kw * std::max(g.x.c, g.y.c) * sizeof(float);
     if (kind == 1) {
-        conv_head_fwd_kernel<<<(unsigned)cdivz(npix, 32), 256, smem, st>>>(g, npix);
+        launch_k(conv_head_fwd_kernel, dim3((unsigned)cdivz(npix, 32)), dim3(256), smem, st, g, npix);
         return check_launch("conv_head_fwd");
     }
     const size_t total = npix * (g.y.c >> 2);
     const unsigned grid = (unsigned)std::min<size_t>(cdivz(total, 256), 148 * 8);
-    conv_head_dgrad_kernel<<<grid, 256, smem, st>>>(g, npix);
+    launch_k(conv_head_dgrad_kernel, dim3(grid), dim3(256), smem, st, g, npix);
     return check_launch("conv_head_dgrad");
 }
 

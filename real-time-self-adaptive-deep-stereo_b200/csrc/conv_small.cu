@@ -29,6 +29,7 @@ constexpr int CS_NT = 128;
 
 template <int CIN, int CO>
 __global__ void __launch_bounds__(CS_NT) conv_small_fwd_kernel(ConvGemm p, int pairs_per_row, int total_pairs) {
+    pdl_prologue();
     __shared__ __align__(16) float ws[9 * CIN * CO];                               // [tap][ci][co]
     __shared__ float bs[CO];
     for (int i = threadIdx.x; i < 9 * CIN * CO; i += CS_NT) ws[i] = p.wmat[i];
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(CS_NT) conv_small_fwd_kernel(ConvGemm p, int p
 constexpr int T16_TH = 8, T16_TW = 32, T16_PH = T16_TH + 2, T16_PW = T16_TW + 2, T16_PS = 20, T16_NT = 128;
 
 __global__ void __launch_bounds__(T16_NT) conv_c16_tiled_kernel(ConvGemm p, int tiles_x, int tiles_y) {
+    pdl_prologue();
     constexpr int CIN = 16, CO = 16;
     __shared__ __align__(16) float ws[9 * CIN * CO];
     __shared__ __align__(16) float patch[T16_PH * T16_PW * T16_PS];
@@ -226,16 +228,16 @@ bool conv_small_fwd_supported(const ConvGemm& p) {
 int conv_small_fwd(const ConvGemm& p, cudaStream_t st) {
     if (small16_mode() == 2 && conv_c16_tiled_supported(p)) {
         const int tiles_x = cdiv(p.y.w, T16_TW), tiles_y = cdiv(p.y.h, T16_TH);
-        conv_c16_tiled_kernel<<<(unsigned)(tiles_x * tiles_y * p.y.n), T16_NT, 0, st>>>(p, tiles_x, tiles_y);
+        launch_k(conv_c16_tiled_kernel, dim3((unsigned)(tiles_x * tiles_y * p.y.n)), dim3(T16_NT), 0, st, p, tiles_x, tiles_y);
         return check_launch("conv_c16_tiled");
     }
     const int pairs_per_row = cdiv(p.y.w, 2);
     const size_t total = (size_t)p.y.n * p.y.h * pairs_per_row;
     MS_REQUIRE(total < (1u << 30), "conv_small_fwd: too many output pixels");
     const unsigned grid = (unsigned)cdivz(total, CS_NT);
-    if (p.x.c == 3) conv_small_fwd_kernel<3, 16><<<grid, CS_NT, 0, st>>>(p, pairs_per_row, (int)total);
-    else if (p.y.c == 16) conv_small_fwd_kernel<16, 16><<<grid, CS_NT, 0, st>>>(p, pairs_per_row, (int)total);
-    else conv_small_fwd_kernel<16, 32><<<grid, CS_NT, 0, st>>>(p, pairs_per_row, (int)total);
+    if (p.x.c == 3) launch_k(conv_small_fwd_kernel<3, 16>, dim3(grid), dim3(CS_NT), 0, st, p, pairs_per_row, (int)total);
+    else if (p.y.c == 16) launch_k(conv_small_fwd_kernel<16, 16>, dim3(grid), dim3(CS_NT), 0, st, p, pairs_per_row, (int)total);
+    else launch_k(conv_small_fwd_kernel<16, 32>, dim3(grid), dim3(CS_NT), 0, st, p, pairs_per_row, (int)total);
     return check_launch("conv_small_fwd");
 }
 
@@ -251,6 +253,7 @@ struct SwOperands { float x[SW_TAPS]; float4 d[SW_CO / 4]; };
 
 template <int RP>   // roles per pixel slot: ci padded to 4 / 8 / 16
 __global__ void __launch_bounds__(SW_NT, 1) conv_small_wgrad_kernel(ConvWgrad p, int P, int chunk, float* __restrict__ partial) {
+    pdl_prologue();
     extern __shared__ float sw_smem[];                       // [warps][RP][144]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int role = tid % RP, slot = tid / RP;
@@ -377,9 +380,9 @@ int conv_small_wgrad(const ConvWgrad& p, int* split_out, cudaStream_t st) {
     }
     const int rp = ci <= 4 ? 4 : (ci <= 8 ? 8 : 16);
     const size_t smem = (size_t)(SW_NT / 32) * rp * SW_ACC * sizeof(float);
-    if (rp == 4) conv_small_wgrad_kernel<4><<<split, SW_NT, smem, st>>>(p, P, chunk, p.workspace);
-    else if (rp == 8) conv_small_wgrad_kernel<8><<<split, SW_NT, smem, st>>>(p, P, chunk, p.workspace);
-    else conv_small_wgrad_kernel<16><<<split, SW_NT, smem, st>>>(p, P, chunk, p.workspace);
+    if (rp == 4) launch_k(conv_small_wgrad_kernel<4>, dim3(split), dim3(SW_NT), smem, st, p, P, chunk, p.workspace);
+    else if (rp == 8) launch_k(conv_small_wgrad_kernel<8>, dim3(split), dim3(SW_NT), smem, st, p, P, chunk, p.workspace);
+    else launch_k(conv_small_wgrad_kernel<16>, dim3(split), dim3(SW_NT), smem, st, p, P, chunk, p.workspace);
     *split_out = split;
     return check_launch("conv_small_wgrad");
 }

@@ -79,6 +79,7 @@ constexpr int LPP = 8;  // lanes per pixel
 // forward
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CORR_NT) corr_fwd_kernel(CorrFwd p, int TW, int nd, int use_tma) {
+    pdl_prologue();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     const int C = p.C, w = p.w, d = p.max_disp;
@@ -159,6 +160,7 @@ __global__ void __launch_bounds__(CORR_NT) corr_fwd_kernel(CorrFwd p, int TW, in
 // ---------------------------------------------------------------------------------------------
 template <int ND_CT>
 __global__ void __launch_bounds__(CORR_NT) corr_fwd2_kernel(CorrFwd p, int TW, int RCAP, int nd_rt, int use_tma) {
+    pdl_prologue();
     const int nd = ND_CT > 0 ? ND_CT : nd_rt;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
@@ -299,6 +301,7 @@ __device__ __forceinline__ int swz_m(int q, int col, int m) { return (q & ~m) | 
 
 template <int ND_CT>
 __global__ void __launch_bounds__(CORR_NT) corr_fwd3_kernel(CorrFwd p, int TW, int LP, int RCAP, int nd_rt, int smask) {
+    pdl_prologue();
     auto swz = [smask](int q, int col) { return swz_m(q, col, smask); };
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int s_lo, s_hi;
@@ -477,8 +480,8 @@ int corr_fwd(const CorrFwd& p, cudaStream_t st) {
             if (smem <= 200 * 1024) {
                 dim3 grid(cdiv(p.w, TW), p.B * p.h);
                 const int smask = nchunk % 8 == 0 ? 7 : (nchunk % 4 == 0 ? 3 : (nchunk % 2 == 0 ? 1 : 0));
-                if (nd == 5) corr_fwd3_kernel<5><<<grid, CORR_NT, smem, st>>>(p, TW, LP, RCAP, nd, smask);
-                else corr_fwd3_kernel<0><<<grid, CORR_NT, smem, st>>>(p, TW, LP, RCAP, nd, smask);
+                if (nd == 5) launch_k(corr_fwd3_kernel<5>, dim3(grid), dim3(CORR_NT), smem, st, p, TW, LP, RCAP, nd, smask);
+                else launch_k(corr_fwd3_kernel<0>, dim3(grid), dim3(CORR_NT), smem, st, p, TW, LP, RCAP, nd, smask);
                 return check_launch("corr_fwd3");
             }
         }
@@ -493,8 +496,8 @@ int corr_fwd(const CorrFwd& p, cudaStream_t st) {
                             (size_t)(TW + 2 * p.max_disp) * sizeof(Tap) + 64;
         if (smem <= 200 * 1024) {
             dim3 grid(cdiv(p.w, TW), p.B * p.h);
-            if (nd == 5) corr_fwd2_kernel<5><<<grid, CORR_NT, smem, st>>>(p, TW, RCAP, nd, tma);
-            else corr_fwd2_kernel<0><<<grid, CORR_NT, smem, st>>>(p, TW, RCAP, nd, tma);
+            if (nd == 5) launch_k(corr_fwd2_kernel<5>, dim3(grid), dim3(CORR_NT), smem, st, p, TW, RCAP, nd, tma);
+            else launch_k(corr_fwd2_kernel<0>, dim3(grid), dim3(CORR_NT), smem, st, p, TW, RCAP, nd, tma);
             return check_launch("corr_fwd2");
         }
     }
@@ -503,7 +506,7 @@ int corr_fwd(const CorrFwd& p, cudaStream_t st) {
     MS_REQUIRE(TW > 0, "corr_fwd: row does not fit in shared memory");
     size_t smem = ((size_t)TW + (warped ? p.w : TW + 2 * p.max_disp)) * p.C * 4 + (warped ? (size_t)p.w * 4 : 0) + 64;
     dim3 grid(cdiv(p.w, TW), p.B * p.h);
-    corr_fwd_kernel<<<grid, CORR_NT, smem, st>>>(p, TW, nd, tma);
+    launch_k(corr_fwd_kernel, dim3(grid), dim3(CORR_NT), smem, st, p, TW, nd, tma);
     return check_launch("corr_fwd");
 }
 
@@ -511,6 +514,7 @@ int corr_fwd(const CorrFwd& p, cudaStream_t st) {
 // backward
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CORR_NT) corr_bwd_kernel(CorrBwd p, int TW, int nd, int use_tma) {
+    pdl_prologue();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     const int C = p.C, w = p.w, d = p.max_disp;
@@ -688,7 +692,7 @@ int corr_bwd(const CorrBwd& p, cudaStream_t st) {
     int tma = corr_use_tma() && p.lcs == p.C && p.rcs == p.C;
     if (corr_init()) return -1;
     dim3 grid(cdiv(p.w, TW), p.B * p.h);
-    corr_bwd_kernel<<<grid, CORR_NT, smem, st>>>(p, TW, nd, tma);
+    launch_k(corr_bwd_kernel, dim3(grid), dim3(CORR_NT), smem, st, p, TW, nd, tma);
     return check_launch("corr_bwd");
 }
 

@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(256) corr_fwd4_kernel(const __grid_constant__ 
                                                         const __grid_constant__ CUtensorMap mapR,
                                                         const __grid_constant__ CUtensorMap mapO,
                                                         const __grid_constant__ CUtensorMap mapO2, const Corr4Params k) {
+    pdl_prologue();
     constexpr int ND = 5, D = 2, QPL = 8 / LP;
     const CorrFwd& p = k.p;
     extern __shared__ unsigned char smem_dyn[];
@@ -310,10 +311,10 @@ int corr_fwd4(const CorrFwd& p, cudaStream_t st) {
     }
     const dim3 grid(cdiv(p.w, TW), rows);
     const int threads = (TW * LP + 31) / 32 * 32;
-    if (LP == 1) corr_fwd4_kernel<1, 0><<<grid, threads, smem, st>>>(mL, mR, mO, mO2, k);
-    else if (ncb == 1) corr_fwd4_kernel<2, 1><<<grid, threads, smem, st>>>(mL, mR, mO, mO2, k);
-    else if (ncb == 2) corr_fwd4_kernel<2, 2><<<grid, threads, smem, st>>>(mL, mR, mO, mO2, k);
-    else corr_fwd4_kernel<2, 0><<<grid, threads, smem, st>>>(mL, mR, mO, mO2, k);
+    if (LP == 1) launch_k(corr_fwd4_kernel<1, 0>, dim3(grid), dim3(threads), smem, st, mL, mR, mO, mO2, k);
+    else if (ncb == 1) launch_k(corr_fwd4_kernel<2, 1>, dim3(grid), dim3(threads), smem, st, mL, mR, mO, mO2, k);
+    else if (ncb == 2) launch_k(corr_fwd4_kernel<2, 2>, dim3(grid), dim3(threads), smem, st, mL, mR, mO, mO2, k);
+    else launch_k(corr_fwd4_kernel<2, 0>, dim3(grid), dim3(threads), smem, st, mL, mR, mO, mO2, k);
     return check_launch("corr_fwd4");
 }
 

@@ -19,6 +19,7 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
 
 __global__ void pad_reflect_kernel(const float* __restrict__ src, int B, int H, int W, int C,
                                    float* __restrict__ dst, int Hp, int Wp, int dcs, float scale, float bias) {
+    pdl_prologue();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t total = (size_t)B * Hp * Wp;
     if (i >= total) return;
@@ -38,7 +39,7 @@ int pad_reflect(const float* src, int B, int H, int W, int C, float* dst, int Hp
                 float scale, float bias, cudaStream_t st) {
     MS_REQUIRE(Hp - H < 2 * H && Wp - W < 2 * W, "pad_reflect: pad larger than image");
     size_t total = (size_t)B * Hp * Wp;
-    pad_reflect_kernel<<<(unsigned)cdivz(total, 256), 256, 0, st>>>(src, B, H, W, C, dst, Hp, Wp, dcs, scale, bias);
+    launch_k(pad_reflect_kernel, dim3((unsigned)cdivz(total, 256)), dim3(256), 0, st, src, B, H, W, C, dst, Hp, Wp, dcs, scale, bias);
     return check_launch("pad_reflect");
 }
 
@@ -73,6 +74,7 @@ __device__ __forceinline__ float resize_at(const float* __restrict__ sb, int scs
 __global__ void resize_kernel(const float* __restrict__ src, int scs, int B, int ih, int iw,
                               float* __restrict__ dst, int dcs, int rh, int rw, int oh, int ow,
                               float ys, float xs, float pre_scale, int pre_relu, float post_scale, int post_relu) {
+    pdl_prologue();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t total = (size_t)B * oh * ow;
     if (i >= total) return;
@@ -93,7 +95,7 @@ int resize_bilinear(const float* src, int scs, int B, int ih, int iw, float* dst
     MS_REQUIRE(oh <= rh && ow <= rw, "resize_bilinear: only centre-crop (no pad) is supported");
     size_t total = (size_t)B * oh * ow;
     float ys = (float)ih / (float)rh, xs = (float)iw / (float)rw;
-    resize_kernel<<<(unsigned)cdivz(total, 256), 256, 0, st>>>(src, scs, B, ih, iw, dst, dcs, rh, rw, oh, ow, ys, xs,
+    launch_k(resize_kernel, dim3((unsigned)cdivz(total, 256)), dim3(256), 0, st, src, scs, B, ih, iw, dst, dcs, rh, rw, oh, ow, ys, xs,
                                                               pre_scale, pre_relu, post_scale, post_relu);
     return check_launch("resize_bilinear");
 }
@@ -103,6 +105,7 @@ __global__ void resize_bwd_x_kernel(const float* __restrict__ dout, int docs, co
                                     int scs, int B, int ih, int iw, float* __restrict__ tmp, int rh, int rw,
                                     int oh, int ow, float ys, float xs, float pre_scale, int pre_relu,
                                     float post_scale, int post_relu) {
+    pdl_prologue();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t total = (size_t)B * oh * iw;
     if (i >= total) return;
@@ -138,6 +141,7 @@ __global__ void resize_bwd_x_kernel(const float* __restrict__ dout, int docs, co
 __global__ void resize_bwd_y_kernel(const float* __restrict__ tmp, const float* __restrict__ src, int scs, int B,
                                     int ih, int iw, float* __restrict__ dsrc, int dscs, int rh, int oh, float ys,
                                     float pre_scale, int pre_relu, int accumulate) {
+    pdl_prologue();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t total = (size_t)B * ih * iw;
     if (i >= total) return;
@@ -176,16 +180,17 @@ int resize_bilinear_bwd(const float* dout, int docs, const float* src, int scs, 
     MS_REQUIRE(tmp != nullptr, "resize_bilinear_bwd: tmp workspace (B*oh*iw floats) required");
     float ys = (float)ih / (float)rh, xs = (float)iw / (float)rw;
     size_t t1 = (size_t)B * oh * iw;
-    resize_bwd_x_kernel<<<(unsigned)cdivz(t1, 256), 256, 0, st>>>(dout, docs, src, scs, B, ih, iw, tmp, rh, rw, oh, ow,
+    launch_k(resize_bwd_x_kernel, dim3((unsigned)cdivz(t1, 256)), dim3(256), 0, st, dout, docs, src, scs, B, ih, iw, tmp, rh, rw, oh, ow,
                                                                  ys, xs, pre_scale, pre_relu, post_scale, post_relu);
     size_t t2 = (size_t)B * ih * iw;
-    resize_bwd_y_kernel<<<(unsigned)cdivz(t2, 256), 256, 0, st>>>(tmp, src, scs, B, ih, iw, dsrc, dscs, rh, oh, ys,
+    launch_k(resize_bwd_y_kernel, dim3((unsigned)cdivz(t2, 256)), dim3(256), 0, st, tmp, src, scs, B, ih, iw, dsrc, dscs, rh, oh, ys,
                                                                  pre_scale, pre_relu, accumulate);
     return check_launch("resize_bilinear_bwd", 2);
 }
 
 __global__ void leaky_bwd_kernel(float* __restrict__ g, int gcs, const float* __restrict__ act, int acs,
                                  size_t pixels, int c, float alpha) {
+    pdl_prologue();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pixels * c) return;
     size_t p = i / c;
@@ -194,12 +199,13 @@ __global__ void leaky_bwd_kernel(float* __restrict__ g, int gcs, const float* __
 }
 
 int leaky_bwd(float* g, int gcs, const float* act, int acs, size_t pixels, int c, float alpha, cudaStream_t st) {
-    leaky_bwd_kernel<<<(unsigned)cdivz(pixels * c, 256), 256, 0, st>>>(g, gcs, act, acs, pixels, c, alpha);
+    launch_k(leaky_bwd_kernel, dim3((unsigned)cdivz(pixels * c, 256)), dim3(256), 0, st, g, gcs, act, acs, pixels, c, alpha);
     return check_launch("leaky_bwd");
 }
 
 __global__ void add_channels_kernel(float* __restrict__ dst, int dcs, const float* __restrict__ src, int scs,
                                     size_t pixels, int c, float scale, int accumulate) {
+    pdl_prologue();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pixels * c) return;
     size_t p = i / c;
@@ -211,22 +217,24 @@ __global__ void add_channels_kernel(float* __restrict__ dst, int dcs, const floa
 
 int add_channels(float* dst, int dcs, const float* src, int scs, size_t pixels, int c, float scale,
                  int accumulate, cudaStream_t st) {
-    add_channels_kernel<<<(unsigned)cdivz(pixels * c, 256), 256, 0, st>>>(dst, dcs, src, scs, pixels, c, scale, accumulate);
+    launch_k(add_channels_kernel, dim3((unsigned)cdivz(pixels * c, 256)), dim3(256), 0, st, dst, dcs, src, scs, pixels, c, scale, accumulate);
     return check_launch("add_channels");
 }
 
 __global__ void fill_kernel(float* p, size_t n, float v) {
+    pdl_prologue();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
 int fill(float* p, size_t n, float v, cudaStream_t st) {
     if (n == 0) return 0;
-    fill_kernel<<<(unsigned)cdivz(n, 256), 256, 0, st>>>(p, n, v);
+    launch_k(fill_kernel, dim3((unsigned)cdivz(n, 256)), dim3(256), 0, st, p, n, v);
     return check_launch("fill");
 }
 
 // uint8 image -> fp32 (what tf.image.decode_* + tf.cast do in the reference input pipeline, Data_utils/data_reader.py)
 __global__ void u8_to_f32_kernel(const uchar4* __restrict__ src, float4* __restrict__ dst, size_t n4) {
+    pdl_prologue();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         const uchar4 v = src[i];
         dst[i] = make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w);
@@ -235,7 +243,7 @@ __global__ void u8_to_f32_kernel(const uchar4* __restrict__ src, float4* __restr
 int u8_to_f32(const unsigned char* src, float* dst, size_t n, cudaStream_t st) {
     MS_REQUIRE((n & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0, "u8_to_f32: size / alignment");
     const size_t n4 = n / 4;
-    u8_to_f32_kernel<<<(unsigned)std::min<size_t>(cdivz(n4, 256), 148 * 8), 256, 0, st>>>(reinterpret_cast<const uchar4*>(src),
+    launch_k(u8_to_f32_kernel, dim3((unsigned)std::min<size_t>(cdivz(n4, 256), 148 * 8)), dim3(256), 0, st, reinterpret_cast<const uchar4*>(src),
                                                                                        reinterpret_cast<float4*>(dst), n4);
     return check_launch("u8_to_f32");
 }

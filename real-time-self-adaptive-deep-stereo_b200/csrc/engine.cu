@@ -848,9 +848,11 @@ int Engine::run(int mode, int group, int disp_mask, int with_update, float lr, f
         if (profiling == 2) { if (prof_collect()) return -1; }
         MS_CHECK_CUDA(cudaStreamBeginCapture(gstream, cudaStreamCaptureModeThreadLocal));
         prof_capturing = profiling == 2;
+        pdl_set_suppressed(prof_capturing);
         if (prof_capturing) { prof_begin(-1, gstream); prof_end(gstream); }      // calibration span (see prof_fold)
         int rc = run_eager(mode, group, disp_mask, with_update, lr, mu, gscale, gstream);
         prof_capturing = false;
+        pdl_set_suppressed(false);
         cudaError_t ce = cudaStreamEndCapture(gstream, &graph);
         if (rc) { if (graph) cudaGraphDestroy(graph); spans.clear(); return rc; }
         MS_CHECK_CUDA(ce);

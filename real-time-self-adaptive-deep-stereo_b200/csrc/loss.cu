@@ -32,6 +32,7 @@ __device__ __forceinline__ float block_sum(float v, float* sm) {
 // pass A: warped image, d(warped)/dD, L1 partial sums
 __global__ void __launch_bounds__(LB) loss_warp_kernel(ReprojLoss p, float* __restrict__ xw, float* __restrict__ dxw,
                                                        float* __restrict__ l1_partial) {
+    pdl_prologue();
     __shared__ float sm[32];
     const size_t total = (size_t)p.B * p.H * p.W;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(LB) loss_warp_kernel(ReprojLoss p, float* __re
 __global__ void __launch_bounds__(LB) loss_ssim_kernel(ReprojLoss p, const float* __restrict__ xw,
                                                        float* __restrict__ coef, float* __restrict__ ss_partial,
                                                        float gwin) {
+    pdl_prologue();
     __shared__ float sm[32];
     const int WH = p.H - 2, WW = p.W - 2;
     const size_t total = (size_t)p.B * WH * WW;
@@ -117,6 +119,7 @@ __global__ void __launch_bounds__(LB) loss_ssim_kernel(ReprojLoss p, const float
 __global__ void __launch_bounds__(LB) loss_grad_kernel(ReprojLoss p, const float* __restrict__ xw,
                                                        const float* __restrict__ dxw, const float* __restrict__ coef,
                                                        float gl1) {
+    pdl_prologue();
     const size_t total = (size_t)p.B * p.H * p.W;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -147,6 +150,7 @@ __global__ void __launch_bounds__(LB) loss_grad_kernel(ReprojLoss p, const float
 
 __global__ void loss_final_kernel(const float* __restrict__ l1_partial, int n1, const float* __restrict__ ss_partial,
                                   int n2, double inv_np, double inv_nw, float* __restrict__ loss) {
+    pdl_prologue();
     __shared__ double sm1[256], sm2[256];
     double a = 0.0, b = 0.0;
     for (int i = threadIdx.x; i < n1; i += 256) a += (double)l1_partial[i];
@@ -176,16 +180,17 @@ int reproj_loss(const ReprojLoss& p, cudaStream_t st) {
     const int nb1 = (int)cdivz(n, LB), nb2 = (int)cdivz(nwin, LB);
     float* ssp = l1p + nb1 + 1;
     const double inv_np = 1.0 / ((double)n * 3.0), inv_nw = 1.0 / ((double)nwin * 3.0);
-    loss_warp_kernel<<<nb1, LB, 0, st>>>(p, xw, dxw, l1p);
-    loss_ssim_kernel<<<nb2, LB, 0, st>>>(p, xw, p.ddisp ? coef : nullptr, ssp, (float)(0.85 * inv_nw));
-    if (p.ddisp) loss_grad_kernel<<<nb1, LB, 0, st>>>(p, xw, dxw, coef, (float)(0.15 * inv_np));
-    loss_final_kernel<<<1, 256, 0, st>>>(l1p, nb1, ssp, nb2, inv_np, inv_nw, p.loss);
+    launch_k(loss_warp_kernel, dim3(nb1), dim3(LB), 0, st, p, xw, dxw, l1p);
+    launch_k(loss_ssim_kernel, dim3(nb2), dim3(LB), 0, st, p, xw, p.ddisp ? coef : nullptr, ssp, (float)(0.85 * inv_nw));
+    if (p.ddisp) launch_k(loss_grad_kernel, dim3(nb1), dim3(LB), 0, st, p, xw, dxw, coef, (float)(0.15 * inv_np));
+    launch_k(loss_final_kernel, dim3(1), dim3(256), 0, st, l1p, nb1, ssp, nb2, inv_np, inv_nw, p.loss);
     return check_launch("reproj_loss", p.ddisp ? 4 : 3);
 }
 
 // EPE / bad3 against ground truth (reference Stereo_Online_Adaptation.py:74-82); out2 = {epe, bad3}
 __global__ void epe_partial_kernel(const float* __restrict__ disp, const float* __restrict__ gt, int n,
                                    float* __restrict__ part) {
+    pdl_prologue();
     __shared__ float sm[32];
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     float e = 0.f, v = 0.f, bad = 0.f;
@@ -199,6 +204,7 @@ __global__ void epe_partial_kernel(const float* __restrict__ disp, const float* 
     if (threadIdx.x == 0) { part[blockIdx.x * 3] = te; part[blockIdx.x * 3 + 1] = tv; part[blockIdx.x * 3 + 2] = tb; }
 }
 __global__ void epe_final_kernel(const float* __restrict__ part, int nb, float* __restrict__ out2) {
+    pdl_prologue();
     __shared__ double s[3][256];
     double a = 0, b = 0, c = 0;
     for (int i = threadIdx.x; i < nb; i += 256) { a += part[i * 3]; b += part[i * 3 + 1]; c += part[i * 3 + 2]; }
@@ -212,8 +218,8 @@ __global__ void epe_final_kernel(const float* __restrict__ part, int nb, float* 
 }
 int epe_bad3(const float* disp, const float* gt, int n, float* out2, float* workspace, cudaStream_t st) {
     int nb = cdiv(n, LB);
-    epe_partial_kernel<<<nb, LB, 0, st>>>(disp, gt, n, workspace);
-    epe_final_kernel<<<1, 256, 0, st>>>(workspace, nb, out2);
+    launch_k(epe_partial_kernel, dim3(nb), dim3(LB), 0, st, disp, gt, n, workspace);
+    launch_k(epe_final_kernel, dim3(1), dim3(256), 0, st, workspace, nb, out2);
     return check_launch("epe_bad3", 2);
 }
 

@@ -8,6 +8,7 @@ namespace ms {
 
 __global__ void momentum_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, size_t n,
                                 float lr, float mu, float gscale) {
+    pdl_prologue();
     size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i + 3 < n) {
         float4 gv = *reinterpret_cast<const float4*>(g + i);
@@ -32,7 +33,7 @@ int momentum_update(float* w, const float* g, float* m, size_t n, float lr, floa
     MS_REQUIRE(((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m)) & 15) == 0,
                "momentum_update: arenas must be 16B aligned");
     size_t nthr = cdivz(n, 4);
-    momentum_kernel<<<(unsigned)cdivz(nthr, 256), 256, 0, st>>>(w, g, m, n, lr, mu, gscale);
+    launch_k(momentum_kernel, dim3((unsigned)cdivz(nthr, 256)), dim3(256), 0, st, w, g, m, n, lr, mu, gscale);
     return check_launch("momentum_update");
 }
 

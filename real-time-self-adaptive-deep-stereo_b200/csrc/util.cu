@@ -1,10 +1,19 @@
 #include "common.cuh"
+#include <cstdlib>
 #include <mutex>
 namespace ms {
 static std::mutex g_mu;
 static std::string g_err;
 void set_error(const std::string& s) { std::lock_guard<std::mutex> l(g_mu); g_err = s; }
 const char* last_error_cstr() { std::lock_guard<std::mutex> l(g_mu); return g_err.c_str(); }
+static bool g_pdl_suppressed = false;
+void pdl_set_suppressed(bool s) { g_pdl_suppressed = s; }
+bool pdl_enabled() {
+    if (g_pdl_suppressed) return false;
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MS_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
 static long long g_launches = 0;
 long long launch_count() { return g_launches; }
 void add_launches(long long n) { g_launches += n; }

@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1)
 wgrad_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl,
                 const __grid_constant__ CUtensorMap mapDh, const __grid_constant__ CUtensorMap mapDl,
                 const __grid_constant__ WgradBfParams p) {
+    pdl_prologue();
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], accum_bar;
     __shared__ uint32_t tmem_slot;
@@ -265,6 +266,7 @@ wgrad_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
 __global__ void wgrad_bf_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, size_t n4, int split,
                                        const float* __restrict__ bpart, float* __restrict__ db, int co, int accumulate,
                                        float wscale, float bscale) {
+    pdl_prologue();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n4) {
         const float4* src = reinterpret_cast<const float4*>(part) + i;
@@ -321,7 +323,10 @@ static WbPlan wb_plan(const ConvWgrad& q) {
         if (TH > 2 && TH >= 2 * q.dy.h) continue;                      // do not pad tiny maps to tall tiles
         const int halo = (kh - 1) * q.dil;
         const bool shared = q.stride == 1 && halo < (kh - 1) * TH && (TH + halo) <= 256;
-        const int nbox = shared ? 1 : kh, box_rows = shared ? TH + halo : TH;
+        // stride 2, dilation 1: taps of equal row parity read the same strided patch (tap r = row r/2 of box r%2)
+        const bool parity = q.stride == 2 && q.dil == 1 && kh > 2;
+        const int nbox = shared ? 1 : (parity ? 2 : kh);
+        const int box_rows = shared ? TH + halo : (parity ? TH + (kh - 1) / 2 : TH);
         const int x_rows = nbox * box_rows;
         const size_t xpb = (size_t)P.xblk * x_rows * WB_ATOM, dpb = (size_t)P.dblk * TH * WB_ATOM;
         const size_t stage = 2 * (xpb + dpb);
@@ -383,11 +388,14 @@ int wgrad_bf(const ConvWgrad& q, const ActPlanes& xp, const ActPlanes& dp, cudaS
     p.kh = q.kh; p.kw = q.kw;
     p.tiles_x = P.tiles_x; p.tiles_y = P.tiles_y; p.ntiles = P.ntiles; p.splits = P.splits;
     p.TH = P.TH; p.sx = q.stride; p.nbox = P.nbox; p.box_rows = P.box_rows; p.x_rows = P.x_rows;
+    const bool parity = q.stride == 2 && q.dil == 1 && q.kh > 2 && P.nbox == 2;
     for (int r = 0; r < q.kh; ++r) {
         if (P.nbox == 1) { p.tap_row[r] = (short)(r * q.dil); }
+        else if (parity) { p.tap_row[r] = (short)((r & 1) * P.box_rows + (r >> 1)); }
         else { p.tap_row[r] = (short)(r * P.TH); p.box_dy[r] = (short)(r * q.dil - q.pad_t); }
     }
     if (P.nbox == 1) p.box_dy[0] = (short)(-q.pad_t);
+    if (parity) { p.box_dy[0] = (short)(-q.pad_t); p.box_dy[1] = (short)(1 - q.pad_t); }
     p.pad_l = q.pad_l; p.dil = q.dil;
     p.ci = ci; p.co = co; p.mblocks = P.mblocks; p.nblocks = P.nblocks; p.BN = P.BN; p.xblk = P.xblk; p.dblk = P.dblk;
     p.nstages = P.nstages; p.stage_bytes = P.stage_bytes; p.x_plane_bytes = P.x_plane_bytes; p.d_plane_bytes = P.d_plane_bytes;
@@ -415,11 +423,11 @@ int wgrad_bf(const ConvWgrad& q, const ActPlanes& xp, const ActPlanes& dp, cudaS
         if (bf_get_map(&mDl, dp.lo, 4, dims, strides, box, es, 128)) return -1;
     }
     const size_t smem = WB_ONES_BYTES + (size_t)P.nstages * P.stage_bytes + 1024;
-    wgrad_bf_kernel<<<dim3(q.kw * P.mblocks * P.nblocks, P.splits), WB_THREADS, smem, st>>>(*mXh, *mXl, *mDh, *mDl, p);
+    launch_k(wgrad_bf_kernel, dim3(dim3(q.kw * P.mblocks * P.nblocks, P.splits)), dim3(WB_THREADS), smem, st, *mXh, *mXl, *mDh, *mDl, p);
     const size_t n4 = wn / 4;
     const size_t work = n4 + (q.db ? (size_t)co : 0);
     const float sx16 = xp.fmt == 1 ? 1.f / xp.scale : 1.f, sd16 = dp.fmt == 1 ? 1.f / dp.scale : 1.f;
-    wgrad_bf_reduce_kernel<<<(unsigned)cdivz(work, 256), 256, 0, st>>>(p.part, q.dw, n4, P.splits, p.bpart, q.db, co, q.accumulate,
+    launch_k(wgrad_bf_reduce_kernel, dim3((unsigned)cdivz(work, 256)), dim3(256), 0, st, p.part, q.dw, n4, P.splits, p.bpart, q.db, co, q.accumulate,
                                                                       sx16 * sd16, sd16);
     return check_launch("wgrad_bf", 2);
 }

@@ -52,14 +52,65 @@ def _crc_table():
 _TABLE = _crc_table()
 
 
-def crc32c(data, crc=0):
-    """CRC32C of bytes / a uint8 array (table driven, processed in numpy-friendly chunks)."""
-    buf = np.frombuffer(bytes(data), dtype=np.uint8) if not isinstance(data, np.ndarray) else data.view(np.uint8).ravel()
-    c = np.uint32(crc ^ 0xFFFFFFFF)
+def _gf2_times(mat, vec):
+    s, i = 0, 0
+    while vec:
+        if vec & 1:
+            s ^= mat[i]
+        vec >>= 1
+        i += 1
+    return s
+
+
+def _gf2_square(mat):
+    return [_gf2_times(mat, mat[n]) for n in range(32)]
+
+
+def _shift_operator(nbytes):
+    """32x32 GF(2) matrix that advances a (reflected, Castagnoli) CRC register over `nbytes` zero bytes -- zlib's
+    crc32_combine construction."""
+    op = [0x82F63B78] + [1 << n for n in range(31)]          # one zero bit
+    op = _gf2_square(_gf2_square(_gf2_square(op)))           # 8 zero bits = one byte
+    result = None
+    n = nbytes
+    while n:
+        if n & 1:
+            result = op if result is None else [_gf2_times(op, result[k]) for k in range(32)]
+        n >>= 1
+        if n:
+            op = _gf2_square(op)
+    return result if result is not None else [1 << k for k in range(32)]
+
+
+def _crc_scalar(buf, c):
     tab = _TABLE
-    for b in buf.tolist():                       # tensors of a few MB: ~1 s per 2 MB; only used when verify=True
-        c = tab[(int(c) ^ b) & 0xFF] ^ (int(c) >> 8)
-    return int(c) ^ 0xFFFFFFFF
+    for b in buf.tolist():
+        c = int(tab[(c ^ b) & 0xFF]) ^ (c >> 8)
+    return c
+
+
+def crc32c(data, crc=0):
+    """CRC32C of bytes / a uint8 array.  Long inputs are cut into 4096 equal lanes whose table-driven CRCs advance together
+    as numpy vectors (one iteration per byte POSITION, not per byte) and are then chained with the zero-shift operator
+    (crc(A||B) = shift_len(B)(crc(A)) xor crc(B)): a 2 MB tensor takes milliseconds instead of a second."""
+    buf = np.frombuffer(bytes(data), dtype=np.uint8) if not isinstance(data, np.ndarray) else data.view(np.uint8).ravel()
+    n = buf.size
+    lanes = 4096
+    if n < 64 * lanes:
+        return _crc_scalar(buf, crc ^ 0xFFFFFFFF) ^ 0xFFFFFFFF
+    seg = n // lanes
+    body = buf[:seg * lanes].reshape(lanes, seg)
+    c = np.full(lanes, 0xFFFFFFFF, dtype=np.uint32)
+    c[0] = np.uint32(crc ^ 0xFFFFFFFF)
+    tab = _TABLE
+    for i in range(seg):
+        c = tab[(c ^ body[:, i]) & np.uint32(0xFF)] ^ (c >> np.uint32(8))
+    finals = (c ^ np.uint32(0xFFFFFFFF)).tolist()             # lane 0 carries the incoming crc, the others start fresh
+    op = _shift_operator(seg)
+    total = finals[0]
+    for f in finals[1:]:
+        total = _gf2_times(op, total) ^ f
+    return _crc_scalar(buf[seg * lanes:], total ^ 0xFFFFFFFF) ^ 0xFFFFFFFF
 
 
 def mask_crc(c):

@@ -15,6 +15,33 @@ from madstereo import tf_checkpoint as tfc  # noqa: E402
 from Data_utils import weights_utils  # noqa: E402
 
 
+def test_reader_on_hand_assembled_tensorbundle():
+    """An INDEPENDENT file: tests/golden/tensorbundle_handmade.* was assembled byte by byte from the LevelDB table format
+    and tensor_bundle.proto by tests/golden/make_tensorbundle_fixture.py, which shares no code with the module under
+    test (own varint / crc32c / protobuf emitters; shared key prefixes, two data blocks, int32 scalar)."""
+    import json
+    prefix = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'tensorbundle_handmade')
+    want = json.load(open(prefix + '.json'))
+    r = tfc.CheckpointReader(prefix, verify=True)                     # block and tensor checksums verified
+    assert sorted(r.get_variable_to_shape_map()) == sorted(want)
+    for name, w in want.items():
+        assert r.has_tensor(name)
+        got = r.get_tensor(name)
+        assert list(got.shape) == w['shape'] and str(got.dtype) == w['dtype'].lstrip('<')
+        assert np.array_equal(got.ravel(), np.asarray(w['values'], dtype=got.dtype))
+    assert int(r.get_tensor('global_step')) == 4200
+    assert r.header['num_shards'] == 1
+
+
+def test_crc32c_lanes_match_the_bytewise_definition():
+    rng = np.random.default_rng(1)
+    for n in (262144 + 17, 1000003):
+        d = rng.integers(0, 256, n, dtype=np.uint8)
+        ref = tfc._crc_scalar(d, 0xFFFFFFFF) ^ 0xFFFFFFFF
+        assert tfc.crc32c(d) == ref
+        assert tfc.crc32c(d[n // 3:], tfc.crc32c(d[:n // 3])) == ref    # incremental form
+
+
 def test_crc32c_known_answers_and_masking():
     assert tfc.crc32c(b'123456789') == 0xE3069283               # the standard CRC-32C check value
     assert tfc.crc32c(b'') == 0
