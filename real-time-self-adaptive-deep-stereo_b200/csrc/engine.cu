@@ -40,6 +40,8 @@ Engine::Engine()
     prof_reset();
     prep_jobs_dev = nullptr; prep_max_total = 0; weights_dirty = true;
     gstream = nullptr; ev_in = nullptr; ev_out = nullptr;
+    wstream = nullptr; ev_fork = nullptr; ev_join = nullptr; wstream_dirty = false;
+    { const char* e8 = getenv("MS_WGRAD_OVERLAP"); use_overlap = (e8 && e8[0] == '0') ? 0 : 1; }
     { const char* e2 = getenv("MS_GRAPHS"); use_graphs = (e2 && e2[0] == '0') ? 0 : 1; }
     { const char* e3 = getenv("MS_TC_WGRAD"); use_tc_wgrad = (e3 && e3[0] == '0') ? 0 : 1; }
     const char* e = getenv("MS_CONV_TC");
@@ -452,20 +454,22 @@ int Engine::conv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, cons
         q.kh = L.kh; q.kw = L.kw; q.stride = L.stride; q.dil = L.dil; q.pad_t = pt; q.pad_l = pl;
         q.workspace = wg_ws; q.workspace_floats = wg_ws_floats; q.accumulate = 0;
         prof_begin(CAT_CONV_WGRAD, st, (int)(&L - &layers[0]));
-        int rc;
+        int rc = 0;
         const ActPlanes* wxp = (conv_impl == 1 && use_bf_wgrad && wgrad_bf_supported(q)) ? planes_of(x) : nullptr;
         const ActPlanes* wdp = wxp ? planes_of(dpre) : nullptr;
-        if (wxp && wdp) {
-            rc = ensure_planes(dpre, st);
-            if (!rc) {      // bf16 copy of the forward activation in scratch planes: kind::f16 MMAs reject f16 x bf16 operand pairs
-                            // (probed on sm_100a: illegal instruction), so the fp16 forward planes cannot serve here
-                ActPlanes xb = wg_xp; xb.cs = (x.c + 7) / 8 * 8;
-                MS_REQUIRE(xb.hi && x.pixels() * (size_t)xb.cs <= wg_xp_halfs, "conv_bwd: wgrad scratch planes too small");
-                rc = split_planes(x, xb, st);
-                if (!rc) rc = wgrad_bf(q, xb, *wdp, st);
-            }
-        } else {
-            rc = (use_tc && use_tc_wgrad && wgrad_tc_supported(q)) ? wgrad_tc(q, st) : conv_wgrad(q, st);
+        // the planes of dpre also feed the dgrad below: they are produced on `st` BEFORE the fork
+        if (wxp && wdp) rc = ensure_planes(dpre, st);
+        cudaStream_t ws = st;
+        if (!rc) rc = fork_wgrad(st, &ws);
+        if (!rc && wxp && wdp) {
+            // bf16 copy of the forward activation in scratch planes: kind::f16 MMAs reject f16 x bf16 operand pairs
+            // (probed on sm_100a: illegal instruction), so the fp16 forward planes cannot serve here
+            ActPlanes xb = wg_xp; xb.cs = (x.c + 7) / 8 * 8;
+            MS_REQUIRE(xb.hi && x.pixels() * (size_t)xb.cs <= wg_xp_halfs, "conv_bwd: wgrad scratch planes too small");
+            rc = split_planes(x, xb, ws);
+            if (!rc) rc = wgrad_bf(q, xb, *wdp, ws);
+        } else if (!rc) {
+            rc = (use_tc && use_tc_wgrad && wgrad_tc_supported(q)) ? wgrad_tc(q, ws) : conv_wgrad(q, ws);
         }
         prof_end(st);
         prof_note((double)dpre.pixels() * L.kh * L.kw * L.cin * L.cout, 0);
@@ -644,7 +648,37 @@ int Engine::loss(int which, int with_grad, int slot, float grad_scale, cudaStrea
 // ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
+// every weight-gradient launch of the backward pass goes to `wstream`, ordered after the point of `st` that produced its
+// operands; they share one workspace, so they serialise among themselves while the dgrad chain proceeds on `st`
+int Engine::fork_wgrad(cudaStream_t st, cudaStream_t* ws) {
+    *ws = st;
+    if (!use_overlap || profiling || net != 0) return 0;
+    if (!wstream) {
+        MS_CHECK_CUDA(cudaStreamCreateWithFlags(&wstream, cudaStreamNonBlocking));
+        MS_CHECK_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        MS_CHECK_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
+    MS_CHECK_CUDA(cudaEventRecord(ev_fork, st));
+    MS_CHECK_CUDA(cudaStreamWaitEvent(wstream, ev_fork, 0));
+    wstream_dirty = true;
+    *ws = wstream;
+    return 0;
+}
+int Engine::join_wgrad(cudaStream_t st) {
+    if (!wstream_dirty) return 0;
+    wstream_dirty = false;
+    MS_CHECK_CUDA(cudaEventRecord(ev_join, wstream));
+    MS_CHECK_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
+    return 0;
+}
+
 int Engine::backward(int mode, int group, cudaStream_t st) {
+    const int rc = backward_impl(mode, group, st);
+    const int rj = join_wgrad(st);            // always: a captured side branch must be joined before the capture ends
+    return rc ? rc : rj;
+}
+
+int Engine::backward_impl(int mode, int group, cudaStream_t st) {
     MS_REQUIRE(bound, "backward: engine not bound");
     if (net == 1) {
         // the reference cannot run MAD on DispNet either: 6 side predictions vs 5 groups trips the assert at

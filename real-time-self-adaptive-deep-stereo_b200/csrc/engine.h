@@ -86,6 +86,13 @@ struct Engine {
     int use_graphs;
     int use_tc_wgrad;                            // MS_TC_WGRAD (default 1)
     cudaStream_t gstream; cudaEvent_t ev_in, ev_out;   // graphs run on a private stream (the legacy default stream cannot be captured)
+    // weight gradients on a side stream: wgrad(layer j) only needs dpre_j and the forward activation, so it runs concurrently
+    // with the dgrad chain (fork / join through events; inside the captured step this becomes a parallel graph branch)
+    int use_overlap;                                   // MS_WGRAD_OVERLAP (default 1; MADNet only, off while profiling)
+    cudaStream_t wstream; cudaEvent_t ev_fork, ev_join; bool wstream_dirty;
+    int fork_wgrad(cudaStream_t st, cudaStream_t* ws);
+    int join_wgrad(cudaStream_t st);
+    int backward_impl(int mode, int group, cudaStream_t st);
     int run(int mode, int group, int disp_mask, int with_update, float lr, float mu, float gscale, cudaStream_t st);
     int run_eager(int mode, int group, int disp_mask, int with_update, float lr, float mu, float gscale, cudaStream_t st);
     int use_tc;                      // route eligible convs through conv_tc (env MS_CONV_TC, default 1)

@@ -18,6 +18,17 @@ LayerInfo = namedtuple('LayerInfo', 'index name scope bias_name kh kw cin cout s
 MODE_NONE, MODE_MAD, MODE_FULL = 0, 1, 2
 
 
+class _NullCtx(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NULL_CTX = _NullCtx()
+
+
 def _stream():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -32,8 +43,9 @@ class StereoEngine:
             raise MadStereoError('a CUDA device is required: libmadstereo has no CPU fallback')
         self.device = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
         self._lib = lib()
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.net_name, self.B, self.H, self.W = net_name, batch, height, width
-        with torch.cuda.device(self.device):
+        with self._on_device():
             self._h = self._lib.ms_engine_create(net_name.encode(), batch, height, width, radius_d, stride,
                                                  1 if warping else 0)
         if not self._h:
@@ -51,6 +63,13 @@ class StereoEngine:
         self.n_groups = 0
         self.bound = False
         self._keep = []
+
+    def _on_device(self):
+        """Context that makes this engine's GPU current -- a no-op object when it already is (the per-frame calls of a
+        one-process-per-GPU run: entering torch.cuda.device() costs ~10 us of host time on the frame's critical path)."""
+        if torch.cuda.current_device() == self._dev_index:
+            return _NULL_CTX
+        return torch.cuda.device(self.device)
 
     def __del__(self):
         try:
@@ -131,12 +150,12 @@ class StereoEngine:
         if self._is_u8(left) and self._is_u8(right):
             l, r = self._as_u8(left), self._as_u8(right)
             self._keep = [l, r]
-            with torch.cuda.device(self.device):
+            with self._on_device():
                 check(self._lib.ms_engine_set_input_u8(self._h, _ptr(l), _ptr(r), _stream()), 'set_input_u8')
             return
         l, r = self._as_f32(left), self._as_f32(right)
         self._keep = [l, r]
-        with torch.cuda.device(self.device):
+        with self._on_device():
             check(self._lib.ms_engine_set_input(self._h, _ptr(l), _ptr(r), _stream()), 'set_input')
 
     @staticmethod
@@ -155,7 +174,7 @@ class StereoEngine:
     def set_gt(self, gt):
         g = self._as_f32(gt, 1)
         self._keep_gt = g
-        with torch.cuda.device(self.device):
+        with self._on_device():
             check(self._lib.ms_engine_set_gt(self._h, _ptr(g), _stream()), 'set_gt')
 
     def _as_f32(self, x, c=3):
@@ -168,24 +187,24 @@ class StereoEngine:
         return x
 
     def forward(self, disp_mask=0b100000):
-        with torch.cuda.device(self.device):
+        with self._on_device():
             check(self._lib.ms_engine_forward(self._h, disp_mask, _stream()), 'forward')
 
     def loss(self, which, with_grad, slot, grad_scale=1.0):
-        with torch.cuda.device(self.device):
+        with self._on_device():
             check(self._lib.ms_engine_loss(self._h, which, 1 if with_grad else 0, slot, grad_scale, _stream()), 'loss')
 
     def backward(self, mode, group=0):
-        with torch.cuda.device(self.device):
+        with self._on_device():
             check(self._lib.ms_engine_backward(self._h, mode, group, _stream()), 'backward')
 
     def update(self, group, lr, mu=0.9, grad_scale=1.0):
-        with torch.cuda.device(self.device):
+        with self._on_device():
             check(self._lib.ms_engine_update(self._h, group, lr, mu, grad_scale, _stream()), 'update')
 
     def run(self, mode, group=0, disp_mask=0, with_update=True, lr=1e-4, mu=0.9, grad_scale=1.0):
         """One whole frame (forward, full-res loss, train op) — replayed as a single CUDA graph."""
-        with torch.cuda.device(self.device):
+        with self._on_device():
             check(self._lib.ms_engine_run(self._h, mode, group, disp_mask, int(with_update), lr, mu, grad_scale,
                                           _stream()), 'run')
 
@@ -195,12 +214,12 @@ class StereoEngine:
         only) and map every peer.  Afterwards run(..., with_update=2) performs all-reduce + momentum update in-graph."""
         import torch.distributed as dist
         mine = (ctypes.c_ubyte * 128)()
-        with torch.cuda.device(self.device):
+        with self._on_device():
             check(self._lib.ms_engine_dp_create(self._h, rank, world, mine), 'dp_create')
         gathered = [None] * world
         dist.all_gather_object(gathered, bytes(mine), group=process_group)
         blob = (ctypes.c_ubyte * (128 * world)).from_buffer_copy(b''.join(gathered))
-        with torch.cuda.device(self.device):
+        with self._on_device():
             check(self._lib.ms_engine_dp_connect(self._h, blob), 'dp_connect')
         dist.barrier(group=process_group)
 
@@ -214,12 +233,12 @@ class StereoEngine:
         check(self._lib.ms_engine_weights_changed(self._h), 'weights_changed')
 
     def metrics(self):
-        with torch.cuda.device(self.device):
+        with self._on_device():
             check(self._lib.ms_engine_metrics(self._h, _stream()), 'metrics')
 
     def read_scalars(self):
         out = (c_float * 4)()
-        with torch.cuda.device(self.device):
+        with self._on_device():
             check(self._lib.ms_engine_read_scalars(self._h, out, _stream()), 'read_scalars')
         return list(out)
 
@@ -236,7 +255,7 @@ class StereoEngine:
     def profile_layers(self):
         n = len(self.layers)
         ms = (ctypes.c_double * (3 * n))(); calls = (ctypes.c_longlong * (3 * n))()
-        with torch.cuda.device(self.device):
+        with self._on_device():
             check(self._lib.ms_engine_profile_layers(self._h, ms, calls), 'profile_layers')
         out = {}
         for d, name in enumerate(('fwd', 'dgrad', 'wgrad')):
@@ -248,7 +267,7 @@ class StereoEngine:
     def profile_read(self):
         ms, macs, byts = ((ctypes.c_double * 7)() for _ in range(3))
         calls = (ctypes.c_longlong * 7)()
-        with torch.cuda.device(self.device):
+        with self._on_device():
             check(self._lib.ms_engine_profile_read(self._h, ms, macs, byts, calls), 'profile_read')
         return {c: {'ms': ms[i], 'macs': macs[i], 'bytes': byts[i], 'calls': calls[i]}
                 for i, c in enumerate(self.CATEGORIES)}

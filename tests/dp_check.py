@@ -65,7 +65,14 @@ def main():
             worst_l2 = per[0][0]
             print('   worst tensors (rel L2, name, max|ref|):', [(round(a, 4), n, '%.2e' % m) for a, n, m in per[:4]], flush=True)
             wv = net.engine.export_params()
-            wworst = max(rel_l2(wv[n] - params[n], orc.net.p[n].detach().numpy() - params[n]) for n in ref['grads'])
+            # weight deltas are compared net of fp32 storage resolution: a tensor whose update lr*g is below one ulp of its
+            # weights (FULL mode touches layers with gradients of 1e-7) has no meaningful relative delta
+            def dw_err(n):
+                ref_d = orc.net.p[n].detach().numpy().astype(np.float64) - params[n]
+                got_d = wv[n].astype(np.float64) - params[n]
+                slack = 1.2e-7 * np.linalg.norm(params[n].astype(np.float64).ravel())
+                return max(0.0, np.linalg.norm((got_d - ref_d).ravel()) - slack) / max(np.linalg.norm(ref_d.ravel()), 1e-30)
+            wworst = max(dw_err(n) for n in ref['grads'])
             # same bounds as the single-GPU step tests (tests/test_madnet_gpu.py): gradients 1e-2 L-inf, and relative L2
             good = same and worst < 1e-2 and worst_l2 < 5e-3 and wworst < 5e-3 and abs(out['loss'] - ref['full_loss']) < 2e-5
             ok = ok and good
