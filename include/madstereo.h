@@ -173,6 +173,13 @@ int ms_engine_set_input(void* e, const float* left, const float* right, void* st
  * (Data_utils/data_reader.py); converted to fp32 on the device. */
 int ms_engine_set_input_u8(void* e, const unsigned char* left, const unsigned char* right, void* stream);
 int ms_engine_set_gt(void* e, const float* gt, void* stream);
+/* Continual-adaptation variant (reference Stereo_Continual_Adaptation.py:75,112,133; Losses/loss_factory.py:304-351
+ * get_proxy_loss('mean_l1')): proxy disparities [B,H,W,1] (host or device) and the loss selector.  kind 0 = reprojection
+ * SSIM + L1 (default), 1 = weight * sum(valid * |d - proxy|) / sum(valid) with valid = !(proxy <= 0 || proxy >= 192);
+ * weight_full (reference 0.01) for the full-resolution loss / FULL train op, weight_module (0.1) for the MAD module losses.
+ * Changing the loss drops the captured step graphs. */
+int ms_engine_set_proxy(void* e, const float* proxy, void* stream);
+int ms_engine_set_loss(void* e, int kind, float weight_full, float weight_module);
 /* disp_mask bit i => materialise get_disparities()[i] (MADNet: D6,D5,D4,D3,D2ctx,full). */
 int ms_engine_forward(void* e, int disp_mask, void* stream);
 /* slot 0 = full-res loss fetched every frame (Stereo_Online_Adaptation.py:70,209), slot 1 = train loss */

@@ -19,14 +19,15 @@ def softmax(x):
 class OracleAdapter:
     """One tf.train.MomentumOptimizer(lr, 0.9) shared by all train ops (one slot per variable)."""
 
-    def __init__(self, params, mode='MAD', lr=1e-4, mu=0.9, dtype=torch.float32, groups=None):
+    def __init__(self, params, mode='MAD', lr=1e-4, mu=0.9, dtype=torch.float32, groups=None, loss='reprojection'):
+        self.loss_kind = loss          # 'proxy': Stereo_Continual_Adaptation.py:75,112,133 (weights 0.01 / 0.1)
         assert mode in ('NONE', 'MAD', 'FULL')
         self.mode, self.lr, self.mu = mode, lr, mu
         self.net = MadNetOracle(params, dtype=dtype, bulkhead=(mode == 'MAD'))
         self.groups = groups if groups is not None else mad_groups_full()
         self.momentum = {k: torch.zeros_like(v) for k, v in self.net.p.items()}
 
-    def step(self, left, right, module=None):
+    def step(self, left, right, module=None, proxy=None):
         """One sess.run: forward, full-res loss, optional train op. Returns dict of numpy results."""
         net = self.net
         if self.mode == 'NONE':
@@ -40,11 +41,16 @@ class OracleAdapter:
         right_t = torch.as_tensor(right).to(net.dtype)
         with torch.set_grad_enabled(bool(names)):
             disps, layers = net.forward(left_t, right_t)
-            full_loss = T.reprojection_loss(disps[-1], left_t, right_t)
-            if self.mode == 'MAD':
-                loss = T.reprojection_loss(disps[module], left_t, right_t)
+            if self.loss_kind == 'proxy':
+                px = torch.as_tensor(proxy).to(net.dtype)
+                full_loss = T.proxy_loss(disps[-1], px, 0.01)
+                loss = T.proxy_loss(disps[module], px, 0.1) if self.mode == 'MAD' else full_loss
             else:
-                loss = full_loss
+                full_loss = T.reprojection_loss(disps[-1], left_t, right_t)
+                if self.mode == 'MAD':
+                    loss = T.reprojection_loss(disps[module], left_t, right_t)
+                else:
+                    loss = full_loss
         out = {'full_loss': float(full_loss.detach()), 'train_loss': float(loss.detach()),
                'disparities': [d.detach().numpy() for d in disps]}
         grads = {}

@@ -244,3 +244,14 @@ def xavier_uniform(rng, shape):
     kh, kw, a, b = shape
     limit = math.sqrt(6.0 / (kh * kw * a + kh * kw * b))
     return rng.uniform(-limit, limit, size=shape).astype('float32')
+
+
+def proxy_loss(disp, proxy, weight):
+    """Losses/loss_factory.py:304-351 get_proxy_loss('mean_l1') for ONE prediction already at the proxy's resolution
+    (resize_to_prediction is the identity, disparity_scale_factor 1): valid = !(proxy <= 0 | proxy >= 192);
+    weight * sum(valid * |disp - proxy|) / sum(valid)   (:28-38 mean_l1).  No valid pixel: 0 (the reference gives nan)."""
+    valid = (~((proxy <= 0) | (proxy >= 192))).to(disp.dtype)
+    cnt = valid.sum()
+    if float(cnt) == 0.0:
+        return disp.sum() * 0.0
+    return weight * (valid * (disp - proxy).abs()).sum() / cnt

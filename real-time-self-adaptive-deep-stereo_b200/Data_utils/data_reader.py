@@ -118,7 +118,7 @@ class dataset():
     float32 arrays [B,H,W,3], [B,H,W,3], [B,H,W,1]."""
 
     def __init__(self, path_file, batch_size=4, crop_shape=[320, 1216], num_epochs=None, augment=False,
-                 is_training=True, shuffle=True, prefetch=30, pin_memory=False, seed=None):
+                 is_training=True, shuffle=True, prefetch=30, pin_memory=False, seed=None, proxies=False):
         if not os.path.exists(path_file):
             raise Exception('File not found during dataset construction')
         if augment:
@@ -132,14 +132,30 @@ class dataset():
         self._prefetch = prefetch
         self._pin = pin_memory
         self._rng = np.random.RandomState(seed)
-        left, right, gt, _ = read_list_file(path_file)
-        self._couples = [[l, r, g] for l, r, g in zip(left, right, gt)]
+        left, right, gt, px = read_list_file(path_file)
+        # proxies=True: the continual-adaptation list format left;right;gt;proxy (Data_utils/continual_data_reader.py:55-78,
+        # :136-160): batches become (left, right, gt, proxy, real_width)
+        self._proxies = proxies
+        if proxies:
+            if len(px) != len(left):
+                raise Exception('the list file must name a proxy disparity for every frame (left;right;gt;proxy)')
+            self._couples = [[l, r, g, p] for l, r, g, p in zip(left, right, gt, px)]
+        else:
+            self._couples = [[l, r, g] for l, r, g in zip(left, right, gt)]
 
     def _load_image(self, files):
         left = read_image_from_disc(files[0])
         right = read_image_from_disc(files[1])
         gt = read_gt_from_disc(files[2])
         gt = gt[:, :left.shape[1], :]                                  # "SGM add some paddings" (:146)
+        if self._proxies:
+            px = read_gt_from_disc(files[3])[:, :left.shape[1], :]      # 16-bit PNG / 256 or 8-bit, like the ground truth
+            real_width = np.float32(left.shape[1])
+            if self._is_training:
+                left, right, gt = random_crop(self._crop_shape, [left, right, gt], self._rng)
+            else:
+                left, right, gt, px = [resize_image_with_crop_or_pad(x, self._crop_shape[0], self._crop_shape[1]) for x in (left, right, gt, px)]
+            return left, right, gt, px, np.full((1,), real_width, np.float32)
         if self._is_training:
             left, right, gt = random_crop(self._crop_shape, [left, right, gt], self._rng)
         else:
@@ -163,7 +179,7 @@ class dataset():
                 self._rng.shuffle(order)
             for b in range(0, len(order) - self._batch_size + 1, self._batch_size):      # drop_remainder=True
                 items = [self._load_image(self._couples[i]) for i in order[b:b + self._batch_size]]
-                batch = tuple(np.stack([it[k] for it in items]).astype(np.float32) for k in range(3))
+                batch = tuple(np.stack([it[k] for it in items]).astype(np.float32) for k in range(5 if self._proxies else 3))
                 if self._pin:
                     import torch
                     batch = tuple(torch.from_numpy(x).pin_memory() for x in batch)

@@ -408,6 +408,22 @@ int ms_engine_set_gt(void* h, const float* gt, void* stream) {
     MS_CHECK_CUDA(cudaMemcpyAsync(e->gt, gt, (size_t)e->B * e->H * e->W * sizeof(float), cudaMemcpyDefault, S(stream)));
     return 0;
 }
+int ms_engine_set_proxy(void* h, const float* proxy, void* stream) {
+    Engine* e = static_cast<Engine*>(h);
+    if (!e->bound) { set_error("engine not bound"); return -2; }
+    MS_CHECK_CUDA(cudaMemcpyAsync(e->proxy, proxy, (size_t)e->B * e->H * e->W * sizeof(float), cudaMemcpyDefault, S(stream)));
+    return 0;
+}
+int ms_engine_set_loss(void* h, int kind, float weight_full, float weight_module) {
+    Engine* e = static_cast<Engine*>(h);
+    if (kind != 0 && kind != 1) { set_error("ms_engine_set_loss: kind must be 0 (reprojection) or 1 (proxy L1)"); return -2; }
+    if (kind != e->loss_kind || weight_full != e->proxy_w_full || weight_module != e->proxy_w_module) {
+        for (auto& g : e->graphs) cudaGraphExecDestroy(g.second.exec);       // the loss kernels are baked into the step graphs
+        e->graphs.clear();
+    }
+    e->loss_kind = kind; e->proxy_w_full = weight_full; e->proxy_w_module = weight_module;
+    return 0;
+}
 int ms_engine_forward(void* h, int disp_mask, void* stream) { return static_cast<Engine*>(h)->forward(disp_mask, S(stream)); }
 int ms_engine_loss(void* h, int which, int with_grad, int slot, float grad_scale, void* stream) {
     return static_cast<Engine*>(h)->loss(which, with_grad, slot, grad_scale, S(stream));

@@ -174,6 +174,9 @@ struct ReprojLoss {
 size_t loss_workspace_floats(int B, int H, int W);
 int reproj_loss(const ReprojLoss& p, cudaStream_t st);
 int epe_bad3(const float* disp, const float* gt, int n, float* out2, float* workspace, cudaStream_t st);
+// masked mean-L1 against proxy disparities (loss_factory.get_proxy_loss('mean_l1')); workspace >= 2 * ceil(n/256) + 2 floats
+int proxy_loss(const float* disp, const float* proxy, int n, float weight, float grad_scale, float* loss, float* ddisp,
+               float* workspace, cudaStream_t st);
 
 // optimizer (optim.cu)
 int momentum_update(float* w, const float* g, float* m, size_t n, float lr, float mu, float gscale,

@@ -36,7 +36,7 @@ Engine::Engine()
     : net(0), B(1), H(0), W(0), Hp(0), Wp(0), radius_d(2), corr_stride(1), warping(1), n_groups(0), n_params(0),
       Wt(nullptr), Gr(nullptr), Mo(nullptr), ws(nullptr), ws_floats(0), bound(false), wT(nullptr), wT_floats(0),
       wg_ws(nullptr), wg_ws_floats(0), rs_tmp(nullptr), rs_tmp_floats(0), loss_ws(nullptr), loss_ws_floats(0),
-      scalars(nullptr), gt(nullptr), profiling(0), prof_capturing(false), prof_event_overhead_ms(0.f) {
+      scalars(nullptr), gt(nullptr), proxy(nullptr), loss_kind(0), proxy_w_full(0.01f), proxy_w_module(0.1f), profiling(0), prof_capturing(false), prof_event_overhead_ms(0.f) {
     prof_reset();
     prep_jobs_dev = nullptr; prep_max_total = 0; weights_dirty = true;
     gstream = nullptr; ev_in = nullptr; ev_out = nullptr;
@@ -374,6 +374,7 @@ size_t Engine::layout(float* base) {
     scalars = alloc(64);
     u8_stage = reinterpret_cast<unsigned char*>(alloc(((size_t)2 * B * H * W * 3 + 3) / 4 + 64));
     gt = alloc((size_t)B * H * W);
+    proxy = alloc((size_t)B * H * W);
     return A.off;
 }
 
@@ -634,6 +635,15 @@ int Engine::forward(int disp_mask, cudaStream_t st) {
 
 int Engine::loss(int which, int with_grad, int slot, float grad_scale, cudaStream_t st) {
     MS_REQUIRE(bound && which >= 0 && which < n_disp && slot >= 0 && slot < 2, "loss: bad arguments");
+    if (loss_kind == 1) {
+        // Stereo_Continual_Adaptation.py:75 (full-resolution loss, weight 0.01; also the FULL train op :133) and :112
+        // (module losses, weight 0.1)
+        const float wgt = slot == 0 ? proxy_w_full : proxy_w_module;
+        prof_begin(CAT_LOSS, st);
+        int rc = proxy_loss(disp[which].p, proxy, B * H * W, wgt, grad_scale, scalars + slot, with_grad ? g_disp.p : nullptr, loss_ws, st);
+        prof_end(st);
+        return rc;
+    }
     ReprojLoss p{};
     p.left = tensors["raw_left"].p; p.right = tensors["raw_right"].p;
     p.disp = disp[which].p; p.loss = scalars + slot;

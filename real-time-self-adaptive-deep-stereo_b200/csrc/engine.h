@@ -126,6 +126,9 @@ struct Engine {
     unsigned char* u8_stage;         // 2 x B*H*W*3 bytes: uint8 input staging (set_input_u8)
     float* scalars;                  // [0]=full loss, [1]=train loss, [2]=epe, [3]=bad3
     float* gt;                       // optional ground truth [B,H,W,1]
+    float* proxy;                    // proxy disparities [B,H,W,1] of the continual-adaptation variant (loss_kind 1)
+    int loss_kind;                   // 0 = reprojection SSIM+L1 (Stereo_Online_Adaptation.py), 1 = masked L1 to proxy labels (Stereo_Continual_Adaptation.py)
+    float proxy_w_full, proxy_w_module;   // loss weights of the reference: 0.01 (full-resolution loss / FULL train op), 0.1 (MAD module losses)
 
     // ---- profiling (off by default): CUDA events around kernel groups on the launching stream
     enum Cat { CAT_CONV_FWD = 0, CAT_CONV_DGRAD, CAT_CONV_WGRAD, CAT_CORR_FWD, CAT_CORR_BWD, CAT_LOSS, CAT_OTHER, N_CAT };

@@ -187,6 +187,69 @@ int reproj_loss(const ReprojLoss& p, cudaStream_t st) {
     return check_launch("reproj_loss", p.ddisp ? 4 : 3);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Proxy-label loss of the continual-adaptation variant (reference Losses/loss_factory.py:304-351 `get_proxy_loss('mean_l1')`,
+// :28-38 `mean_l1`; used by Stereo_Continual_Adaptation.py:75,112):
+//     valid = !(proxy <= 0 || proxy >= 192);   loss = weight * sum(valid * |d - proxy|) / sum(valid)
+// (prediction already at the proxy's resolution: `resize_to_prediction` is the identity on this path, scale factor 1).
+// Three small kernels: per-block partial sums (fixed order), one fp64 final sum that also leaves 1 / sum(valid) for the
+// gradient pass, and d loss / d d = weight * valid * sign(d - proxy) / sum(valid).  An image without a single valid proxy
+// pixel gives 0 / 0 = NaN in the reference; here the loss and its gradient are 0 (documented difference).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void proxy_partial_kernel(const float* __restrict__ disp, const float* __restrict__ proxy, int n, float* __restrict__ part) {
+    pdl_prologue();
+    __shared__ float sm[32];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float e = 0.f, v = 0.f;
+    if (i < n) {
+        const float p = proxy[i];
+        if (!(p <= 0.f || p >= 192.f)) { v = 1.f; e = fabsf(disp[i] - p); }
+    }
+    const float te = block_sum(e, sm);
+    const float tv = block_sum(v, sm);
+    if (threadIdx.x == 0) { part[blockIdx.x * 2] = te; part[blockIdx.x * 2 + 1] = tv; }
+}
+__global__ void proxy_final_kernel(const float* __restrict__ part, int nb, float weight, float* __restrict__ loss, float* __restrict__ inv_count) {
+    pdl_prologue();
+    __shared__ double s[2][256];
+    double a = 0, b = 0;
+    for (int i = threadIdx.x; i < nb; i += 256) { a += part[i * 2]; b += part[i * 2 + 1]; }
+    s[0][threadIdx.x] = a; s[1][threadIdx.x] = b;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { s[0][threadIdx.x] += s[0][threadIdx.x + o]; s[1][threadIdx.x] += s[1][threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double cnt = s[1][0];
+        *loss = cnt > 0.0 ? (float)((double)weight * s[0][0] / cnt) : 0.f;
+        *inv_count = cnt > 0.0 ? (float)(1.0 / cnt) : 0.f;
+    }
+}
+__global__ void proxy_grad_kernel(const float* __restrict__ disp, const float* __restrict__ proxy, int n, float scale,
+                                  const float* __restrict__ inv_count, float* __restrict__ ddisp) {
+    pdl_prologue();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float p = proxy[i];
+    float g = 0.f;
+    if (!(p <= 0.f || p >= 192.f)) {
+        const float d = disp[i] - p;
+        g = (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * scale * __ldg(inv_count);      // tf.abs' gradient is sign(x): 0 at 0
+    }
+    ddisp[i] = g;
+}
+// workspace: >= 2 * ceil(n / 256) + 2 floats
+int proxy_loss(const float* disp, const float* proxy, int n, float weight, float grad_scale, float* loss, float* ddisp,
+               float* workspace, cudaStream_t st) {
+    const int nb = cdiv(n, LB);
+    float* inv_count = workspace + (size_t)nb * 2;
+    launch_k(proxy_partial_kernel, dim3(nb), dim3(LB), 0, st, disp, proxy, n, workspace);
+    launch_k(proxy_final_kernel, dim3(1), dim3(256), 0, st, workspace, nb, weight, loss, inv_count);
+    if (ddisp) launch_k(proxy_grad_kernel, dim3(nb), dim3(LB), 0, st, disp, proxy, n, weight * grad_scale, inv_count, ddisp);
+    return check_launch("proxy_loss", ddisp ? 3 : 2);
+}
+
 // EPE / bad3 against ground truth (reference Stereo_Online_Adaptation.py:74-82); out2 = {epe, bad3}
 __global__ void epe_partial_kernel(const float* __restrict__ disp, const float* __restrict__ gt, int n,
                                    float* __restrict__ part) {

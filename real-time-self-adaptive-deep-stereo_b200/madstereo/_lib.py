@@ -66,6 +66,8 @@ _SIGS = {
     'ms_engine_set_input': (I, [P, P, P, P]),
     'ms_engine_set_input_u8': (I, [P, P, P, P]),
     'ms_engine_set_gt': (I, [P, P, P]),
+    'ms_engine_set_proxy': (I, [P, P, P]),
+    'ms_engine_set_loss': (I, [P, I, F, F]),
     'ms_engine_dp_create': (I, [P, I, I, P]),
     'ms_engine_dp_connect': (I, [P, P]),
     'ms_engine_dp_error': (I, [P, P]),

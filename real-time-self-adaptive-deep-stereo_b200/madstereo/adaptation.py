@@ -30,8 +30,14 @@ def softmax(x):
 
 class OnlineAdaptation(object):
     def __init__(self, net, mode='MAD', train_config=None, lr=0.0001, momentum=0.9, sample_mode='SEQUENTIAL',
-                 num_blocks=1, fixed_id=0, sample_frequency=1, ssim_th=0.5, process_group=None):
+                 num_blocks=1, fixed_id=0, sample_frequency=1, ssim_th=0.5, process_group=None,
+                 loss='reprojection', decay=0.99, uf=0.01, dilation=1):
+        """loss='proxy', decay, uf, dilation: the continual-adaptation variant (Stereo_Continual_Adaptation.py): masked L1 to
+        proxy disparities (weights 0.01 full-resolution / FULL, 0.1 per MAD module, :75,112), reward recurrence
+        h <- decay*h, h[i] += uf*gain (:232-234), a train op only every `dilation`-th frame (:212)."""
         assert mode in ('NONE', 'FULL', 'MAD')
+        assert loss in ('reprojection', 'proxy')
+        self.loss_kind, self.decay, self.uf, self.dilation = loss, float(decay), float(uf), int(dilation)
         self.net, self.engine, self.mode = net, net.engine, mode
         self.lr, self.mu = float(lr), float(momentum)
         self.sample_frequency, self.ssim_th = sample_frequency, ssim_th
@@ -58,6 +64,8 @@ class OnlineAdaptation(object):
             self.sampler = sampler_factory.get_sampler(sample_mode, num_blocks, fixed_id)
         self.engine.set_groups(self.groups)
         self.engine.bind()
+        if loss == 'proxy':
+            self.engine.set_loss('proxy')
         self.num_actions = len(self.groups) if mode == 'MAD' else (1 if mode == 'FULL' else 0)
         self.fetch_counter = [0] * self.num_actions
         self.sample_distribution = np.zeros(shape=[self.num_actions])
@@ -170,7 +178,7 @@ class OnlineAdaptation(object):
         else:
             eng.set_input(left, right)
 
-    def step(self, left, right, gt=None, want_disp_mask=0, prefetch=None):
+    def step(self, left, right, gt=None, want_disp_mask=0, prefetch=None, proxy=None):
         """One frame == one sess.run of the reference loop (Stereo_Online_Adaptation.py:176-253).
         prefetch=(next_left, next_right): start copying the next frame's host buffers while this frame computes."""
         eng = self.engine
@@ -194,10 +202,15 @@ class OnlineAdaptation(object):
         self._set_input(left, right)
         if gt is not None:
             eng.set_gt(gt)
+        if self.loss_kind == 'proxy':
+            if proxy is None:
+                raise MadStereoError('loss="proxy" needs the proxy disparities of every frame: step(..., proxy=...)')
+            eng.set_proxy(proxy)
         mask = want_disp_mask
+        adapt_now = step % self.dilation == 0          # Stereo_Continual_Adaptation.py:212: train ops every `dilation` frames
         gscale = 1.0 / self.world
         solo = self.world == 1
-        if self.mode == 'NONE':
+        if self.mode == 'NONE' or not adapt_now:
             eng.run(MODE_NONE, 0, mask, False)
         elif self.mode == 'FULL':
             fused = self.dp_peer
@@ -229,7 +242,7 @@ class OnlineAdaptation(object):
             self.prefetch(*prefetch)     # copies (side stream) no longer delays this frame's kernels
         sc = eng.read_scalars()
         new_loss = sc[0]
-        fused_loss = self.dp_peer and (self.mode == 'FULL' or (self.mode == 'MAD' and len(self.blocks_to_train) == 1))
+        fused_loss = self.dp_peer and adapt_now and (self.mode == 'FULL' or (self.mode == 'MAD' and len(self.blocks_to_train) == 1))
         if fused_loss:                  # the exchange kernel already wrote the mean over the ranks
             if new_loss != new_loss:
                 raise MadStereoError('data-parallel exchange failed (code %d: 1 = peer timeout, 2 = ranks adapt '
@@ -245,9 +258,9 @@ class OnlineAdaptation(object):
                 self.loss_t_1 = new_loss
             expected_loss = 2 * self.loss_t_1 - self.loss_t_2
             gain_loss = expected_loss - new_loss
-            self.sample_distribution = 0.99 * self.sample_distribution
+            self.sample_distribution = self.decay * self.sample_distribution
             for i in self.last_trained_blocks:
-                self.sample_distribution[i] += 0.01 * gain_loss
+                self.sample_distribution[i] += self.uf * gain_loss
             self.last_trained_blocks = self.blocks_to_train
             self.loss_t_2 = self.loss_t_1
             self.loss_t_1 = new_loss

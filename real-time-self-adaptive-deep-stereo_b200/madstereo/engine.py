@@ -177,6 +177,18 @@ class StereoEngine:
         with self._on_device():
             check(self._lib.ms_engine_set_gt(self._h, _ptr(g), _stream()), 'set_gt')
 
+    def set_proxy(self, proxy):
+        """Proxy disparities [B,H,W,1] of the continual-adaptation variant (Stereo_Continual_Adaptation.py:54)."""
+        g = self._as_f32(proxy, 1)
+        self._keep_proxy = g
+        with self._on_device():
+            check(self._lib.ms_engine_set_proxy(self._h, _ptr(g), _stream()), 'set_proxy')
+
+    def set_loss(self, kind, weight_full=0.01, weight_module=0.1):
+        """kind: 'reprojection' (SSIM + L1, Stereo_Online_Adaptation.py) or 'proxy' (masked L1 to proxy labels)."""
+        k = {'reprojection': 0, 'proxy': 1}[kind]
+        check(self._lib.ms_engine_set_loss(self._h, k, weight_full, weight_module), 'set_loss')
+
     def _as_f32(self, x, c=3):
         if isinstance(x, np.ndarray):
             x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))

@@ -60,7 +60,7 @@ if __name__ == '__main__':
     main()
 
 
-def driver_cli():
+def driver_cli(script='Stereo_Online_Adaptation.py'):
     """The argparse definition of the reference's Stereo_Online_Adaptation.py, captured by running the script as __main__
     with `tensorflow` replaced by the eager shim and `parse_args` intercepted (nothing else of the script executes)."""
     import argparse
@@ -71,8 +71,10 @@ def driver_cli():
     sys.path.insert(0, root)
     from oracle import tf1_shim
     sys.modules['tensorflow'] = tf1_shim.as_module()
-    mpl = types.ModuleType('matplotlib'); mpl.cm = types.ModuleType('matplotlib.cm'); mpl.pyplot = types.ModuleType('matplotlib.pyplot')
-    for k, v in (('matplotlib', mpl), ('matplotlib.cm', mpl.cm), ('matplotlib.pyplot', mpl.pyplot)):
+    mpl = types.ModuleType('matplotlib'); mpl.__path__ = []
+    mpl.cm = types.ModuleType('matplotlib.cm'); mpl.pyplot = types.ModuleType('matplotlib.pyplot')
+    mpl.colors = types.ModuleType('matplotlib.colors'); mpl.colors.LinearSegmentedColormap = object
+    for k, v in (('matplotlib', mpl), ('matplotlib.cm', mpl.cm), ('matplotlib.pyplot', mpl.pyplot), ('matplotlib.colors', mpl.colors)):
         sys.modules.setdefault(k, v)
     for k in [k for k in sys.modules if k.split('.')[0] in ('Nets', 'Losses', 'Data_utils', 'Sampler')]:
         del sys.modules[k]
@@ -90,8 +92,8 @@ def driver_cli():
     sys.path.insert(0, REF)
     old_argv = sys.argv
     try:
-        sys.argv = ['Stereo_Online_Adaptation.py']
-        runpy.run_path(os.path.join(REF, 'Stereo_Online_Adaptation.py'), run_name='__main__')
+        sys.argv = [script]
+        runpy.run_path(os.path.join(REF, script), run_name='__main__')
     except Stop:
         pass
     finally:
@@ -112,6 +114,10 @@ def main_cli():
     out_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'reference_driver_cli.json')
     json.dump({'source': 'CVLAB-Unibo/Real-time-self-adaptive-deep-stereo: Stereo_Online_Adaptation.py (argparse actions)',
                'actions': driver_cli()}, open(out_path, 'w'), indent=1)
+    print('wrote', out_path)
+    out_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'reference_continual_cli.json')
+    json.dump({'source': 'CVLAB-Unibo/Real-time-self-adaptive-deep-stereo: Stereo_Continual_Adaptation.py (argparse actions)',
+               'actions': driver_cli('Stereo_Continual_Adaptation.py')}, open(out_path, 'w'), indent=1)
     print('wrote', out_path)
 
 

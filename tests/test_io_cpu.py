@@ -346,3 +346,90 @@ def test_driver_main_end_to_end_with_a_stub_engine(tmp_path):
     assert png.shape == (16, 32) and int(png[0, 0]) == int(7.5 * 256)
     with pytest.raises(SystemExit):
         d.main(d.build_parser().parse_args(['-l', lst, '-o', str(out), '--weights', 'x', '--blockConfig', cfg, '--reprojectionScale', '2']), build=build)
+
+
+# ---------------------------------------------------------------------------------------------------- continual adaptation
+def _continual():
+    import importlib
+    return importlib.import_module('Stereo_Continual_Adaptation')
+
+
+def test_continual_driver_command_line_equals_the_reference():
+    """tests/golden/reference_continual_cli.json: the argparse actions of the reference's Stereo_Continual_Adaptation.py."""
+    import argparse
+    import json
+    g = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'reference_continual_cli.json')))['actions']
+    mine = []
+    for a in _continual().build_parser()._actions:
+        if a.dest == 'help':
+            continue
+        mine.append({'flags': list(a.option_strings), 'dest': a.dest, 'required': bool(a.required), 'default': a.default,
+                     'type': getattr(a.type, '__name__', None), 'nargs': a.nargs, 'choices': sorted(a.choices) if a.choices else None,
+                     'store_true': isinstance(a, argparse._StoreTrueAction)})
+    assert mine == g
+
+
+def test_proxy_loss_oracle_known_answers():
+    """Losses/loss_factory.py:304-351 + :28-38: valid = !(proxy <= 0 | proxy >= 192); w * sum(valid*|d-p|) / sum(valid)."""
+    import torch
+    from oracle import tf1_ops as T
+    d = torch.tensor([[[[1.0], [5.0], [7.0], [300.0]]]])
+    p = torch.tensor([[[[2.0], [0.0], [4.0], [192.0]]]])                 # pixels 1 (proxy 0) and 3 (proxy 192) are invalid
+    assert abs(float(T.proxy_loss(d, p, 0.1)) - 0.1 * (1.0 + 3.0) / 2.0) < 1e-7
+    assert float(T.proxy_loss(d, torch.zeros_like(p), 0.1)) == 0.0     # no valid pixel (the reference: nan)
+    d.requires_grad_(True)
+    T.proxy_loss(d, p, 0.01).backward()
+    assert torch.allclose(d.grad.ravel(), torch.tensor([-0.005, 0.0, 0.005, 0.0]))
+
+
+def test_reader_with_proxies_and_continual_loop(tmp_path):
+    """List format left;right;gt;proxy (continual_data_reader.py:55-78), 16-bit proxies / 256, and the driver loop with its
+    output files around a stub adaptation object (EPE / D1 as :243-249)."""
+    import cv2
+    from Data_utils import data_reader
+    rng = np.random.default_rng(3)
+    lines = []
+    for i in range(3):
+        l = rng.integers(0, 255, (20, 30, 3), dtype=np.uint8); r = rng.integers(0, 255, (20, 30, 3), dtype=np.uint8)
+        gt = (rng.uniform(1, 40, (20, 30)) * 256).astype(np.uint16); px = (rng.uniform(0, 60, (20, 34)) * 256).astype(np.uint16)
+        names = [str(tmp_path / ('%s_%d.png' % (k, i))) for k in ('l', 'r', 'g', 'p')]
+        for n, img in zip(names, (l, r, gt, px)):
+            cv2.imwrite(n, img)
+        lines.append(';'.join(names))
+    lst = tmp_path / 'list.csv'
+    lst.write_text('\n'.join(lines) + '\n')
+    ds = data_reader.dataset(str(lst), batch_size=1, crop_shape=[16, 24], num_epochs=1, is_training=False, shuffle=False, proxies=True)
+    batches = list(ds)
+    assert len(batches) == 3 and [b.shape for b in batches[0][:4]] == [(1, 16, 24, 3), (1, 16, 24, 3), (1, 16, 24, 1), (1, 16, 24, 1)]
+    px0 = cv2.imread(lines[0].split(';')[3], -1).astype(np.float32)[:, :30] / 256.0      # cut to the image width, centre crop
+    assert np.allclose(batches[0][3][0, :, :, 0], px0[2:18, 3:27])
+    assert float(batches[0][4][0, 0]) == 30.0
+
+    C = _continual()
+
+    class Stub:
+        fetch_counter = [0] * 5
+
+        def __init__(self):
+            self.calls = []
+
+        def step(self, left, right, gt=None, want_disp_mask=0, prefetch=None, proxy=None):
+            assert proxy is not None and proxy.shape == (1, 16, 24, 1) and want_disp_mask == 0b100000
+            self.calls.append(float(proxy.mean()))
+            return {'loss': 0.1}
+
+    out = tmp_path / 'out'
+    (out / 'disparities').mkdir(parents=True)
+    args = C.build_parser().parse_args(['-l', str(lst), '-o', str(out), '--weights', 'w', '--blockConfig', 'b', '--logDispStep', '2'])
+    stub = Stub()
+    disp = np.full((1, 16, 24, 1), 7.6, np.float32)
+    avg, d1, steps, _ = C.run_loop(stub, batches, args, get_disparity=lambda: disp, log=lambda *a: None)
+    assert steps == 3 and len(stub.calls) == 3
+    e0, o0 = C.frame_errors(disp[-1], batches[0][2][-1])
+    assert avg[0] == e0 and d1[0] == o0 and 0.0 <= o0 <= 100.0
+    C.write_outputs(args, avg, d1)
+    assert (out / 'overall.csv').read_text().splitlines()[0] == 'EPE\tD1'
+    assert (out / 'series.csv').read_text().splitlines()[1].startswith('0 & ')
+    assert (out / 'histogram.csv').exists()
+    saved = cv2.imread(str(out / 'disparities' / 'disparity_2.png'), -1)
+    assert saved.dtype == np.uint16 and int(saved[0, 0]) == 7 * 256                          # cast to uint16 first, then x 256 (:279-280)

@@ -175,6 +175,45 @@ def test_mad_two_blocks_per_frame():
             assert np.array_equal(v, params[n]), n
 
 
+@pytest.mark.parametrize('mode,module', [('MAD', 1), ('MAD', 4), ('FULL', None)])
+def test_continual_proxy_loss_step(mode, module):
+    """SURVEY 8f-3: one adaptation step supervised by proxy disparities (Stereo_Continual_Adaptation.py:75,112,133;
+    get_proxy_loss('mean_l1'), weights 0.01 / 0.1) against the oracle: losses, gradients, adapted weights; plus --dilation."""
+    from madstereo.adaptation import OnlineAdaptation
+    from madstereo.synthetic import make_pair
+    from oracle.adaptation import OracleAdapter
+    from oracle.madnet import init_params
+    import Nets
+    left, right, gt = make_pair(64, 128, seed=3)
+    proxy = gt.copy()
+    proxy[:, ::7, ::5] = 0.0                           # holes, as in SGM proxies
+    proxy[:, 3, 4] = 200.0                             # >= 192: invalid
+    lt = torch.as_tensor(left).cuda(); rt = torch.as_tensor(right).cuda()
+    net = Nets.get_stereo_net('MADNet', dict(left_img=lt, right_img=rt, split_layers=[None], sequence=True, train_portion='BEGIN',
+                                             bulkhead=(mode == 'MAD'), warping=True, context_net=True, radius_d=2, stride=1))
+    cfg = json.load(open(os.path.join(PKG, 'block_config', 'MadNet_full.json')))
+    ad = OnlineAdaptation(net, mode=mode, train_config=cfg, lr=1e-4, sample_mode='FIXED', fixed_id=module or 0, loss='proxy',
+                          ssim_th=1e9, dilation=2)
+    params = init_params(seed=42)
+    ad.load_weights(params)
+    out = ad.step(lt, rt, proxy=proxy)
+    orc = OracleAdapter(params, mode=mode, lr=1e-4, loss='proxy')
+    ref = orc.step(left, right, module, proxy=proxy)
+    assert abs(out['loss'] - ref['full_loss']) < 2e-5 * max(1.0, abs(ref['full_loss']))
+    if mode == 'MAD':
+        assert abs(out['train_loss'] - ref['train_loss']) < 2e-5 * max(1.0, abs(ref['train_loss']))
+    gviews = net.engine.param_views(net.engine.grads)
+    for n, gr in ref['grads'].items():
+        assert rel_linf(gviews[n].cpu().numpy(), gr) < TOL_GRAD, n
+    w1 = net.engine.export_params()
+    for n in ref['grads']:
+        dw_ref = orc.net.p[n].detach().numpy() - params[n]
+        assert np.abs((w1[n] - params[n]) - dw_ref).max() <= TOL_DW * np.abs(dw_ref).max() + 1e-7, n
+    ad.step(lt, rt, proxy=proxy)                       # step 1 with --dilation 2: inference only, no train op
+    w2 = net.engine.export_params()
+    assert all(np.array_equal(w1[n], w2[n]) for n in w1)
+
+
 def test_mad_golden_gradients():
     g = np.load(GOLDEN)
     left = g['left'].astype(np.float32); right = g['right'].astype(np.float32)
