@@ -124,6 +124,25 @@ int ms_conv2d_transpose_fwd(const float* x, int n, int h, int w, int cin, int x_
                             const float* bias, float* y, int cout, int y_cs, int kh, int kw, int stride,
                             float alpha, float* scratch, void* stream);
 
+/* The same layer and its two gradients on the split-16-bit tcgen05 path (csrc/conv_bf.cu, csrc/wgrad_bf.cu): forward as a
+ * fractionally strided gather in four output-parity launches (fp16 planes of x*act_scale), input gradient as the
+ * stride-`stride` conv of dy with the filter read as HWIO [kh,kw,cout,cin], weight gradient as that conv's wgrad with the
+ * big map in the activation role (both bf16 planes).  dy [n,h*stride,w*stride,cout]; dw [kh,kw,cout,cin]; db [cout] or NULL.
+ * Backward of Nets/sharedLayers.py:80-92 as tf.gradients derives it (Stereo_Online_Adaptation.py:143-151).
+ * scratch: 256-byte aligned, ms_conv2d_transpose_bf_scratch / ms_conv2d_transpose_wgrad_bf_scratch bytes. */
+int ms_conv2d_transpose_fwd_bf(const float* x, int n, int h, int w, int cin, int x_cs, const float* weights, const float* bias,
+                               float* y, int cout, int y_cs, int kh, int kw, int stride, float alpha, float act_scale,
+                               void* scratch, size_t scratch_bytes, void* stream);
+int ms_conv2d_transpose_dgrad_bf(const float* dy, int n, int h, int w, int cout, int dy_cs, const float* weights, float* dx,
+                                 int cin, int dx_cs, int kh, int kw, int stride, void* scratch, size_t scratch_bytes,
+                                 void* stream);
+size_t ms_conv2d_transpose_bf_scratch(int n, int h, int w, int kh, int kw, int cin, int cout, int stride);
+int ms_conv2d_transpose_wgrad_bf(const float* x, int n, int h, int w, int cin, int x_cs, const float* dy, int cout, int dy_cs,
+                                 float* dw, float* db, int kh, int kw, int stride, void* scratch, size_t scratch_bytes,
+                                 void* stream);
+size_t ms_conv2d_transpose_wgrad_bf_scratch(int n, int h, int w, int kh, int kw, int cin, int cout, int stride);
+
+
 /* Replaces tf.image.resize_images (legacy bilinear) + resize_image_with_crop_or_pad + the relu/scale
  * of MadNet._make_disp (Nets/MadNet.py:68-71,274,362-364): dst = post(resize(pre(src)))[centre crop]. */
 int ms_resize_bilinear(const float* src, int src_cs, int B, int ih, int iw, float* dst, int dst_cs, int rh,

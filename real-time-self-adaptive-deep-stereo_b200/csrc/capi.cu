@@ -172,6 +172,74 @@ size_t ms_conv2d_wgrad_bf_scratch(int n, int h, int w, int oh, int ow, int kh, i
     q.x = view(nullptr, n, h, w, cin, cin); q.dy = view(nullptr, n, oh, ow, cout, cout); q.kh = kh; q.kw = kw;
     return wgrad_bf_oneshot_scratch_bytes(q);
 }
+// ---- conv2d_transpose (Nets/sharedLayers.py:80-92) and its two gradients on the split-16-bit tcgen05 path.
+//      weights [kh,kw,cout,cin] (TF layout); x [n,h,w,cin]; y / dy [n,h*stride,w*stride,cout]
+static void transpose_geom(int h, int w, int kh, int kw, int stride, int& oh, int& ow, int& pt, int& pl) {
+    oh = h * stride; ow = w * stride;
+    int t0, t1;
+    same_pad_c(oh, kh, stride, 1, t0, pt);
+    same_pad_c(ow, kw, stride, 1, t1, pl);
+}
+int ms_conv2d_transpose_fwd_bf(const float* x, int n, int h, int w, int cin, int x_cs, const float* weights, const float* bias,
+                               float* y, int cout, int y_cs, int kh, int kw, int stride, float alpha, float act_scale,
+                               void* scratch, size_t scratch_bytes, void* stream) {
+    int oh, ow, pt, pl;
+    transpose_geom(h, w, kh, kw, stride, oh, ow, pt, pl);
+    ConvGemm p{};
+    p.x = view(const_cast<float*>(x), n, h, w, cin, x_cs);
+    p.y = view(y, n, oh, ow, cout, y_cs);
+    p.wmat = weights; p.bias = bias; p.kh = kh; p.kw = kw;
+    p.mul = 1; p.off_y = pt; p.off_x = pl; p.step = -1; p.div = stride;
+    p.alpha = alpha; p.mask = nullptr; p.mask_alpha = 1.f; p.res = nullptr; p.accumulate = 0;
+    if (!conv_bf_supported(p)) { set_error("ms_conv2d_transpose_fwd_bf: shape not supported by the tcgen05 path"); return -3; }
+    return conv_bf_oneshot(p, 1, 1, act_scale, scratch, scratch_bytes, S(stream));     // [tap][M = cout][K = cin], fp16 planes
+}
+int ms_conv2d_transpose_dgrad_bf(const float* dy, int n, int h, int w, int cout, int dy_cs, const float* weights, float* dx,
+                                 int cin, int dx_cs, int kh, int kw, int stride, void* scratch, size_t scratch_bytes,
+                                 void* stream) {
+    int oh, ow, pt, pl;
+    transpose_geom(h, w, kh, kw, stride, oh, ow, pt, pl);
+    ConvGemm p{};
+    p.x = view(const_cast<float*>(dy), n, oh, ow, cout, dy_cs);
+    p.y = view(dx, n, h, w, cin, dx_cs);
+    p.wmat = weights; p.bias = nullptr; p.kh = kh; p.kw = kw;
+    p.mul = stride; p.off_y = -pt; p.off_x = -pl; p.step = 1; p.div = 1;      // = the strided conv of dy with HWIO [.,.,cout,cin]
+    p.alpha = 1.f; p.mask = nullptr; p.mask_alpha = 1.f; p.res = nullptr; p.accumulate = 0;
+    if (!conv_bf_supported(p)) { set_error("ms_conv2d_transpose_dgrad_bf: shape not supported by the tcgen05 path"); return -3; }
+    return conv_bf_oneshot(p, 0, 0, 1.f, scratch, scratch_bytes, S(stream));           // [tap][K = cout][M = cin], bf16 planes
+}
+size_t ms_conv2d_transpose_bf_scratch(int n, int h, int w, int kh, int kw, int cin, int cout, int stride) {
+    ConvGemm a{}, b{};
+    a.x = view(nullptr, n, h, w, cin, cin); a.y = view(nullptr, n, h * stride, w * stride, cout, cout); a.kh = kh; a.kw = kw;
+    b.x = view(nullptr, n, h * stride, w * stride, cout, cout); b.y = view(nullptr, n, h, w, cin, cin); b.kh = kh; b.kw = kw;
+    size_t sa = conv_bf_oneshot_scratch_bytes(a), sb = conv_bf_oneshot_scratch_bytes(b);
+    return sa > sb ? sa : sb;
+}
+static ConvWgrad transpose_wgrad_geom(const float* x, int n, int h, int w, int cin, int x_cs, const float* dy, int cout, int dy_cs,
+                                      int kh, int kw, int stride) {
+    int oh, ow, pt, pl;
+    transpose_geom(h, w, kh, kw, stride, oh, ow, pt, pl);
+    ConvWgrad q{};
+    q.x = view(const_cast<float*>(dy), n, oh, ow, cout, dy_cs);      // the strided conv's input is the big map ...
+    q.dy = view(const_cast<float*>(x), n, h, w, cin, x_cs);          // ... and its "output gradient" the layer's input
+    q.kh = kh; q.kw = kw; q.stride = stride; q.dil = 1; q.pad_t = pt; q.pad_l = pl; q.accumulate = 0;
+    return q;
+}
+size_t ms_conv2d_transpose_wgrad_bf_scratch(int n, int h, int w, int kh, int kw, int cin, int cout, int stride) {
+    ConvWgrad q = transpose_wgrad_geom(nullptr, n, h, w, cin, cin, nullptr, cout, cout, kh, kw, stride);
+    return wgrad_bf_oneshot_scratch_bytes(q);
+}
+int ms_conv2d_transpose_wgrad_bf(const float* x, int n, int h, int w, int cin, int x_cs, const float* dy, int cout, int dy_cs,
+                                 float* dw, float* db, int kh, int kw, int stride, void* scratch, size_t scratch_bytes,
+                                 void* stream) {
+    ConvWgrad q = transpose_wgrad_geom(x, n, h, w, cin, x_cs, dy, cout, dy_cs, kh, kw, stride);
+    q.dw = dw; q.db = nullptr;                                        // dw [kh,kw,cout,cin]
+    if (!wgrad_bf_supported(q)) { set_error("ms_conv2d_transpose_wgrad_bf: shape not supported by the tcgen05 path"); return -3; }
+    if (wgrad_bf_oneshot(q, scratch, scratch_bytes, S(stream))) return -1;
+    if (!db) return 0;
+    // bias gradient = per-channel sum of dy; the partial-sum region of the scratch is free again after the reduction
+    return bias_grad(q.x, db, static_cast<float*>(scratch), scratch_bytes / sizeof(float), S(stream));
+}
 // ---- plane-level entry points of the split-bf16 path: what the engine calls per layer in steady state (operands
 //      already split: activations by the producing epilogue, weights once per update)
 int ms_bf_split(const float* x, int n, int h, int w, int c, int x_cs, void* hi, void* lo, int plane_cs, int fmt, float scale,

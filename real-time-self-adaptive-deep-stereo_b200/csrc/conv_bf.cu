@@ -650,26 +650,6 @@ static int conv_bf_launch(const ConvGemm& g, const ActPlanes& xp, const void* wt
     p.fmt = xp.fmt; p.acc_scale = xp.fmt == 1 ? 1.f / xp.scale : 1.f;
     MS_REQUIRE(xp.fmt == 0 || xp.scale > 0.f, "conv_bf: fp16 planes need a positive scale");
     const uint32_t row_unit = (uint32_t)p.kch * 2u;                 // bytes of one pixel of a patch plane
-    // ---- pixel tile: the largest N in {256,128,64} that still gives ~100 CTAs; 8-pixel rows unless that wastes a tile row
-    const int mblocks = Mpad / 128;
-    static int force_n = -1;
-    if (force_n < 0) { const char* e = getenv("MS_BF_N"); force_n = e ? atoi(e) : 0; }
-    int N = 64, TW = 8;
-    {
-        const int cand_n[3] = {256, 128, 64};
-        for (int ci = 0; ci < 3; ++ci) {
-            const int n = cand_n[ci];
-            int tw = 8;
-            if (n == 256 && (Hj % 32) != 0 && (Hj % 16) == 0) tw = 16;
-            const int th = n / tw;
-            const long tiles = (long)g.y.n * cdiv(Wj, tw) * cdiv(Hj, th) * mblocks;
-            const bool take = force_n ? (n == force_n || ci == 2) : (tiles >= 100 || ci == 2);
-            if (take) { N = n; TW = tw; break; }
-        }
-    }
-    const int TH = N / TW;
-    p.TW = TW; p.tw_shift = TW == 8 ? 3 : 4; p.N = N;
-    p.tiles_x = cdiv(Wj, TW); p.tiles_y = cdiv(Hj, TH);
     // ---- patches: taps of one filter column (same dx; same row parity for an input lattice of stride 2) share a halo
     //      patch; a tap is a row offset into it
     auto posmod = [](int a, int m) { return ((a % m) + m) % m; };
@@ -693,6 +673,46 @@ static int conv_bf_launch(const ConvGemm& g, const ActPlanes& xp, const void* wt
         }
         ++np;
     }
+    // ---- pixel tile TW x TH (N = TW * TH MMA columns, a multiple of 32, 64 <= N <= 256).  One CTA per tile and no
+    //      second wave to hide a ragged tail, so the tile shape decides how many of the 148 SMs work: a 96 x 320 map in
+    //      8 x 32 tiles is 120 CTAs of 256 pixels (81 % of the SMs); in 16 x 14 tiles it is 140 CTAs of 224.
+    //      cost = waves x (N + fixed overhead in pixel units); ties go to the taller tile (smaller halo).
+    const int mblocks = Mpad / 128;
+    static int force_n = -1, tile_search = -1;
+    if (force_n < 0) { const char* e = getenv("MS_BF_N"); force_n = e ? atoi(e) : 0; }
+    if (tile_search < 0) { const char* e = getenv("MS_BF_TILE_SEARCH"); tile_search = (e && e[0] == '0') ? 0 : 1; }
+    int N = 64, TW = 8;
+    if (force_n || !tile_search) {
+        const int cand_n[3] = {256, 128, 64};
+        for (int ci = 0; ci < 3; ++ci) {
+            const int n = cand_n[ci];
+            int tw = 8;
+            if (n == 256 && (Hj % 32) != 0 && (Hj % 16) == 0) tw = 16;
+            const int th = n / tw;
+            const long tiles = (long)g.y.n * cdiv(Wj, tw) * cdiv(Hj, th) * mblocks;
+            const bool take = force_n ? (n == force_n || ci == 2) : (tiles >= 100 || ci == 2);
+            if (take) { N = n; TW = tw; break; }
+        }
+    } else {
+        long best = -1; int best_th = 0;
+        const int tws[3] = {8, 16, 32};
+        for (int wi = 0; wi < 3; ++wi) {
+            const int tw = tws[wi];
+            if (tw * sx > 256) continue;
+            for (int th = 1; th * tw <= 256; ++th) {
+                const int n = th * tw;
+                if (n < 64 || (n & 31)) continue;
+                if ((th + max_off) * sx > 256) continue;
+                const long tiles = (long)g.y.n * cdiv(Wj, tw) * cdiv(Hj, th) * mblocks;
+                // (halo rows are loaded, not multiplied: a quarter weight keeps 32 x 2 tiles for the cases that save a wave)
+                const long cost = cdiv((int)std::min<long>(tiles, 1 << 30), 148) * (long)(n + 32 + max_off * tw / 4);
+                if (best < 0 || cost < best || (cost == best && th > best_th)) { best = cost; best_th = th; N = n; TW = tw; }
+            }
+        }
+    }
+    const int TH = N / TW;
+    p.TW = TW; p.tw_shift = TW == 8 ? 3 : (TW == 16 ? 4 : 5); p.N = N;
+    p.tiles_x = cdiv(Wj, TW); p.tiles_y = cdiv(Hj, TH);
     p.n_patches = np;
     int rows = TH + max_off;
     const size_t wslot = 2 * (size_t)p.wtile_bytes;

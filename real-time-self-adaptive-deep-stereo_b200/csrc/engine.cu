@@ -58,7 +58,8 @@ Engine::Engine()
 
 void Engine::add_planes(Bump& A, const TView& v, int fmt) {
     if (conv_impl != 1) return;
-    if (v.p && planes.count(v.p)) return;          // (sizing pass: every pointer is null -- never dedupe there)
+    const bool sizing = A.base == nullptr;         // (sizing pass: pointers are null or null + a slice offset -- never dedupe)
+    if (!sizing && planes.count(v.p)) return;
     ActPlanes pl;
     pl.fmt = fmt;
     pl.scale = fmt == 1 ? act_scale : 1.f;
@@ -66,7 +67,7 @@ void Engine::add_planes(Bump& A, const TView& v, int fmt) {
     const size_t floats = (v.pixels() * pl.cs + 1) / 2;     // bf16 elements -> floats
     pl.hi = A.alloc(floats);
     pl.lo = A.alloc(floats);
-    if (v.p) planes[v.p] = pl;
+    if (!sizing) planes[v.p] = pl;
 }
 const ActPlanes* Engine::planes_of(const TView& v) const {
     auto it = planes.find(v.p);
@@ -335,7 +336,7 @@ size_t Engine::layout(float* base) {
             if (lg != gidx || (L.cin < 8 && !stem) || L.cout < 8 || L.kh * L.kw > 49 || L.stride > 2) continue;
             if (L.transposed) {
                 // conv2d_transpose forward = fractionally strided gather: M = cout, K = cin, canonical W is already
-                // [tap][cout][cin] = [tap][M][K].  (Its two gradients still run on the fp32 path.)
+                // [tap][cout][cin] = [tap][M][K]
                 int Mpad, Kpad; conv_bf_weight_dims(L.cout, L.cin, Mpad, Kpad);
                 const size_t halfs = conv_bf_weight_halfs(L.kh * L.kw, L.cout, L.cin);
                 BfW t; t.ok = true;
@@ -344,6 +345,16 @@ size_t Engine::layout(float* base) {
                 BfPrepJob j{base ? Wt + L.w_off : nullptr, t.tiles, L.kh * L.kw, L.cout, L.cin, Mpad, Kpad, 0, 1};
                 bf_jobs.push_back(j);
                 bf_max_total = std::max(bf_max_total, halfs);
+                // its input gradient = the stride-2 conv of dY with the same filter read as HWIO [.,.,cout,cin]:
+                // M = cin, K = cout, canonical W = [tap][K][M]; bf16 (gradient planes)
+                conv_bf_weight_dims(L.cin, L.cout, Mpad, Kpad);
+                const size_t halfs_d = conv_bf_weight_halfs(L.kh * L.kw, L.cin, L.cout);
+                BfW td; td.ok = true;
+                td.tiles = alloc((halfs_d + 1) / 2);
+                bfw[1][li] = td;
+                BfPrepJob jd{base ? Wt + L.w_off : nullptr, td.tiles, L.kh * L.kw, L.cin, L.cout, Mpad, Kpad, 1, 0};
+                bf_jobs.push_back(jd);
+                bf_max_total = std::max(bf_max_total, halfs_d);
                 continue;
             }
             for (int dir = 0; dir < 2; ++dir) {

@@ -58,6 +58,12 @@ void Engine::layout_dispnet(Bump& A, size_t& max_wg, size_t& max_wt) {
             max_wg = std::max(max_wg, std::min<size_t>(wgrad_bf_workspace_floats(L.kh, L.kw, L.cin, L.cout), (size_t)48 << 20));
             wg_xp_halfs = std::max(wg_xp_halfs, pixels * L.stride * L.stride * (size_t)((L.cin + 7) / 8 * 8));
         }
+        if (conv_impl == 1 && L.transposed && L.cin >= 16 && L.cout >= 8) {
+            // conv2d_transpose: its weight gradient is the wgrad of the stride-2 conv big map (cout) -> small map (cin);
+            // `pixels` counts the big map, the bf16 scratch copy is of the small one (the layer's forward input)
+            max_wg = std::max(max_wg, std::min<size_t>(wgrad_bf_workspace_floats(L.kh, L.kw, L.cout, L.cin), (size_t)48 << 20));
+            wg_xp_halfs = std::max(wg_xp_halfs, pixels / (L.stride * L.stride) * (size_t)((L.cin + 7) / 8 * 8));
+        }
         if (L.stride == 1 && !L.transposed && L.cout <= 192)
             max_wg = std::max(max_wg, pixels * L.cout + 64 * (size_t)L.kh * L.kw * L.cin * L.cout + 128 * (size_t)L.cout + 8192);
     };
@@ -91,6 +97,8 @@ void Engine::layout_dispnet(Bump& A, size_t& max_wg, size_t& max_wt) {
         d_cat[u] = A.tens(B, 2 * bh, 2 * bw, ct, pad4i(ct)); gd_cat[u] = A.tens(B, 2 * bh, 2 * bw, ct, pad4i(ct));
         d_cc[u] = A.tens(B, 2 * bh, 2 * bw, S.cout); gd_cc[u] = A.tens(B, 2 * bh, 2 * bw, S.cout);
         add_planes(A, d_cat[u], 1); add_planes(A, d_cc[u], 1); add_planes(A, gd_cc[u], 0);
+        // compact bf16 planes of the deconv output's gradient (a channel slice of gd_cat[u], keyed by the slice pointer)
+        add_planes(A, slice(gd_cat[u], S.skip, S.cout), 0);
         for (int j = 0; j < 4; ++j) track(layers[up_layer(u, j)], (size_t)B * 4 * bh * bw);
         std::string n(S.name);
         tensors[n + "/predict"] = d_pr[u];
@@ -162,13 +170,25 @@ int Engine::deconv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, co
     const int pt = total / 2;
     total = std::max((x.w - 1) * L.stride + L.kw - dpre.w, 0);
     const int pl = total / 2;
+    const int li = (int)(&L - &layers[0]);
+    const ActPlanes* dpl = conv_impl == 1 ? planes_of(dpre) : nullptr;       // bf16 planes of the big map's gradient
+    if (dpl) { fresh.erase(dpre.p); if (ensure_planes(dpre, st)) return -1; }
     {
         ConvWgrad q{};
         q.x = dpre; q.dy = x; q.dw = Gr + L.w_off; q.db = nullptr;
         q.kh = L.kh; q.kw = L.kw; q.stride = L.stride; q.dil = 1; q.pad_t = pt; q.pad_l = pl;
         q.workspace = wg_ws; q.workspace_floats = wg_ws_floats; q.accumulate = 0;
-        prof_begin(CAT_CONV_WGRAD, st);
-        int rc = conv_wgrad(q, st);
+        prof_begin(CAT_CONV_WGRAD, st, li);
+        int rc;
+        if (dpl && use_bf_wgrad && wg_xp.hi && wgrad_bf_supported(q)) {
+            // tcgen05: "x" = dY planes, "dy" = a bf16 re-split of the layer's forward input (kind::f16 rejects f16 x bf16)
+            ActPlanes xb = wg_xp; xb.cs = (x.c + 7) / 8 * 8;
+            MS_REQUIRE(x.pixels() * (size_t)xb.cs <= wg_xp_halfs, "deconv_bwd: wgrad scratch planes too small");
+            rc = split_planes(x, xb, st);
+            if (!rc) rc = wgrad_bf(q, *dpl, xb, st);
+        } else {
+            rc = conv_wgrad(q, st);
+        }
         if (!rc) rc = bias_grad(dpre, Gr + L.b_off, wg_ws, wg_ws_floats, st);
         prof_end(st);
         prof_note((double)x.pixels() * L.kh * L.kw * L.cin * L.cout, 0);
@@ -180,8 +200,14 @@ int Engine::deconv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, co
         p.mul = L.stride; p.off_y = -pt; p.off_x = -pl; p.step = 1; p.div = 1;
         p.alpha = 1.f; p.mask = nullptr; p.mask_alpha = 1.f; p.res = nullptr; p.accumulate = dx_acc;
         p.part = tc_part; p.part_floats = conv_tc_part_floats();
-        prof_begin(CAT_CONV_DGRAD, st);
-        int rc = conv_gemm(p, st);
+        prof_begin(CAT_CONV_DGRAD, st, li);
+        int rc;
+        if (dpl && bfw[1][li].ok && conv_bf_supported(p)) {
+            fresh.erase(dx->p);                         // (accumulating launches leave dx's own planes stale)
+            rc = conv_bf(p, *dpl, bfw[1][li].tiles, nullptr, bf_part, bf_tickets, st);
+        } else {
+            rc = conv_gemm(p, st);
+        }
         prof_end(st);
         prof_note((double)x.pixels() * L.kh * L.kw * L.cin * L.cout, 0);
         if (rc) return -1;

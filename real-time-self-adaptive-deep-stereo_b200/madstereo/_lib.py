@@ -48,6 +48,11 @@ _SIGS = {
     'ms_conv2d_wgrad_workspace': (Z, [I, I, I, I, Z]),
     'ms_conv2d_wgrad': (I, [P, I, I, I, I, I, P, I, I, I, I, P, P, I, I, I, I, P, Z, P]),
     'ms_conv2d_transpose_fwd': (I, [P, I, I, I, I, I, P, P, P, I, I, I, I, I, F, P, P]),
+    'ms_conv2d_transpose_fwd_bf': (I, [P, I, I, I, I, I, P, P, P, I, I, I, I, I, F, F, P, Z, P]),
+    'ms_conv2d_transpose_dgrad_bf': (I, [P, I, I, I, I, I, P, P, I, I, I, I, I, P, Z, P]),
+    'ms_conv2d_transpose_bf_scratch': (Z, [I, I, I, I, I, I, I, I]),
+    'ms_conv2d_transpose_wgrad_bf': (I, [P, I, I, I, I, I, P, I, I, P, P, I, I, I, P, Z, P]),
+    'ms_conv2d_transpose_wgrad_bf_scratch': (Z, [I, I, I, I, I, I, I, I]),
     'ms_resize_bilinear': (I, [P, I, I, I, I, P, I, I, I, I, I, F, I, F, I, P]),
     'ms_resize_bilinear_bwd': (I, [P, I, P, I, I, I, I, P, I, I, I, I, I, F, I, F, I, I, P, P]),
     'ms_reproj_loss_workspace': (Z, [I, I, I]),

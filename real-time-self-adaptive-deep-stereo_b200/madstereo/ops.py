@@ -153,6 +153,49 @@ def conv2d_wgrad_bf(x, dy, kh, kw, stride=1, dilation=1):
     return dw, db
 
 
+def _scratch256(nbytes, device):
+    buf = torch.empty(nbytes + 256, device=device, dtype=torch.uint8)
+    return buf, c_void_p(buf.data_ptr() + (-buf.data_ptr()) % 256)
+
+
+def conv2d_transpose_bf(x, w, b, stride=2, alpha=1.0, act_scale=0.0625):
+    """sharedLayers.conv2d_transpose on the tcgen05 path (fp16 hi/lo planes). w [kh,kw,cout,cin]."""
+    n, h, wd, cin = x.shape
+    kh, kw, cout, _ = w.shape
+    y = torch.empty(n, h * stride, wd * stride, cout, device=x.device, dtype=torch.float32)
+    ns = lib().ms_conv2d_transpose_bf_scratch(n, h, wd, kh, kw, cin, cout, stride)
+    keep, sp = _scratch256(ns, x.device)
+    check(lib().ms_conv2d_transpose_fwd_bf(_p(x), n, h, wd, cin, cin, _p(w), _p(b), _p(y), cout, cout, kh, kw, stride,
+                                           float(alpha), float(act_scale), sp, ns, _s()), 'ms_conv2d_transpose_fwd_bf')
+    return y
+
+
+def conv2d_transpose_dgrad_bf(dy, w, stride=2):
+    """d(conv2d_transpose)/dx on the tcgen05 path (bf16 hi/lo planes). dy [n,h*s,w*s,cout], w [kh,kw,cout,cin]."""
+    n, oh, ow, cout = dy.shape
+    kh, kw, _, cin = w.shape
+    h, wd = oh // stride, ow // stride
+    dx = torch.empty(n, h, wd, cin, device=dy.device, dtype=torch.float32)
+    ns = lib().ms_conv2d_transpose_bf_scratch(n, h, wd, kh, kw, cin, cout, stride)
+    keep, sp = _scratch256(ns, dy.device)
+    check(lib().ms_conv2d_transpose_dgrad_bf(_p(dy), n, h, wd, cout, cout, _p(w), _p(dx), cin, cin, kh, kw, stride, sp, ns,
+                                             _s()), 'ms_conv2d_transpose_dgrad_bf')
+    return dx
+
+
+def conv2d_transpose_wgrad_bf(x, dy, kh, kw, stride=2):
+    """d(conv2d_transpose)/dW [kh,kw,cout,cin] and /db [cout] on the tcgen05 path (bf16 hi/lo planes)."""
+    n, h, wd, cin = x.shape
+    cout = dy.shape[3]
+    dw = torch.empty(kh, kw, cout, cin, device=x.device, dtype=torch.float32)
+    db = torch.empty(cout, device=x.device, dtype=torch.float32)
+    ns = lib().ms_conv2d_transpose_wgrad_bf_scratch(n, h, wd, kh, kw, cin, cout, stride)
+    keep, sp = _scratch256(ns, x.device)
+    check(lib().ms_conv2d_transpose_wgrad_bf(_p(x), n, h, wd, cin, cin, _p(dy), cout, cout, _p(dw), _p(db), kh, kw, stride,
+                                             sp, ns, _s()), 'ms_conv2d_transpose_wgrad_bf')
+    return dw, db
+
+
 def conv2d_dgrad(dy, w, in_hw, stride=1, dilation=1):
     n, oh, ow, cout = dy.shape
     kh, kw, cin, _ = w.shape

@@ -145,3 +145,63 @@ def test_conv_bf_forward_activation_range(mag, scale):
     assert np.isfinite(out.cpu().numpy()).all()
     good_range = 6e-5 * 64 < mag * scale < 6e4 / 8
     assert err < (TOL_FWD if good_range else 5e-3), (mag, scale, err)
+
+
+# conv2d_transpose (DispNet's 4x4 stride-2 up-convolutions, Nets/DispNet.py:45-57) and its two gradients on the tcgen05 path.
+# The gradients are checked against autograd THROUGH the oracle's conv2d_transpose (tf.gradients of the same op).
+TCASES = [
+    # n, h, w, cin, cout
+    (1, 6, 20, 1024, 512),        # up5/deconv at 1280x384 (8 output-channel blocks in the input gradient)
+    (1, 12, 40, 512, 256),        # up4/deconv
+    (1, 48, 160, 128, 64),        # up2/deconv
+    (1, 96, 320, 64, 32),         # up1/deconv
+    (2, 10, 12, 64, 32),          # ragged tiles, batch 2
+    (1, 7, 9, 96, 48),            # odd sizes
+]
+
+
+def _transpose_case(case):
+    from oracle import tf1_ops as T
+    n, h, w, cin, cout = case
+    rng = np.random.default_rng(sum(case))
+    x = rng.standard_normal((n, h, w, cin)).astype(np.float32)
+    wt = (rng.standard_normal((4, 4, cout, cin)) / np.sqrt(4.0 * cin)).astype(np.float32)
+    b = rng.uniform(-0.1, 0.1, cout).astype(np.float32)
+    g = rng.standard_normal((n, 2 * h, 2 * w, cout)).astype(np.float32)
+    xt, wtt, bt = (torch.tensor(v, requires_grad=True) for v in (x, wt, b))
+    pre = T.conv2d_transpose(xt, wtt, bt, 2, None)
+    gx, gw, gb = torch.autograd.grad(pre, [xt, wtt, bt], grad_outputs=torch.tensor(g))
+    return x, wt, b, g, pre.detach().numpy(), gx.numpy(), gw.numpy(), gb.numpy()
+
+
+@pytest.mark.parametrize('case', TCASES)
+def test_conv_transpose_bf_forward(case):
+    from madstereo import ops
+    x, wt, b, g, ref, _, _, _ = _transpose_case(case)
+    out = ops.conv2d_transpose_bf(cu(x), cu(wt), cu(b), 2, 1.0)
+    torch.cuda.synchronize()
+    err = rel_linf(out.cpu().numpy(), ref)
+    _log({'op': 'transpose_fwd', 'case': list(case), 'rel_linf': err})
+    assert err < TOL_FWD
+
+
+@pytest.mark.parametrize('case', TCASES)
+def test_conv_transpose_bf_dgrad(case):
+    from madstereo import ops
+    x, wt, b, g, _, gx, _, _ = _transpose_case(case)
+    dx = ops.conv2d_transpose_dgrad_bf(cu(g), cu(wt), 2)
+    torch.cuda.synchronize()
+    err = rel_linf(dx.cpu().numpy(), gx)
+    _log({'op': 'transpose_dgrad', 'case': list(case), 'rel_linf': err})
+    assert err < TOL
+
+
+@pytest.mark.parametrize('case', TCASES)
+def test_conv_transpose_bf_wgrad(case):
+    from madstereo import ops
+    x, wt, b, g, _, _, gw, gb = _transpose_case(case)
+    dw, db = ops.conv2d_transpose_wgrad_bf(cu(x), cu(g), 4, 4, 2)
+    torch.cuda.synchronize()
+    e_w = rel_linf(dw.cpu().numpy(), gw); e_b = rel_linf(db.cpu().numpy(), gb)
+    _log({'op': 'transpose_wgrad', 'case': list(case), 'rel_linf': e_w, 'rel_linf_bias': e_b})
+    assert e_w < TOL and e_b < 5e-5
