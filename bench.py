@@ -174,10 +174,13 @@ def corr_large_shapes(dev):
     b, h, w, c, d = 1, 96, 320, 128, 40
     nd = 2 * d + 1
     x = torch.randn(b, h, w, c, device=dev); y = torch.randn(b, h, w, c, device=dev); o = torch.empty(b, h, w, nd, device=dev)
-    us = timeit(lambda: check(lib().ms_corr_fwd(P(x), c, P(y), c, P(None), 1, P(o), nd, b, h, w, c, d, 1, 0, 0, st), 'corr_fwd'))
+    us_cc = timeit(lambda: check(lib().ms_corr_fwd(P(x), c, P(y), c, P(None), 1, P(o), nd, b, h, w, c, d, 1, 0, 0, st), 'corr_fwd'))
+    us = timeit(lambda: check(lib().ms_corr_fwd_wide(P(x), c, P(y), c, P(o), nd, b, h, w, c, d, 64.0, st), 'corr_fwd_wide'))
     byts = b * h * w * (2 * c + nd) * 4
     out['dispnet_1280x384'] = {'us': us, 'bytes': byts, 'gbs': byts / us / 1e3, 'flops': 2.0 * b * h * w * c * nd,
-                               'note': 'compute-shaped (15 FLOP/B): HBM-equivalent figure'}
+                               'cuda_core_kernel_us': us_cc,
+                               'note': 'what the DispNet engine launches: the band of L R^T on mma.sync tiles (fp16 hi/lo, 3 MMAs per '
+                                       'product, csrc/corr_mma.cu); 15 FLOP/B, HBM-equivalent figure'}
     return out
 
 

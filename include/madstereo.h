@@ -33,6 +33,14 @@ int ms_corr_fwd(const float* left, int left_cs, const float* right, int right_cs
                 float* out, int out_cs, int B, int h, int w, int C, int max_disp, int stride, int copy_left,
                 int u_chan, void* stream);
 
+/* Wide-window variant for DispNet-C (Nets/DispNet.py:92-101 -> Nets/sharedLayers.py:23-51 with max_disp = 40): the band
+ * |x' - x| <= max_disp of L R^T per image row on mma.sync tensor-core tiles, fp16 hi/lo operands split on the fly
+ * (x * act_scale = hi + lo, three MMAs per product, fp32 accumulation).  out channels [0, 2*max_disp+1) of a buffer with
+ * channel stride out_cs.  act_scale: power of two with |feature * act_scale| < 65504 (the engine passes its activation
+ * scale).  csrc/corr_mma.cu. */
+int ms_corr_fwd_wide(const float* left, int left_cs, const float* right, int right_cs, float* out, int out_cs, int B, int h,
+                     int w, int C, int max_disp, float act_scale, void* stream);
+
 /* Replaces ShiftCorrGradKernelLauncher (Nets/Native/shift_corr.cu.cc:235-289) / TF op "ShiftCorrGrad"
  * (Nets/Native/shift_corr.cc:11-17,62-93) with the mathematical gradient of correlation_tf (the native
  * backward is defective: wrong input wiring shift_corr.cc:76, CHW/NHWC mix-up and out-of-bounds writes

@@ -40,6 +40,17 @@ int ms_corr_fwd(const float* left, int left_cs, const float* right, int right_cs
     return corr_fwd(p, S(stream));
 }
 
+int ms_corr_fwd_wide(const float* left, int left_cs, const float* right, int right_cs, float* out, int out_cs, int B, int h,
+                     int w, int C, int max_disp, float act_scale, void* stream) {
+    CorrFwd p{};
+    p.left = left; p.lcs = left_cs; p.right = right; p.rcs = right_cs; p.u = nullptr; p.ucs = 0;
+    p.out = out; p.ocs = out_cs; p.out2 = nullptr; p.o2cs = 0;
+    p.B = B; p.h = h; p.w = w; p.C = C; p.max_disp = max_disp; p.stride = 1; p.copy_left = 0; p.u_chan = 0;
+    p.plane_scale = act_scale;
+    if (!corr_mma_supported(p)) { set_error("ms_corr_fwd_wide: needs >= 17 displacements (max_disp 8..40), C % 16 == 0, 16-byte aligned rows, act_scale > 0"); return -3; }
+    return corr_mma(p, S(stream));
+}
+
 int ms_corr_bwd(const float* left, int left_cs, const float* right, int right_cs, const float* u, int u_cs,
                 const float* dcost, int dcost_cs, float* dleft, int dleft_cs, float* dright, int dright_cs,
                 float* du, int du_cs, int B, int h, int w, int C, int max_disp, int stride, int add_left_slice,

@@ -125,8 +125,12 @@ struct CorrFwd {
     float* out2; int o2cs;           // optional 2nd destination for the left copy (context input)
     int B, h, w, C, max_disp, stride, copy_left;
     int u_chan;                      // 1 if the concat buffer keeps a `u` channel right after the corr channels
+    float plane_scale;               // > 0: power-of-two scale s with |feature * s| < 65504 -- enables the fp16 hi/lo banded
+                                     // tensor-core kernel for wide windows (corr_mma.cu); 0: CUDA-core kernels only
 };
 int corr_fwd(const CorrFwd& p, cudaStream_t st);
+bool corr_mma_supported(const CorrFwd& p);          // corr_mma.cu: wide window (>= 17 displacements), no warp, stride 1
+int corr_mma(const CorrFwd& p, cudaStream_t st);
 int corr_fwd4(const CorrFwd& p, cudaStream_t st);   // corr_tma.cu: 0 launched, 1 shape not handled, -1 error
 
 struct CorrBwd {
@@ -141,6 +145,8 @@ struct CorrBwd {
     int gcoff;                       // channel offset of the corr grads inside dcost (-1 => C, the concat layout)
 };
 int corr_bwd(const CorrBwd& p, cudaStream_t st);
+bool corr_mma_bwd_supported(const CorrBwd& p);       // corr_mma.cu: wide window, no warp, stride 1, C in {32, 64, 96, 128}
+int corr_mma_bwd(const CorrBwd& p, cudaStream_t st);
 
 // elementwise / resampling (elementwise.cu)
 int pad_reflect(const float* src, int B, int H, int W, int C, float* dst, int Hp, int Wp, int dcs,

@@ -464,6 +464,7 @@ int corr_fwd(const CorrFwd& p, cudaStream_t st) {
     if (corr_init()) return -1;
     static int ver = -1;
     if (ver < 0) { const char* e = getenv("MS_CORR_V"); ver = e ? atoi(e) : 4; }
+    if (ver >= 4 && corr_mma_supported(p)) return corr_mma(p, st);      // DispNet: 81 displacements as a banded tensor-core product
     if (ver >= 4) {                                     // MADNet cost volume (d=2, C%32==0): tensor-map TMA kernel, corr_tma.cu
         const int r = corr_fwd4(p, st);
         if (r <= 0) return r;
@@ -668,6 +669,11 @@ int corr_bwd(const CorrBwd& p, cudaStream_t st) {
                "corr_bwd: C and strides must be multiples of 4");
     MS_REQUIRE(a16(p.left) && a16(p.right) && a16(p.dleft) && a16(p.dright), "corr_bwd: pointers must be 16B aligned");
     MS_REQUIRE(!p.add_left_slice || (p.dcs % 4 == 0 && a16(p.dcost)), "corr_bwd: dcost slice alignment");
+    {
+        static int ver = -1;
+        if (ver < 0) { const char* e = getenv("MS_CORR_V"); ver = e ? atoi(e) : 4; }
+        if (ver >= 4 && corr_mma_bwd_supported(p)) return corr_mma_bwd(p, st);     // DispNet: banded tensor-core products
+    }
     const bool warped = p.u != nullptr;
     const int nd = (2 * p.max_disp) / p.stride + 1;
     const size_t budget = 220 * 1024;

@@ -124,6 +124,7 @@ int Engine::forward_dispnet(int disp_mask, cudaStream_t st) {
         cf.left = c2a.p; cf.lcs = c2a.cs; cf.right = c2b.p; cf.rcs = c2b.cs; cf.u = nullptr; cf.ucs = 0;
         cf.out = d_cat3.p; cf.ocs = d_cat3.cs; cf.out2 = nullptr; cf.o2cs = 0;
         cf.B = B; cf.h = d_c2.h; cf.w = d_c2.w; cf.C = 128; cf.max_disp = DN_MAXD; cf.stride = 1; cf.copy_left = 0; cf.u_chan = 0;
+        cf.plane_scale = conv_impl == 1 ? act_scale : 0.f;   // same fp16 hi/lo arithmetic as the forward convs
         prof_begin(CAT_CORR_FWD, st);
         int rc = corr_fwd(cf, st);
         prof_end(st);

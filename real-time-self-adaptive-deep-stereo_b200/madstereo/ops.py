@@ -40,6 +40,19 @@ def correlation(x, y, max_disp, stride=1, u=None):
     return out
 
 
+def correlation_wide(x, y, max_disp, act_scale=64.0, out=None):
+    """sharedLayers.correlation for wide windows (DispNet: max_disp = 40) on the banded tensor-core kernel
+    (csrc/corr_mma.cu): fp16 hi/lo operands of x * act_scale, fp32 accumulation."""
+    _chk(x, 'x'); _chk(y, 'y')
+    b, h, w, c = x.shape
+    nd = 2 * max_disp + 1
+    if out is None:
+        out = torch.empty(b, h, w, nd, device=x.device, dtype=torch.float32)
+    check(lib().ms_corr_fwd_wide(_p(x), c, _p(y), c, _p(out), out.shape[-1], b, h, w, c, max_disp, float(act_scale), _s()),
+          'ms_corr_fwd_wide')
+    return out
+
+
 def correlation_into(x, y, max_disp, out, stride=1):
     """correlation() into a pre-allocated [b,h,w,nd] tensor (no allocation inside a timed region)."""
     b, h, w, c = x.shape

@@ -20,6 +20,9 @@ SHAPES = [  # n, h, w, cin, cout, k, stride, dil
     (1, 96, 320, 38, 128, 3, 1, 1), (1, 96, 320, 64, 32, 3, 1, 1), (1, 48, 160, 128, 128, 3, 1, 1), (1, 24, 80, 128, 128, 3, 1, 1),
     (1, 6, 20, 197, 128, 3, 1, 1), (2, 96, 320, 32, 32, 3, 1, 1), (2, 192, 640, 16, 32, 3, 2, 1), (2, 48, 160, 64, 96, 3, 2, 1),
     (1, 96, 320, 128, 256, 5, 2, 1), (1, 24, 80, 256, 512, 3, 2, 1), (1, 12, 40, 512, 512, 3, 1, 1),
+    # 15..: DispNet conv2 (5x5 stride 2) and a stride-1 problem of the same output size; DispNet stem; stride-2 3x3 pair
+    (2, 192, 640, 64, 128, 5, 2, 1), (2, 96, 320, 64, 128, 5, 1, 1), (2, 384, 1280, 3, 64, 7, 2, 1),
+    (2, 192, 640, 64, 128, 3, 2, 1), (2, 96, 320, 64, 128, 3, 1, 1),
 ]
 
 

@@ -81,6 +81,52 @@ def test_cost_volume_concat(ops, shape):
     assert rel_linf(plain.cpu().numpy(), ref.numpy()[..., c:c + 5]) < 2e-5
 
 
+WIDE_SHAPES = [(1, 12, 40, 128, 40), (1, 5, 100, 64, 40), (2, 7, 70, 48, 20), (1, 3, 64, 16, 8), (1, 96, 320, 128, 40)]
+
+
+@pytest.mark.parametrize('shape', WIDE_SHAPES)
+def test_correlation_wide_window(ops, shape):
+    """DispNet's 81-displacement correlation on the banded tensor-core kernel (csrc/corr_mma.cu) vs the oracle; also through
+    the generic entry point (same numbers as the CUDA-core kernel within the same tolerance)."""
+    T = _oracle()
+    b, h, w, c, d = shape
+    rng = np.random.default_rng(sum(shape))
+    x = (rng.standard_normal((b, h, w, c)) * 3.0).astype(np.float32)
+    y = (rng.standard_normal((b, h, w, c)) * 3.0).astype(np.float32)
+    ref = T.correlation(torch.tensor(x), torch.tensor(y), d, 1).numpy()
+    out = ops.correlation_wide(cu(x), cu(y), d, act_scale=64.0)
+    torch.cuda.synchronize()
+    assert out.shape == ref.shape
+    assert rel_linf(out.cpu().numpy(), ref) < 2e-5
+    plain = ops.correlation(cu(x), cu(y), d, 1)
+    assert rel_linf(plain.cpu().numpy(), ref) < 2e-5
+    # into a wider buffer (the engine writes channels [0, 81) of a 148-channel concat buffer): neighbours untouched
+    buf = torch.full((b, h, w, 2 * d + 1 + 7), 7.0, device='cuda')
+    ops.correlation_wide(cu(x), cu(y), d, act_scale=64.0, out=buf)
+    torch.cuda.synchronize()
+    assert rel_linf(buf[..., :2 * d + 1].cpu().numpy(), ref) < 2e-5
+    assert bool((buf[..., 2 * d + 1:] == 7.0).all())
+
+
+@pytest.mark.parametrize('shape', [(1, 12, 40, 128, 40), (1, 5, 100, 64, 40), (2, 7, 70, 32, 20), (1, 24, 320, 128, 40)])
+def test_correlation_wide_window_bwd(ops, shape):
+    """Gradients of the 81-displacement correlation: two banded products on mma.sync tiles with bf16 hi/lo operands
+    (csrc/corr_mma.cu) -- the arithmetic class of the convolution gradients, tolerance 1e-4 relative L-inf."""
+    T = _oracle()
+    b, h, w, c, d = shape
+    rng = np.random.default_rng(sum(shape) + 1)
+    x = rng.standard_normal((b, h, w, c)).astype(np.float32)
+    y = rng.standard_normal((b, h, w, c)).astype(np.float32)
+    xt = torch.tensor(x, requires_grad=True); yt = torch.tensor(y, requires_grad=True)
+    ref = T.correlation(xt, yt, d, 1)
+    g = (rng.standard_normal(ref.shape) * 1e-3).astype(np.float32)          # gradient-sized values: no fixed scale to rely on
+    gx, gy = torch.autograd.grad(ref, [xt, yt], grad_outputs=torch.tensor(g))
+    dx, dy, _ = ops.correlation_bwd(cu(x), cu(y), cu(g), d, 1)
+    torch.cuda.synchronize()
+    assert rel_linf(dx.cpu().numpy(), gx.numpy()) < 1e-4
+    assert rel_linf(dy.cpu().numpy(), gy.numpy()) < 1e-4
+
+
 def test_correlation_matches_reference_native_kernel(ops):
     """The reference's own CorrelateData kernel (compiled unmodified into oracle/_ref) on padded inputs."""
     path = os.path.join(ROOT, 'oracle', '_ref', 'libref_shift_corr.so')
@@ -140,7 +186,10 @@ def test_correlation_speed_vs_reference_native_kernel(ops):
         # the reference launches on the legacy default stream: make torch's stream the default one for its timing
         with torch.cuda.stream(torch.cuda.default_stream()):
             t_ref = timeit(lambda: ref.ref_shift_corr(xp.data_ptr(), yp.data_ptr(), d, b, h, w + 2 * d, c, out_nchw.data_ptr()))
-        t_mine = timeit(lambda: ops.correlation_into(x, y, d, mine))
+        if d >= 8:      # DispNet: the banded tensor-core kernel the engine runs (fp16 hi/lo, activation scale 64)
+            t_mine = timeit(lambda: ops.correlation_wide(x, y, d, 64.0, out=mine))
+        else:
+            t_mine = timeit(lambda: ops.correlation_into(x, y, d, mine))
         assert rel_linf(mine.cpu().numpy(), out_nchw.permute(0, 2, 3, 1).cpu().numpy()) < 2e-5
         byts = b * h * w * (2 * c + 2 * d + 1) * 4
         rows[name] = {'reference_us': t_ref, 'ours_us': t_mine, 'speedup': t_ref / t_mine, 'bytes': byts,
