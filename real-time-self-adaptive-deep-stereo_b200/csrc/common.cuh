@@ -103,6 +103,10 @@ struct ConvWgrad {
     int accumulate;       // dw += (shared weights called twice); normally 0
 };
 int conv_wgrad(const ConvWgrad& p, cudaStream_t st);
+// conv_head.cu: weight gradient of a single-output-channel conv (disparity heads, DispNet up_predict)
+bool conv_head_wgrad_supported(const ConvWgrad& q);
+size_t conv_head_wgrad_workspace_floats(const ConvWgrad& q);
+int conv_head_wgrad(const ConvWgrad& q, cudaStream_t st);
 size_t conv_wgrad_workspace_floats(int taps, int ci, int co, size_t pixels);
 
 // conv_small.cu: direct kernels for the full-resolution 3->16 / 16->16 pyramid layers

@@ -483,6 +483,7 @@ size_t conv_wgrad_workspace_floats(int taps, int ci, int co, size_t P) {
     int tiles = taps * cdiv(ci, 16 * tm) * cdiv(co, 16 * tn);
     size_t main_part = (size_t)wgrad_split(tiles, P) * taps * ci * co;
     if (conv_small_wgrad_shape(taps, ci, co)) main_part = std::max(main_part, conv_small_wgrad_workspace_floats(taps, ci, co, P));
+    if (co == 1) main_part = std::max(main_part, (size_t)2 * 148 * ((size_t)taps * ci + 1));      // conv_head_wgrad partials
     return main_part + (size_t)bias_blocks(P) * co + 64;
 }
 
@@ -492,6 +493,11 @@ int conv_wgrad(const ConvWgrad& p, cudaStream_t st) {
     MS_REQUIRE(Pz < (1u << 30), "conv_wgrad: too many pixels");
     const int P = (int)Pz;
     const int taps = p.kh * p.kw, ci = p.x.c, co = p.dy.c;
+    {   // single output channel (disparity heads): dedicated reduction kernel, conv_head.cu
+        static int heads = -1;
+        if (heads < 0) { const char* e = getenv("MS_HEADS"); heads = (e && e[0] == '0') ? 0 : 1; }
+        if (heads && conv_head_wgrad_supported(p) && p.workspace_floats >= conv_head_wgrad_workspace_floats(p)) return conv_head_wgrad(p, st);
+    }
     int tm, tn; wgrad_tiles(ci, co, tm, tn);
     const int mtiles = cdiv(ci, 16 * tm), ntiles = cdiv(co, 16 * tn);
     const size_t wn = (size_t)taps * ci * co;

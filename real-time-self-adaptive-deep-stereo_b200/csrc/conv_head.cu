@@ -140,6 +140,126 @@ int conv_one_channel(const ConvGemm& g, cudaStream_t st) {
     return check_launch("conv_one_channel");
 }
 
+// weight (+ bias) gradient of a conv with ONE output channel: dw[tap][c] = sum_p x[p * stride - pad + tap * dil][c] * dy[p].
+// (DispNet `prediction` 32 -> 1 at 192 x 640, `predict` heads, the 1 -> 1 `up_predict` transposed convs with the big map
+// in the x role; MADNet `disp-6` / `context-7`.)  288 ... 16 k outputs reduced over up to 123 k pixels: the generic fp32
+// wgrad GEMM pads co = 1 to a 16-wide tile (156 us for `prediction`); here G lanes share a pixel (4 channels each), every
+// thread keeps its K x K x 4 partial sums in registers over a grid-stride pixel loop, and the CTA folds them in a fixed
+// order (deterministic) into one partial vector.
+template <int K>
+__global__ void __launch_bounds__(256)
+conv_head_wgrad_kernel(ConvWgrad q, int gshift, size_t npix, float* __restrict__ part, int vec) {
+    pdl_prologue();
+    extern __shared__ float hw_s[];                      // [256 / G pixel slots][K*K][G*4]  +  [256] bias partials
+    constexpr int TAPS = K * K;
+    const int G = 1 << gshift, PP = 256 >> gshift;
+    const int C = q.x.c;
+    const int cg = threadIdx.x & (G - 1), ps = threadIdx.x >> gshift;
+    const int c = cg * 4;
+    const int nvalid = max(0, min(4, C - c));
+    float acc[TAPS][4];
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
+    float bsum = 0.f;
+    const int W = q.dy.w, H = q.dy.h;
+    for (size_t pix = (size_t)blockIdx.x * PP + ps; pix < npix; pix += (size_t)gridDim.x * PP) {
+        const int ox = (int)(pix % W);
+        const size_t t0 = pix / W;
+        const int oy = (int)(t0 % H);
+        const size_t img = t0 / H;
+        const float d = __ldg(q.dy.p + pix * q.dy.cs);
+        if (cg == 0) bsum += d;
+        if (nvalid == 0) continue;
+#pragma unroll
+        for (int r = 0; r < K; ++r) {
+            const int iy = oy * q.stride - q.pad_t + r * q.dil;
+            if (iy < 0 || iy >= q.x.h) continue;
+#pragma unroll
+            for (int s = 0; s < K; ++s) {
+                const int ix = ox * q.stride - q.pad_l + s * q.dil;
+                if (ix < 0 || ix >= q.x.w) continue;
+                const float* xp = q.x.p + ((img * q.x.h + iy) * q.x.w + ix) * q.x.cs + c;
+                if (vec) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(xp));
+                    acc[r * K + s][0] = fmaf(v.x, d, acc[r * K + s][0]); acc[r * K + s][1] = fmaf(v.y, d, acc[r * K + s][1]);
+                    acc[r * K + s][2] = fmaf(v.z, d, acc[r * K + s][2]); acc[r * K + s][3] = fmaf(v.w, d, acc[r * K + s][3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j < nvalid) acc[r * K + s][j] = fmaf(__ldg(xp + j), d, acc[r * K + s][j]);
+                }
+            }
+        }
+    }
+    // fold the pixel slots in slot order
+    const int row = TAPS * G * 4;
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t)
+        *reinterpret_cast<float4*>(hw_s + (size_t)ps * row + (t * G + cg) * 4) = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
+    float* bs = hw_s + (size_t)PP * row;
+    bs[threadIdx.x] = cg == 0 ? bsum : 0.f;
+    __syncthreads();
+    float* mine = part + (size_t)blockIdx.x * (TAPS * C + 1);
+    for (int i = threadIdx.x; i < TAPS * C; i += 256) {
+        const int t = i / C, ch = i - t * C;
+        float sum = 0.f;
+        for (int k = 0; k < PP; ++k) sum += hw_s[(size_t)k * row + t * G * 4 + ch];
+        mine[i] = sum;
+    }
+    if (threadIdx.x == 0) {
+        float sum = 0.f;
+        for (int k = 0; k < 256; ++k) sum += bs[k];
+        mine[TAPS * C] = sum;
+    }
+}
+
+__global__ void conv_head_wgrad_reduce_kernel(const float* __restrict__ part, int nparts, int n, float* __restrict__ dw,
+                                              float* __restrict__ db, int accumulate) {
+    pdl_prologue();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    float sum = 0.f;
+    for (int k = 0; k < nparts; ++k) sum += part[(size_t)k * (n + 1) + i];
+    if (i < n) dw[i] = accumulate ? dw[i] + sum : sum;
+    else if (db) db[0] = accumulate ? db[0] + sum : sum;
+}
+
+static int head_wgrad_grid(const ConvWgrad& q, int& gshift) {
+    const int c4 = (q.x.c + 3) / 4;
+    gshift = 0;
+    while ((1 << gshift) < c4) ++gshift;
+    const size_t pp = 256 >> gshift;
+    return (int)std::min<size_t>(cdivz(q.dy.pixels(), pp), 2 * 148);
+}
+bool conv_head_wgrad_supported(const ConvWgrad& q) {
+    return q.dy.c == 1 && q.kh == q.kw && (q.kh == 3 || q.kh == 4) && q.x.c >= 1 && q.x.c <= 1024 && q.x.n == q.dy.n;
+}
+size_t conv_head_wgrad_workspace_floats(const ConvWgrad& q) {
+    int gs;
+    return (size_t)head_wgrad_grid(q, gs) * ((size_t)q.kh * q.kw * q.x.c + 1);
+}
+// q.dw: [tap][cin] (= [tap][cin][1]); q.db: [1] or nullptr
+int conv_head_wgrad(const ConvWgrad& q, cudaStream_t st) {
+    MS_REQUIRE(conv_head_wgrad_supported(q), "conv_head_wgrad: not a single-output-channel weight gradient");
+    int gshift;
+    const int grid = head_wgrad_grid(q, gshift);
+    const int taps = q.kh * q.kw, n = taps * q.x.c;
+    MS_REQUIRE(q.workspace_floats >= (size_t)grid * (n + 1), "conv_head_wgrad: workspace too small");
+    const size_t smem = (size_t)256 * taps * 16 + 256 * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+        MS_CHECK_CUDA(cudaFuncSetAttribute(conv_head_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+        MS_CHECK_CUDA(cudaFuncSetAttribute(conv_head_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+        attr_done = true;
+    }
+    const int vec = ((q.x.c & 3) == 0 && (q.x.cs & 3) == 0 && aligned16(q.x.p)) ? 1 : 0;
+    const size_t npix = q.dy.pixels();
+    if (q.kh == 3) launch_k(conv_head_wgrad_kernel<3>, dim3(grid), dim3(256), smem, st, q, gshift, npix, q.workspace, vec);
+    else launch_k(conv_head_wgrad_kernel<4>, dim3(grid), dim3(256), smem, st, q, gshift, npix, q.workspace, vec);
+    launch_k(conv_head_wgrad_reduce_kernel, dim3(cdiv(n + 1, 256)), dim3(256), 0, st, (const float*)q.workspace, grid, n, q.dw, q.db, q.accumulate);
+    return check_launch("conv_head_wgrad", 2);
+}
+
 int conv_head_kind(const ConvGemm& g) {
     if (g.mul != 1 || g.div != 1) return 0;
     if (g.x.h != g.y.h || g.x.w != g.y.w) return 0;

@@ -221,6 +221,7 @@ size_t Engine::layout(float* base) {
         if (L.stride == 1 && L.cout <= 192)   // tcgen05 wgrad: NCHW copy of dY + <=64 split partials + bias partials
             max_wg = std::max(max_wg, pixels * L.cout + 64 * (size_t)L.kh * L.kw * L.cin * L.cout + 128 * (size_t)L.cout + 8192);
         max_wt = std::max(max_wt, (size_t)L.kh * L.kw * L.cin * L.cout);
+        if (L.cout == 1) max_wg = std::max(max_wg, (size_t)2 * 148 * ((size_t)L.kh * L.kw * L.cin + 1));    // conv_head_wgrad partials
         if (conv_impl == 1 && !L.transposed && L.cin >= 3 && L.cout >= 16) {
             max_wg = std::max(max_wg, std::min<size_t>(wgrad_bf_workspace_floats(L.kh, L.kw, L.cin, L.cout), (size_t)48 << 20));
             wg_xp_halfs = std::max(wg_xp_halfs, pixels * L.stride * L.stride * (size_t)((L.cin + 7) / 8 * 8));
@@ -480,6 +481,8 @@ int Engine::conv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, cons
             MS_REQUIRE(xb.hi && x.pixels() * (size_t)xb.cs <= wg_xp_halfs, "conv_bwd: wgrad scratch planes too small");
             rc = split_planes(x, xb, ws);
             if (!rc) rc = wgrad_bf(q, xb, *wdp, ws);
+        } else if (!rc && use_heads && conv_head_wgrad_supported(q)) {
+            rc = conv_head_wgrad(q, ws);                 // single-channel disparity heads
         } else if (!rc) {
             rc = (use_tc && use_tc_wgrad && wgrad_tc_supported(q)) ? wgrad_tc(q, ws) : conv_wgrad(q, ws);
         }

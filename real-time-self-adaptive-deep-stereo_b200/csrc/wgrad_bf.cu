@@ -59,6 +59,7 @@ struct WgradBfParams {
     int xfmt, dfmt;                // plane formats of X and dY (0 = bf16, 1 = fp16 of value / 16)
     float* part;                   // [split][tap][ci][co]
     float* bpart;                  // [split][co]
+    int debug;                     // MS_WB_DEBUG bit mask (diagnosis): 1 no MMAs, 2 no TMA loads, 4 main product only, 8 product-major issue order
 };
 
 __device__ __forceinline__ void wb_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -129,6 +130,7 @@ wgrad_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
                 const int rem = t - img * tiles_img;
                 const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
                 mb_wait(&empty_bar[st], ph ^ 1u);
+                if (p.debug & 2) { mb_arrive(&full_bar[st]); if (++st == p.nstages) { st = 0; ph ^= 1u; } continue; }
                 mb_expect_tx(&full_bar[st], p.stage_bytes);
                 unsigned char* dst = gbase + stage0 + (size_t)st * p.stage_bytes;
                 for (int pl = 0; pl < 2; ++pl) {
@@ -169,9 +171,22 @@ wgrad_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
                 const uint32_t sb = base + stage0 + (uint32_t)st * p.stage_bytes;
                 const uint32_t xh = sb, xl = sb + p.x_plane_bytes;
                 const uint32_t dh = sb + 2u * p.x_plane_bytes, dl = dh + p.d_plane_bytes;
-                for (int j = 0; j < ksteps; ++j) {
+                for (int j = 0; j < ((p.debug & 1) ? 0 : ksteps); ++j) {
                     const uint64_t bh = umma_desc_mn_sw128(dh + (uint32_t)(2 * j) * WB_ATOM, lbo_d, 1024u);
                     const uint64_t bl = umma_desc_mn_sw128(dl + (uint32_t)(2 * j) * WB_ATOM, lbo_d, 1024u);
+                    if (p.debug & 12) {                 // diagnosis variants: main product only (4) / product-major order (8)
+                        for (int pr = (p.debug & 4) ? 2 : 0; pr < 3; ++pr)
+                            for (int r = 0; r < p.kh; ++r) {
+                                const uint32_t ro = (uint32_t)(p.tap_row[r] + 2 * j) * WB_ATOM;
+                                const uint64_t ah = umma_desc_mn_sw128(xh + ro, lbo_x, 1024u);
+                                const uint64_t al = umma_desc_mn_sw128(xl + ro, lbo_x, 1024u);
+                                const uint32_t acc = tmem + (uint32_t)(r * p.BN);
+                                const bool first = pr == ((p.debug & 4) ? 2 : 0);
+                                wb_mma_f16(acc, pr == 0 ? al : ah, pr == 1 ? bl : bh, idesc, first ? started : 1u);
+                            }
+                        started = 1u;
+                        continue;
+                    }
                     for (int r = 0; r < p.kh; ++r) {
                         const uint32_t ro = (uint32_t)(p.tap_row[r] + 2 * j) * WB_ATOM;
                         const uint64_t ah = umma_desc_mn_sw128(xh + ro, lbo_x, 1024u);
@@ -403,6 +418,7 @@ int wgrad_bf(const ConvWgrad& q, const ActPlanes& xp, const ActPlanes& dp, cudaS
     p.with_bias = q.db ? 1 : 0;
     p.xfmt = xp.fmt; p.dfmt = dp.fmt;
     p.part = q.workspace;
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MS_WB_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
     p.bpart = q.workspace + (size_t)P.splits * wn;
 
     const CUtensorMap *mXh, *mXl, *mDh, *mDl;

@@ -212,6 +212,11 @@ CONV_CASES = [
     # full-resolution pyramid layers (direct small-channel kernels, csrc/conv_small.cu): >= 4096 output pixels, odd widths
     (2, 96, 130, 3, 16, 3, 2, 1, 0.2), (1, 70, 72, 16, 16, 3, 1, 1, 0.2), (1, 65, 67, 3, 16, 3, 1, 1, 1.0),
     (1, 68, 64, 8, 16, 3, 1, 2, 0.2),
+    # single output channel: weight gradient through the dedicated head kernel (csrc/conv_head.cu:conv_head_wgrad) --
+    # 8 / 16 / 256 lanes per pixel, a channel count that is not a multiple of 4, and the 4x4 stride-2 1 -> 1 geometry of
+    # DispNet's up_predict gradient
+    (2, 20, 36, 64, 1, 3, 1, 1, 1.0), (1, 6, 20, 1024, 1, 3, 1, 1, 1.0), (1, 9, 11, 5, 1, 3, 1, 2, 1.0),
+    (2, 16, 24, 1, 1, 4, 2, 1, 1.0), (1, 192, 640, 32, 1, 3, 1, 1, 1.0),
 ]
 
 
