@@ -132,6 +132,16 @@ int ms_conv2d_transpose_fwd(const float* x, int n, int h, int w, int cin, int x_
                             const float* bias, float* y, int cout, int y_cs, int kh, int kw, int stride,
                             float alpha, float* scratch, void* stream);
 
+/* DispNet conv1 -- sharedLayers.conv2d 7x7 stride 2, 3 -> 64 (Nets/DispNet.py:82-86; Nets/sharedLayers.py:54-63) -- and its
+ * filter / bias gradient on direct CUDA-core kernels (csrc/conv_stem.cu): with 3 input channels the tensor-core tiles are
+ * 90 % padding.  x4: [n,h,w,3] stored with a channel stride of 4 floats; weights HWIO [7,7,3,64]; y / dy [n,ceil(h/2),
+ * ceil(w/2),64]; workspace: ms_conv2d_stem_wgrad_workspace floats. */
+int ms_conv2d_stem_fwd(const float* x4, int n, int h, int w, const float* weights, const float* bias, float* y, int y_cs,
+                       float alpha, void* stream);
+size_t ms_conv2d_stem_wgrad_workspace(int n, int h, int w);
+int ms_conv2d_stem_wgrad(const float* x4, int n, int h, int w, const float* dy, int dy_cs, float* dw, float* db, float* workspace,
+                         size_t workspace_floats, void* stream);
+
 /* The same layer and its two gradients on the split-16-bit tcgen05 path (csrc/conv_bf.cu, csrc/wgrad_bf.cu): forward as a
  * fractionally strided gather in four output-parity launches (fp16 planes of x*act_scale), input gradient as the
  * stride-`stride` conv of dy with the filter read as HWIO [kh,kw,cout,cin], weight gradient as that conv's wgrad with the

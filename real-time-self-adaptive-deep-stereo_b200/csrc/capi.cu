@@ -183,6 +183,41 @@ size_t ms_conv2d_wgrad_bf_scratch(int n, int h, int w, int oh, int ow, int kh, i
     q.x = view(nullptr, n, h, w, cin, cin); q.dy = view(nullptr, n, oh, ow, cout, cout); q.kh = kh; q.kw = kw;
     return wgrad_bf_oneshot_scratch_bytes(q);
 }
+// ---- DispNet conv1 (7x7 stride 2, 3 -> 64; Nets/DispNet.py:82-86) on the direct CUDA-core kernels (csrc/conv_stem.cu).
+//      x: [n,h,w,3] stored with a channel stride of 4 floats (the engine's padded image layout)
+int ms_conv2d_stem_fwd(const float* x4, int n, int h, int w, const float* weights, const float* bias, float* y, int y_cs,
+                       float alpha, void* stream) {
+    int oh, ow, pt, pl;
+    same_pad_c(h, 7, 2, 1, oh, pt);
+    same_pad_c(w, 7, 2, 1, ow, pl);
+    ConvGemm p{};
+    p.x = view(const_cast<float*>(x4), n, h, w, 3, 4);
+    p.y = view(y, n, oh, ow, 64, y_cs);
+    p.wmat = weights; p.bias = bias; p.kh = 7; p.kw = 7;
+    p.mul = 2; p.off_y = -pt; p.off_x = -pl; p.step = 1; p.div = 1;
+    p.alpha = alpha; p.mask = nullptr; p.mask_alpha = 1.f; p.res = nullptr; p.accumulate = 0;
+    if (!conv_stem_fwd_supported(p)) { set_error("ms_conv2d_stem_fwd: unsupported layout"); return -3; }
+    return conv_stem_fwd(p, nullptr, S(stream));
+}
+size_t ms_conv2d_stem_wgrad_workspace(int n, int h, int w) {
+    ConvWgrad q{};
+    q.x = view(nullptr, n, h, w, 3, 4); q.dy = view(nullptr, n, (h + 1) / 2, (w + 1) / 2, 64, 64); q.kh = q.kw = 7; q.stride = 2; q.dil = 1;
+    return conv_stem_wgrad_workspace_floats(q);
+}
+int ms_conv2d_stem_wgrad(const float* x4, int n, int h, int w, const float* dy, int dy_cs, float* dw, float* db, float* workspace,
+                         size_t workspace_floats, void* stream) {
+    int oh, ow, pt, pl;
+    same_pad_c(h, 7, 2, 1, oh, pt);
+    same_pad_c(w, 7, 2, 1, ow, pl);
+    ConvWgrad q{};
+    q.x = view(const_cast<float*>(x4), n, h, w, 3, 4);
+    q.dy = view(const_cast<float*>(dy), n, oh, ow, 64, dy_cs);
+    q.dw = dw; q.db = db; q.kh = q.kw = 7; q.stride = 2; q.dil = 1; q.pad_t = pt; q.pad_l = pl;
+    q.workspace = workspace; q.workspace_floats = workspace_floats; q.accumulate = 0;
+    if (!conv_stem_wgrad_supported(q)) { set_error("ms_conv2d_stem_wgrad: unsupported layout"); return -3; }
+    return conv_stem_wgrad(q, S(stream));
+}
+
 // ---- conv2d_transpose (Nets/sharedLayers.py:80-92) and its two gradients on the split-16-bit tcgen05 path.
 //      weights [kh,kw,cout,cin] (TF layout); x [n,h,w,cin]; y / dy [n,h*stride,w*stride,cout]
 static void transpose_geom(int h, int w, int kh, int kw, int stride, int& oh, int& ow, int& pt, int& pl) {

@@ -103,6 +103,13 @@ struct ConvWgrad {
     int accumulate;       // dw += (shared weights called twice); normally 0
 };
 int conv_wgrad(const ConvWgrad& p, cudaStream_t st);
+// conv_stem.cu: DispNet conv1 (7x7 stride 2, 3 -> 64) on the CUDA cores, forward and weight gradient
+bool conv_stem_fwd_supported(const ConvGemm& g);
+struct ActPlanes;
+int conv_stem_fwd(const ConvGemm& g, const ActPlanes* yp, cudaStream_t st);
+bool conv_stem_wgrad_supported(const ConvWgrad& q);
+size_t conv_stem_wgrad_workspace_floats(const ConvWgrad& q);
+int conv_stem_wgrad(const ConvWgrad& q, cudaStream_t st);
 // conv_head.cu: weight gradient of a single-output-channel conv (disparity heads, DispNet up_predict)
 bool conv_head_wgrad_supported(const ConvWgrad& q);
 size_t conv_head_wgrad_workspace_floats(const ConvWgrad& q);

@@ -49,6 +49,7 @@ Engine::Engine()
     { const char* e4 = getenv("MS_CONV_IMPL"); conv_impl = (e4 && (!strcmp(e4, "tf32") || !strcmp(e4, "0"))) ? 0 : 1; }
     if (!use_tc) conv_impl = 0;
     { const char* e5 = getenv("MS_HEADS"); use_heads = (e5 && e5[0] == '0') ? 0 : 1; }
+    { const char* e7 = getenv("MS_STEM"); use_stem = (e7 && e7[0] == '0') ? 0 : 1; }
     { const char* e6 = getenv("MS_BF_WGRAD"); use_bf_wgrad = (e6 && e6[0] == '0') ? 0 : 1; }
     wg_xp.hi = wg_xp.lo = nullptr; wg_xp.cs = 0; wg_xp.fmt = 0; wg_xp.scale = 1.f; wg_xp_halfs = 0;
     act_scale = 0.f;
@@ -431,6 +432,11 @@ int Engine::conv_fwd(const ConvLayer& L, const TView& x, const TView& y, const f
         fresh.erase(y.p);
         p.wmat = Wt + L.w_off;                       // [tap][1][1]: canonical weights serve either orientation
         rc = conv_one_channel(p, st);
+    } else if (use_stem && !L.transposed && (p.wmat = Wt + L.w_off, conv_stem_fwd_supported(p))) {
+        // DispNet conv1: 3 real channels per 32-wide K block on the tensor-core path; the CUDA cores do it in a third of the time
+        const ActPlanes* ypl = planes_of(y);
+        rc = conv_stem_fwd(p, ypl, st);
+        if (ypl) fresh.insert(y.p); else fresh.erase(y.p);
     } else if (!L.transposed && L.cout <= 16 && conv_small_fwd_supported(p)) {
         // full-resolution 16-channel layers (conv2: 2 x 192 x 640 x 16): M = cout = 16 would waste 7/8 of the swap-AB
         // tile's TMEM lanes and epilogue threads (183 us on the split-16-bit path); the shared-memory tiled direct
@@ -468,7 +474,8 @@ int Engine::conv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, cons
         q.workspace = wg_ws; q.workspace_floats = wg_ws_floats; q.accumulate = 0;
         prof_begin(CAT_CONV_WGRAD, st, (int)(&L - &layers[0]));
         int rc = 0;
-        const ActPlanes* wxp = (conv_impl == 1 && use_bf_wgrad && wgrad_bf_supported(q)) ? planes_of(x) : nullptr;
+        const bool stem_w = use_stem && conv_stem_wgrad_supported(q);
+        const ActPlanes* wxp = (!stem_w && conv_impl == 1 && use_bf_wgrad && wgrad_bf_supported(q)) ? planes_of(x) : nullptr;
         const ActPlanes* wdp = wxp ? planes_of(dpre) : nullptr;
         // the planes of dpre also feed the dgrad below: they are produced on `st` BEFORE the fork
         if (wxp && wdp) rc = ensure_planes(dpre, st);
@@ -481,6 +488,8 @@ int Engine::conv_bwd(const ConvLayer& L, const TView& x, const TView& dpre, cons
             MS_REQUIRE(xb.hi && x.pixels() * (size_t)xb.cs <= wg_xp_halfs, "conv_bwd: wgrad scratch planes too small");
             rc = split_planes(x, xb, ws);
             if (!rc) rc = wgrad_bf(q, xb, *wdp, ws);
+        } else if (!rc && stem_w) {
+            rc = conv_stem_wgrad(q, ws);                 // DispNet conv1
         } else if (!rc && use_heads && conv_head_wgrad_supported(q)) {
             rc = conv_head_wgrad(q, ws);                 // single-channel disparity heads
         } else if (!rc) {

@@ -97,6 +97,7 @@ struct Engine {
     int run_eager(int mode, int group, int disp_mask, int with_update, float lr, float mu, float gscale, cudaStream_t st);
     int use_tc;                      // route eligible convs through conv_tc (env MS_CONV_TC, default 1)
     // ---- split-bf16 tcgen05 path (conv_bf.cu), the default implementation of every eligible conv / dgrad
+    int use_stem;                                  // direct CUDA-core kernels for DispNet conv1 (MS_STEM=0: tensor-core path)
     int use_bf_wgrad;                              // split-bf16 weight gradients (MS_BF_WGRAD=0: the 3xTF32 / fp32 kernels)
     int use_heads;                                 // direct kernels for the 3x3 -> 1 heads (MS_HEADS=0: generic path)
     int conv_impl;                                 // 1 = split-bf16 (default), 0 = the 3xTF32 kernels (MS_CONV_IMPL=tf32)

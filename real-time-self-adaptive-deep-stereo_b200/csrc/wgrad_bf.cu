@@ -59,6 +59,7 @@ struct WgradBfParams {
     int xfmt, dfmt;                // plane formats of X and dY (0 = bf16, 1 = fp16 of value / 16)
     float* part;                   // [split][tap][ci][co]
     float* bpart;                  // [split][co]
+    int tap0, taps_total;          // this launch covers filter rows [tap0 / kw, tap0 / kw + kh) of a taps_total-tap filter
     int debug;                     // MS_WB_DEBUG bit mask (diagnosis): 1 no MMAs, 2 no TMA loads, 4 main product only, 8 product-major issue order
 };
 
@@ -223,7 +224,7 @@ wgrad_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
         const int chunks = p.kh * cpt;
         const int cb = half ? (chunks + 1) / 2 : 0, ce = half ? chunks : (chunks + 1) / 2;
         const bool vec = (p.co & 3) == 0;
-        const int taps = p.kh * p.kw;
+        const int taps = p.taps_total;
         for (int c = cb; c < ce; ++c) {
             const int r = c / cpt, c0 = (c - r * cpt) * 16;
             uint32_t v[16];
@@ -235,7 +236,7 @@ wgrad_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
                 for (int j = 0; j < 16; ++j) v[j] = 0u;
             }
             if (!valid) continue;
-            const int tap = r * p.kw + s;
+            const int tap = p.tap0 + r * p.kw + s;
             const int co0 = nb * p.BN + c0;
             float* prow = p.part + (((size_t)split * taps + tap) * p.ci + ci_g) * p.co + co0;
             if (vec && co0 + 16 <= p.co) {
@@ -380,19 +381,24 @@ int wgrad_bf_init() {
     return 0;
 }
 
-// xp / dp: bf16 planes of q.x / q.dy
-int wgrad_bf(const ConvWgrad& q, const ActPlanes& xp, const ActPlanes& dp, cudaStream_t st) {
+// One kernel launch over the filter rows [r0, r0 + q.kh) of a kh_total-row filter (q.pad_t already shifted to row r0).
+// splits_force > 0: use that split factor (all row groups of one filter share the partial-sum layout).  Returns the split
+// factor used through *splits_out.
+static int wgrad_bf_launch(const ConvWgrad& q, const ActPlanes& xp, const ActPlanes& dp, int r0, int kh_total, int splits_force,
+                           int* splits_out, cudaStream_t st) {
     WbPlan P = wb_plan(q);
     MS_REQUIRE(P.ok, "wgrad_bf: unsupported geometry");
     {   // the split factor never outgrows the caller's workspace
-        const size_t per = (size_t)q.kh * q.kw * q.x.c * q.dy.c + (size_t)q.dy.c;
+        const size_t per = (size_t)kh_total * q.kw * q.x.c * q.dy.c + (size_t)q.dy.c;
         P.splits = (int)std::max<size_t>(1, std::min<size_t>((size_t)P.splits, q.workspace_floats / std::max<size_t>(per, 1)));
+        if (splits_force > 0) P.splits = std::max(1, std::min(splits_force, P.ntiles));
+        MS_REQUIRE(splits_force <= 0 || P.splits == splits_force, "wgrad_bf: row groups disagree on the split factor");
     }
     MS_REQUIRE(xp.fmt == dp.fmt, "wgrad_bf: tcgen05 kind::f16 rejects mixed f16 x bf16 operands (probed: illegal instruction); both plane sets must share a format");
     MS_REQUIRE(xp.hi && xp.lo && dp.hi && dp.lo && (xp.cs & 7) == 0 && (dp.cs & 7) == 0 && xp.cs >= q.x.c && dp.cs >= q.dy.c,
                "wgrad_bf: operand planes missing");
     if (wgrad_bf_init()) return -1;
-    const int ci = q.x.c, co = q.dy.c, taps = q.kh * q.kw;
+    const int ci = q.x.c, co = q.dy.c, taps = kh_total * q.kw;
     const size_t wn = (size_t)taps * ci * co;
     MS_REQUIRE((wn & 3) == 0, "wgrad_bf: taps*ci*co must be a multiple of 4");
     MS_REQUIRE(q.workspace_floats >= wn + co, "wgrad_bf: workspace too small");
@@ -415,7 +421,8 @@ int wgrad_bf(const ConvWgrad& q, const ActPlanes& xp, const ActPlanes& dp, cudaS
     p.ci = ci; p.co = co; p.mblocks = P.mblocks; p.nblocks = P.nblocks; p.BN = P.BN; p.xblk = P.xblk; p.dblk = P.dblk;
     p.nstages = P.nstages; p.stage_bytes = P.stage_bytes; p.x_plane_bytes = P.x_plane_bytes; p.d_plane_bytes = P.d_plane_bytes;
     p.tmem_cols = P.tmem_cols;
-    p.with_bias = q.db ? 1 : 0;
+    p.with_bias = (q.db && r0 == 0) ? 1 : 0;
+    p.tap0 = r0 * q.kw; p.taps_total = taps;
     p.xfmt = xp.fmt; p.dfmt = dp.fmt;
     p.part = q.workspace;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MS_WB_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
@@ -440,12 +447,59 @@ int wgrad_bf(const ConvWgrad& q, const ActPlanes& xp, const ActPlanes& dp, cudaS
     }
     const size_t smem = WB_ONES_BYTES + (size_t)P.nstages * P.stage_bytes + 1024;
     launch_k(wgrad_bf_kernel, dim3(dim3(q.kw * P.mblocks * P.nblocks, P.splits)), dim3(WB_THREADS), smem, st, *mXh, *mXl, *mDh, *mDl, p);
+    if (splits_out) *splits_out = P.splits;
+    return check_launch("wgrad_bf");
+}
+
+// Filter rows per launch.  Every filter row keeps its own accumulator (BN TMEM columns each, plus the bias row), so a tall
+// filter narrows BN: 5 rows leave 64 columns.  Measured (profiles/r2_wgrad_bf_killswitch.log, MMAs only, no loads):
+// 5 rows x BN 64 cost 200 cycles per MMA, 3 rows x BN 128 cost 119 -- per column three times dearer -- so filters with
+// more than 3 rows run as groups of <= 3 rows (4 x 4: 2 + 2), each group its own launch with its own, shorter halo.
+static int wb_group_rows(const ConvWgrad& q) {
+    static int grp = -1;
+    if (grp < 0) { const char* e = getenv("MS_WB_GROUPS"); grp = (e && e[0] == '0') ? 0 : 1; }
+    if (!grp || q.kh <= 3) return q.kh;
+    return q.kh == 4 ? 2 : 3;
+}
+
+// xp / dp: bf16 planes of q.x / q.dy
+int wgrad_bf(const ConvWgrad& q, const ActPlanes& xp, const ActPlanes& dp, cudaStream_t st) {
+    const int khg = wb_group_rows(q);
+    int splits = 0;
+    for (int r0 = 0; r0 < q.kh; r0 += khg) {
+        ConvWgrad g = q;
+        g.kh = std::min(khg, q.kh - r0);
+        g.pad_t = q.pad_t - r0 * q.dil;
+        if (r0) g.db = q.db;                       // (bias only in the first group; the launch looks at r0)
+        MS_REQUIRE(wb_plan(g).ok, "wgrad_bf: unsupported geometry");
+        if (r0 == 0 && khg < q.kh) {               // the shortest group has the same tile count: plans agree on ntiles, take the first group's split
+            WbPlan P0 = wb_plan(g);
+            const size_t per = (size_t)q.kh * q.kw * q.x.c * q.dy.c + (size_t)q.dy.c;
+            splits = (int)std::max<size_t>(1, std::min<size_t>((size_t)P0.splits, q.workspace_floats / std::max<size_t>(per, 1)));
+            for (int r1 = khg; r1 < q.kh; r1 += khg) {      // ... clamped to what every group can honour
+                ConvWgrad h = q; h.kh = std::min(khg, q.kh - r1); h.pad_t = q.pad_t - r1 * q.dil;
+                WbPlan P1 = wb_plan(h);
+                MS_REQUIRE(P1.ok, "wgrad_bf: unsupported geometry");
+                splits = std::min(splits, P1.ntiles);
+            }
+            splits = std::min(splits, P0.ntiles);
+        }
+        int used = 0;
+        if (wgrad_bf_launch(g, xp, dp, r0, q.kh, splits, &used, st)) return -1;
+        splits = used;
+    }
+    const int ci = q.x.c, co = q.dy.c, taps = q.kh * q.kw;
+    const size_t wn = (size_t)taps * ci * co;
+    float* part = q.workspace;
+    float* bpart = q.workspace + (size_t)splits * wn;
+    struct { int splits; } P{splits};
+    struct { float* part; float* bpart; } p{part, bpart};
     const size_t n4 = wn / 4;
     const size_t work = n4 + (q.db ? (size_t)co : 0);
     const float sx16 = xp.fmt == 1 ? 1.f / xp.scale : 1.f, sd16 = dp.fmt == 1 ? 1.f / dp.scale : 1.f;
     launch_k(wgrad_bf_reduce_kernel, dim3((unsigned)cdivz(work, 256)), dim3(256), 0, st, p.part, q.dw, n4, P.splits, p.bpart, q.db, co, q.accumulate,
                                                                       sx16 * sd16, sd16);
-    return check_launch("wgrad_bf", 2);
+    return check_launch("wgrad_bf_reduce", 1);
 }
 
 // one-shot convenience (operator-level C ABI / tests): splits x and dy into planes, runs the kernel.

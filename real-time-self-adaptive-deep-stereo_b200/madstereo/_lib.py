@@ -49,6 +49,9 @@ _SIGS = {
     'ms_conv2d_wgrad_workspace': (Z, [I, I, I, I, Z]),
     'ms_conv2d_wgrad': (I, [P, I, I, I, I, I, P, I, I, I, I, P, P, I, I, I, I, P, Z, P]),
     'ms_conv2d_transpose_fwd': (I, [P, I, I, I, I, I, P, P, P, I, I, I, I, I, F, P, P]),
+    'ms_conv2d_stem_fwd': (I, [P, I, I, I, P, P, P, I, F, P]),
+    'ms_conv2d_stem_wgrad_workspace': (Z, [I, I, I]),
+    'ms_conv2d_stem_wgrad': (I, [P, I, I, I, P, I, P, P, P, Z, P]),
     'ms_conv2d_transpose_fwd_bf': (I, [P, I, I, I, I, I, P, P, P, I, I, I, I, I, F, F, P, Z, P]),
     'ms_conv2d_transpose_dgrad_bf': (I, [P, I, I, I, I, I, P, P, I, I, I, I, I, P, Z, P]),
     'ms_conv2d_transpose_bf_scratch': (Z, [I, I, I, I, I, I, I, I]),

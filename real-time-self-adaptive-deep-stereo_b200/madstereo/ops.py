@@ -166,6 +166,33 @@ def conv2d_wgrad_bf(x, dy, kh, kw, stride=1, dilation=1):
     return dw, db
 
 
+def _pad4(x):
+    n, h, w, c = x.shape
+    x4 = torch.zeros(n, h, w, 4, device=x.device, dtype=torch.float32)
+    x4[..., :c] = x
+    return x4
+
+
+def conv2d_stem(x, w, b, alpha=0.1):
+    """DispNet conv1 (7x7 stride 2, 3 -> 64) on the direct kernel (csrc/conv_stem.cu). x [n,h,w,3]."""
+    n, h, wd, _ = x.shape
+    y = torch.empty(n, same_out(h, 2), same_out(wd, 2), 64, device=x.device, dtype=torch.float32)
+    x4 = _pad4(x)
+    check(lib().ms_conv2d_stem_fwd(_p(x4), n, h, wd, _p(w), _p(b), _p(y), 64, float(alpha), _s()), 'ms_conv2d_stem_fwd')
+    return y
+
+
+def conv2d_stem_wgrad(x, dy):
+    n, h, wd, _ = x.shape
+    dw = torch.empty(7, 7, 3, 64, device=x.device, dtype=torch.float32)
+    db = torch.empty(64, device=x.device, dtype=torch.float32)
+    nws = lib().ms_conv2d_stem_wgrad_workspace(n, h, wd)
+    ws = torch.empty(nws, device=x.device, dtype=torch.float32)
+    x4 = _pad4(x)
+    check(lib().ms_conv2d_stem_wgrad(_p(x4), n, h, wd, _p(dy), 64, _p(dw), _p(db), _p(ws), nws, _s()), 'ms_conv2d_stem_wgrad')
+    return dw, db
+
+
 def _scratch256(nbytes, device):
     buf = torch.empty(nbytes + 256, device=device, dtype=torch.uint8)
     return buf, c_void_p(buf.data_ptr() + (-buf.data_ptr()) % 256)

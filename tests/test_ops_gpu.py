@@ -245,6 +245,28 @@ def test_conv2d_fwd_dgrad_wgrad(ops, case):
     assert rel_linf(db.cpu().numpy(), gb.numpy()) < 5e-5
 
 
+@pytest.mark.parametrize('shape', [(1, 32, 32), (2, 37, 51), (2, 96, 160)])
+def test_conv2d_stem_direct_kernels(ops, shape):
+    """DispNet conv1 (7x7 stride 2, 3 -> 64) forward and filter / bias gradient on the direct CUDA-core kernels."""
+    T = _oracle()
+    n, h, w = shape
+    rng = np.random.default_rng(sum(shape))
+    x = rng.standard_normal((n, h, w, 3)).astype(np.float32)
+    wt = (rng.standard_normal((7, 7, 3, 64)) / np.sqrt(147.0)).astype(np.float32)
+    b = rng.uniform(-0.1, 0.1, 64).astype(np.float32)
+    xt = torch.tensor(x); wtt = torch.tensor(wt, requires_grad=True); bt = torch.tensor(b, requires_grad=True)
+    ref = T.conv2d(xt, wtt, bt, stride=2, dilation=1, alpha=0.1)
+    out = ops.conv2d_stem(cu(x), cu(wt), cu(b), 0.1)
+    assert out.shape == ref.shape
+    assert rel_linf(out.cpu().numpy(), ref.detach().numpy()) < 2e-5
+    pre = T.conv2d(xt, wtt, bt, stride=2, dilation=1, alpha=None)
+    g = rng.standard_normal(pre.shape).astype(np.float32)
+    gw, gb = torch.autograd.grad(pre, [wtt, bt], grad_outputs=torch.tensor(g))
+    dw, db = ops.conv2d_stem_wgrad(cu(x), cu(g))
+    assert rel_linf(dw.cpu().numpy(), gw.numpy()) < 5e-5
+    assert rel_linf(db.cpu().numpy(), gb.numpy()) < 5e-5
+
+
 @pytest.mark.parametrize('case', [(1, 6, 8, 32, 16, 0.1), (2, 5, 7, 1, 1, 1.0), (1, 4, 4, 64, 32, 0.1)])
 def test_conv2d_transpose_fwd(ops, case):
     T = _oracle()
