@@ -9,8 +9,8 @@
 //   wgrad  : a CTA stages an 8 x 16 output tile (input patch 21 x 37 x 3, dY 128 x 64) in shared memory; a thread owns
 //            5 (tap, ci) pairs x 8 output channels = 40 partial sums and reads 5 x + 8 dY values per 40 FMAs; CTAs are
 //            persistent over tiles and leave one partial vector each, folded in a fixed order (deterministic).
-//   forward: same tile; a thread owns 2 adjacent output pixels x 16 output channels and reads 2 x + 16 w per 32 FMAs
-//            (the 147 x 64 filter sits in shared memory, float4 broadcast).
+//   forward: same tile; a thread owns 4 adjacent output pixels x 8 output channels; per filter row the 13 input pixels
+//            they touch are held in registers for all 7 horizontal taps (the 147 x 64 filter sits in shared memory).
 #include <algorithm>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -195,61 +195,69 @@ conv_stem_fwd_kernel(ConvGemm g, int tiles_x, int tiles_y, unsigned short* __res
     const int oy0 = ty * ST_TH, ox0 = tx * ST_TW;
     stem_load_patch(xs, g.x.p, g.x.h, g.x.w, img, oy0 * ST_S + g.off_y, ox0 * ST_S + g.off_x);
     __syncthreads();
-    // thread: 16 output channels (cq) of 2 horizontally adjacent output pixels (pp): 64 pixel pairs x 4 channel quarters
-    const int cq = threadIdx.x & 3, pp = threadIdx.x >> 2;
-    const int py = pp / (ST_TW / 2), px = (pp % (ST_TW / 2)) * 2;
-    float a0[16], a1[16];
+    // thread: 8 output channels (cq) of 4 horizontally adjacent output pixels (pg): 32 pixel groups x 8 channel groups.
+    // Per filter row the 13 input pixels the 4 outputs touch (columns 2*px0 ... 2*px0 + 12) sit in registers and serve all
+    // 7 horizontal taps: 13 + 42 128-bit shared loads per 672 FMAs.  (First version: 2 pixels x 16 channels, 6 loads per
+    // 32 FMAs -- 300 us, shared-memory bound.)
+    const int cq = threadIdx.x & 7, pg = threadIdx.x >> 3;
+    const int py = pg / (ST_TW / 4), px = (pg % (ST_TW / 4)) * 4;
+    float acc[4][8];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) { a0[k] = 0.f; a1[k] = 0.f; }
-    const float* xsf = reinterpret_cast<const float*>(xs);
-    const int pbase = (py * ST_S * ST_PW + px * ST_S) * 4;
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[i][k] = 0.f;
+    const float4* xrow0 = xs + (py * ST_S) * ST_PW + px * ST_S;
     for (int r = 0; r < ST_K; ++r) {
+        float4 xv[13];
+#pragma unroll
+        for (int c = 0; c < 13; ++c) xv[c] = xrow0[r * ST_PW + c];
 #pragma unroll
         for (int s = 0; s < ST_K; ++s) {
 #pragma unroll
             for (int c = 0; c < ST_CI; ++c) {
-                const float x0 = xsf[pbase + (r * ST_PW + s) * 4 + c];
-                const float x1 = xsf[pbase + (r * ST_PW + s + ST_S) * 4 + c];
-                const float4* w4 = reinterpret_cast<const float4*>(ws + ((r * ST_K + s) * ST_CI + c) * ST_CO + cq * 16);
+                const float4* w4 = reinterpret_cast<const float4*>(ws + ((r * ST_K + s) * ST_CI + c) * ST_CO + cq * 8);
+                const float4 w0 = w4[0], w1 = w4[1];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float4 w = w4[k];
-                    a0[4 * k] = fmaf(x0, w.x, a0[4 * k]); a0[4 * k + 1] = fmaf(x0, w.y, a0[4 * k + 1]);
-                    a0[4 * k + 2] = fmaf(x0, w.z, a0[4 * k + 2]); a0[4 * k + 3] = fmaf(x0, w.w, a0[4 * k + 3]);
-                    a1[4 * k] = fmaf(x1, w.x, a1[4 * k]); a1[4 * k + 1] = fmaf(x1, w.y, a1[4 * k + 1]);
-                    a1[4 * k + 2] = fmaf(x1, w.z, a1[4 * k + 2]); a1[4 * k + 3] = fmaf(x1, w.w, a1[4 * k + 3]);
+                for (int i = 0; i < 4; ++i) {
+                    const float4 xp = xv[2 * i + s];
+                    const float x = c == 0 ? xp.x : (c == 1 ? xp.y : xp.z);
+                    acc[i][0] = fmaf(x, w0.x, acc[i][0]); acc[i][1] = fmaf(x, w0.y, acc[i][1]);
+                    acc[i][2] = fmaf(x, w0.z, acc[i][2]); acc[i][3] = fmaf(x, w0.w, acc[i][3]);
+                    acc[i][4] = fmaf(x, w1.x, acc[i][4]); acc[i][5] = fmaf(x, w1.y, acc[i][5]);
+                    acc[i][6] = fmaf(x, w1.z, acc[i][6]); acc[i][7] = fmaf(x, w1.w, acc[i][7]);
                 }
             }
         }
     }
     const int oy = oy0 + py;
     if (oy >= g.y.h) return;
+    float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+    if (g.bias) { b0 = __ldg(reinterpret_cast<const float4*>(g.bias + cq * 8)); b1 = __ldg(reinterpret_cast<const float4*>(g.bias + cq * 8 + 4)); }
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        const int ox = ox0 + px + half;
+    for (int i = 0; i < 4; ++i) {
+        const int ox = ox0 + px + i;
         if (ox >= g.y.w) continue;
         const size_t pix = ((size_t)img * g.y.h + oy) * g.y.w + ox;
-        float* yp = g.y.p + pix * g.y.cs + cq * 16;
-        const float* a = half ? a1 : a0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            float4 v;
-            v.x = a[4 * k] + (g.bias ? __ldg(g.bias + cq * 16 + 4 * k) : 0.f);
-            v.y = a[4 * k + 1] + (g.bias ? __ldg(g.bias + cq * 16 + 4 * k + 1) : 0.f);
-            v.z = a[4 * k + 2] + (g.bias ? __ldg(g.bias + cq * 16 + 4 * k + 2) : 0.f);
-            v.w = a[4 * k + 3] + (g.bias ? __ldg(g.bias + cq * 16 + 4 * k + 3) : 0.f);
-            v.x = fmaxf(g.alpha * v.x, v.x); v.y = fmaxf(g.alpha * v.y, v.y); v.z = fmaxf(g.alpha * v.z, v.z); v.w = fmaxf(g.alpha * v.w, v.w);
-            *reinterpret_cast<float4*>(yp + 4 * k) = v;
-            if (ohi) {
-                unsigned short h[4], l[4];
-                stem_split16(v.x, ofmt, oscale, h[0], l[0]); stem_split16(v.y, ofmt, oscale, h[1], l[1]);
-                stem_split16(v.z, ofmt, oscale, h[2], l[2]); stem_split16(v.w, ofmt, oscale, h[3], l[3]);
-                uint2 hv, lv;
-                hv.x = (uint32_t)h[0] | ((uint32_t)h[1] << 16); hv.y = (uint32_t)h[2] | ((uint32_t)h[3] << 16);
-                lv.x = (uint32_t)l[0] | ((uint32_t)l[1] << 16); lv.y = (uint32_t)l[2] | ((uint32_t)l[3] << 16);
-                *reinterpret_cast<uint2*>(ohi + pix * ocs + cq * 16 + 4 * k) = hv;
-                *reinterpret_cast<uint2*>(olo + pix * ocs + cq * 16 + 4 * k) = lv;
-            }
+        float* yp = g.y.p + pix * g.y.cs + cq * 8;
+        float4 v0 = make_float4(acc[i][0] + b0.x, acc[i][1] + b0.y, acc[i][2] + b0.z, acc[i][3] + b0.w);
+        float4 v1 = make_float4(acc[i][4] + b1.x, acc[i][5] + b1.y, acc[i][6] + b1.z, acc[i][7] + b1.w);
+        v0.x = fmaxf(g.alpha * v0.x, v0.x); v0.y = fmaxf(g.alpha * v0.y, v0.y); v0.z = fmaxf(g.alpha * v0.z, v0.z); v0.w = fmaxf(g.alpha * v0.w, v0.w);
+        v1.x = fmaxf(g.alpha * v1.x, v1.x); v1.y = fmaxf(g.alpha * v1.y, v1.y); v1.z = fmaxf(g.alpha * v1.z, v1.z); v1.w = fmaxf(g.alpha * v1.w, v1.w);
+        *reinterpret_cast<float4*>(yp) = v0;
+        *reinterpret_cast<float4*>(yp + 4) = v1;
+        if (ohi) {
+            unsigned short h[8], l[8];
+            stem_split16(v0.x, ofmt, oscale, h[0], l[0]); stem_split16(v0.y, ofmt, oscale, h[1], l[1]);
+            stem_split16(v0.z, ofmt, oscale, h[2], l[2]); stem_split16(v0.w, ofmt, oscale, h[3], l[3]);
+            stem_split16(v1.x, ofmt, oscale, h[4], l[4]); stem_split16(v1.y, ofmt, oscale, h[5], l[5]);
+            stem_split16(v1.z, ofmt, oscale, h[6], l[6]); stem_split16(v1.w, ofmt, oscale, h[7], l[7]);
+            uint4 hv, lv;
+            hv.x = (uint32_t)h[0] | ((uint32_t)h[1] << 16); hv.y = (uint32_t)h[2] | ((uint32_t)h[3] << 16);
+            hv.z = (uint32_t)h[4] | ((uint32_t)h[5] << 16); hv.w = (uint32_t)h[6] | ((uint32_t)h[7] << 16);
+            lv.x = (uint32_t)l[0] | ((uint32_t)l[1] << 16); lv.y = (uint32_t)l[2] | ((uint32_t)l[3] << 16);
+            lv.z = (uint32_t)l[4] | ((uint32_t)l[5] << 16); lv.w = (uint32_t)l[6] | ((uint32_t)l[7] << 16);
+            *reinterpret_cast<uint4*>(ohi + pix * ocs + cq * 8) = hv;
+            *reinterpret_cast<uint4*>(olo + pix * ocs + cq * 8) = lv;
         }
     }
 }
@@ -272,7 +280,7 @@ int conv_stem_fwd(const ConvGemm& g, const ActPlanes* yp, cudaStream_t st) {
     unsigned short *ohi = nullptr, *olo = nullptr;
     int ocs = 0, ofmt = 0; float oscale = 1.f;
     if (yp && yp->hi) {
-        MS_REQUIRE(yp->cs >= ST_CO && (yp->cs & 3) == 0, "conv_stem_fwd: bad output planes");
+        MS_REQUIRE(yp->cs >= ST_CO && (yp->cs & 7) == 0, "conv_stem_fwd: bad output planes");
         ohi = reinterpret_cast<unsigned short*>(yp->hi); olo = reinterpret_cast<unsigned short*>(yp->lo);
         ocs = yp->cs; ofmt = yp->fmt; oscale = yp->fmt == 1 ? yp->scale : 1.f;
     }

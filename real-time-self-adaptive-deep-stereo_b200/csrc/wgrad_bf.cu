@@ -454,12 +454,14 @@ static int wgrad_bf_launch(const ConvWgrad& q, const ActPlanes& xp, const ActPla
 // Filter rows per launch.  Every filter row keeps its own accumulator (BN TMEM columns each, plus the bias row), so a tall
 // filter narrows BN: 5 rows leave 64 columns.  Measured (profiles/r2_wgrad_bf_killswitch.log, MMAs only, no loads):
 // 5 rows x BN 64 cost 200 cycles per MMA, 3 rows x BN 128 cost 119 -- per column three times dearer -- so filters with
-// more than 3 rows run as groups of <= 3 rows (4 x 4: 2 + 2), each group its own launch with its own, shorter halo.
+// 5 or more rows run as groups of <= 3 rows, each group its own launch with its own, shorter halo.
 static int wb_group_rows(const ConvWgrad& q) {
     static int grp = -1;
     if (grp < 0) { const char* e = getenv("MS_WB_GROUPS"); grp = (e && e[0] == '0') ? 0 : 1; }
-    if (!grp || q.kh <= 3) return q.kh;
-    return q.kh == 4 ? 2 : 3;
+    // in the DispNet step graph (profiles/r2_layers_in_graph_cfg4.json vs r2_layers_cfg4_groups.json): 5 x 5 layers gain
+    // (conv2 462 -> 349 us, conv3 238 -> 152 us), the 4 x 4 transposed-conv gradients as 2 + 2 rows lose (36 -> 73 us)
+    if (!grp || q.kh <= 4) return q.kh;
+    return 3;
 }
 
 // xp / dp: bf16 planes of q.x / q.dy
@@ -500,6 +502,71 @@ int wgrad_bf(const ConvWgrad& q, const ActPlanes& xp, const ActPlanes& dp, cudaS
     launch_k(wgrad_bf_reduce_kernel, dim3((unsigned)cdivz(work, 256)), dim3(256), 0, st, p.part, q.dw, n4, P.splits, p.bpart, q.db, co, q.accumulate,
                                                                       sx16 * sd16, sd16);
     return check_launch("wgrad_bf_reduce", 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05.mma cost probe (diagnosis, scripts/mma_probe.py): one CTA per SM, one thread issues `iters` back-to-back
+// kind::f16 MMAs (M = 128, K = 16, bf16) on zero-filled shared memory -- no loads, no epilogue -- and the cycles between the
+// first issue and the completion of the last one are reported per CTA.
+//   a_mn / b_mn : operand layout (0 = K-major SW128 as in conv_bf, 1 = MN-major SW128 as in wgrad_bf)
+//   n           : MMA N;   n_acc : accumulators visited round-robin (each n columns);  rot : 1 = rotate the operand
+//   addresses over 4 atoms like the real K loop, 0 = the same operands every time
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t probe_desc_k_sw128(uint32_t smem_byte_addr) {
+    return (uint64_t)((smem_byte_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__global__ void __launch_bounds__(128, 1) mma_probe_kernel(int a_mn, int b_mn, int n, int n_acc, int rot, int iters, long long* out) {
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const uint32_t base = (s_addr(smem_dyn) + 1023u) & ~1023u;
+    unsigned char* gbase = smem_dyn + (base - s_addr(smem_dyn));
+    for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(gbase)[i] = 0u;
+    fence_async_smem();
+    if (threadIdx.x == 0) { mb_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_addr(&tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+                               ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t a0 = base, b0 = base + 48 * 1024;
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            const uint32_t step = rot ? (uint32_t)(i & 3) : 0u;
+            // K-major: a K = 16 step is 32 bytes inside the 128-byte swizzle row; MN-major: two 8-row atoms (2 KB)
+            const uint64_t ad = a_mn ? umma_desc_mn_sw128(a0 + step * 2048u, 8u * 1024u, 1024u) : probe_desc_k_sw128(a0) + (uint64_t)(step * 2u);
+            const uint64_t bd = b_mn ? umma_desc_mn_sw128(b0 + step * 2048u, 8u * 1024u, 1024u) : probe_desc_k_sw128(b0) + (uint64_t)(step * 2u);
+            wb_mma_f16(tmem + (uint32_t)((i % n_acc) * n), ad, bd, idesc, i >= n_acc ? 1u : 0u);
+        }
+        const long long t1 = clock64();
+        tc_commit(&bar);
+        mb_wait(&bar, 0);
+        const long long t2 = clock64();
+        out[2 * blockIdx.x] = t1 - t0;          // issue loop
+        out[2 * blockIdx.x + 1] = t2 - t0;      // until the last MMA retired
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+int mma_probe(int a_mn, int b_mn, int n, int n_acc, int rot, int iters, int ctas, long long* out_dev, cudaStream_t st) {
+    MS_REQUIRE(n >= 16 && n <= 256 && (n & 15) == 0 && n_acc >= 1 && n_acc * n <= 512 && ctas >= 1, "mma_probe: bad arguments");
+    static bool init = false;
+    if (!init) {
+        MS_CHECK_CUDA(cudaFuncSetAttribute(mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        init = true;
+    }
+    mma_probe_kernel<<<ctas, 128, 97 * 1024 + 1024, st>>>(a_mn, b_mn, n, n_acc, rot, iters, out_dev);
+    return check_launch("mma_probe");
 }
 
 // one-shot convenience (operator-level C ABI / tests): splits x and dy into planes, runs the kernel.
