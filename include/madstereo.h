@@ -263,9 +263,10 @@ long long ms_launch_count(void);
  * environment selects its profiling build (MS_TC_DEBUG=8, scripts/tc_prof.py). out32: 32 counters; reset != 0 clears. */
 int ms_debug_tc_prof(unsigned long long* out32, int reset);
 /* Diagnosis: cycles per tcgen05.mma.kind::f16 (M = 128, K = 16, bf16) issued back to back by one thread per CTA on zeroed
- * shared memory, for K-major / MN-major operand layouts, MMA N, number of accumulators visited round-robin.  out_dev:
+ * shared memory, for K-major / MN-major operand layouts, MMA N, number of accumulators visited round-robin, and the
+ * issue scheme (uni = 0: loop on lane 0 only; 1: warp-uniform loop, elected lane issues).  out_dev:
  * 2 * ctas int64 (issue-loop cycles, cycles until the last MMA retired).  scripts/mma_probe.py prints the table. */
-int ms_debug_mma_probe(int a_mn, int b_mn, int n, int n_acc, int rot, int iters, int ctas, long long* out_dev, void* stream);
+int ms_debug_mma_probe(int a_mn, int b_mn, int n, int n_acc, int rot, int iters, int uni, int ctas, long long* out_dev, void* stream);
 
 /* MS_BF_PROF=1: clock64 stamps of the last conv_bf launch, 8 per CTA (entry, setup done, first data, MMAs issued,
  * accumulator seen, epilogue done, exit, MMA-thread wait cycles); returns the number of CTAs copied */

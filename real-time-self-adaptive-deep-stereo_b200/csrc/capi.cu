@@ -40,8 +40,8 @@ int ms_corr_fwd(const float* left, int left_cs, const float* right, int right_cs
     return corr_fwd(p, S(stream));
 }
 
-int ms_debug_mma_probe(int a_mn, int b_mn, int n, int n_acc, int rot, int iters, int ctas, long long* out_dev, void* stream) {
-    return mma_probe(a_mn, b_mn, n, n_acc, rot, iters, ctas, out_dev, S(stream));
+int ms_debug_mma_probe(int a_mn, int b_mn, int n, int n_acc, int rot, int iters, int uni, int ctas, long long* out_dev, void* stream) {
+    return mma_probe(a_mn, b_mn, n, n_acc, rot, iters, uni, ctas, out_dev, S(stream));
 }
 int ms_corr_fwd_wide(const float* left, int left_cs, const float* right, int right_cs, float* out, int out_cs, int B, int h,
                      int w, int C, int max_disp, float act_scale, void* stream) {

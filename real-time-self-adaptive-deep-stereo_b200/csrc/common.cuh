@@ -140,7 +140,7 @@ struct CorrFwd {
                                      // tensor-core kernel for wide windows (corr_mma.cu); 0: CUDA-core kernels only
 };
 int corr_fwd(const CorrFwd& p, cudaStream_t st);
-int mma_probe(int a_mn, int b_mn, int n, int n_acc, int rot, int iters, int ctas, long long* out_dev, cudaStream_t st);   // wgrad_bf.cu (diagnosis)
+int mma_probe(int a_mn, int b_mn, int n, int n_acc, int rot, int iters, int uni, int ctas, long long* out_dev, cudaStream_t st);   // wgrad_bf.cu (diagnosis)
 bool corr_mma_supported(const CorrFwd& p);          // corr_mma.cu: wide window (>= 17 displacements), no warp, stride 1
 int corr_mma(const CorrFwd& p, cudaStream_t st);
 int corr_fwd4(const CorrFwd& p, cudaStream_t st);   // corr_tma.cu: 0 launched, 1 shape not handled, -1 error

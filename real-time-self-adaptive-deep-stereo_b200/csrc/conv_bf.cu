@@ -127,7 +127,7 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
     __shared__ uint32_t tmem_slot;
     __shared__ int last_flag;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const uint32_t base = (s_addr(smem_dyn) + 1023u) & ~1023u;
     unsigned char* gbase = smem_dyn + (base - s_addr(smem_dyn));
     const uint32_t pslot = 2u * p.slot_bytes;                 // hi plane | lo plane
@@ -167,7 +167,8 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
 
     if (warp == 0) {
         // ================= producer: halo patches by TMA (per K block x filter column) + weight tiles by bulk copy (per tap) ===
-        if (lane == 0) {
+        const bool leader = elect_one();               // warp-uniform loop, elected lane issues (tc_ptx.cuh:elect_one)
+        {
             int ps = 0, ws = 0;
             uint32_t pph = 0, wph = 0;
             const unsigned char* wbase = p.wtiles + (size_t)blockIdx.y * p.taps_total * p.kblocks * wslot;
@@ -176,8 +177,8 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
                 const BfPatch pt = p.patch[pi];
                 mb_wait(&pempty[ps], pph ^ 1u);
                 unsigned char* dst = gbase + (size_t)ps * pslot;
-                if (p.debug & 4) mb_arrive(&pfull[ps]);
-                else {
+                if (p.debug & 4) { if (leader) mb_arrive(&pfull[ps]); }
+                else if (leader) {
                     mb_expect_tx(&pfull[ps], pslot);
                     tma_load_4d(dst, &mapXh, &pfull[ps], kb * p.kch, x0 * p.sx + pt.dx, y0 * p.sx + pt.dy, img);
                     tma_load_4d(dst + p.slot_bytes, &mapXl, &pfull[ps], kb * p.kch, x0 * p.sx + pt.dx, y0 * p.sx + pt.dy, img);
@@ -185,8 +186,8 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
                 if (++ps == p.NP) { ps = 0; pph ^= 1u; }
                 for (int t = pt.tap0; t < pt.tap0 + pt.ntaps; ++t) {
                     mb_wait(&wempty[ws], wph ^ 1u);
-                    if (p.debug & 2) mb_arrive(&wfull[ws]);
-                    else {
+                    if (p.debug & 2) { if (leader) mb_arrive(&wfull[ws]); }
+                    else if (leader) {
                         mb_expect_tx(&wfull[ws], wslot);
                         bulk_load(gbase + w_off + (size_t)ws * wslot, wbase + ((size_t)p.tap[t].widx * p.kblocks + kb) * wslot, wslot, &wfull[ws]);
                     }
@@ -196,8 +197,10 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer: the whole warp runs the loop (uniform registers), one elected lane issues =================
+        const bool leader = elect_one();
+        const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0);       // (a shuffle from lane 0 is warp-uniform to the compiler)
+        {
             // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (bit 4), A/B format at bits 7 / 10 (0 = f16,
             // 1 = bf16), both K-major, N>>3 at bit 17, M>>4 at bit 24
             const uint32_t f = p.fmt == 0 ? 1u : 0u;
@@ -215,7 +218,7 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
                 const BfPatch pt = p.patch[pi];
                 long long tw0 = prof ? clock64() : 0;
                 mb_wait(&pfull[ps], pph);
-                if (prof) { const long long tw1 = clock64(); waited += tw1 - tw0; if (u == u0) prof[2] = tw1; }
+                if (prof) { const long long tw1 = clock64(); waited += tw1 - tw0; if (u == u0 && leader) prof[2] = tw1; }
                 const uint32_t pb = base + (uint32_t)ps * pslot;
                 for (int t = pt.tap0; t < pt.tap0 + pt.ntaps; ++t) {
                     tw0 = prof ? clock64() : 0;
@@ -229,24 +232,27 @@ conv_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant_
                     for (int j = 0; j < ((p.debug & 1) ? 0 : k16); ++j) {   // K = 16 elements = 32 bytes inside the swizzle row
                         const uint64_t o = (uint64_t)(j * 2);
                         if (p.nprod == 3) {
-                            tc_mma_f16(tmem, wl + o, xh + o, idesc, started_cross);
-                            tc_mma_f16(tmem, wh + o, xl + o, idesc, 1u);
+                            if (leader) {
+                                tc_mma_f16(tmem, wl + o, xh + o, idesc, started_cross);
+                                tc_mma_f16(tmem, wh + o, xl + o, idesc, 1u);
+                            }
                             started_cross = 1u;
                             if (p.nacc == 1) started_main = 1u;
                         }
-                        tc_mma_f16(acc_main, wh + o, xh + o, idesc, started_main);
+                        if (leader) tc_mma_f16(acc_main, wh + o, xh + o, idesc, started_main);
                         started_main = 1u;
                         if (p.nacc == 1) started_cross = 1u;
                     }
-                    tc_commit(&wempty[ws]);
+                    if (leader) tc_commit(&wempty[ws]);
                     if (++ws == p.NW) { ws = 0; wph ^= 1u; }
                 }
-                tc_commit(&pempty[ps]);
+                if (leader) tc_commit(&pempty[ps]);
                 if (++ps == p.NP) { ps = 0; pph ^= 1u; }
                 if (++pi == p.n_patches) pi = 0;
             }
-            if (prof) { prof[3] = clock64(); prof[7] = (unsigned long long)waited; }
-            tc_commit(&accum_bar);
+            if (prof && leader) { prof[3] = clock64(); prof[7] = (unsigned long long)waited; }
+            if (leader) tc_commit(&accum_bar);
+            __syncwarp();
         }
     } else {
         // ================= epilogue (warps 2..9): thread <-> output channel, columns <-> pixels =================

@@ -44,6 +44,17 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
         ::"r"(s_addr(dst)), "l"(map), "r"(s_addr(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// One lane of a converged warp (cute::elect_one_sync).  The tcgen05 / TMA instructions take their descriptors from UNIFORM
+// registers: issued from a loop that only lane 0 runs (`if (lane == 0)`), every operand first crosses over with an
+// ELECT + R2UR.BROADCAST pair -- measured 152 cycles per tcgen05.mma regardless of its shape (scripts/mma_probe.py,
+// profiles/r2_mma_probe.log).  Run the loop on the whole warp with warp-uniform control flow (warp index through a shuffle)
+// and predicate only the instruction itself: the operands then live in uniform registers from the start.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -86,7 +86,7 @@ wgrad_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
     __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], accum_bar;
     __shared__ uint32_t tmem_slot;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const uint32_t base = (s_addr(smem_dyn) + 1023u) & ~1023u;
     unsigned char* gbase = smem_dyn + (base - s_addr(smem_dyn));
     const uint32_t stage0 = WB_ONES_BYTES;
@@ -121,8 +121,9 @@ wgrad_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
     const uint32_t tmem = tmem_slot;
 
     if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0 && total > 0) {
+        // ================= TMA producer: warp-uniform loop, elected lane issues =================
+        const bool leader = elect_one();
+        if (total > 0) {
             int st = 0; uint32_t ph = 0;
             const int tiles_img = p.tiles_x * p.tiles_y;
             const int offx = s * p.dil - p.pad_l;
@@ -131,10 +132,10 @@ wgrad_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
                 const int rem = t - img * tiles_img;
                 const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
                 mb_wait(&empty_bar[st], ph ^ 1u);
-                if (p.debug & 2) { mb_arrive(&full_bar[st]); if (++st == p.nstages) { st = 0; ph ^= 1u; } continue; }
-                mb_expect_tx(&full_bar[st], p.stage_bytes);
+                if (p.debug & 2) { if (leader) mb_arrive(&full_bar[st]); if (++st == p.nstages) { st = 0; ph ^= 1u; } continue; }
+                if (leader) mb_expect_tx(&full_bar[st], p.stage_bytes);
                 unsigned char* dst = gbase + stage0 + (size_t)st * p.stage_bytes;
-                for (int pl = 0; pl < 2; ++pl) {
+                for (int pl = 0; pl < 2 && leader; ++pl) {
                     const CUtensorMap* mx = pl ? &mapXl : &mapXh;
                     unsigned char* xd = dst + (size_t)pl * p.x_plane_bytes;
                     for (int b = 0; b < p.xblk; ++b)
@@ -150,8 +151,10 @@ wgrad_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0 && total > 0) {
+        // ================= MMA issuer: warp-uniform loop, one elected lane issues (tc_ptx.cuh:elect_one) =================
+        const bool leader = elect_one();
+        const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0);
+        if (total > 0) {
             // D = f32, A = B = bf16, both MN-major (bits 15, 16), N >> 3 at bit 17, M >> 4 at bit 24
             // A (= X) / B (= dY) element formats follow the planes: 0 = f16, 1 = bf16 in the descriptor
             const uint32_t fa = p.xfmt == 0 ? 1u : 0u, fb = p.dfmt == 0 ? 1u : 0u;
@@ -183,7 +186,7 @@ wgrad_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
                                 const uint64_t al = umma_desc_mn_sw128(xl + ro, lbo_x, 1024u);
                                 const uint32_t acc = tmem + (uint32_t)(r * p.BN);
                                 const bool first = pr == ((p.debug & 4) ? 2 : 0);
-                                wb_mma_f16(acc, pr == 0 ? al : ah, pr == 1 ? bl : bh, idesc, first ? started : 1u);
+                                if (leader) wb_mma_f16(acc, pr == 0 ? al : ah, pr == 1 ? bl : bh, idesc, first ? started : 1u);
                             }
                         started = 1u;
                         continue;
@@ -193,20 +196,23 @@ wgrad_bf_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
                         const uint64_t ah = umma_desc_mn_sw128(xh + ro, lbo_x, 1024u);
                         const uint64_t al = umma_desc_mn_sw128(xl + ro, lbo_x, 1024u);
                         const uint32_t acc = tmem + (uint32_t)(r * p.BN);
-                        wb_mma_f16(acc, al, bh, idesc, started);
-                        wb_mma_f16(acc, ah, bl, idesc, 1u);
-                        wb_mma_f16(acc, ah, bh, idesc, 1u);
+                        if (leader) {
+                            wb_mma_f16(acc, al, bh, idesc, started);
+                            wb_mma_f16(acc, ah, bl, idesc, 1u);
+                            wb_mma_f16(acc, ah, bh, idesc, 1u);
+                        }
                     }
-                    if (do_bias) {
+                    if (do_bias && leader) {
                         wb_mma_f16(acc_bias, ones, bl, idesc_ones, started);
                         wb_mma_f16(acc_bias, ones, bh, idesc_ones, 1u);
                     }
                     started = 1u;
                 }
-                tc_commit(&empty_bar[st]);
+                if (leader) tc_commit(&empty_bar[st]);
                 if (++st == p.nstages) { st = 0; ph ^= 1u; }
             }
-            tc_commit(&accum_bar);
+            if (leader) tc_commit(&accum_bar);
+            __syncwarp();
         }
     } else {
         // ================= epilogue (warps 2..9): thread <-> ci row, columns <-> (tap, co) =================
@@ -510,12 +516,12 @@ int wgrad_bf(const ConvWgrad& q, const ActPlanes& xp, const ActPlanes& dp, cudaS
 // first issue and the completion of the last one are reported per CTA.
 //   a_mn / b_mn : operand layout (0 = K-major SW128 as in conv_bf, 1 = MN-major SW128 as in wgrad_bf)
 //   n           : MMA N;   n_acc : accumulators visited round-robin (each n columns);  rot : 1 = rotate the operand
-//   addresses over 4 atoms like the real K loop, 0 = the same operands every time
+//   addresses over 4 atoms like the real K loop, 0 = the same operands every time;  uni : issue scheme (see the kernel)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t probe_desc_k_sw128(uint32_t smem_byte_addr) {
     return (uint64_t)((smem_byte_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-__global__ void __launch_bounds__(128, 1) mma_probe_kernel(int a_mn, int b_mn, int n, int n_acc, int rot, int iters, long long* out) {
+__global__ void __launch_bounds__(128, 1) mma_probe_kernel(int a_mn, int b_mn, int n, int n_acc, int rot, int iters, int uni, long long* out) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_slot;
@@ -531,8 +537,12 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(int a_mn, int b_mn, i
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = tmem_slot;
-    if (threadIdx.x == 0) {
+    const int warp = uniform_warp_idx();
+    // uni = 0: the loop runs on lane 0 only (round-2 kernels before this probe); uni = 1: on the whole warp, uniform control
+    // flow, the MMA itself predicated on an elected lane
+    if ((uni && warp == 0) || (!uni && threadIdx.x == 0)) {
+        const bool leader = uni ? elect_one() : true;
+        const uint32_t tmem = uni ? __shfl_sync(0xffffffffu, tmem_slot, 0) : tmem_slot;
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
                                ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
         const uint32_t a0 = base, b0 = base + 48 * 1024;
@@ -542,30 +552,32 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(int a_mn, int b_mn, i
             // K-major: a K = 16 step is 32 bytes inside the 128-byte swizzle row; MN-major: two 8-row atoms (2 KB)
             const uint64_t ad = a_mn ? umma_desc_mn_sw128(a0 + step * 2048u, 8u * 1024u, 1024u) : probe_desc_k_sw128(a0) + (uint64_t)(step * 2u);
             const uint64_t bd = b_mn ? umma_desc_mn_sw128(b0 + step * 2048u, 8u * 1024u, 1024u) : probe_desc_k_sw128(b0) + (uint64_t)(step * 2u);
-            wb_mma_f16(tmem + (uint32_t)((i % n_acc) * n), ad, bd, idesc, i >= n_acc ? 1u : 0u);
+            if (leader) wb_mma_f16(tmem + (uint32_t)((i % n_acc) * n), ad, bd, idesc, i >= n_acc ? 1u : 0u);
         }
         const long long t1 = clock64();
-        tc_commit(&bar);
+        if (leader) tc_commit(&bar);
         mb_wait(&bar, 0);
         const long long t2 = clock64();
-        out[2 * blockIdx.x] = t1 - t0;          // issue loop
-        out[2 * blockIdx.x + 1] = t2 - t0;      // until the last MMA retired
+        if (leader) {
+            out[2 * blockIdx.x] = t1 - t0;          // issue loop
+            out[2 * blockIdx.x + 1] = t2 - t0;      // until the last MMA retired
+        }
     }
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x < 32) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
     }
 }
-int mma_probe(int a_mn, int b_mn, int n, int n_acc, int rot, int iters, int ctas, long long* out_dev, cudaStream_t st) {
+int mma_probe(int a_mn, int b_mn, int n, int n_acc, int rot, int iters, int uni, int ctas, long long* out_dev, cudaStream_t st) {
     MS_REQUIRE(n >= 16 && n <= 256 && (n & 15) == 0 && n_acc >= 1 && n_acc * n <= 512 && ctas >= 1, "mma_probe: bad arguments");
     static bool init = false;
     if (!init) {
         MS_CHECK_CUDA(cudaFuncSetAttribute(mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         init = true;
     }
-    mma_probe_kernel<<<ctas, 128, 97 * 1024 + 1024, st>>>(a_mn, b_mn, n, n_acc, rot, iters, out_dev);
+    mma_probe_kernel<<<ctas, 128, 97 * 1024 + 1024, st>>>(a_mn, b_mn, n, n_acc, rot, iters, uni, out_dev);
     return check_launch("mma_probe");
 }
 

@@ -24,7 +24,7 @@ _SIGS = {
     'ms_version': (I, []),
     'ms_last_error': (c_char_p, []),
     'ms_corr_fwd': (I, [P, I, P, I, P, I, P, I, I, I, I, I, I, I, I, I, P]),
-    'ms_debug_mma_probe': (I, [I, I, I, I, I, I, I, P, P]),
+    'ms_debug_mma_probe': (I, [I, I, I, I, I, I, I, I, P, P]),
     'ms_corr_fwd_wide': (I, [P, I, P, I, P, I, I, I, I, I, I, F, P]),
     'ms_corr_bwd': (I, [P, I, P, I, P, I, P, I, P, I, P, I, P, I, I, I, I, I, I, I, I, P]),
     'ms_conv2d_fwd': (I, [P, I, I, I, I, I, P, P, P, I, I, I, I, I, I, F, P]),
