@@ -22,4 +22,4 @@ ab cfg4_base 4 MS_NOP=1
 ab cfg4_nogroups 4 MS_WB_GROUPS=0
 ab cfg4_nostem 4 MS_STEM=0
 ab cfg2_base 2 MS_NOP=1
-ab cfg2_overlap 2 MS_WGRAD_OVERLAP=1
+ab cfg2_nooverlap 2 MS_WGRAD_OVERLAP=0
