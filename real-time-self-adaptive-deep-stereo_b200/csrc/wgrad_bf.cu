@@ -546,13 +546,27 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(int a_mn, int b_mn, i
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
                                ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
         const uint32_t a0 = base, b0 = base + 48 * 1024;
+        // operands and accumulators of 4 consecutive K steps, fixed before the loop: the loop body is 4 MMAs and a counter
+        // (the first version of this probe selected layouts, rotated addresses and took `i % n_acc` INSIDE the loop and
+        // measured its own 150 - 240 cycles of integer work per iteration, profiles/r2_mma_probe_lane0_loop.log)
+        uint64_t ad[4], bd[4];
+        uint32_t acc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t step = rot ? (uint32_t)k : 0u;
+            ad[k] = a_mn ? umma_desc_mn_sw128(a0 + step * 2048u, 8u * 1024u, 1024u) : probe_desc_k_sw128(a0) + (uint64_t)(step * 2u);
+            bd[k] = b_mn ? umma_desc_mn_sw128(b0 + step * 2048u, 8u * 1024u, 1024u) : probe_desc_k_sw128(b0) + (uint64_t)(step * 2u);
+            acc[k] = tmem + (uint32_t)((k % n_acc) * n);
+        }
         const long long t0 = clock64();
-        for (int i = 0; i < iters; ++i) {
-            const uint32_t step = rot ? (uint32_t)(i & 3) : 0u;
-            // K-major: a K = 16 step is 32 bytes inside the 128-byte swizzle row; MN-major: two 8-row atoms (2 KB)
-            const uint64_t ad = a_mn ? umma_desc_mn_sw128(a0 + step * 2048u, 8u * 1024u, 1024u) : probe_desc_k_sw128(a0) + (uint64_t)(step * 2u);
-            const uint64_t bd = b_mn ? umma_desc_mn_sw128(b0 + step * 2048u, 8u * 1024u, 1024u) : probe_desc_k_sw128(b0) + (uint64_t)(step * 2u);
-            if (leader) wb_mma_f16(tmem + (uint32_t)((i % n_acc) * n), ad, bd, idesc, i >= n_acc ? 1u : 0u);
+        for (int i = 0; i < iters; i += 4) {
+            const uint32_t on = i ? 1u : 0u;
+            if (leader) {
+                wb_mma_f16(acc[0], ad[0], bd[0], idesc, on);
+                wb_mma_f16(acc[1], ad[1], bd[1], idesc, n_acc > 1 ? on : 1u);
+                wb_mma_f16(acc[2], ad[2], bd[2], idesc, n_acc > 2 ? on : 1u);
+                wb_mma_f16(acc[3], ad[3], bd[3], idesc, n_acc > 3 ? on : 1u);
+            }
         }
         const long long t1 = clock64();
         if (leader) tc_commit(&bar);
@@ -571,7 +585,8 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(int a_mn, int b_mn, i
     }
 }
 int mma_probe(int a_mn, int b_mn, int n, int n_acc, int rot, int iters, int uni, int ctas, long long* out_dev, cudaStream_t st) {
-    MS_REQUIRE(n >= 16 && n <= 256 && (n & 15) == 0 && n_acc >= 1 && n_acc * n <= 512 && ctas >= 1, "mma_probe: bad arguments");
+    MS_REQUIRE(n >= 16 && n <= 256 && (n & 15) == 0 && (n_acc == 1 || n_acc == 2 || n_acc == 4) && n_acc * n <= 512 && ctas >= 1 && (iters & 3) == 0,
+               "mma_probe: bad arguments");
     static bool init = false;
     if (!init) {
         MS_CHECK_CUDA(cudaFuncSetAttribute(mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
