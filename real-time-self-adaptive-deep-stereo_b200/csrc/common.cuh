@@ -56,6 +56,9 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_prologue() { pdl_trigger(); pdl_wait(); }
 #endif
 bool pdl_enabled();
+// MS_CARVEOUT=1: every kernel launched through launch_k() asks for the maximum shared-memory carve-out, so consecutive
+// kernels of the step never make an SM re-partition L1 / shared memory (experiment; off by default)
+void carveout_once(const void* kernel);
 void pdl_set_suppressed(bool s);      // the instrumented (event-node) graphs of ms_engine_profile(2) are captured without PDL edges
 template <typename... KArgs, typename... Args>
 inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
@@ -65,6 +68,7 @@ inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    carveout_once(reinterpret_cast<const void*>(kernel));
     (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);      // errors surface in check_launch()
 }
 

@@ -45,10 +45,12 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
         : "memory");
 }
 // One lane of a converged warp (cute::elect_one_sync).  The tcgen05 / TMA instructions take their descriptors from UNIFORM
-// registers: issued from a loop that only lane 0 runs (`if (lane == 0)`), every operand first crosses over with an
-// ELECT + R2UR.BROADCAST pair -- measured 152 cycles per tcgen05.mma regardless of its shape (scripts/mma_probe.py,
-// profiles/r2_mma_probe.log).  Run the loop on the whole warp with warp-uniform control flow (warp index through a shuffle)
-// and predicate only the instruction itself: the operands then live in uniform registers from the start.
+// registers: issued from a loop that only lane 0 runs (`if (lane == 0)`), the descriptors are computed in vector registers and
+// every operand crosses over with an ELECT + R2UR.BROADCAST pair in front of each instruction -- wgrad_bf spent 200 cycles
+// per MMA with its loads switched off (profiles/r2_wgrad_bf_killswitch.log) where the instruction itself costs
+// max(N / 2, 50) cycles (scripts/mma_probe.py, profiles/r2_mma_probe.log).  Run the loop on the whole warp with warp-uniform
+// control flow (warp index through a shuffle) and predicate only the instruction itself: the descriptor arithmetic then
+// runs on the uniform datapath (UIADD3 / UMOV) and nothing crosses over.
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));

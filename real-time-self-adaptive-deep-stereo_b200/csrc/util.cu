@@ -1,6 +1,7 @@
 #include "common.cuh"
 #include <cstdlib>
 #include <mutex>
+#include <set>
 namespace ms {
 static std::mutex g_mu;
 static std::string g_err;
@@ -13,6 +14,16 @@ bool pdl_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("MS_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
     return v != 0;
+}
+void carveout_once(const void* kernel) {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("MS_CARVEOUT"); on = (e && e[0] == '1') ? 1 : 0; }
+    if (!on) return;
+    static std::set<const void*> seen;
+    std::lock_guard<std::mutex> l(g_mu);
+    if (!seen.insert(kernel).second) return;
+    (void)cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    (void)cudaGetLastError();
 }
 static long long g_launches = 0;
 long long launch_count() { return g_launches; }
