@@ -450,6 +450,9 @@ def run_ours(args, cfg):
                                'useful FLOPs = 2*MACs (the 3 MMAs per product are not counted)',
                      'achieved': conv_tflops, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
                      'frac': conv_tflops / pk['bf16_tflops_sustained'],
+                     'frac_issued_mmas': 3.0 * conv_tflops / pk['bf16_tflops_sustained'],
+                     'frac_note': 'frac counts useful FLOPs; the fp32-class arithmetic issues three 16-bit MMAs per product (frac_issued_mmas, an '
+                                  'upper bound: the direct CUDA-core layers of the stack issue none)',
                      'peak_src': pk['src'] + ' bf16 sustained (kernels timed inside a long step)',
                      'timing': 'CUDA event-record nodes around every conv launch group INSIDE the replayed step graph '
                                '(ms_engine_profile(2)), %d steps' % n_prof,
