@@ -6,8 +6,8 @@ make -C real-time-self-adaptive-deep-stereo_b200/csrc -j16 2>&1 | tail -1
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 timeout -s KILL 400 $TR --master-port 29511 tests/dp_check.py > gpurun_out/w_dp${N}_check.log 2>&1
 echo "dp_check rc=$?" >> gpurun_out/w_dp${N}_check.log
-timeout -s KILL 300 python bench.py --gpus 1 --steps 60 --warmup 10 --no-cpu-baseline --no-corr-shapes --no-parity-check > gpurun_out/w_dp${N}_bench1.log 2>&1
-timeout -s KILL 400 $TR --master-port 29513 bench.py --gpus $N --steps 60 --warmup 10 --no-corr-shapes > gpurun_out/w_dp${N}_bench.log 2>&1
-echo "bench rc=$?" >> gpurun_out/w_dp${N}_bench.log
+
+
+
 grep -h "DP \|rc=" gpurun_out/w_dp${N}_check.log
 for f in gpurun_out/w_dp${N}_bench1.log gpurun_out/w_dp${N}_bench.log; do tail -n 2 $f | cut -c1-170; done
