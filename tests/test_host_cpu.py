@@ -26,6 +26,49 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib().ms_version() >= 100
 
 
+def test_ctypes_table_matches_the_header_prototypes():
+    """Every prototype of include/madstereo.h against madstereo/_lib.py:_SIGS -- argument count and the C type class of each
+    argument and of the return value (a mismatch here is a silent stack / register mix-up at call time)."""
+    hdr = open(os.path.join(ROOT, 'include', 'madstereo.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', ' ', hdr, flags=re.S)
+    hdr = re.sub(r'//[^\n]*', ' ', hdr)
+    hdr = re.sub(r'^\s*#[^\n]*', ' ', hdr, flags=re.M)           # preprocessor lines
+    hdr = re.sub(r'extern\s+"C"\s*\{', ' ', hdr)
+    protos = re.findall(r'([A-Za-z_][\w\s\*]*?)\b(ms_\w+)\s*\(([^;{]*?)\)\s*;', hdr)
+    assert len(protos) >= 30
+
+    def cls(t):
+        t = t.strip()
+        if '*' in t:
+            return 'char*' if re.match(r'(const\s+)?char\s*\*$', t) else 'ptr'
+        base = re.sub(r'\bconst\b', '', t).strip()
+        return {'int': 'int', 'float': 'float', 'size_t': 'size_t', 'long long': 'll', 'double': 'double', 'void': 'void',
+                'unsigned int': 'uint'}.get(base, base)
+
+    want_cls = {ctypes.c_int: 'int', ctypes.c_float: 'float', ctypes.c_size_t: 'size_t', ctypes.c_void_p: 'ptr',
+                ctypes.c_char_p: 'char*', ctypes.c_longlong: 'll', ctypes.c_double: 'double', ctypes.c_uint: 'uint', None: 'void'}
+    seen = set()
+    for ret, name, args in protos:
+        assert name in _lib._SIGS, 'header declares %s, the ctypes table does not know it' % name
+        seen.add(name)
+        restype, argtypes = _lib._SIGS[name]
+        params = [a.strip() for a in args.split(',')] if args.strip() not in ('', 'void') else []
+        ptypes = []
+        for a in params:
+            a = re.sub(r'\[[^\]]*\]', '*', a)                       # array parameter = pointer
+            m = re.match(r'(.*?)(\b\w+)?\s*$', a)                   # strip the parameter name
+            t = a if a.rstrip().endswith('*') else m.group(1)
+            ptypes.append(cls(t))
+        got = [want_cls.get(t, 'ptr' if hasattr(t, 'contents') or getattr(t, '__name__', '').startswith('LP_') else str(t)) for t in argtypes]
+        got = ['ptr' if g == 'char*' else g for g in got]
+        exp = ['ptr' if g == 'char*' else g for g in ptypes]
+        assert len(got) == len(exp), '%s: header has %d parameters, ctypes table %d' % (name, len(exp), len(got))
+        assert got == exp, '%s: header %s vs ctypes %s' % (name, exp, got)
+        r = cls(ret.split(';')[-1].split('}')[-1])
+        assert ('ptr' if r in ('char*', 'ptr') else r) == ('ptr' if want_cls.get(restype, str(restype)) in ('char*', 'ptr') else want_cls.get(restype, str(restype))), name
+    assert seen == set(_lib._SIGS), sorted(set(_lib._SIGS) - seen)
+
+
 def _engine_tables(groups_cfg):
     L = _lib.lib()
     e = L.ms_engine_create(b'MADNet', 1, 384, 1280, 2, 1, 1)
