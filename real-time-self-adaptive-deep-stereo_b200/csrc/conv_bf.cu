@@ -738,11 +738,17 @@ static int conv_bf_launch(const ConvGemm& g, const ActPlanes& xp, const void* wt
     const size_t pslot = 2 * (size_t)p.slot_bytes;
     const size_t budget = 220 * 1024;
     MS_REQUIRE(2 * pslot + 2 * wslot <= budget, "conv_bf: patch does not fit shared memory");
+    // MS_BF_SMEM_KB: cap on the two rings (default: all of the SM).  A CTA that leaves half of the shared memory free lets the
+    // NEXT kernel's CTA become resident while this one drains (programmatic dependent launch: barrier set-up, TMEM
+    // allocation and tensor-map fetch then overlap); deeper rings only help while loads are the bound.
+    static long ring_cap = -1;
+    if (ring_cap < 0) { const char* e = getenv("MS_BF_SMEM_KB"); ring_cap = e ? std::max(32L, atol(e)) * 1024 : (long)budget; }
+    const size_t grow_budget = std::max<size_t>(std::min<size_t>(budget, (size_t)ring_cap), 2 * pslot + 2 * wslot);
     int NP = 2, NW = 2;
     for (;;) {                                       // grow the two rings alternately while they fit (weights first: smaller)
         bool grew = false;
-        if (NW < 8 && (size_t)NP * pslot + (size_t)(NW + 1) * wslot <= budget && NW <= 2 * NP) { ++NW; grew = true; }
-        if (NP < 4 && (size_t)(NP + 1) * pslot + (size_t)NW * wslot <= budget) { ++NP; grew = true; }
+        if (NW < 8 && (size_t)NP * pslot + (size_t)(NW + 1) * wslot <= grow_budget && NW <= 2 * NP) { ++NW; grew = true; }
+        if (NP < 4 && (size_t)(NP + 1) * pslot + (size_t)NW * wslot <= grow_budget) { ++NP; grew = true; }
         if (!grew) break;
     }
     p.NP = NP; p.NW = NW;
