@@ -456,9 +456,9 @@ def run_ours(args, cfg):
                      'peak_src': pk['src'] + ' bf16 sustained (kernels timed inside a long step)',
                      'timing': 'CUDA event-record nodes around every conv launch group INSIDE the replayed step graph '
                                '(ms_engine_profile(2)), %d steps' % n_prof,
-                     'traffic': 16432640 if (args.config in (2, 3) and B == 1) else None,
+                     'traffic': 16399616 if (args.config in (2, 3) and B == 1) else None,
                      'traffic_src': 'dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (conv_bf_kernel, 128->128 3x3 '
-                                    '@96x320 forward) from ncu --set full, profiles/r2_ncu_conv_bf_128x128_96x320.txt; algorithmic: 15.7 MB of fp16 '
+                                    '@96x320 forward) from ncu --set full, profiles/r2_final_ncu_conv_bf_128x128_96x320.txt (16.394 MB read + 5.6 KB written); algorithmic: 15.7 MB of fp16 '
                                     'planes + 0.6 MB of weight tiles read, the 31 MB it writes stay in L2',
                      'avg_launch_us': 1e3 * conv_ms / max(conv_calls, 1),
                      'share_of_step': conv_ms / prof_total if prof_total else None,
